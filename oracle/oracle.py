@@ -1,0 +1,213 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the CPU oracle (oracle/*.c).
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs
+may import this module.  The product package ``alphasurf_b200`` never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.oracle_cubic_solve.restype = C.c_int
+    return _LIB
+
+
+class OGrid(C.Structure):
+    _fields_ = [("size", C.c_int32 * 3), ("links", C.c_void_p), ("density", C.c_void_p), ("surface", C.c_void_p),
+                ("sh", C.c_void_p), ("level_set", C.c_void_p), ("level_set_num", C.c_int32),
+                ("basis_dim", C.c_int32), ("sh_dim", C.c_int32), ("offset", C.c_float * 3),
+                ("scaling", C.c_float * 3), ("fake_sample_std", C.c_float), ("truncated_vol_render_a", C.c_float)]
+
+
+class OOpt(C.Structure):
+    _fields_ = [("background_brightness", C.c_float), ("step_size", C.c_float), ("sigma_thresh", C.c_float),
+                ("stop_thresh", C.c_float), ("near_clip", C.c_float), ("use_spheric_clip", C.c_int32),
+                ("last_sample_opaque", C.c_int32), ("surf_fake_sample", C.c_int32),
+                ("surf_fake_sample_min_vox_len", C.c_float), ("limited_fake_sample", C.c_int32),
+                ("no_surf_grad_from_sh", C.c_int32), ("alpha_activation_type", C.c_int32),
+                ("fake_sample_l_dist", C.c_int32), ("fake_sample_normalize_surf", C.c_int32),
+                ("only_outward_intersect", C.c_int32), ("truncated_vol_render", C.c_int32),
+                ("trunc_vol_weight_min", C.c_float)]
+
+
+class OFused(C.Structure):
+    _fields_ = [("beta_loss", C.c_float), ("sparsity_loss", C.c_float), ("lambda_l2", C.c_float),
+                ("lambda_l1", C.c_float), ("lambda_l_dist", C.c_float), ("lambda_l_entropy", C.c_float),
+                ("no_norm_weight_l_entropy", C.c_int32), ("lambda_l_dist_a", C.c_float),
+                ("lambda_l_entropy_a", C.c_float), ("lambda_l_samp_dist", C.c_float), ("lambda_l_di", C.c_float),
+                ("l_di_alpha_thresh", C.c_float), ("surf_sparse_alpha_thresh", C.c_float),
+                ("lambda_inplace_surf_sparse", C.c_float), ("lambda_inwards_norm_loss", C.c_float),
+                ("lambda_conv_mode_samp", C.c_float), ("l_dist_max_sample", C.c_int32)]
+
+
+class OGrads(C.Structure):
+    _fields_ = [("grad_density", C.c_void_p), ("grad_surface", C.c_void_p), ("grad_sh", C.c_void_p),
+                ("grad_fake_sample_std", C.c_void_p), ("mask", C.c_void_p)]
+
+
+class OTrace(C.Structure):
+    _fields_ = [("max_hits", C.c_int32), ("hit_count", C.c_void_p), ("hit_cell", C.c_void_p),
+                ("hit_kind", C.c_void_p), ("hit_t", C.c_void_p), ("counters", C.c_void_p)]
+
+
+def _np(t, dtype):
+    """torch tensor / ndarray -> contiguous ndarray of dtype (copy only if needed)."""
+    if t is None:
+        return None
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().numpy()
+    return np.ascontiguousarray(t, dtype=dtype)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Grid:
+    """Holds numpy copies of a SynthGrid-like object (attributes links/density/surface/sh/level_set/offset/scaling)."""
+
+    def __init__(self, g):
+        self.links = _np(g.links, np.int32)
+        self.density = _np(g.density, np.float32)
+        self.surface = _np(g.surface, np.float32)
+        self.sh = _np(g.sh, np.float32)
+        self.level_set = _np(g.level_set, np.float32)
+        self.offset = _np(g.offset, np.float32)
+        self.scaling = _np(g.scaling, np.float32)
+        self.basis_dim = int(g.basis_dim)
+        self.fake_sample_std = float(g.fake_sample_std)
+        self.truncated_vol_render_a = float(g.truncated_vol_render_a)
+        s = OGrid()
+        s.size[:] = list(self.links.shape)
+        s.links = _ptr(self.links)
+        s.density = _ptr(self.density)
+        s.surface = _ptr(self.surface)
+        s.sh = _ptr(self.sh)
+        s.level_set = _ptr(self.level_set)
+        s.level_set_num = 0 if self.level_set is None else int(self.level_set.shape[0])
+        s.basis_dim = self.basis_dim
+        s.sh_dim = int(self.sh.shape[1])
+        s.offset[:] = self.offset.tolist()
+        s.scaling[:] = self.scaling.tolist()
+        s.fake_sample_std = self.fake_sample_std
+        s.truncated_vol_render_a = self.truncated_vol_render_a
+        self.c = s
+
+    @property
+    def N(self):
+        return self.density.shape[0]
+
+
+def make_opt(d: dict) -> OOpt:
+    o = OOpt()
+    for name, ctype in OOpt._fields_:
+        v = d[name]
+        setattr(o, name, float(v) if ctype is C.c_float else int(v))
+    return o
+
+
+def make_fused(d: dict) -> OFused:
+    f = OFused()
+    for name, ctype in OFused._fields_:
+        v = d.get(name, 0)
+        setattr(f, name, float(v) if ctype is C.c_float else int(v))
+    return f
+
+
+class Grads:
+    def __init__(self, grid: Grid, with_mask=True, with_std=True):
+        self.density = np.zeros_like(grid.density)
+        self.surface = None if grid.surface is None else np.zeros_like(grid.surface)
+        self.sh = np.zeros_like(grid.sh)
+        self.fake_sample_std = np.zeros((1,), np.float32) if with_std else None
+        self.mask = np.zeros((grid.N,), np.uint8) if with_mask else None
+        c = OGrads()
+        c.grad_density = _ptr(self.density)
+        c.grad_surface = _ptr(self.surface)
+        c.grad_sh = _ptr(self.sh)
+        c.grad_fake_sample_std = _ptr(self.fake_sample_std)
+        c.mask = _ptr(self.mask)
+        self.c = c
+
+
+class Trace:
+    def __init__(self, Q, max_hits=64):
+        self.hit_count = np.zeros((Q,), np.int32)
+        self.hit_cell = np.full((Q, max_hits), -1, np.int32)
+        self.hit_kind = np.full((Q, max_hits), -1, np.int32)
+        self.hit_t = np.zeros((Q, max_hits), np.float32)
+        self.counters = np.zeros((Q, 4), np.int64)
+        c = OTrace()
+        c.max_hits = max_hits
+        c.hit_count = _ptr(self.hit_count)
+        c.hit_cell = _ptr(self.hit_cell)
+        c.hit_kind = _ptr(self.hit_kind)
+        c.hit_t = _ptr(self.hit_t)
+        c.counters = _ptr(self.counters)
+        self.c = c
+
+
+def surf_trav_forward(grid: Grid, opt: dict, origins, dirs, xf=None, trace: Trace = None):
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    xf = _np(xf, np.float32)
+    Q = o.shape[0]
+    out = np.zeros((Q, 3), np.float32)
+    lib().oracle_surf_trav_forward(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf),
+                                   C.c_int64(Q), _ptr(out), C.c_int(0), None, None, None,
+                                   C.byref(trace.c) if trace else None)
+    return out
+
+
+def surf_trav_backward(grid: Grid, opt: dict, origins, dirs, grad_out, color_cache, xf=None, grads: Grads = None):
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    xf = _np(xf, np.float32)
+    go, cc = _np(grad_out, np.float32), _np(color_cache, np.float32)
+    grads = grads or Grads(grid, with_mask=False)
+    lib().oracle_surf_trav_backward(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf),
+                                    C.c_int64(o.shape[0]), _ptr(go), _ptr(cc), C.byref(grads.c))
+    return grads
+
+
+def surf_trav_fused(grid: Grid, opt: dict, origins, dirs, rgb_gt, fused: dict, xf=None, grads: Grads = None,
+                    trace: Trace = None, q_norm=None):
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    xf = _np(xf, np.float32)
+    gt = _np(rgb_gt, np.float32)
+    Q = o.shape[0]
+    out = np.zeros((Q, 3), np.float32)
+    grads = grads or Grads(grid)
+    lib().oracle_surf_trav_fused(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q),
+                                 C.c_int64(Q if q_norm is None else q_norm), _ptr(gt), C.byref(make_fused(fused)),
+                                 _ptr(out), C.byref(grads.c), C.byref(trace.c) if trace else None)
+    return out, grads
+
+
+def cubic_solve(fs):
+    fs = np.ascontiguousarray(fs, np.float64)
+    st = np.zeros(3, np.float64)
+    typ = lib().oracle_cubic_solve(_ptr(fs), _ptr(st))
+    return typ, st
+
+
+def cubic_root_grad(typ, st_id, fs):
+    fs = np.ascontiguousarray(fs, np.float64)
+    g = np.ones(4, np.float32)
+    lib().oracle_cubic_root_grad(C.c_int(typ), C.c_int(st_id), _ptr(fs), _ptr(g))
+    return g
