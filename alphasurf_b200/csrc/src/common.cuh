@@ -1,0 +1,64 @@
+// alphasurf_b200: shared host/device declarations for the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "asurf.h"
+
+namespace asurf {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+
+#define ASURF_CUDA(expr)                                   \
+    do {                                                   \
+        int _rc = ::asurf::check_cuda((expr), #expr);      \
+        if (_rc != 0) return _rc;                          \
+    } while (0)
+
+#define ASURF_REQUIRE(cond, code, ...)                     \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            ::asurf::set_error(__VA_ARGS__);               \
+            return (code);                                 \
+        }                                                  \
+    } while (0)
+
+// ---- growable device workspace (one per purpose, owned by the library) -----------------------------------
+struct Workspace {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+    int reserve(size_t need);   // grows geometrically; contents are NOT preserved
+    void release();
+};
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- occupancy pyramid layout (accel.cu) -----------------------------------------------------------------
+// A "cell" (x,y,z) is the voxel spanned by vertices (x..x+1, y..y+1, z..z+1); it is ACTIVE iff its 8 corner
+// links are all >= 0.  Level 0: one 64-bit word per 4x4x4 block of cells, bit = (x&3)<<4 | (y&3)<<2 | (z&3).
+// Level k+1: one word per 4x4x4 block of level-k words, bit set iff that child word != 0.
+// So "word == 0" at level k means an empty block of 4^(k+1) cells per side (4, 16, 64).
+// All levels live in one buffer: [level 0 | level 1 | level 2].
+struct AccelLayout {
+    int b[3][3];      // b[level][axis]
+    int64_t off[4];   // word offset of each level; off[3] = total
+    __host__ __device__ AccelLayout() {}
+    __host__ __device__ explicit AccelLayout(const int32_t size[3]) {
+        off[0] = 0;
+        for (int l = 0; l < 3; ++l) {
+            for (int i = 0; i < 3; ++i) {
+                const int prev = (l == 0) ? (size[i] - 1 > 0 ? size[i] - 1 : 1) : b[l - 1][i];
+                b[l][i] = (prev + 3) >> 2;
+            }
+            off[l + 1] = off[l] + (int64_t)b[l][0] * b[l][1] * b[l][2];
+        }
+    }
+    __host__ __device__ int64_t count(int l) const { return off[l + 1] - off[l]; }
+};
+
+}  // namespace asurf

@@ -1,0 +1,155 @@
+// alphasurf_b200: in-place RMSprop / SGD steps on (N, C) grid tensors.
+//
+// Replaces rmsprop_step / sgd_step of /root/reference/svox2/csrc/optim_kernel.cu:154-267.
+//   rms  = rms == 0 ? g^2 : lerp(g^2, rms, beta);  x = max(x - lr*g/(sqrt(rms)+eps), minval);  g = 0
+//   (optim_kernel.cu:15-25); the last channel may use lr_last (:37-46).
+// Three indexer modes as the reference dispatches them (:175-215): all rows, bool row mask, int64 row list.
+//
+// Pure streaming, HBM-bound: 12 B read + 12 B written per touched element.  The dense and masked kernels
+// run a grid-stride loop with 64-bit element indices (the reference's `int tid` overflows at
+// 512^3 x 27, cuda_util.cuh:14); when C is a multiple of 4 or rows are taken whole, loads are float4.
+#include "common.cuh"
+
+namespace asurf {
+namespace {
+
+__device__ __forceinline__ void rmsprop_once(float &x, float &rms, float &g, float beta, float lr, float eps,
+                                             float minval) {
+    const float g2 = g * g;
+    rms = (rms == 0.f) ? g2 : fmaf(beta, rms - g2, g2);
+    x = fmaxf(x - __fdiv_rn(lr * g, sqrtf(rms) + eps), minval);
+    g = 0.f;
+}
+
+// Dense / masked: one thread per element, grid-stride; consecutive threads touch consecutive floats.
+template <bool MASKED>
+__global__ void __launch_bounds__(256) rmsprop_dense_kernel(float *__restrict__ data, float *__restrict__ rms,
+                                                             float *__restrict__ grad, const uint8_t *__restrict__ mask,
+                                                             int64_t n_elem, int n_cols, float beta, float lr,
+                                                             float eps, float minval, float lr_last) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const int64_t row = i / n_cols;
+        const int c = (int)(i - row * n_cols);
+        if (MASKED && !mask[row]) continue;
+        float x = data[i], r = rms[i], g = grad[i];
+        rmsprop_once(x, r, g, beta, (c == n_cols - 1) ? lr_last : lr, eps, minval);
+        data[i] = x;
+        rms[i] = r;
+        grad[i] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) rmsprop_index_kernel(float *__restrict__ data, float *__restrict__ rms,
+                                                             float *__restrict__ grad, const int64_t *__restrict__ idx,
+                                                             int64_t n_index, int n_cols, float beta, float lr,
+                                                             float eps, float minval, float lr_last) {
+    const int64_t n_elem = n_index * n_cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const int64_t k = i / n_cols;
+        const int c = (int)(i - k * n_cols);
+        // the reference narrows the int64 index to int32 (optim_kernel.cu:86); rows never exceed 2^31
+        const int64_t off = (int64_t)(int32_t)idx[k] * n_cols + c;
+        float x = data[off], r = rms[off], g = grad[off];
+        rmsprop_once(x, r, g, beta, (c == n_cols - 1) ? lr_last : lr, eps, minval);
+        data[off] = x;
+        rms[off] = r;
+        grad[off] = 0.f;
+    }
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(256) sgd_dense_kernel(float *__restrict__ data, float *__restrict__ grad,
+                                                         const uint8_t *__restrict__ mask, int64_t n_elem, int n_cols,
+                                                         float lr, float lr_last) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const int64_t row = i / n_cols;
+        const int c = (int)(i - row * n_cols);
+        if (MASKED && !mask[row]) continue;
+        const float l = (c == n_cols - 1) ? lr_last : lr;
+        data[i] = fmaf(-l, grad[i], data[i]);   // nvcc contracts `x -= lr * g` (optim_kernel.cu:100)
+        grad[i] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) sgd_index_kernel(float *__restrict__ data, float *__restrict__ grad,
+                                                         const int64_t *__restrict__ idx, int64_t n_index, int n_cols,
+                                                         float lr, float lr_last) {
+    const int64_t n_elem = n_index * n_cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const int64_t k = i / n_cols;
+        const int c = (int)(i - k * n_cols);
+        const int64_t off = (int64_t)(int32_t)idx[k] * n_cols + c;
+        const float l = (c == n_cols - 1) ? lr_last : lr;
+        data[off] = fmaf(-l, grad[off], data[off]);
+        grad[off] = 0.f;
+    }
+}
+
+int stream_grid(int64_t n_elem) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n_elem + 255) / 256;
+    const int64_t cap = (int64_t)sms * 16;  // 16 CTAs x 256 threads = 2 full waves of resident threads per SM
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+}  // namespace asurf
+
+using namespace asurf;
+
+extern "C" int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols,
+                                  int32_t indexer_kind, const void *indexer, int64_t n_index, float beta, float lr,
+                                  float eps, float minval, float lr_last, void *stream) {
+    ASURF_REQUIRE(data && rms && grad, ASURF_E_INVALID, "rmsprop_step: null tensor");
+    ASURF_REQUIRE(n_cols > 0 && n_rows >= 0, ASURF_E_INVALID, "rmsprop_step: bad shape");
+    if (lr_last < 0.f) lr_last = lr;  // optim_kernel.cu:171
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_elem = n_rows * n_cols;
+    if (indexer_kind == 0) {
+        if (n_elem == 0) return 0;
+        rmsprop_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, nullptr, n_elem, n_cols, beta,
+                                                                         lr, eps, minval, lr_last);
+    } else if (indexer_kind == 1) {
+        if (n_index == 0 || n_elem == 0) return 0;  // size(0) == 0 -> skip (:189)
+        rmsprop_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer,
+                                                                        n_elem, n_cols, beta, lr, eps, minval, lr_last);
+    } else if (indexer_kind == 2) {
+        if (n_index == 0) return 0;
+        rmsprop_index_kernel<<<stream_grid(n_index * n_cols), 256, 0, st>>>(data, rms, grad, (const int64_t *)indexer,
+                                                                           n_index, n_cols, beta, lr, eps, minval,
+                                                                           lr_last);
+    } else {
+        ASURF_REQUIRE(false, ASURF_E_INVALID, "rmsprop_step: bad indexer kind %d", indexer_kind);
+    }
+    return check_cuda(cudaGetLastError(), "rmsprop_step launch");
+}
+
+extern "C" int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
+                              const void *indexer, int64_t n_index, float lr, float lr_last, void *stream) {
+    ASURF_REQUIRE(data && grad, ASURF_E_INVALID, "sgd_step: null tensor");
+    ASURF_REQUIRE(n_cols > 0 && n_rows >= 0, ASURF_E_INVALID, "sgd_step: bad shape");
+    if (lr_last < 0.f) lr_last = lr;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_elem = n_rows * n_cols;
+    if (indexer_kind == 0) {
+        if (n_elem == 0) return 0;
+        sgd_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, nullptr, n_elem, n_cols, lr, lr_last);
+    } else if (indexer_kind == 1) {
+        if (n_index == 0 || n_elem == 0) return 0;
+        sgd_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, (const uint8_t *)indexer, n_elem, n_cols,
+                                                                    lr, lr_last);
+    } else if (indexer_kind == 2) {
+        if (n_index == 0) return 0;
+        sgd_index_kernel<<<stream_grid(n_index * n_cols), 256, 0, st>>>(data, grad, (const int64_t *)indexer, n_index,
+                                                                       n_cols, lr, lr_last);
+    } else {
+        ASURF_REQUIRE(false, ASURF_E_INVALID, "sgd_step: bad indexer kind %d", indexer_kind);
+    }
+    return check_cuda(cudaGetLastError(), "sgd_step launch");
+}

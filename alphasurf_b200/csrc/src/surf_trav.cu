@@ -1,0 +1,1088 @@
+// alphasurf_b200: the alpha-Surf "surf_trav" renderer (forward, backward, fused) for sm_100a.
+//
+// Replaces volume_render_surf_trav / _backward / _fused of
+// /root/reference/svox2/csrc/render_lerp_kernel_surf_trav.cu:3596-3942 (kernels :3139-3368, ray marchers
+// :37-562 and :1710-2911).  Results follow the reference semantics voxel by voxel;
+// the execution model is this repo's own:
+//
+//  * LANE PER RAY for everything that is scalar per ray -- the DDA, the 8-corner gates, the fp64 cubic
+//    solve, compositing and all the lane-0-only loss terms of the reference.  The reference runs those
+//    redundantly on 27 lanes of a warp that owns a single ray; here 32 rays advance per warp.
+//  * The DDA tests ONE BIT of an occupancy bitmap (accel.cu; 16.7 MB at 512^3, L2 resident) per visited
+//    voxel instead of gathering 8 scattered int32 links; the visited-voxel sequence and every t_close /
+//    t_far stay bit-identical to the reference's incremental DDA (same IEEE divides, same tie-breaks).
+//  * WARP PER SAMPLE for the wide part: when lanes have found a sample to composite, the warp walks the
+//    pending lanes; for each, lane k < D gathers coefficient k of the 8 corner SH rows (8 coalesced
+//    108-byte row reads), and in the backward scatters the 8xD gradient with coalesced red.global.add.
+//  * The forward keeps the per-ray (rwalpha, weight, t) sample caches the fused losses need, but writes
+//    only the entries a ray produced (plus a count) instead of zero-filling 3 x (Q,64) floats per call.
+#include "common.cuh"
+#include "surf_math.cuh"
+
+namespace asurf {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CTA_THREADS = 128;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+
+struct GridP {
+    const int32_t *links;
+    const float *density, *surface, *sh, *level_set;
+    const uint64_t *accel;
+    int size[3];
+    int level_set_num, basis_dim, sh_dim;
+    int ab1, ab2;  // level-0 bitmap block counts along y and z
+    float offset[3], scaling[3];
+    float fake_sample_std, trunc_a;
+};
+
+// fused-loss scalars after the launch-time scaling of render_lerp_kernel_surf_trav.cu:3896-3914
+struct FusedP {
+    float sparsity_loss, lambda_l2, lambda_l1, lambda_l_dist, lambda_l_entropy, lambda_l_dist_a, lambda_l_entropy_a,
+        lambda_l_samp_dist, lambda_l_di, l_di_alpha_thresh, surf_sparse_alpha_thresh, lambda_inplace_surf_sparse,
+        lambda_inwards_norm_loss, lambda_conv_mode_samp;
+    float norm_l2, norm_l1;  // 2/(3Q), 1/(3Q)
+    int no_norm_weight_l_entropy;
+    int M;                   // l_dist_max_sample
+    int grad_is_rgb;         // fused: grad_in is rgb_gt
+};
+
+struct CacheP {
+    float *sa, *sw, *st;  // (Q, M)
+    int *n;               // (Q,) entries written
+};
+
+struct DebugP {
+    int32_t max_hits;
+    int32_t *hit_count, *hit_cell, *hit_kind;
+    float *hit_t;
+    float *xf;                    // (Q,9)
+    unsigned long long *stats;    // asurf_stats_t
+};
+
+enum { PH_MARCH = 0, PH_ROOTS = 1, PH_FAKE = 2, PH_POST = 3 };
+
+struct Lane {
+    // ray in grid space
+    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+    // DDA
+    int nx, ny, nz;
+    float tfx, tfy, tfz, t;
+    // current voxel
+    int vx, vy, vz;
+    float t_close, t_far;
+    uint64_t word;
+    int wkey;
+    int lk[8];
+    float sf[8], dn[8];
+    float smin, smax;
+    double fs[4];
+    double fs0;          // fs[0] before the level set is subtracted
+    double st0, st1, st2;
+    double nno[3];       // entry point relative to the voxel
+    float nof[3];        // entry point, float
+    int root_type, lv_i, j;
+    int phase;
+    bool done, has_sample, has_surf, dn_loaded, fs_ready;
+    // compositing state
+    float logT;
+    int intersect_i, sample_i;
+    // pending sample
+    float px, py, pz;
+    float weight;
+    bool fake;
+    // backward-only pending data
+    int st_id;
+    float raw_alpha, alpha, trunc_rw_, rwalpha, pcnt;
+    float fake_dist, reweight;
+    double surf_miu, surf_std;
+    float ts;            // t of the sample
+};
+
+__device__ __forceinline__ float plane_t(int plane, float o, float d) { return ((float)plane - o) / d; }
+
+__device__ __forceinline__ void load_density(const GridP &g, Lane &L) {
+    if (!L.dn_loaded) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) L.dn[c] = __ldg(g.density + L.lk[c]);
+        L.dn_loaded = true;
+    }
+}
+
+// Ray set-up: world -> grid transform and AABB bounds (ray_find_bounds, include/render_util.cuh:651-701;
+// transform_coord, include/cuda_util.cuh:63-69; _get_delta_scale, render_util.cuh:536-547).
+__device__ __forceinline__ void ray_bounds(const GridP &g, const asurf_opt_t &opt, Lane &L, float &world_step) {
+    L.ox = fmaf(L.ox, g.scaling[0], g.offset[0]);
+    L.oy = fmaf(L.oy, g.scaling[1], g.offset[1]);
+    L.oz = fmaf(L.oz, g.scaling[2], g.offset[2]);
+    L.dx *= g.scaling[0];
+    L.dy *= g.scaling[1];
+    L.dz *= g.scaling[2];
+    const float delta_scale = rnorm3df(L.dx, L.dy, L.dz);
+    L.dx *= delta_scale;
+    L.dy *= delta_scale;
+    L.dz *= delta_scale;
+    world_step = delta_scale * opt.step_size;
+    if (opt.use_spheric_clip) {
+        // ConcentricSpheresIntersector, render_util.cuh:619-649
+        const float s0 = 2.f / (float)g.size[0], s1 = 2.f / (float)g.size[1], s2 = 2.f / (float)g.size[2];
+        const float so0 = fmaf(L.ox + 0.5f, s0, -1.f), so1 = fmaf(L.oy + 0.5f, s1, -1.f), so2 = fmaf(L.oz + 0.5f, s2, -1.f);
+        const float sd0 = L.dx * s0, sd1 = L.dy * s1, sd2 = L.dz * s2;
+        const float q2a = 2 * (sd0 * sd0 + sd1 * sd1 + sd2 * sd2);
+        const float qb = 2 * (so0 * sd0 + so1 * sd1 + so2 * sd2);
+        const float f = qb * qb - 2 * q2a * (so0 * so0 + so1 * so1 + so2 * so2);
+        const float r2 = 1.f - opt.near_clip;
+        const float det1 = f + 2 * q2a * 1.f * 1.f, det2 = f + 2 * q2a * r2 * r2;
+        bool ok = true;
+        if (det1 < 0) ok = false; else L.tmax = (-qb + sqrtf(det1)) / q2a;
+        if (ok) { if (det2 < 0) ok = false; else L.tmin = (-qb - sqrtf(det2)) / q2a; }
+        if (!ok) { L.tmin = 1e-9f; L.tmax = 0.f; }
+    } else {
+        L.tmin = opt.near_clip / world_step * opt.step_size;
+        L.tmax = 2e3f;
+        {
+            const float inv = (float)(1.0 / (double)L.dx);
+            const float t1 = (-0.5f - L.ox) * inv, t2 = ((float)g.size[0] - 0.5f - L.ox) * inv;
+            if (L.dx != 0.f) { L.tmin = fmaxf(L.tmin, fminf(t1, t2)); L.tmax = fminf(L.tmax, fmaxf(t1, t2)); }
+        }
+        {
+            const float inv = (float)(1.0 / (double)L.dy);
+            const float t1 = (-0.5f - L.oy) * inv, t2 = ((float)g.size[1] - 0.5f - L.oy) * inv;
+            if (L.dy != 0.f) { L.tmin = fmaxf(L.tmin, fminf(t1, t2)); L.tmax = fminf(L.tmax, fmaxf(t1, t2)); }
+        }
+        {
+            const float inv = (float)(1.0 / (double)L.dz);
+            const float t1 = (-0.5f - L.oz) * inv, t2 = ((float)g.size[2] - 0.5f - L.oz) * inv;
+            if (L.dz != 0.f) { L.tmin = fmaxf(L.tmin, fminf(t1, t2)); L.tmax = fminf(L.tmax, fmaxf(t1, t2)); }
+        }
+    }
+}
+
+__device__ __forceinline__ void dda_init(const GridP &g, Lane &L) {
+    L.t = L.tmin;
+    L.nx = min(max((int)fmaf(L.t, L.dx, L.ox), 0), g.size[0] - 2);
+    L.ny = min(max((int)fmaf(L.t, L.dy, L.oy), 0), g.size[1] - 2);
+    L.nz = min(max((int)fmaf(L.t, L.dz, L.oz), 0), g.size[2] - 2);
+    L.tfx = plane_t(L.nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx);
+    L.tfy = plane_t(L.ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
+    L.tfz = plane_t(L.nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
+    L.wkey = -1;
+    L.word = 0;
+    L.phase = PH_MARCH;
+}
+
+struct Counters {
+    unsigned long long steps, linked, active, samples;
+};
+
+// Advance one ray until it has a sample to composite (returns true; the sample is described in L) or the ray
+// is finished (returns false, L.done set).  Follows trace_ray_surf_trav (:86-551) and, with BWD, the loop of
+// trace_ray_surf_trav_backward (:1834-2897) including its `t += step_size` on unlinked voxels (:1935).
+template <bool BWD, bool DEBUG>
+__device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, Lane &L, const CacheP &cache,
+                                        int64_t ray_id, int M, Counters &cnt) {
+    const int offy = g.size[2];
+    const int64_t offx = (int64_t)g.size[1] * g.size[2];
+    for (;;) {
+        if (L.phase == PH_MARCH) {
+            if (!(L.t <= L.tmax)) {
+                L.done = true;
+                return false;
+            }
+            L.vx = L.nx; L.vy = L.ny; L.vz = L.nz;
+            const float t_far = fminf(fminf(L.tfx, L.tfy), L.tfz);
+            L.t_far = t_far;
+            L.t = t_far;
+            if (t_far == L.tfx) {
+                L.nx += (L.dx > 0.f) ? 1 : -1;
+                if ((L.nx < 0) || (L.nx >= g.size[0] - 1)) L.t = L.tmax + 1.f;
+                else L.tfx = plane_t(L.nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx);
+            } else if (t_far == L.tfy) {
+                L.ny += (L.dy > 0.f) ? 1 : -1;
+                if ((L.ny < 0) || (L.ny >= g.size[1] - 1)) L.t = L.tmax + 1.f;
+                else L.tfy = plane_t(L.ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
+            } else {
+                L.nz += (L.dz > 0.f) ? 1 : -1;
+                if ((L.nz < 0) || (L.nz >= g.size[2] - 1)) L.t = L.tmax + 1.f;
+                else L.tfz = plane_t(L.nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
+            }
+            if (DEBUG) ++cnt.steps;
+            // occupancy: all 8 corner links >= 0  <=>  bit set
+            const int key = ((L.vx >> 2) * g.ab1 + (L.vy >> 2)) * g.ab2 + (L.vz >> 2);
+            if (key != L.wkey) {
+                L.wkey = key;
+                L.word = __ldg(g.accel + key);
+            }
+            const int bit = ((L.vx & 3) << 4) | ((L.vy & 3) << 2) | (L.vz & 3);
+            if (!((L.word >> bit) & 1ull)) {
+                if (BWD) L.t += opt.step_size;
+                continue;
+            }
+            if (DEBUG) ++cnt.linked;
+            const int32_t *lp = g.links + (offx * L.vx + (int64_t)offy * L.vy + L.vz);
+            L.lk[0] = __ldg(lp);
+            L.lk[1] = __ldg(lp + 1);
+            L.lk[2] = __ldg(lp + offy);
+            L.lk[3] = __ldg(lp + offy + 1);
+            L.lk[4] = __ldg(lp + offx);
+            L.lk[5] = __ldg(lp + offx + 1);
+            L.lk[6] = __ldg(lp + offx + offy);
+            L.lk[7] = __ldg(lp + offx + offy + 1);
+            // 8-corner density gate (:230-239): skip only if ALL corners are below the threshold
+            bool pass = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (!pass) pass = !(__ldg(g.density + L.lk[c]) < opt.sigma_thresh);
+            }
+            if (!pass) continue;
+            if (DEBUG) ++cnt.active;
+            L.dn_loaded = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) L.sf[c] = __ldg(g.surface + L.lk[c]);
+            L.smin = L.sf[0];
+            L.smax = L.sf[0];
+#pragma unroll
+            for (int c = 1; c < 8; ++c) {
+                L.smin = fminf(L.smin, L.sf[c]);
+                L.smax = fmaxf(L.smax, L.sf[c]);
+            }
+            const float tcx = plane_t(L.vx + (L.dx > 0.f ? 0 : 1), L.ox, L.dx);
+            const float tcy = plane_t(L.vy + (L.dy > 0.f ? 0 : 1), L.oy, L.dy);
+            const float tcz = plane_t(L.vz + (L.dz > 0.f ? 0 : 1), L.oz, L.dz);
+            L.t_close = fmaxf(fmaxf(fmaxf(tcx, tcy), tcz), 0.f);
+            L.nof[0] = fmaf(L.t_close, L.dx, L.ox);
+            L.nof[1] = fmaf(L.t_close, L.dy, L.oy);
+            L.nof[2] = fmaf(L.t_close, L.dz, L.oz);
+            L.fs_ready = false;
+            L.has_sample = false;
+            L.has_surf = false;
+            L.lv_i = 0;
+            L.j = 3;
+            L.phase = PH_ROOTS;
+        }
+        if (L.phase == PH_ROOTS) {
+            bool found = false;
+            for (;;) {
+                if (L.j >= 3) {
+                    // next level set that crosses this voxel (:273-277)
+                    bool have_lv = false;
+                    double lv_set = 0.;
+                    while (L.lv_i < g.level_set_num) {
+                        const float lv = __ldg(g.level_set + L.lv_i);
+                        ++L.lv_i;
+                        if ((lv < L.smin) || (lv > L.smax)) continue;
+                        lv_set = (double)lv;
+                        have_lv = true;
+                        break;
+                    }
+                    if (!have_lv) break;
+                    L.has_surf = true;
+                    if (!L.fs_ready) {
+                        double s[8], dd[3];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) s[c] = (double)L.sf[c];
+                        L.nno[0] = (double)L.nof[0] - L.vx;
+                        L.nno[1] = (double)L.nof[1] - L.vy;
+                        L.nno[2] = (double)L.nof[2] - L.vz;
+                        dd[0] = (double)L.dx; dd[1] = (double)L.dy; dd[2] = (double)L.dz;
+                        field_to_cubic(s, L.nno, dd, L.fs);
+                        L.fs0 = L.fs[0];
+                        L.fs_ready = true;
+                    }
+                    L.fs[0] = L.fs0 - lv_set;
+                    double st[3] = {-1, -1, -1};
+                    L.root_type = solve_cubic(L.fs[0], L.fs[1], L.fs[2], L.fs[3], st);
+                    L.st0 = st[0]; L.st1 = st[1]; L.st2 = st[2];
+                    L.j = 0;
+                }
+                while (L.j < 3) {
+                    const int j = L.j++;
+                    const double stj = (j == 0) ? L.st0 : ((j == 1) ? L.st1 : L.st2);
+                    if (stj <= 0) continue;
+                    const float stf = (float)stj;
+                    const float px = fmaf(stf, L.dx, L.nof[0]) - (float)L.vx;
+                    const float py = fmaf(stf, L.dy, L.nof[1]) - (float)L.vy;
+                    const float pz = fmaf(stf, L.dz, L.nof[2]) - (float)L.vz;
+                    if ((px < 0) | (px > 1) | (py < 0) | (py > 1) | (pz < 0) | (pz > 1)) continue;
+                    L.has_sample = true;
+                    const float pos[3] = {px, py, pz};
+                    if (opt.only_outward_intersect) {
+                        float sg[3];
+                        field_grad8(L.sf, pos, sg);
+                        const float norm_dir_dot = -(sg[0] * L.dx + sg[1] * L.dy + sg[2] * L.dz);
+                        if (norm_dir_dot >= 0.f) continue;
+                    }
+                    ++L.intersect_i;
+                    load_density(g, L);
+                    const float raw_alpha = trilerp8(L.dn, pos);
+                    if (!(raw_alpha > opt.sigma_thresh)) continue;
+                    const float alpha = alpha_act(raw_alpha, opt.alpha_activation_type);
+                    const float trw = opt.truncated_vol_render ? trunc_rw(L.intersect_i, g.trunc_a, opt.trunc_vol_weight_min) : 1.f;
+                    const float rwalpha = alpha * trw;
+                    L.px = px; L.py = py; L.pz = pz;
+                    L.fake = false;
+                    L.st_id = j;
+                    L.ts = (float)((double)L.t_close + stj);
+                    if (!BWD) {
+                        const float pcnt = -1 * __logf(1 - rwalpha);
+                        L.weight = __expf(L.logT) * (1.f - __expf(-pcnt));
+                        L.logT -= pcnt;
+                        if (L.sample_i < M) {
+                            cache.sa[ray_id * M + L.sample_i] = rwalpha;
+                            cache.sw[ray_id * M + L.sample_i] = L.weight;
+                            cache.st[ray_id * M + L.sample_i] = L.ts;
+                            L.sample_i += 1;
+                        }
+                    } else {
+                        L.raw_alpha = raw_alpha;
+                        L.alpha = alpha;
+                        L.trunc_rw_ = trw;
+                        L.rwalpha = rwalpha;
+                        L.pcnt = -__logf(fmaxf(1.f - rwalpha, 1e-8f));
+                        L.weight = __expf(L.logT) * (1.f - __expf(-L.pcnt));
+                    }
+                    if (DEBUG) ++cnt.samples;
+                    found = true;
+                    break;
+                }
+                if (found) break;
+            }
+            if (found) return true;
+            L.phase = PH_FAKE;
+        }
+        if (L.phase == PH_FAKE) {
+            L.phase = PH_POST;
+            // fake sample at the voxel midpoint (:423-541 / :2460-2866)
+            if (opt.surf_fake_sample && !L.has_sample && (!opt.limited_fake_sample || L.has_surf) &&
+                ((L.t_far - L.t_close) > opt.surf_fake_sample_min_vox_len)) {
+                const float tm = (L.t_far + L.t_close) / 2.f;
+                const float px = fmaf(tm, L.dx, L.ox) - (float)L.vx;
+                const float py = fmaf(tm, L.dy, L.oy) - (float)L.vy;
+                const float pz = fmaf(tm, L.dz, L.oz) - (float)L.vz;
+                const float pos[3] = {px, py, pz};
+                load_density(g, L);
+                const float raw_alpha = trilerp8(L.dn, pos);
+                if (raw_alpha > opt.sigma_thresh) {
+                    const float alpha = alpha_act(raw_alpha, opt.alpha_activation_type);
+                    double s[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) s[c] = (double)L.sf[c];
+                    double const surf_miu = (s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7]) / 8;
+                    double const var = (((s[0] - surf_miu) * (s[0] - surf_miu)) + ((s[1] - surf_miu) * (s[1] - surf_miu)) +
+                                        ((s[2] - surf_miu) * (s[2] - surf_miu)) + ((s[3] - surf_miu) * (s[3] - surf_miu)) +
+                                        ((s[4] - surf_miu) * (s[4] - surf_miu)) + ((s[5] - surf_miu) * (s[5] - surf_miu)) +
+                                        ((s[6] - surf_miu) * (s[6] - surf_miu)) + ((s[7] - surf_miu) * (s[7] - surf_miu))) / 8;
+                    double surf_std = (double)sqrtf((float)fmax((double)1e-9f, var));
+                    if (!opt.fake_sample_normalize_surf) surf_std = 1.;
+                    float ns[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ns[c] = (float)(s[c] / surf_std);
+                    const float fake_s = trilerp8(ns, pos);
+                    float fake_dist = INFINITY;
+                    for (int i = 0; i < g.level_set_num; ++i) {
+                        const float lv = __ldg(g.level_set + i);
+                        fake_dist = fabsf(fake_s - lv) < fabsf(fake_dist) ? (fake_s - lv) : fake_dist;
+                    }
+                    const float q = fake_dist / g.fake_sample_std;
+                    const float reweight = __expf((float)(-.5 * (double)(q * q)));
+                    const float trw = opt.truncated_vol_render ? trunc_rw(L.intersect_i, g.trunc_a, opt.trunc_vol_weight_min) : 1.f;
+                    L.px = px; L.py = py; L.pz = pz;
+                    L.fake = true;
+                    L.ts = tm;
+                    if (!BWD) {
+                        float a = alpha * reweight;
+                        a = a * trw;
+                        const float pcnt = -1 * __logf(1 - a);
+                        L.weight = __expf(L.logT) * (1.f - __expf(-pcnt));
+                        L.logT -= pcnt;
+                        if ((L.sample_i < M) && opt.fake_sample_l_dist) {
+                            cache.sa[ray_id * M + L.sample_i] = a;
+                            cache.sw[ray_id * M + L.sample_i] = L.weight;
+                            cache.st[ray_id * M + L.sample_i] = tm;
+                            L.sample_i += 1;
+                        }
+                    } else {
+                        L.raw_alpha = raw_alpha;
+                        L.alpha = alpha;
+                        L.trunc_rw_ = trw;
+                        L.reweight = reweight;
+                        L.fake_dist = fake_dist;
+                        L.surf_miu = surf_miu;
+                        L.surf_std = surf_std;
+                        L.rwalpha = alpha * reweight * trw;
+                        L.pcnt = -1 * __logf(fmaxf(1.f - L.rwalpha, 1e-8f));
+                        L.weight = __expf(L.logT) * (1.f - __expf(-L.pcnt));
+                    }
+                    if (DEBUG) ++cnt.samples;
+                    return true;
+                }
+            }
+        }
+        // PH_POST: early stop (:544-547 / :2893-2895)
+        L.phase = PH_MARCH;
+        if (__expf(L.logT) < opt.stop_thresh) {
+            if (!BWD) L.logT = -1e3f;
+            L.done = true;
+            return false;
+        }
+    }
+}
+
+// Sum of `bd` consecutive lanes starting at a segment head, same add order as the reference's
+// cub::WarpReduce::HeadSegmentedSum (shuffle-down tree clamped to the segment).
+__device__ __forceinline__ float segment_sum(float v, int pos_in_seg, int bd) {
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+        const float o = __shfl_down_sync(FULL, v, off);
+        if (pos_in_seg + off < bd) v += o;
+    }
+    return v;
+}
+// full-warp shuffle-down tree (cub::WarpReduce::Sum order); the total lands in lane 0
+__device__ __forceinline__ float warp_sum_down(float v, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float o = __shfl_down_sync(FULL, v, off);
+        if (lane + off < 32) v += o;
+    }
+    return v;
+}
+
+// ---- per-ray constants of the fused losses (preamble of trace_ray_surf_trav_backward, :1756-1793) --------
+struct Pre {
+    float asum, wsum, Den_Dasum, Den_Dwsum, t_mean, Dmeant_sign;
+    int valid_n, max_id;
+};
+
+struct CacheView {
+    const float *sa, *sw, *st;
+    int n;
+    __device__ __forceinline__ float A(int i) const { return (i < n) ? sa[i] : 0.f; }
+    __device__ __forceinline__ float W(int i) const { return (i < n) ? sw[i] : 0.f; }
+    __device__ __forceinline__ float T(int i) const { return (i < n) ? st[i] : 0.f; }
+};
+
+__device__ __forceinline__ float log_clamped_ratio(float v, float sum) {
+    // _LOG(max(v, 1e-8) / sum) with the reference's double promotion
+    return __logf((float)(fmax((double)v, 1e-8) / (double)sum));
+}
+
+__device__ void fused_preamble(const CacheView &c, Pre &p) {
+    p.asum = 0.f; p.wsum = 0.f;
+    for (int i = 0; i < c.n; ++i) { p.asum += c.sa[i]; p.wsum += c.sw[i]; }
+    p.asum = fmaxf(p.asum, 1e-8f);
+    p.wsum = fmaxf(p.wsum, 1e-8f);
+    p.Den_Dasum = 0.f; p.Den_Dwsum = 0.f; p.t_mean = 0.f;
+    for (int i = 0; i < c.n; ++i) {
+        p.Den_Dasum += c.sa[i] * (log_clamped_ratio(c.sa[i], p.asum) + 1.f) / (p.asum * p.asum);
+        p.Den_Dwsum += c.sw[i] * (log_clamped_ratio(c.sw[i], p.wsum) + 1.f) / (p.wsum * p.wsum);
+        p.t_mean += c.sw[i] / p.wsum * c.st[i];
+    }
+    p.valid_n = 0; p.Dmeant_sign = 0.f;
+    for (int i = 0; i < c.n; ++i) {
+        if (c.st[i] > 0.f) {
+            p.valid_n++;
+            p.Dmeant_sign += (p.t_mean > c.st[i]) ? 1.f : ((p.t_mean < c.st[i]) ? -1.f : 0.f);
+        }
+    }
+    p.max_id = 0;
+    float max_w = 0.f;
+    for (int i = 0; i < c.n; ++i)
+        if (c.sw[i] > max_w) { max_w = c.sw[i]; p.max_id = i; }
+}
+
+// l_dist(w) and l_entropy(w) contributions to d/d(rwalpha) (:2141-2210)
+__device__ float extra_grad_rwalpha_w(const FusedP &f, const Pre &p, const CacheView &c, int sample_i, float logT,
+                                      float rwalpha) {
+    float add = 0.f;
+    const float denom = fminf(rwalpha - 1.f, -1e-8f);
+    if (f.lambda_l_dist > 0.f) {
+        float Dldist_Dai = 0.f, log_Tk = logT;
+        for (int k = sample_i; k < p.valid_n; ++k) {
+            float Dldist_Dwk = 0.f;
+            for (int j = 0; j < c.n; ++j) Dldist_Dwk += c.sw[j] * fabsf(c.T(k) - c.st[j]);
+            // entries j >= n are zero-weight in the reference's zero-filled cache
+            if (k == sample_i) {
+                Dldist_Dai += Dldist_Dwk * __expf(logT);
+            } else {
+                log_Tk += __logf(fmaxf(1.f - c.A(k - 1), 1e-8f));
+                Dldist_Dai += Dldist_Dwk * __expf(log_Tk) * c.A(k) / denom;
+            }
+        }
+        add += f.lambda_l_dist * Dldist_Dai;
+    }
+    if (f.lambda_l_entropy > 0.f) {
+        float Den_Dai, log_Tk = logT;
+        if (f.no_norm_weight_l_entropy) {
+            const float Den_Dwi = -(__logf(fmaxf(c.W(sample_i), 1e-8f)) + 1.f);
+            Den_Dai = Den_Dwi * __expf(logT);
+            for (int k = sample_i + 1; k < p.valid_n; ++k) {
+                const float Den_Dwk = -(__logf(fmaxf(c.W(k), 1e-8f)) + 1.f);
+                log_Tk += __logf(fmaxf(1.f - c.A(k - 1), 1e-8f));
+                Den_Dai += Den_Dwk * __expf(log_Tk) * c.A(k) / denom;
+            }
+        } else {
+            const float Den_Dwi = -(log_clamped_ratio(c.W(sample_i), p.wsum) + 1.f) / p.wsum + p.Den_Dwsum;
+            Den_Dai = Den_Dwi * __expf(logT);
+            for (int k = sample_i + 1; k < p.valid_n; ++k) {
+                const float Den_Dwk = -(log_clamped_ratio(c.W(k), p.wsum) + 1.f) / p.wsum + p.Den_Dwsum;
+                log_Tk += __logf(fmaxf(1.f - c.A(k - 1), 1e-8f));
+                Den_Dai += Den_Dwk * __expf(log_Tk) * c.A(k) / denom;
+            }
+        }
+        add += f.lambda_l_entropy * Den_Dai;
+    }
+    return add;
+}
+
+__device__ __forceinline__ void scatter8(float *__restrict__ grad, uint8_t *__restrict__ mask, const int *lk,
+                                         const float *pos, float gval) {
+    float w[8];
+    corner_weights(pos, gval, w);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        atomicAdd(grad + lk[c], w[c]);
+        if (mask) mask[lk[c]] = 1;
+    }
+}
+
+// Everything of a REAL sample's backward that is scalar per ray (:2137-2448, lane-0 parts).
+__device__ void finish_real_bwd(const GridP &g, const asurf_opt_t &opt, const FusedP &f, const Pre &p, const CacheView &c,
+                                const asurf_grads_t &grads, Lane &L, float &accum, float total_color, float gx, float gy,
+                                float gz) {
+    const float pos[3] = {L.px, L.py, L.pz};
+    accum -= L.weight * total_color;
+    float curr_grad_rwalpha = accum / fminf(L.rwalpha - 1.f, -1e-8f) + total_color * __expf(L.logT);
+    curr_grad_rwalpha += extra_grad_rwalpha_w(f, p, c, L.sample_i, L.logT, L.rwalpha);
+    L.logT -= L.pcnt;
+    if (f.lambda_l_dist_a > 0.f) {
+        float a = 0.f;
+        for (int j = 0; j < c.n; ++j) a += c.sa[j] * fabsf(c.T(L.sample_i) - c.st[j]);
+        curr_grad_rwalpha += f.lambda_l_dist_a * a;
+    }
+    if (f.lambda_l_entropy_a > 0.f) {
+        const float Den_Dai = -(log_clamped_ratio(c.A(L.sample_i), p.asum) + 1.f) / p.asum;
+        curr_grad_rwalpha += f.lambda_l_entropy_a * (Den_Dai + p.Den_Dasum);
+    }
+    if ((f.sparsity_loss > 0.f) && (L.raw_alpha > 0.f)) {
+        const float _1_a = fmaxf(1.f - L.alpha, 1e-8f);
+        const double m = fmin((double)(_1_a * __logf(_1_a)), -1e-8);
+        curr_grad_rwalpha = (float)((double)curr_grad_rwalpha +
+                                    (double)(-f.sparsity_loss) * (1.0 / m) * (double)(1.f - L.weight / p.wsum));
+    }
+    if (f.lambda_inwards_norm_loss > 0.f) {
+        float sg[3];
+        field_grad8(L.sf, pos, sg);
+        const float surf_n = fmaxf(sqrtf(sg[0] * sg[0] + sg[1] * sg[1] + sg[2] * sg[2]), 1e-8f);
+        const float nd = (-sg[0] / surf_n) * L.dx + (-sg[1] / surf_n) * L.dy + (-sg[2] / surf_n) * L.dz;
+        if (nd > 0.f) curr_grad_rwalpha += f.lambda_inwards_norm_loss * (nd * nd);
+    }
+    const float curr_grad_alpha = curr_grad_rwalpha * L.trunc_rw_;
+    const float act_g = alpha_act_grad(L.alpha, opt.alpha_activation_type);
+    float curr_grad_raw_alpha = curr_grad_alpha * act_g;
+    scatter8(grads.grad_density, grads.mask, L.lk, pos, curr_grad_raw_alpha);
+    if ((f.lambda_l_di > 0.f) && (L.alpha < f.l_di_alpha_thresh)) curr_grad_raw_alpha += f.lambda_l_di * -1.f * act_g;
+    float gxyz[3] = {gx, gy, gz};
+    trilerp8_pos_grad(L.dn, pos, curr_grad_raw_alpha, gxyz);
+    float grad_st = gxyz[0] * L.dx + gxyz[1] * L.dy + gxyz[2] * L.dz;
+    if ((f.lambda_l_dist > 0.f) || (f.lambda_l_dist_a > 0.f)) {
+        float gw = 0.f, ga = 0.f;
+        const float ti = c.T(L.sample_i);
+        for (int j = 0; j < f.M; ++j) {
+            const float tj = c.T(j);
+            const float sgn = (ti > tj) ? 1.f : ((ti < tj) ? -1.f : 0.f);
+            gw += sgn * c.W(L.sample_i) * c.W(j);
+            ga += sgn * c.A(L.sample_i) * c.A(j);
+        }
+        grad_st += f.lambda_l_dist * gw + f.lambda_l_dist_a * ga;
+    }
+    if (f.lambda_l_samp_dist > 0.f) {
+        const float ti = c.T(L.sample_i);
+        const float sgn = (p.t_mean > ti) ? 1.f : ((p.t_mean < ti) ? -1.f : 0.f);
+        grad_st += f.lambda_l_samp_dist * (p.Dmeant_sign * c.A(L.sample_i) / p.wsum + sgn * (-1.f));
+    }
+    if ((f.lambda_conv_mode_samp > 0.f) && (L.trunc_rw_ > opt.trunc_vol_weight_min)) {
+        const float ti = c.T(L.sample_i), tm = c.T(p.max_id);
+        grad_st += f.lambda_conv_mode_samp * ((ti > tm) ? 1.f : ((ti < tm) ? -1.f : 0.f));
+    }
+    if (grads.grad_surface) {
+        float grad_fs[4] = {grad_st, grad_st, grad_st, grad_st};
+        root_grad(L.root_type, L.st_id, L.fs, grad_fs);
+        const float nno_f[3] = {(float)L.nno[0], (float)L.nno[1], (float)L.nno[2]};
+        const float dir[3] = {L.dx, L.dy, L.dz};
+        float gs[8];
+        cubic_to_corner_grad(nno_f, dir, grad_fs, gs);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            atomicAdd(grads.grad_surface + L.lk[k], gs[k]);
+            if (grads.mask) grads.mask[L.lk[k]] = 1;
+        }
+        if (L.alpha < f.surf_sparse_alpha_thresh)
+            scatter8(grads.grad_surface, grads.mask, L.lk, pos, f.lambda_inplace_surf_sparse);
+    }
+    if (L.sample_i < f.M - 1) L.sample_i += 1;
+}
+
+// Scalar part of a FAKE sample's backward (:2590-2866).
+__device__ void finish_fake_bwd(const GridP &g, const asurf_opt_t &opt, const FusedP &f, const Pre &p, const CacheView &c,
+                                const asurf_grads_t &grads, Lane &L, float &accum, float total_color) {
+    const float pos[3] = {L.px, L.py, L.pz};
+    accum -= L.weight * total_color;
+    float curr_grad_rwalpha = accum / fminf(L.rwalpha - 1.f, -1e-8f) + total_color * __expf(L.logT);
+    if (opt.fake_sample_l_dist) curr_grad_rwalpha += extra_grad_rwalpha_w(f, p, c, L.sample_i, L.logT, L.rwalpha);
+    L.logT -= L.pcnt;
+    if (opt.fake_sample_l_dist) {
+        if (f.lambda_l_dist_a > 0.f) {
+            float a = 0.f;
+            for (int j = 0; j < c.n; ++j) a += c.sa[j] * fabsf(c.T(L.sample_i) - c.st[j]);
+            curr_grad_rwalpha += f.lambda_l_dist_a * a;
+        }
+        if (f.lambda_l_entropy_a > 0.f) {
+            const float Den_Dai = -(log_clamped_ratio(c.A(L.sample_i), p.asum) + 1.f) / p.asum;
+            curr_grad_rwalpha += f.lambda_l_entropy_a * (Den_Dai + p.Den_Dasum);
+        }
+        if (L.sample_i < f.M - 1) L.sample_i += 1;
+    }
+    if ((f.sparsity_loss > 0.f) && (L.raw_alpha > 0.f)) {
+        const float _1_a = fmaxf(1.f - L.rwalpha, 1e-8f);
+        const double m = fmin((double)(_1_a * __logf(_1_a)), -1e-8);
+        curr_grad_rwalpha = (float)((double)curr_grad_rwalpha +
+                                    (double)(-f.sparsity_loss) * (1.0 / m) * (double)(1.f - L.weight / p.wsum));
+    }
+    if (f.lambda_inwards_norm_loss > 0.f) {
+        float sg[3];
+        field_grad8(L.sf, pos, sg);
+        const float surf_n = fmaxf(sqrtf(sg[0] * sg[0] + sg[1] * sg[1] + sg[2] * sg[2]), 1e-8f);
+        const float nd = (-sg[0] / surf_n) * L.dx + (-sg[1] / surf_n) * L.dy + (-sg[2] / surf_n) * L.dz;
+        if (nd > 0.f) curr_grad_rwalpha += f.lambda_inwards_norm_loss * (nd * nd);
+    }
+    const float curr_grad_alpha = curr_grad_rwalpha * L.reweight * L.trunc_rw_;
+    const float curr_grad_raw_alpha = curr_grad_alpha * alpha_act_grad(L.alpha, opt.alpha_activation_type);
+    scatter8(grads.grad_density, grads.mask, L.lk, pos, curr_grad_raw_alpha);
+    const float std_ = g.fake_sample_std;
+    const float grad_fake_dist = curr_grad_rwalpha * (-L.alpha * L.trunc_rw_ * L.fake_dist * L.reweight / (std_ * std_));
+    if (grads.grad_surface) {
+        float gns[8];
+        corner_weights(pos, grad_fake_dist, gns);
+        float gs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!opt.fake_sample_normalize_surf) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gs[k] = gns[k];
+        } else {
+            const double sd3 = L.surf_std * L.surf_std * L.surf_std;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double s_ks = (double)L.sf[ks];
+#pragma unroll
+                for (int kn = 0; kn < 8; ++kn) {
+                    const double s_kn = (double)L.sf[kn];
+                    if (ks == kn)
+                        gs[ks] += (float)(gns[kn] * (s_ks * (L.surf_miu - s_ks) / 8.f / sd3 + 1.f / L.surf_std));
+                    else
+                        gs[ks] += (float)(gns[kn] * (s_kn * (L.surf_miu - s_ks) / 8.f / sd3));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            atomicAdd(grads.grad_surface + L.lk[k], gs[k]);
+            if (grads.mask) grads.mask[L.lk[k]] = 1;
+        }
+    }
+    if (grads.grad_fake_sample_std) {
+        const float grad_std = curr_grad_rwalpha * L.alpha * (L.fake_dist * L.fake_dist) * L.reweight * L.trunc_rw_ /
+                               (std_ * std_ * std_);
+        atomicAdd(grads.grad_fake_sample_std, grad_std);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+template <bool BWD, bool DEBUG>
+__global__ void __launch_bounds__(CTA_THREADS)
+surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins,
+                 const float *__restrict__ dirs, const int64_t Q, float *__restrict__ rgb_out,
+                 const float *__restrict__ grad_in, const float *__restrict__ color_cache, const FusedP f,
+                 const CacheP cache, const asurf_grads_t grads, const DebugP dbg) {
+    __shared__ float s_sph[CTA_WARPS][32][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ray_id = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int D = g.sh_dim, bd = g.basis_dim;
+    const int M = f.M;
+
+    Lane L;
+    L.done = true;
+    L.logT = 0.f;
+    L.intersect_i = -1;
+    L.sample_i = 0;
+    float out0 = 0.f, out1 = 0.f, out2 = 0.f;  // FWD: colour; BWD: dL/dRGB
+    float accum = 0.f;
+    Pre pre;
+    CacheView cv;
+    cv.sa = cv.sw = cv.st = nullptr;
+    cv.n = 0;
+    Counters cnt = {0, 0, 0, 0};
+    int n_hits = 0;
+
+    if (ray_id < Q) {
+        L.ox = origins[ray_id * 3 + 0]; L.oy = origins[ray_id * 3 + 1]; L.oz = origins[ray_id * 3 + 2];
+        L.dx = dirs[ray_id * 3 + 0]; L.dy = dirs[ray_id * 3 + 1]; L.dz = dirs[ray_id * 3 + 2];
+        eval_sh(bd, L.dx, L.dy, L.dz, s_sph[warp][lane]);  // world-space direction (:3165-3171)
+        float world_step;
+        ray_bounds(g, opt, L, world_step);
+        if (DEBUG && dbg.xf) {
+            float *x = dbg.xf + ray_id * 9;
+            x[0] = L.ox; x[1] = L.oy; x[2] = L.oz; x[3] = L.dx; x[4] = L.dy; x[5] = L.dz;
+            x[6] = L.tmin; x[7] = L.tmax; x[8] = world_step;
+        }
+        if (BWD) {
+            if (f.grad_is_rgb) {  // fused: dL/dRGB from the L2 / L1 mix (:3306-3316)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float resid = color_cache[ray_id * 3 + i] - grad_in[ray_id * 3 + i];
+                    float gi = resid * f.norm_l2 * f.lambda_l2;
+                    gi += (resid > 0.f) ? (f.norm_l1 * f.lambda_l1) : (-f.norm_l1 * f.lambda_l1);
+                    if (i == 0) out0 = gi; else if (i == 1) out1 = gi; else out2 = gi;
+                }
+            } else {
+                out0 = grad_in[ray_id * 3 + 0]; out1 = grad_in[ray_id * 3 + 1]; out2 = grad_in[ray_id * 3 + 2];
+            }
+            if (M > 0) {
+                cv.sa = cache.sa + ray_id * M; cv.sw = cache.sw + ray_id * M; cv.st = cache.st + ray_id * M;
+                cv.n = cache.n[ray_id];
+            }
+            fused_preamble(cv, pre);
+            accum = fmaf(color_cache[ray_id * 3 + 0], out0,
+                         fmaf(color_cache[ray_id * 3 + 1], out1, color_cache[ray_id * 3 + 2] * out2));
+        }
+        if (!(L.tmin > L.tmax)) {
+            L.done = false;
+            dda_init(g, L);
+        }
+    }
+    __syncwarp();
+
+    for (;;) {
+        bool have = false;
+        if (!L.done) have = advance<BWD, DEBUG>(g, opt, L, cache, ray_id, M, cnt);
+        unsigned pend = __ballot_sync(FULL, have);
+        if (pend == 0) break;
+        if (DEBUG && have && dbg.hit_count) {
+            if (n_hits < dbg.max_hits) {
+                const int64_t o = ray_id * dbg.max_hits + n_hits;
+                dbg.hit_cell[o] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
+                dbg.hit_kind[o] = (L.fake ? 3 : L.st_id) + 8 * L.intersect_i;
+                dbg.hit_t[o] = L.ts;
+            }
+            ++n_hits;
+        }
+        float tot_color = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+        while (pend) {
+            const int src = __ffs(pend) - 1;
+            pend &= pend - 1;
+            int lk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) lk[c] = __shfl_sync(FULL, L.lk[c], src);
+            float pos[3];
+            pos[0] = __shfl_sync(FULL, L.px, src);
+            pos[1] = __shfl_sync(FULL, L.py, src);
+            pos[2] = __shfl_sync(FULL, L.pz, src);
+            float v[8];
+            float lane_color = 0.f;
+            const int kb = (lane < D) ? (lane % bd) : 0;
+            float sph = 0.f;
+            if (lane < D) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(g.sh + (int64_t)lk[c] * D + lane);
+                sph = s_sph[warp][src][kb];
+                lane_color = trilerp8(v, pos) * sph;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = 0.f;
+            }
+            const float seg = segment_sum(lane_color, (lane < D) ? kb : 32, bd);
+            const float c0 = __shfl_sync(FULL, seg, 0);
+            const float c1 = __shfl_sync(FULL, seg, bd);
+            const float c2 = __shfl_sync(FULL, seg, 2 * bd);
+            if (!BWD) {
+                if (lane == src) {
+                    out0 += L.weight * fmaxf(c0 + 0.5f, 0.f);
+                    out1 += L.weight * fmaxf(c1 + 0.5f, 0.f);
+                    out2 += L.weight * fmaxf(c2 + 0.5f, 0.f);
+                }
+            } else {
+                const float g0 = __shfl_sync(FULL, out0, src);
+                const float g1 = __shfl_sync(FULL, out1, src);
+                const float g2 = __shfl_sync(FULL, out2, src);
+                const float weight = __shfl_sync(FULL, L.weight, src);
+                const float l0 = c0 + 0.5f, l1 = c1 + 0.5f, l2 = c2 + 0.5f;
+                const float t0 = fmaxf(l0, 0.f), t1 = fmaxf(l1, 0.f), t2 = fmaxf(l2, 0.f);
+                float total_color = t0 * g0;  // shuffle order of the reference (:2112-2115): (c0 + c2) + c1
+                total_color += t2 * g2;
+                total_color += t1 * g1;
+                float gacc[3] = {0.f, 0.f, 0.f};
+                if (lane < D) {
+                    const int ch = lane / bd;
+                    const float in01 = (ch == 0) ? ((t0 == l0) ? 1.f : 0.f) : ((ch == 1) ? ((t1 == l1) ? 1.f : 0.f) : ((t2 == l2) ? 1.f : 0.f));
+                    const float gch = (ch == 0) ? g0 : ((ch == 1) ? g1 : g2);
+                    const float grad_common = weight * in01 * gch;
+                    const float curr_grad_color = sph * grad_common;
+                    float w[8];
+                    corner_weights(pos, curr_grad_color, w);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) atomicAdd(grads.grad_sh + (int64_t)lk[c] * D + lane, w[c]);
+                    if (!opt.no_surf_grad_from_sh) trilerp8_pos_grad(v, pos, curr_grad_color, gacc);
+                }
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                if (!opt.no_surf_grad_from_sh) {
+                    sx = __shfl_sync(FULL, warp_sum_down(gacc[0], lane), 0);
+                    sy = __shfl_sync(FULL, warp_sum_down(gacc[1], lane), 0);
+                    sz = __shfl_sync(FULL, warp_sum_down(gacc[2], lane), 0);
+                }
+                if (lane == src) { tot_color = total_color; gx = sx; gy = sy; gz = sz; }
+            }
+        }
+        if (BWD && have) {
+            if (!L.fake) finish_real_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color, gx, gy, gz);
+            else finish_fake_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color);
+        }
+    }
+
+    if (ray_id < Q) {
+        if (!BWD) {
+            const float bg = __expf(L.logT) * opt.background_brightness;  // tmin > tmax: logT == 0 -> background
+            rgb_out[ray_id * 3 + 0] = out0 + bg;
+            rgb_out[ray_id * 3 + 1] = out1 + bg;
+            rgb_out[ray_id * 3 + 2] = out2 + bg;
+            if (M > 0) cache.n[ray_id] = L.sample_i;
+        }
+        if (DEBUG) {
+            if (dbg.hit_count) dbg.hit_count[ray_id] = n_hits;
+            if (dbg.stats) {
+                atomicAdd(dbg.stats + 0, cnt.steps);
+                atomicAdd(dbg.stats + 2, cnt.linked);
+                atomicAdd(dbg.stats + 3, cnt.active);
+                atomicAdd(dbg.stats + 4, cnt.samples);
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace asurf
+
+using namespace asurf;
+
+namespace {
+
+Workspace g_ws_accel, g_ws_cache, g_ws_dbg;
+
+int make_grid(const asurf_grid_t *grid, cudaStream_t st, GridP &g) {
+    ASURF_REQUIRE(grid, ASURF_E_INVALID, "surf_trav: null grid");
+    ASURF_REQUIRE(grid->links && grid->density && grid->sh, ASURF_E_INVALID, "surf_trav: null grid tensor");
+    ASURF_REQUIRE(grid->surface && grid->level_set, ASURF_E_INVALID,
+                  "surf_trav: the grid has no surface / level set data (surface_type none)");
+    ASURF_REQUIRE(grid->size[0] >= 2 && grid->size[1] >= 2 && grid->size[2] >= 2, ASURF_E_INVALID,
+                  "surf_trav: grid smaller than 2^3");
+    ASURF_REQUIRE(grid->basis_dim == 1 || grid->basis_dim == 4 || grid->basis_dim == 9, ASURF_E_UNSUPPORTED,
+                  "surf_trav: basis_dim %d not supported (SH with 1, 4 or 9 functions)", grid->basis_dim);
+    ASURF_REQUIRE(grid->sh_dim == 3 * grid->basis_dim, ASURF_E_INVALID, "surf_trav: sh_dim must be 3*basis_dim");
+    g.links = grid->links;
+    g.density = grid->density;
+    g.surface = grid->surface;
+    g.sh = grid->sh;
+    g.level_set = grid->level_set;
+    for (int i = 0; i < 3; ++i) {
+        g.size[i] = grid->size[i];
+        g.offset[i] = grid->offset[i];
+        g.scaling[i] = grid->scaling[i];
+    }
+    g.level_set_num = grid->level_set_num;
+    g.basis_dim = grid->basis_dim;
+    g.sh_dim = grid->sh_dim;
+    g.fake_sample_std = grid->fake_sample_std;
+    g.trunc_a = grid->truncated_vol_render_a;
+    AccelLayout lay(grid->size);
+    g.ab1 = lay.b[0][1];
+    g.ab2 = lay.b[0][2];
+    if (grid->accel) {
+        g.accel = grid->accel;
+    } else {
+        int rc = g_ws_accel.reserve((size_t)lay.off[3] * sizeof(uint64_t));
+        if (rc) return rc;
+        rc = asurf_accel_build(grid->links, grid->size, (uint64_t *)g_ws_accel.ptr, st);
+        if (rc) return rc;
+        g.accel = (const uint64_t *)g_ws_accel.ptr;
+    }
+    return 0;
+}
+
+int check_rays(const asurf_rays_t *rays, const asurf_opt_t *opt) {
+    ASURF_REQUIRE(rays && opt, ASURF_E_INVALID, "surf_trav: null rays / options");
+    ASURF_REQUIRE(rays->n_rays >= 0, ASURF_E_INVALID, "surf_trav: negative ray count");
+    ASURF_REQUIRE(rays->n_rays == 0 || (rays->origins && rays->dirs), ASURF_E_INVALID, "surf_trav: null ray tensor");
+    return 0;
+}
+
+inline int n_ctas(int64_t Q) { return (int)((Q + CTA_THREADS - 1) / CTA_THREADS); }
+
+}  // namespace
+
+extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                       float *rgb_out, asurf_stats_t *stats_dev, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rays(rays, opt);
+    if (rc) return rc;
+    if (rays->n_rays == 0) return 0;
+    ASURF_REQUIRE(rgb_out, ASURF_E_INVALID, "surf_trav_forward: null output");
+    GridP g;
+    rc = make_grid(grid, st, g);
+    if (rc) return rc;
+    FusedP f = {};
+    CacheP cache = {};
+    asurf_grads_t grads = {};
+    DebugP dbg = {};
+    if (stats_dev) {
+        dbg.stats = (unsigned long long *)stats_dev;
+        surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
+            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg);
+    } else {
+        surf_trav_kernel<false, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
+            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg);
+    }
+    return check_cuda(cudaGetLastError(), "surf_trav_forward launch");
+}
+
+extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                        const float *grad_out, const float *color_cache, const asurf_grads_t *grads,
+                                        void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rays(rays, opt);
+    if (rc) return rc;
+    if (rays->n_rays == 0) return 0;
+    ASURF_REQUIRE(grad_out && color_cache && grads, ASURF_E_INVALID, "surf_trav_backward: null tensor");
+    ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "surf_trav_backward: null gradient buffer");
+    GridP g;
+    rc = make_grid(grid, st, g);
+    if (rc) return rc;
+    FusedP f = {};
+    CacheP cache = {};
+    DebugP dbg = {};
+    surf_trav_kernel<true, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
+        g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg);
+    return check_cuda(cudaGetLastError(), "surf_trav_backward launch");
+}
+
+extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                     const float *rgb_gt, const asurf_fused_t *fu, float *rgb_out,
+                                     const asurf_grads_t *grads, asurf_stats_t *stats_dev, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rays(rays, opt);
+    if (rc) return rc;
+    ASURF_REQUIRE(fu && grads, ASURF_E_INVALID, "surf_trav_fused: null argument");
+    ASURF_REQUIRE(!(fu->fused_surf_norm_reg_scale > 0.f), ASURF_E_UNSUPPORTED,
+                  "surf_trav_fused: fused_surf_norm_reg_scale > 0 is not supported (the reference asserts)");
+    ASURF_REQUIRE(fu->l_dist_max_sample >= 0, ASURF_E_INVALID, "surf_trav_fused: negative l_dist_max_sample");
+    const int64_t Q = rays->n_rays;
+    if (Q == 0) return 0;
+    ASURF_REQUIRE(rgb_gt && rgb_out, ASURF_E_INVALID, "surf_trav_fused: null colour tensor");
+    ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "surf_trav_fused: null gradient buffer");
+    GridP g;
+    rc = make_grid(grid, st, g);
+    if (rc) return rc;
+    const int M = fu->l_dist_max_sample;
+    CacheP cache = {};
+    if (M > 0) {
+        const size_t per = (size_t)Q * M * sizeof(float);
+        rc = g_ws_cache.reserve(3 * per + (size_t)Q * sizeof(int));
+        if (rc) return rc;
+        char *base = (char *)g_ws_cache.ptr;
+        cache.sa = (float *)base;
+        cache.sw = (float *)(base + per);
+        cache.st = (float *)(base + 2 * per);
+        cache.n = (int *)(base + 3 * per);
+    }
+    const int64_t qn = fu->norm_rays > 0 ? fu->norm_rays : Q;
+    const float Qf = (float)qn;
+    FusedP f = {};
+    f.sparsity_loss = fu->sparsity_loss;
+    f.lambda_l2 = fu->lambda_l2;
+    f.lambda_l1 = fu->lambda_l1;
+    f.lambda_l_dist = fu->lambda_l_dist / Qf;
+    f.lambda_l_entropy = fu->lambda_l_entropy / Qf;
+    f.lambda_l_dist_a = fu->lambda_l_dist_a / Qf;
+    f.lambda_l_entropy_a = fu->lambda_l_entropy_a / Qf;
+    f.lambda_l_samp_dist = fu->lambda_l_samp_dist / Qf;
+    f.lambda_l_di = fu->lambda_l_di;
+    f.l_di_alpha_thresh = fu->l_di_alpha_thresh;
+    f.surf_sparse_alpha_thresh = fu->surf_sparse_alpha_thresh;
+    f.lambda_inplace_surf_sparse = fu->lambda_inplace_surf_sparse;
+    f.lambda_inwards_norm_loss = fu->lambda_inwards_norm_loss;
+    f.lambda_conv_mode_samp = fu->lambda_conv_mode_samp;
+    f.norm_l2 = 2.f / (float)(3 * (int)qn);
+    f.norm_l1 = 1.f / (float)(3 * (int)qn);
+    f.no_norm_weight_l_entropy = fu->no_norm_weight_l_entropy;
+    f.M = M;
+    f.grad_is_rgb = 1;
+    asurf_grads_t nog = {};
+    DebugP dbg = {};
+    FusedP ff = {};
+    ff.M = M;
+    if (stats_dev) {
+        dbg.stats = (unsigned long long *)stats_dev;
+        surf_trav_kernel<false, true><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
+                                                                          nullptr, nullptr, ff, cache, nog, dbg);
+    } else {
+        surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
+                                                                           nullptr, nullptr, ff, cache, nog, dbg);
+    }
+    DebugP nodbg = {};
+    surf_trav_kernel<true, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, nullptr, rgb_gt,
+                                                                      rgb_out, f, cache, *grads, nodbg);
+    return check_cuda(cudaGetLastError(), "surf_trav_fused launch");
+}
+
+static int debug_launch(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, DebugP dbg,
+                        cudaStream_t st) {
+    int rc = check_rays(rays, opt);
+    if (rc) return rc;
+    if (rays->n_rays == 0) return 0;
+    GridP g;
+    rc = make_grid(grid, st, g);
+    if (rc) return rc;
+    rc = g_ws_dbg.reserve((size_t)rays->n_rays * 3 * sizeof(float));
+    if (rc) return rc;
+    FusedP f = {};
+    CacheP cache = {};
+    asurf_grads_t grads = {};
+    surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
+        g, *opt, rays->origins, rays->dirs, rays->n_rays, (float *)g_ws_dbg.ptr, nullptr, nullptr, f, cache, grads, dbg);
+    return check_cuda(cudaGetLastError(), "surf_trav debug launch");
+}
+
+extern "C" int asurf_debug_ray_bounds(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                      float *xf_out, void *stream) {
+    ASURF_REQUIRE(xf_out, ASURF_E_INVALID, "debug_ray_bounds: null output");
+    DebugP dbg = {};
+    dbg.xf = xf_out;
+    return debug_launch(grid, rays, opt, dbg, (cudaStream_t)stream);
+}
+
+extern "C" int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                 int32_t max_hits, int32_t *hit_count, int32_t *hit_cell, int32_t *hit_kind, float *hit_t,
+                                 void *stream) {
+    ASURF_REQUIRE(hit_count && hit_cell && hit_kind && hit_t && max_hits > 0, ASURF_E_INVALID, "debug_trace: bad argument");
+    DebugP dbg = {};
+    dbg.max_hits = max_hits;
+    dbg.hit_count = hit_count;
+    dbg.hit_cell = hit_cell;
+    dbg.hit_kind = hit_kind;
+    dbg.hit_t = hit_t;
+    return debug_launch(grid, rays, opt, dbg, (cudaStream_t)stream);
+}
+
+extern "C" void asurf_release(void) {
+    g_ws_accel.release();
+    g_ws_cache.release();
+    g_ws_dbg.release();
+}

@@ -1,0 +1,373 @@
+"""Drop-in replacement for the reference's ``svox2.csrc`` extension module (hot path only).
+
+The reference's ``svox2`` Python package does ``import svox2.csrc as _C`` (/root/reference/svox2/utils.py:32-46)
+and calls ``_C.<function>(specs..., scalars..., tensors...)`` positionally
+(/root/reference/svox2/csrc/svox2.cpp:139-291).  This module offers the same names, argument order, spec classes
+and error behaviour (``RuntimeError`` where the reference's ``TORCH_CHECK`` fires) on top of the C ABI in
+``include/asurf.h``.  Installing it as ``svox2/csrc.py`` makes ``svox2.SparseGrid`` run on
+the B200 kernels unchanged.  Torch is used for memory and streams only; nothing is computed in Python.
+
+Deliberately absent (part of the contract): ``volume_render_surf_trav_image``.
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+
+BASIS_TYPE_SH = 1
+SURFACE_TYPE_NONE = 100
+
+
+# ---- spec classes: default-constructible, fields as svox2.cpp:209-290 ------------------------------------------
+class SparseGridSpec:
+    def __init__(self):
+        self.density_data = None
+        self.surface_data = None
+        self.level_set_data = None
+        self.sh_data = None
+        self.links = None
+        self._offset = None
+        self._scaling = None
+        self.basis_dim = 0
+        self.basis_type = BASIS_TYPE_SH
+        self.surface_type = SURFACE_TYPE_NONE
+        self.basis_data = None
+        self.background_links = None
+        self.background_data = None
+        self.fake_sample_std = 1.0
+        self.truncated_vol_render_a = 1.0
+
+
+class CameraSpec:
+    def __init__(self):
+        self.c2w = None
+        self.fx = self.fy = self.cx = self.cy = 0.0
+        self.width = self.height = 0
+        self.ndc_coeffx = self.ndc_coeffy = -1.0
+
+
+class RaysSpec:
+    def __init__(self):
+        self.origins = None
+        self.dirs = None
+        self.masks = None
+
+
+class RayVoxIntersecSpec:
+    def __init__(self):
+        self.voxel_ls = None
+        self.vox_start_i = None
+        self.vox_num = None
+
+
+class RenderOptions:
+    def __init__(self):
+        self.background_brightness = 1.0
+        self.step_size = 0.5
+        self.sigma_thresh = 1e-10
+        self.stop_thresh = 1e-7
+        self.near_clip = 0.0
+        self.use_spheric_clip = False
+        self.last_sample_opaque = False
+        self.surf_fake_sample = False
+        self.surf_fake_sample_min_vox_len = 0.0
+        self.limited_fake_sample = False
+        self.no_surf_grad_from_sh = False
+        self.alpha_activation_type = 0
+        self.fake_sample_l_dist = True
+        self.fake_sample_normalize_surf = False
+        self.only_outward_intersect = False
+        self.truncated_vol_render = False
+        self.trunc_vol_weight_min = 0.0
+
+
+class GridOutputGrads:
+    def __init__(self):
+        self.grad_density_out = None
+        self.grad_sh_out = None
+        self.grad_surface_out = None
+        self.grad_fake_sample_std_out = None
+        self.grad_basis_out = None
+        self.grad_background_out = None
+        self.mask_out = None
+        self.mask_background_out = None
+
+
+# ---- argument checks (include/util.hpp:3-12, include/data_spec.hpp:58-81) ----------------------------------------
+def _check_input(t, name):
+    if t is None or not torch.is_tensor(t):
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+
+
+def _check_cpu_input(t, name):
+    if t is None or not torch.is_tensor(t) or t.is_cuda:
+        raise RuntimeError("%s must be a CPU tensor" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+
+
+def _check_f32(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+
+
+def _defined(t):
+    return t is not None and torch.is_tensor(t)
+
+
+def _check_grid(grid: SparseGridSpec):
+    _check_input(grid.density_data, "density_data")
+    _check_input(grid.sh_data, "sh_data")
+    _check_input(grid.links, "links")
+    if grid.surface_type != SURFACE_TYPE_NONE:
+        _check_input(grid.surface_data, "surface_data")
+        _check_input(grid.level_set_data, "level_set_data")
+    _check_cpu_input(grid._offset, "_offset")
+    _check_cpu_input(grid._scaling, "_scaling")
+    if grid.density_data.dim() != 2 or grid.sh_data.dim() != 2 or grid.links.dim() != 3:
+        raise RuntimeError("density_data / sh_data must be 2-D and links 3-D")
+    if grid.links.dtype != torch.int32:
+        raise RuntimeError("links must be int32")
+    _check_f32(grid.density_data, "density_data")
+    _check_f32(grid.sh_data, "sh_data")
+    if _defined(grid.background_links) and grid.background_links.numel() > 0:
+        raise NotImplementedError("MSI background layers are outside the B200 hot path (SURVEY.md 8f #4)")
+    if grid.basis_type != BASIS_TYPE_SH:
+        raise NotImplementedError("only the SH basis is on the B200 hot path")
+
+
+def _check_rays(rays: RaysSpec):
+    _check_input(rays.origins, "origins")
+    _check_input(rays.dirs, "dirs")
+    if rays.masks is not None:
+        _check_input(rays.masks, "masks")
+    _check_f32(rays.origins, "origins")
+    _check_f32(rays.dirs, "dirs")
+
+
+def _check_grads(g: GridOutputGrads):
+    for n in ("grad_density_out", "grad_sh_out", "grad_surface_out", "grad_fake_sample_std_out"):
+        t = getattr(g, n)
+        if _defined(t):
+            _check_input(t, n)
+            _check_f32(t, n)
+    if _defined(g.mask_out) and g.mask_out.numel() > 0:
+        _check_input(g.mask_out, "mask_out")
+
+
+# ---- occupancy pyramid cache: one per (links storage, version) ------------------------------------------------------
+_ACCEL = {}
+
+
+def accel_for(links: torch.Tensor) -> torch.Tensor:
+    """Bitmap pyramid of ``links`` (built by asurf_accel_build); rebuilt when links is modified in place."""
+    key = (links.data_ptr(), tuple(links.shape), links.device.index)
+    ver = links._version
+    hit = _ACCEL.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    L = capi.lib()
+    words = L.asurf_accel_words(capi.size3(links.shape))
+    acc = torch.empty((words,), dtype=torch.int64, device=links.device)
+    capi.check(L.asurf_accel_build(capi.ptr(links), capi.size3(links.shape), capi.ptr(acc),
+                                   capi.current_stream(links.device)), "asurf_accel_build")
+    if len(_ACCEL) > 8:
+        _ACCEL.clear()
+    _ACCEL[key] = (ver, acc)
+    return acc
+
+
+def _grid_t(grid: SparseGridSpec, need_surface=True):
+    g = capi.GridT()
+    g.links = grid.links.data_ptr()
+    g.size[:] = [int(s) for s in grid.links.shape]
+    g.density = grid.density_data.data_ptr()
+    has_surf = grid.surface_type != SURFACE_TYPE_NONE and _defined(grid.surface_data)
+    g.surface = grid.surface_data.data_ptr() if has_surf else None
+    g.level_set = grid.level_set_data.data_ptr() if has_surf else None
+    g.level_set_num = int(grid.level_set_data.shape[0]) if has_surf else 0
+    g.sh = grid.sh_data.data_ptr()
+    g.basis_dim = int(grid.basis_dim)
+    g.sh_dim = int(grid.sh_data.shape[1])
+    g.capacity = int(grid.density_data.shape[0])
+    g.offset[:] = [float(v) for v in grid._offset.tolist()]
+    g.scaling[:] = [float(v) for v in grid._scaling.tolist()]
+    g.fake_sample_std = float(grid.fake_sample_std)
+    g.truncated_vol_render_a = float(grid.truncated_vol_render_a)
+    acc = accel_for(grid.links)
+    g.accel = acc.data_ptr()
+    return g, acc
+
+
+def _rays_t(rays: RaysSpec):
+    r = capi.RaysT()
+    r.origins = rays.origins.data_ptr()
+    r.dirs = rays.dirs.data_ptr()
+    r.n_rays = int(rays.origins.shape[0])
+    return r
+
+
+def _grads_t(g: GridOutputGrads):
+    o = capi.GradsT()
+    o.grad_density = g.grad_density_out.data_ptr() if _defined(g.grad_density_out) else None
+    o.grad_surface = g.grad_surface_out.data_ptr() if _defined(g.grad_surface_out) else None
+    o.grad_sh = g.grad_sh_out.data_ptr() if _defined(g.grad_sh_out) else None
+    o.grad_fake_sample_std = (g.grad_fake_sample_std_out.data_ptr()
+                              if _defined(g.grad_fake_sample_std_out) and g.grad_fake_sample_std_out.numel() > 0 else None)
+    o.mask = g.mask_out.data_ptr() if _defined(g.mask_out) and g.mask_out.numel() > 0 else None
+    return o
+
+
+# ---- alpha-Surf renderer (render_lerp_kernel_surf_trav.cu:3596-3942) -------------------------------------------------
+def volume_render_surf_trav(grid, rays, opt):
+    _check_grid(grid)
+    _check_rays(rays)
+    out = torch.empty_like(rays.origins)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_surf_trav_forward(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                      capi.ptr(out), None, capi.current_stream()),
+                   "volume_render_surf_trav")
+    return out
+
+
+def volume_render_surf_trav_backward(grid, rays, opt, grad_out, color_cache, grads):
+    _check_grid(grid)
+    _check_rays(rays)
+    _check_grads(grads)
+    _check_input(grad_out, "grad_out")
+    _check_input(color_cache, "color_cache")
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_surf_trav_backward(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                       capi.ptr(grad_out), capi.ptr(color_cache),
+                                                       C.byref(_grads_t(grads)), capi.current_stream()),
+                   "volume_render_surf_trav_backward")
+
+
+# Global batch size used to normalise the fused losses; None = this call's ray count (the reference behaviour).
+# The ray-sharded data-parallel wrapper (alphasurf_b200.dist) sets it to the global Q.
+_NORM_RAYS = None
+
+
+def set_loss_norm_rays(n):
+    global _NORM_RAYS
+    _NORM_RAYS = None if n is None else int(n)
+
+
+def volume_render_surf_trav_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss, fused_surf_norm_reg_scale,
+                                  fused_surf_norm_reg_con_check, fused_surf_norm_reg_ignore_empty, lambda_l2, lambda_l1,
+                                  lambda_l_dist, lambda_l_entropy, no_norm_weight_l_entropy, lambda_l_dist_a,
+                                  lambda_l_entropy_a, lambda_l_samp_dist, lambda_l_di, l_di_alpha_thresh,
+                                  surf_sparse_alpha_thresh, lambda_inplace_surf_sparse, lambda_inwards_norm_loss,
+                                  lambda_conv_mode_samp, l_dist_max_sample, rgb_out, grads):
+    _check_input(rgb_gt, "rgb_gt")
+    _check_input(rgb_out, "rgb_out")
+    _check_grid(grid)
+    _check_rays(rays)
+    _check_grads(grads)
+    f = capi.make_fused(dict(
+        beta_loss=beta_loss, sparsity_loss=sparsity_loss, fused_surf_norm_reg_scale=fused_surf_norm_reg_scale,
+        lambda_l2=lambda_l2, lambda_l1=lambda_l1, lambda_l_dist=lambda_l_dist, lambda_l_entropy=lambda_l_entropy,
+        no_norm_weight_l_entropy=no_norm_weight_l_entropy, lambda_l_dist_a=lambda_l_dist_a,
+        lambda_l_entropy_a=lambda_l_entropy_a, lambda_l_samp_dist=lambda_l_samp_dist, lambda_l_di=lambda_l_di,
+        l_di_alpha_thresh=l_di_alpha_thresh, surf_sparse_alpha_thresh=surf_sparse_alpha_thresh,
+        lambda_inplace_surf_sparse=lambda_inplace_surf_sparse, lambda_inwards_norm_loss=lambda_inwards_norm_loss,
+        lambda_conv_mode_samp=lambda_conv_mode_samp, l_dist_max_sample=l_dist_max_sample), _NORM_RAYS or 0)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_surf_trav_fused(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                    capi.ptr(rgb_gt), C.byref(f), capi.ptr(rgb_out),
+                                                    C.byref(_grads_t(grads)), None, capi.current_stream()),
+                   "volume_render_surf_trav_fused")
+
+
+# ---- optimizer steps (optim_kernel.cu:154-267) -------------------------------------------------------------------------
+def _indexer(indexer):
+    """-> (kind, pointer, n): 0 all rows (0-dim tensor), bool mask, int64 row list; n == 0 means skip."""
+    _check_input(indexer, "indexer")
+    if indexer.dim() == 0:
+        return 0, None, -1
+    if indexer.shape[0] == 0:
+        return 1, None, 0
+    if indexer.dtype == torch.bool:
+        return 1, capi.ptr(indexer), int(indexer.shape[0])
+    if indexer.dtype != torch.int64:
+        raise RuntimeError("indexer must be a bool mask or an int64 index list")
+    return 2, capi.ptr(indexer), int(indexer.shape[0])
+
+
+def rmsprop_step(data, rms, grad, indexer, beta, lr, epsilon, minval, lr_last):
+    _check_input(data, "data")
+    _check_input(rms, "rms")
+    _check_input(grad, "grad")
+    kind, p, n = _indexer(indexer)
+    if n == 0:
+        return
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_rmsprop_step(
+            capi.ptr(data), capi.ptr(rms), capi.ptr(grad), C.c_int64(data.shape[0]), C.c_int32(data.shape[1]),
+            C.c_int32(kind), p, C.c_int64(max(n, 0)), C.c_float(beta), C.c_float(lr), C.c_float(epsilon),
+            C.c_float(minval), C.c_float(lr_last), capi.current_stream()), "rmsprop_step")
+
+
+def sgd_step(data, grad, indexer, lr, lr_last):
+    _check_input(data, "data")
+    _check_input(grad, "grad")
+    kind, p, n = _indexer(indexer)
+    if n == 0:
+        return
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_sgd_step(
+            capi.ptr(data), capi.ptr(grad), C.c_int64(data.shape[0]), C.c_int32(data.shape[1]), C.c_int32(kind), p,
+            C.c_int64(max(n, 0)), C.c_float(lr), C.c_float(lr_last), capi.current_stream()), "sgd_step")
+
+
+# ---- test hooks -----------------------------------------------------------------------------------------------------------
+def debug_ray_bounds(grid, rays, opt):
+    """(Q,9) grid-space rays as the kernels see them: origin3, dir3, tmin, tmax, world_step."""
+    _check_grid(grid)
+    _check_rays(rays)
+    xf = torch.zeros((rays.origins.shape[0], 9), dtype=torch.float32, device=rays.origins.device)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_debug_ray_bounds(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                     capi.ptr(xf), capi.current_stream()), "debug_ray_bounds")
+    return xf
+
+
+def debug_trace(grid, rays, opt, max_hits=64):
+    """Composited-sample trace of the forward march: (count (Q,), cell (Q,H), kind (Q,H), t (Q,H))."""
+    _check_grid(grid)
+    _check_rays(rays)
+    Q, dev = rays.origins.shape[0], rays.origins.device
+    cnt = torch.zeros((Q,), dtype=torch.int32, device=dev)
+    cell = torch.full((Q, max_hits), -1, dtype=torch.int32, device=dev)
+    kind = torch.full((Q, max_hits), -1, dtype=torch.int32, device=dev)
+    t = torch.zeros((Q, max_hits), dtype=torch.float32, device=dev)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_debug_trace(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                C.c_int32(max_hits), capi.ptr(cnt), capi.ptr(cell), capi.ptr(kind),
+                                                capi.ptr(t), capi.current_stream()), "debug_trace")
+    return cnt, cell, kind, t
+
+
+def render_stats(grid, rays, opt):
+    """Counters of SURVEY.md 8(d) for one forward march: dict(n_steps, n_linked, n_active, n_samples)."""
+    _check_grid(grid)
+    _check_rays(rays)
+    st = torch.zeros((6,), dtype=torch.int64, device=rays.origins.device)
+    out = torch.empty_like(rays.origins)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_surf_trav_forward(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                      capi.ptr(out), capi.ptr(st), capi.current_stream()),
+                   "render_stats")
+    v = st.tolist()
+    return dict(n_steps=v[0], n_skips=v[1], n_linked=v[2], n_active=v[3], n_samples=v[4])

@@ -1,0 +1,168 @@
+/*
+ * alphasurf_b200 -- C ABI of the B200-native replacement for the `svox2.csrc` hot path.
+ *
+ * Every entry point takes plain device pointers, sizes, POD option blocks and a CUDA stream (passed as
+ * void*), and returns 0 on success or a non-zero code (cudaError_t value, or ASURF_E_* below);
+ * asurf_last_error() gives the message.  No torch types cross this boundary.  The pybind11 functions of the
+ * reference that each entry replaces are cited as /root/reference/svox2/csrc/<file>:<line>.
+ *
+ * Tensors keep the layouts the reference's Python API owns:
+ *   links   int32 (X,Y,Z) contiguous, value = row in the data tensors or < 0 for an empty vertex
+ *   density float32 (N,1);  surface float32 (N,1);  sh float32 (N,D) channel-major, D = 3*basis_dim
+ * Gradients are ACCUMULATED (+=) into caller-owned buffers; mask bytes are set to 1 for touched rows.
+ */
+#ifndef ASURF_H
+#define ASURF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASURF_ABI_VERSION 1
+
+enum {
+    ASURF_OK = 0,
+    ASURF_E_INVALID = -1,      /* bad argument (the reference raises TORCH_CHECK errors here) */
+    ASURF_E_UNSUPPORTED = -2,  /* feature outside the hot path (MSI background, non-SH basis, ...) */
+    ASURF_E_NOMEM = -3
+};
+
+/* include/data_spec.hpp:39-56 (SparseGridSpec) / include/data_spec_packed.cuh:11-83 */
+typedef struct {
+    const int32_t *links;
+    int32_t size[3];
+    const float *density;
+    const float *surface;        /* NULL when surface_type == SURFACE_TYPE_NONE */
+    const float *sh;
+    const float *level_set;      /* device (L,) */
+    int32_t level_set_num;
+    int32_t basis_dim;
+    int32_t sh_dim;
+    int64_t capacity;            /* N */
+    float offset[3];             /* SparseGridSpec._offset  (host values) */
+    float scaling[3];            /* SparseGridSpec._scaling (host values) */
+    float fake_sample_std;
+    float truncated_vol_render_a;
+    /* Optional occupancy pyramid built by asurf_accel_build() for exactly these `links`
+     * (NULL: the library builds a transient one for this call). */
+    const uint64_t *accel;
+} asurf_grid_t;
+
+/* include/data_spec.hpp:168-201 (RenderOptions); bools widened to int32 */
+typedef struct {
+    float background_brightness;
+    float step_size;
+    float sigma_thresh;
+    float stop_thresh;
+    float near_clip;
+    int32_t use_spheric_clip;
+    int32_t last_sample_opaque;
+    int32_t surf_fake_sample;
+    float surf_fake_sample_min_vox_len;
+    int32_t limited_fake_sample;
+    int32_t no_surf_grad_from_sh;
+    int32_t alpha_activation_type;
+    int32_t fake_sample_l_dist;
+    int32_t fake_sample_normalize_surf;
+    int32_t only_outward_intersect;
+    int32_t truncated_vol_render;
+    float trunc_vol_weight_min;
+} asurf_opt_t;
+
+/* include/data_spec.hpp:139-147 (RaysSpec) */
+typedef struct {
+    const float *origins;        /* (Q,3) */
+    const float *dirs;           /* (Q,3) */
+    int64_t n_rays;              /* Q */
+} asurf_rays_t;
+
+/* include/data_spec.hpp:83-122 (GridOutputGrads) */
+typedef struct {
+    float *grad_density;         /* (N,1) */
+    float *grad_surface;         /* (N,1) or NULL */
+    float *grad_sh;              /* (N,D) */
+    float *grad_fake_sample_std; /* (1,) or NULL */
+    uint8_t *mask;               /* (N,) bool or NULL */
+} asurf_grads_t;
+
+/* scalar arguments of volume_render_surf_trav_fused, render_lerp_kernel_surf_trav.cu:3802-3828 */
+typedef struct {
+    float beta_loss;
+    float sparsity_loss;
+    float fused_surf_norm_reg_scale;     /* must be 0: the reference asserts (:2872-2875) */
+    float lambda_l2;
+    float lambda_l1;
+    float lambda_l_dist;
+    float lambda_l_entropy;
+    int32_t no_norm_weight_l_entropy;
+    float lambda_l_dist_a;
+    float lambda_l_entropy_a;
+    float lambda_l_samp_dist;
+    float lambda_l_di;
+    float l_di_alpha_thresh;
+    float surf_sparse_alpha_thresh;
+    float lambda_inplace_surf_sparse;
+    float lambda_inwards_norm_loss;
+    float lambda_conv_mode_samp;
+    int32_t l_dist_max_sample;
+    /* Ray count used to normalise the losses (2/(3Q), lambda/Q).  0 means "this call's Q" (the reference
+     * behaviour, :3308-3309, :3896-3908); the ray-sharded multi-GPU wrapper passes the global batch size. */
+    int64_t norm_rays;
+} asurf_fused_t;
+
+/* per-call statistics (SURVEY.md 8d counters), filled when a non-NULL device pointer is passed */
+typedef struct {
+    unsigned long long n_steps;      /* DDA voxel visits actually executed */
+    unsigned long long n_skips;      /* hierarchical empty-block skips */
+    unsigned long long n_linked;     /* visited voxels with all 8 links >= 0 (Nl) */
+    unsigned long long n_active;     /* ... that also pass the density gate and need work (Na) */
+    unsigned long long n_samples;    /* composited samples (S) */
+    unsigned long long n_ref_steps;  /* reserved */
+} asurf_stats_t;
+
+const char *asurf_last_error(void);
+int asurf_abi_version(void);
+
+/* ---- occupancy pyramid (ours; the reference marches voxel by voxel with USE_ACC_SKIP=false,
+ *      render_lerp_kernel_surf_trav.cu:31) ---- */
+int64_t asurf_accel_words(const int32_t size[3]);            /* number of uint64 words needed */
+int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream);
+
+/* ---- surf_trav renderer ---- */
+/* volume_render_surf_trav, render_lerp_kernel_surf_trav.cu:3596-3654 (forward only; rgb_out (Q,3)) */
+int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                            float *rgb_out, asurf_stats_t *stats_dev, void *stream);
+/* volume_render_surf_trav_backward, :3708-3800 (grad_out = dL/dRGB (Q,3), color_cache = forward RGB) */
+int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                             const float *grad_out, const float *color_cache, const asurf_grads_t *grads,
+                             void *stream);
+/* volume_render_surf_trav_fused, :3802-3942 (rgb_gt (Q,3) in, rgb_out (Q,3) out, grads +=) */
+int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                          const float *rgb_gt, const asurf_fused_t *fused, float *rgb_out,
+                          const asurf_grads_t *grads, asurf_stats_t *stats_dev, void *stream);
+/* test hooks: grid-space rays as the kernels see them, (Q,9) = origin3, dir3, tmin, tmax, world_step
+ * (ray_find_bounds, include/render_util.cuh:651-701); composited-sample trace of the last march:
+ * per ray up to max_hits entries of (cell, kind = st_id | fake<<2 | intersect_i<<3, t). */
+int asurf_debug_ray_bounds(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                           float *xf_out, void *stream);
+int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                      int32_t max_hits, int32_t *hit_count, int32_t *hit_cell, int32_t *hit_kind, float *hit_t,
+                      void *stream);
+
+/* ---- optimizer steps, optim_kernel.cu:154-267 ----
+ * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */
+int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
+                       const void *indexer, int64_t n_index, float beta, float lr, float eps, float minval,
+                       float lr_last, void *stream);
+int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
+                   const void *indexer, int64_t n_index, float lr, float lr_last, void *stream);
+
+/* release the library's device workspaces (arena, scratch) */
+void asurf_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASURF_H */

@@ -1,0 +1,136 @@
+"""GPU parity of the surf_trav renderer: ours (through the svox2.csrc-compatible module -> C ABI -> sm_100a kernels)
+against (a) the CPU oracle (oracle/*.c) and (b) the UNMODIFIED reference CUDA extension built for sm_100a.
+
+Tolerances: voxel / hit selection bit-exact; colours and gradients <= 1e-4 relative (north_star), where relative means
+max|a-b| / max|b| per tensor (fp32 atomics reorder sums).
+"""
+import numpy as np
+import pytest
+import torch
+
+from alphasurf_b200 import svox2_csrc as ours
+from alphasurf_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _setup(reso, basis_dim, Q, variant, opts, seed=0):
+    dev = "cuda"
+    sg = synth.make_shell_grid(reso, basis_dim=basis_dim, variant=variant).to(dev)
+    o, d, gt = synth.make_camera_rays(Q, device=dev, seed=synth.SEED + seed)
+    return sg, o, d, gt
+
+
+def _oracle_fused(sg, opts, o, d, gt, fused, xf):
+    from oracle import oracle
+    og = oracle.Grid(sg.to("cpu"))
+    tr = oracle.Trace(o.shape[0], 64)
+    rgb, grads = oracle.surf_trav_fused(og, opts, o.cpu(), d.cpu(), gt.cpu(), fused, xf=xf.cpu(), trace=tr)
+    return rgb, grads, tr
+
+
+CASES = [
+    ("parity-G*", 32, 4, 512, "G*", synth.parity_render_options, dict(lambda_l2=1.0, lambda_l1=0.5, l_dist_max_sample=64)),
+    ("syn-G", 64, 9, 1024, "G", synth.alphasurf_render_options, synth.alphasurf_fused_args()),
+    ("syn-G*", 48, 9, 512, "G*", synth.alphasurf_render_options, synth.alphasurf_fused_args()),
+    ("alllosses-G*", 32, 9, 256, "G*", synth.parity_render_options,
+     dict(lambda_l2=1.0, lambda_l1=0.1, lambda_l_dist=1e-2, lambda_l_entropy=1e-2, lambda_l_dist_a=1e-2,
+          lambda_l_entropy_a=1e-2, lambda_l_samp_dist=1e-2, lambda_l_di=1e-3, l_di_alpha_thresh=0.5,
+          surf_sparse_alpha_thresh=0.3, lambda_inplace_surf_sparse=1e-3, lambda_inwards_norm_loss=1e-2,
+          lambda_conv_mode_samp=1e-3, sparsity_loss=1e-3, l_dist_max_sample=64)),
+]
+
+
+def _full_fused(fd):
+    f = synth.alphasurf_fused_args()
+    for k in f:
+        if isinstance(f[k], float):
+            f[k] = 0.0
+    f.update(fd)
+    return f
+
+
+@pytest.mark.parametrize("name,reso,bd,Q,variant,optfn,fd", CASES, ids=[c[0] for c in CASES])
+def test_fused_vs_cpu_oracle(name, reso, bd, Q, variant, optfn, fd):
+    opts = optfn()
+    fused = _full_fused(fd)
+    sg, o, d, gt = _setup(reso, bd, Q, variant, opts)
+    grid = H.fill_grid_spec(ours, sg)
+    rays = H.fill_rays_spec(ours, o, d)
+    opt = H.fill_opt(ours, opts)
+    xf = ours.debug_ray_bounds(grid, rays, opt)
+    G = H.GradSet(sg, "cuda")
+    rgb = torch.zeros_like(o)
+    ours.volume_render_surf_trav_fused(grid, rays, opt, gt, *H.fused_positional(fused), rgb, G.spec(ours))
+    cnt, cell, kind, t = ours.debug_trace(grid, rays, opt)
+    torch.cuda.synchronize()
+
+    rgb_o, grads_o, tr = _oracle_fused(sg, opts, o, d, gt, fused, xf)
+    # hit selection: bit-exact (count, voxel, root id / intersection index)
+    assert np.array_equal(cnt.cpu().numpy(), tr.hit_count), "composited-sample counts differ"
+    m = np.arange(64)[None, :] < np.minimum(tr.hit_count, 64)[:, None]
+    assert np.array_equal(cell.cpu().numpy()[m], tr.hit_cell[m])
+    assert np.array_equal(kind.cpu().numpy()[m], tr.hit_kind[m])
+    assert tr.hit_count.sum() > 0
+    np.testing.assert_allclose(t.cpu().numpy()[m], tr.hit_t[m], rtol=1e-5, atol=1e-5)
+    assert H.rel_err(rgb.cpu(), torch.from_numpy(rgb_o)) < TOL
+    assert H.rel_err(G.sh.cpu(), torch.from_numpy(grads_o.sh)) < TOL
+    assert H.rel_err(G.density.cpu(), torch.from_numpy(grads_o.density)) < TOL
+    assert H.rel_err(G.surface.cpu(), torch.from_numpy(grads_o.surface)) < 5e-4, "surface grad (fp64 libm differs CPU/GPU)"
+    assert np.array_equal(G.mask.cpu().numpy().astype(np.uint8), grads_o.mask)
+    if opts["surf_fake_sample"]:
+        assert H.rel_err(G.std.cpu().reshape(-1), torch.from_numpy(grads_o.fake_sample_std)) < TOL
+
+
+REF_CASES = [
+    ("syn-G-128", 128, 9, 4096, "G", synth.alphasurf_render_options, synth.alphasurf_fused_args()),
+    ("syn-G*-64", 64, 9, 2048, "G*", synth.alphasurf_render_options, synth.alphasurf_fused_args()),
+    ("parity-G*-64-sh1", 64, 4, 2048, "G*", synth.parity_render_options,
+     dict(lambda_l2=1.0, lambda_l1=0.5, lambda_l_entropy=1e-3, lambda_conv_mode_samp=1e-4, l_dist_max_sample=64)),
+    ("alllosses-G*-32", 32, 9, 512, "G*", synth.parity_render_options, CASES[3][6]),
+]
+
+
+@pytest.mark.parametrize("name,reso,bd,Q,variant,optfn,fd", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_fused_vs_reference_cuda(name, reso, bd, Q, variant, optfn, fd):
+    ref = H.load_reference_cuda()
+    if ref is None:
+        pytest.skip("oracle/_ref reference extension not built")
+    opts = optfn()
+    fused = _full_fused(fd)
+    sg, o, d, gt = _setup(reso, bd, Q, variant, opts)
+
+    G = H.GradSet(sg, "cuda")
+    rgb = torch.zeros_like(o)
+    ours.volume_render_surf_trav_fused(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts),
+                                       gt, *H.fused_positional(fused), rgb, G.spec(ours))
+    Gr = H.GradSet(sg, "cuda")
+    rgb_r = torch.zeros_like(o)
+    ref.volume_render_surf_trav_fused(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts),
+                                      gt, *H.fused_positional(fused), rgb_r, Gr.spec(ref))
+    torch.cuda.synchronize()
+    assert torch.equal(G.mask, Gr.mask), "touched-voxel masks differ (hit selection not bit-exact)"
+    assert H.rel_err(rgb, rgb_r) < TOL
+    assert H.rel_err(G.sh, Gr.sh) < TOL
+    assert H.rel_err(G.density, Gr.density) < TOL
+    assert H.rel_err(G.surface, Gr.surface) < TOL
+    if opts["surf_fake_sample"]:
+        assert H.rel_err(G.std, Gr.std) < TOL
+
+    # non-fused forward + backward entry points
+    out = ours.volume_render_surf_trav(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts))
+    out_r = ref.volume_render_surf_trav(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts))
+    assert H.rel_err(out, out_r) < TOL
+    gout = torch.randn_like(out)
+    G2, G2r = H.GradSet(sg, "cuda"), H.GradSet(sg, "cuda")
+    ours.volume_render_surf_trav_backward(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d),
+                                          H.fill_opt(ours, opts), gout, out_r, G2.spec(ours))
+    ref.volume_render_surf_trav_backward(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts),
+                                         gout, out_r, G2r.spec(ref))
+    torch.cuda.synchronize()
+    assert torch.equal(G2.mask, G2r.mask)
+    assert H.rel_err(G2.sh, G2r.sh) < TOL
+    assert H.rel_err(G2.density, G2r.density) < TOL
+    assert H.rel_err(G2.surface, G2r.surface) < TOL
