@@ -25,7 +25,8 @@ class GridT(C.Structure):
     _fields_ = [("links", C.c_void_p), ("size", C.c_int32 * 3), ("density", C.c_void_p), ("surface", C.c_void_p),
                 ("sh", C.c_void_p), ("level_set", C.c_void_p), ("level_set_num", C.c_int32), ("basis_dim", C.c_int32),
                 ("sh_dim", C.c_int32), ("capacity", C.c_int64), ("offset", C.c_float * 3), ("scaling", C.c_float * 3),
-                ("fake_sample_std", C.c_float), ("truncated_vol_render_a", C.c_float), ("accel", C.c_void_p)]
+                ("fake_sample_std", C.c_float), ("truncated_vol_render_a", C.c_float), ("accel", C.c_void_p),
+                ("work", C.c_void_p)]
 
 
 class OptT(C.Structure):
@@ -78,9 +79,9 @@ def lib():
 
 # every symbol include/asurf.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
-    "asurf_last_error", "asurf_abi_version", "asurf_accel_words", "asurf_accel_build", "asurf_surf_trav_forward",
-    "asurf_surf_trav_backward", "asurf_surf_trav_fused", "asurf_debug_ray_bounds", "asurf_debug_trace",
-    "asurf_rmsprop_step", "asurf_sgd_step", "asurf_release",
+    "asurf_last_error", "asurf_abi_version", "asurf_accel_words", "asurf_accel_build", "asurf_work_build", "asurf_surf_trav_forward",
+    "asurf_surf_trav_backward", "asurf_surf_trav_fused", "asurf_debug_ray_bounds", "asurf_debug_trace", "asurf_debug_set_skip",
+    "asurf_rmsprop_step", "asurf_sgd_step", "asurf_profile_enable", "asurf_profile_read", "asurf_release",
 ]
 
 

@@ -63,7 +63,7 @@ __device__ __forceinline__ void field_to_cubic(const double *__restrict__ s, con
 
 // Real roots, ascending, of f0 + f1 t + f2 t^2 + f3 t^3 (Vieta / trigonometric; render_util.cuh:1126-1203).
 // st must be pre-set to -1.  Returns the root class.
-__device__ __noinline__ int solve_cubic(double f0, double f1, double f2, double f3, double *__restrict__ st) {
+__device__ __forceinline__ int solve_cubic(double f0, double f1, double f2, double f3, double *__restrict__ st) {
     const double eps = 1e-10;
     if (fabs(f3) < eps) {
         if (fabs(f2) < eps) {
@@ -108,7 +108,7 @@ __device__ __noinline__ int solve_cubic(double f0, double f1, double f2, double 
 }
 
 // d(root)/d(f0..f3), multiplied into g[0..3] (render_util.cuh:1206-1415).
-__device__ __noinline__ void root_grad(int type, int st_id, const double *__restrict__ fs, float *__restrict__ g) {
+__device__ __forceinline__ void root_grad(int type, int st_id, const double *__restrict__ fs, float *__restrict__ g) {
 #define SQR_(x) ((x) * (x))
 #define CUB_(x) ((x) * (x) * (x))
     if (type == ROOT_LINEAR) {

@@ -29,10 +29,13 @@ constexpr int CTA_WARPS = CTA_THREADS / 32;
 struct GridP {
     const int32_t *links;
     const float *density, *surface, *sh, *level_set;
-    const uint64_t *accel;
+    const uint64_t *accel;  // occupancy pyramid: bit = all 8 links >= 0
+    const uint64_t *work;   // work pyramid: bit = voxel can contribute a sample (asurf_work_build)
     int size[3];
     int level_set_num, basis_dim, sh_dim;
     int ab1, ab2;  // level-0 bitmap block counts along y and z
+    AccelLayout lay;
+    int use_skip;   // hierarchical empty-block skipping (off for the counting kernel)
     float offset[3], scaling[3];
     float fake_sample_std, trunc_a;
 };
@@ -72,8 +75,8 @@ struct Lane {
     // current voxel
     int vx, vy, vz;
     float t_close, t_far;
-    uint64_t word;
-    int wkey;
+    uint64_t word, w1, w2;   // cached pyramid words: level 0 (4^3 voxels), level 1 (16^3), level 2 (64^3)
+    int wkey, k1, k2;
     int lk[8];
     float sf[8], dn[8];
     float smin, smax;
@@ -168,12 +171,77 @@ __device__ __forceinline__ void dda_init(const GridP &g, Lane &L) {
     L.tfy = plane_t(L.ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
     L.tfz = plane_t(L.nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
     L.wkey = -1;
+    L.k1 = -1;
+    L.k2 = -1;
     L.word = 0;
+    L.w1 = 0;
+    L.w2 = 0;
     L.phase = PH_MARCH;
 }
 
+// ---- exact hierarchical skipping -----------------------------------------------------------------------------------
+// The reference DDA is a 3-way merge of the per-axis plane-crossing events ordered by (t, axis): each step takes the
+// smallest t_far, ties going to the lowest axis (:188-197), and every t is the correctly rounded (plane - o) / d.
+// Jumping over an empty aligned block therefore lands on EXACTLY the voxel the voxel-by-voxel DDA would reach, if we
+// (a) find the first event (T, A) that leaves the block and (b) for the other two axes count the planes whose event
+// precedes (T, A) in that order -- estimated from o + T*d and then corrected with the same divides the DDA uses.
+__device__ __forceinline__ bool crossed(int p, float o, float d, float T, bool tie_before) {
+    const float tp = plane_t(p, o, d);
+    return (tp < T) || ((tp == T) && tie_before);
+}
+__device__ __forceinline__ int axis_after(int v, float o, float d, float T, bool tie_before, int lo, int hi) {
+    if (d > 0.f) {   // crossing plane p enters voxel p
+        int n = min(max((int)floorf(fmaf(T, d, o)), v), hi - 1);
+        while (n < hi - 1 && crossed(n + 1, o, d, T, tie_before)) ++n;
+        while (n > v && !crossed(n, o, d, T, tie_before)) --n;
+        return n;
+    }
+    int n = min(max((int)floorf(fmaf(T, d, o)), lo), v);   // crossing plane p enters voxel p - 1
+    while (n > lo && crossed(n, o, d, T, tie_before)) --n;
+    while (n < v && !crossed(n + 1, o, d, T, tie_before)) ++n;
+    return n;
+}
+
+// Skip the empty aligned block of 2^s voxels per side that contains the next voxel.
+// Returns 0: skipped, keep marching; 1: the ray ends inside / at the exit of the block; 2: not skipped (the backward
+// pass must walk the last voxels one by one because of the `t += step_size` quirk, :1935).
+template <bool BWD>
+__device__ __forceinline__ int skip_block(const GridP &g, const asurf_opt_t &opt, Lane &L, int s) {
+    const int lox = (L.nx >> s) << s, loy = (L.ny >> s) << s, loz = (L.nz >> s) << s;
+    const int hix = min(lox + (1 << s), g.size[0] - 1), hiy = min(loy + (1 << s), g.size[1] - 1),
+              hiz = min(loz + (1 << s), g.size[2] - 1);
+    const int Px = (L.dx > 0.f) ? hix : lox, Py = (L.dy > 0.f) ? hiy : loy, Pz = (L.dz > 0.f) ? hiz : loz;
+    const float Tx = plane_t(Px, L.ox, L.dx), Ty = plane_t(Py, L.oy, L.dy), Tz = plane_t(Pz, L.oz, L.dz);
+    const float T = fminf(fminf(Tx, Ty), Tz);
+    if (BWD && !(T + opt.step_size <= L.tmax)) return 2;
+    if (!(T <= L.tmax)) return 1;   // `while (t <= tmax)` fails at a voxel of this (empty) block
+    int nx, ny, nz;
+    if (T == Tx) {
+        nx = (L.dx > 0.f) ? Px : Px - 1;
+        if ((nx < 0) || (nx >= g.size[0] - 1)) return 1;
+        ny = axis_after(L.ny, L.oy, L.dy, T, false, loy, hiy);
+        nz = axis_after(L.nz, L.oz, L.dz, T, false, loz, hiz);
+    } else if (T == Ty) {
+        ny = (L.dy > 0.f) ? Py : Py - 1;
+        if ((ny < 0) || (ny >= g.size[1] - 1)) return 1;
+        nx = axis_after(L.nx, L.ox, L.dx, T, true, lox, hix);
+        nz = axis_after(L.nz, L.oz, L.dz, T, false, loz, hiz);
+    } else {
+        nz = (L.dz > 0.f) ? Pz : Pz - 1;
+        if ((nz < 0) || (nz >= g.size[2] - 1)) return 1;
+        nx = axis_after(L.nx, L.ox, L.dx, T, true, lox, hix);
+        ny = axis_after(L.ny, L.oy, L.dy, T, true, loy, hiy);
+    }
+    L.nx = nx; L.ny = ny; L.nz = nz;
+    L.tfx = plane_t(nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx);
+    L.tfy = plane_t(ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
+    L.tfz = plane_t(nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
+    L.t = T;
+    return 0;
+}
+
 struct Counters {
-    unsigned long long steps, linked, active, samples;
+    unsigned long long steps, linked, active, samples, skips;
 };
 
 // Advance one ray until it has a sample to composite (returns true; the sample is described in L) or the ray
@@ -189,6 +257,45 @@ __device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, 
             if (!(L.t <= L.tmax)) {
                 L.done = true;
                 return false;
+            }
+            if (g.use_skip) {
+                const int k0 = ((L.nx >> 2) * g.ab1 + (L.ny >> 2)) * g.ab2 + (L.nz >> 2);
+                if (k0 != L.wkey) {   // entering another 4^3 block: consult the pyramid top-down
+                    const uint64_t *bm = DEBUG ? g.accel : g.work;
+                    const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
+                    if (k2 != L.k2) {
+                        L.k2 = k2;
+                        L.w2 = __ldg(bm + g.lay.off[2] + k2);
+                    }
+                    int s = 0;
+                    if (L.w2 == 0) {
+                        s = 6;
+                    } else {
+                        const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
+                        if (!((L.w2 >> bit1) & 1ull)) {
+                            s = 4;
+                        } else {
+                            const int k1 = ((L.nx >> 4) * g.lay.b[1][1] + (L.ny >> 4)) * g.lay.b[1][2] + (L.nz >> 4);
+                            if (k1 != L.k1) {
+                                L.k1 = k1;
+                                L.w1 = __ldg(bm + g.lay.off[1] + k1);
+                            }
+                            const int bit0 = (((L.nx >> 2) & 3) << 4) | (((L.ny >> 2) & 3) << 2) | ((L.nz >> 2) & 3);
+                            if (!((L.w1 >> bit0) & 1ull)) s = 2;
+                        }
+                    }
+                    if (s) {
+                        const int r = skip_block<BWD>(g, opt, L, s);
+                        if (r == 1) {
+                            L.done = true;
+                            return false;
+                        }
+                        if (r == 0) {
+                            if (DEBUG) ++cnt.skips;
+                            continue;
+                        }
+                    }
+                }
             }
             L.vx = L.nx; L.vy = L.ny; L.vz = L.nz;
             const float t_far = fminf(fminf(L.tfx, L.tfy), L.tfz);
@@ -209,14 +316,24 @@ __device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, 
             }
             if (DEBUG) ++cnt.steps;
             // occupancy: all 8 corner links >= 0  <=>  bit set
+            // DEBUG kernels walk the occupancy bitmap (bit = all 8 corner links >= 0) and apply the gates themselves;
+            // the production kernels walk the work bitmap, whose bit already includes the gates.
             const int key = ((L.vx >> 2) * g.ab1 + (L.vy >> 2)) * g.ab2 + (L.vz >> 2);
             if (key != L.wkey) {
                 L.wkey = key;
-                L.word = __ldg(g.accel + key);
+                L.word = __ldg((DEBUG ? g.accel : g.work) + key);
             }
             const int bit = ((L.vx & 3) << 4) | ((L.vy & 3) << 2) | (L.vz & 3);
             if (!((L.word >> bit) & 1ull)) {
-                if (BWD) L.t += opt.step_size;
+                if (BWD) {
+                    // reference quirk (:1935): an UNLINKED voxel adds step_size to t before the loop test.  t is
+                    // overwritten by the next step, so this only matters when it ends the loop.
+                    if (DEBUG) {
+                        L.t += opt.step_size;
+                    } else if (!(L.t + opt.step_size <= L.tmax)) {
+                        if (!((__ldg(g.accel + key) >> bit) & 1ull)) L.t += opt.step_size;
+                    }
+                }
                 continue;
             }
             if (DEBUG) ++cnt.linked;
@@ -230,13 +347,13 @@ __device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, 
             L.lk[6] = __ldg(lp + offx + offy);
             L.lk[7] = __ldg(lp + offx + offy + 1);
             // 8-corner density gate (:230-239): skip only if ALL corners are below the threshold
-            bool pass = false;
+            if (DEBUG) {
+                bool pass = false;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (!pass) pass = !(__ldg(g.density + L.lk[c]) < opt.sigma_thresh);
+                for (int c = 0; c < 8; ++c) pass |= !(__ldg(g.density + L.lk[c]) < opt.sigma_thresh);
+                if (!pass) continue;
+                ++cnt.active;
             }
-            if (!pass) continue;
-            if (DEBUG) ++cnt.active;
             L.dn_loaded = false;
 #pragma unroll
             for (int c = 0; c < 8; ++c) L.sf[c] = __ldg(g.surface + L.lk[c]);
@@ -468,7 +585,7 @@ __device__ __forceinline__ float log_clamped_ratio(float v, float sum) {
     return __logf((float)(fmax((double)v, 1e-8) / (double)sum));
 }
 
-__device__ void fused_preamble(const CacheView &c, Pre &p) {
+__device__ __forceinline__ void fused_preamble(const CacheView &c, Pre &p) {
     p.asum = 0.f; p.wsum = 0.f;
     for (int i = 0; i < c.n; ++i) { p.asum += c.sa[i]; p.wsum += c.sw[i]; }
     p.asum = fmaxf(p.asum, 1e-8f);
@@ -493,7 +610,7 @@ __device__ void fused_preamble(const CacheView &c, Pre &p) {
 }
 
 // l_dist(w) and l_entropy(w) contributions to d/d(rwalpha) (:2141-2210)
-__device__ float extra_grad_rwalpha_w(const FusedP &f, const Pre &p, const CacheView &c, int sample_i, float logT,
+__device__ __forceinline__ float extra_grad_rwalpha_w(const FusedP &f, const Pre &p, const CacheView &c, int sample_i, float logT,
                                       float rwalpha) {
     float add = 0.f;
     const float denom = fminf(rwalpha - 1.f, -1e-8f);
@@ -548,7 +665,7 @@ __device__ __forceinline__ void scatter8(float *__restrict__ grad, uint8_t *__re
 }
 
 // Everything of a REAL sample's backward that is scalar per ray (:2137-2448, lane-0 parts).
-__device__ void finish_real_bwd(const GridP &g, const asurf_opt_t &opt, const FusedP &f, const Pre &p, const CacheView &c,
+__device__ __forceinline__ void finish_real_bwd(const GridP &g, const asurf_opt_t &opt, const FusedP &f, const Pre &p, const CacheView &c,
                                 const asurf_grads_t &grads, Lane &L, float &accum, float total_color, float gx, float gy,
                                 float gz) {
     const float pos[3] = {L.px, L.py, L.pz};
@@ -625,7 +742,7 @@ __device__ void finish_real_bwd(const GridP &g, const asurf_opt_t &opt, const Fu
 }
 
 // Scalar part of a FAKE sample's backward (:2590-2866).
-__device__ void finish_fake_bwd(const GridP &g, const asurf_opt_t &opt, const FusedP &f, const Pre &p, const CacheView &c,
+__device__ __forceinline__ void finish_fake_bwd(const GridP &g, const asurf_opt_t &opt, const FusedP &f, const Pre &p, const CacheView &c,
                                 const asurf_grads_t &grads, Lane &L, float &accum, float total_color) {
     const float pos[3] = {L.px, L.py, L.pz};
     accum -= L.weight * total_color;
@@ -721,7 +838,7 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
     CacheView cv;
     cv.sa = cv.sw = cv.st = nullptr;
     cv.n = 0;
-    Counters cnt = {0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0};
     int n_hits = 0;
 
     if (ray_id < Q) {
@@ -860,6 +977,7 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
             if (dbg.hit_count) dbg.hit_count[ray_id] = n_hits;
             if (dbg.stats) {
                 atomicAdd(dbg.stats + 0, cnt.steps);
+                atomicAdd(dbg.stats + 1, cnt.skips);
                 atomicAdd(dbg.stats + 2, cnt.linked);
                 atomicAdd(dbg.stats + 3, cnt.active);
                 atomicAdd(dbg.stats + 4, cnt.samples);
@@ -875,9 +993,17 @@ using namespace asurf;
 
 namespace {
 
-Workspace g_ws_accel, g_ws_cache, g_ws_dbg;
+Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg;
 
-int make_grid(const asurf_grid_t *grid, cudaStream_t st, GridP &g) {
+int g_skip_enabled = 1;  // asurf_debug_set_skip
+
+// per-kernel timing ring (asurf_profile_*)
+struct ProfRing {
+    cudaEvent_t *ev = nullptr;  // 3 events per call: start, mid, end
+    int cap = 0, n = 0;
+} g_prof;
+
+int make_grid(const asurf_grid_t *grid, const asurf_opt_t *opt, bool need_work, cudaStream_t st, GridP &g) {
     ASURF_REQUIRE(grid, ASURF_E_INVALID, "surf_trav: null grid");
     ASURF_REQUIRE(grid->links && grid->density && grid->sh, ASURF_E_INVALID, "surf_trav: null grid tensor");
     ASURF_REQUIRE(grid->surface && grid->level_set, ASURF_E_INVALID,
@@ -905,6 +1031,8 @@ int make_grid(const asurf_grid_t *grid, cudaStream_t st, GridP &g) {
     AccelLayout lay(grid->size);
     g.ab1 = lay.b[0][1];
     g.ab2 = lay.b[0][2];
+    g.lay = lay;
+    g.use_skip = g_skip_enabled;
     if (grid->accel) {
         g.accel = grid->accel;
     } else {
@@ -913,6 +1041,16 @@ int make_grid(const asurf_grid_t *grid, cudaStream_t st, GridP &g) {
         rc = asurf_accel_build(grid->links, grid->size, (uint64_t *)g_ws_accel.ptr, st);
         if (rc) return rc;
         g.accel = (const uint64_t *)g_ws_accel.ptr;
+    }
+    g.work = grid->work;
+    if (need_work && !grid->work) {
+        int rc = g_ws_work.reserve((size_t)lay.off[3] * sizeof(uint64_t));
+        if (rc) return rc;
+        asurf_grid_t tmp = *grid;
+        tmp.accel = g.accel;
+        rc = asurf_work_build(&tmp, opt, (uint64_t *)g_ws_work.ptr, st);
+        if (rc) return rc;
+        g.work = (const uint64_t *)g_ws_work.ptr;
     }
     return 0;
 }
@@ -936,7 +1074,7 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     if (rays->n_rays == 0) return 0;
     ASURF_REQUIRE(rgb_out, ASURF_E_INVALID, "surf_trav_forward: null output");
     GridP g;
-    rc = make_grid(grid, st, g);
+    rc = make_grid(grid, opt, stats_dev == nullptr, st, g);
     if (rc) return rc;
     FusedP f = {};
     CacheP cache = {};
@@ -944,6 +1082,7 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     DebugP dbg = {};
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
+        g.use_skip = 0;   // count every voxel of the reference DDA
         surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
             g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg);
     } else {
@@ -963,7 +1102,7 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     ASURF_REQUIRE(grad_out && color_cache && grads, ASURF_E_INVALID, "surf_trav_backward: null tensor");
     ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "surf_trav_backward: null gradient buffer");
     GridP g;
-    rc = make_grid(grid, st, g);
+    rc = make_grid(grid, opt, true, st, g);
     if (rc) return rc;
     FusedP f = {};
     CacheP cache = {};
@@ -988,7 +1127,7 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     ASURF_REQUIRE(rgb_gt && rgb_out, ASURF_E_INVALID, "surf_trav_fused: null colour tensor");
     ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "surf_trav_fused: null gradient buffer");
     GridP g;
-    rc = make_grid(grid, st, g);
+    rc = make_grid(grid, opt, true, st, g);
     if (rc) return rc;
     const int M = fu->l_dist_max_sample;
     CacheP cache = {};
@@ -1028,17 +1167,27 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     DebugP dbg = {};
     FusedP ff = {};
     ff.M = M;
+    const bool prof = g_prof.cap > 0 && g_prof.n < g_prof.cap;
+    cudaEvent_t *pe = prof ? g_prof.ev + 3 * g_prof.n : nullptr;
+    if (prof) cudaEventRecord(pe[0], st);
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
-        surf_trav_kernel<false, true><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
+        GridP gs = g;
+        gs.use_skip = 0;
+        surf_trav_kernel<false, true><<<n_ctas(Q), CTA_THREADS, 0, st>>>(gs, *opt, rays->origins, rays->dirs, Q, rgb_out,
                                                                           nullptr, nullptr, ff, cache, nog, dbg);
     } else {
         surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
                                                                            nullptr, nullptr, ff, cache, nog, dbg);
     }
     DebugP nodbg = {};
+    if (prof) cudaEventRecord(pe[1], st);
     surf_trav_kernel<true, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, nullptr, rgb_gt,
                                                                       rgb_out, f, cache, *grads, nodbg);
+    if (prof) {
+        cudaEventRecord(pe[2], st);
+        ++g_prof.n;
+    }
     return check_cuda(cudaGetLastError(), "surf_trav_fused launch");
 }
 
@@ -1048,7 +1197,7 @@ static int debug_launch(const asurf_grid_t *grid, const asurf_rays_t *rays, cons
     if (rc) return rc;
     if (rays->n_rays == 0) return 0;
     GridP g;
-    rc = make_grid(grid, st, g);
+    rc = make_grid(grid, opt, false, st, g);
     if (rc) return rc;
     rc = g_ws_dbg.reserve((size_t)rays->n_rays * 3 * sizeof(float));
     if (rc) return rc;
@@ -1081,8 +1230,41 @@ extern "C" int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *r
     return debug_launch(grid, rays, opt, dbg, (cudaStream_t)stream);
 }
 
+extern "C" void asurf_debug_set_skip(int32_t enabled) { g_skip_enabled = enabled ? 1 : 0; }
+
+extern "C" int asurf_profile_enable(int32_t capacity) {
+    for (int i = 0; i < 3 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
+    delete[] g_prof.ev;
+    g_prof = ProfRing();
+    if (capacity <= 0) return 0;
+    g_prof.ev = new cudaEvent_t[3 * (size_t)capacity];
+    for (int i = 0; i < 3 * capacity; ++i) ASURF_CUDA(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.cap = capacity;
+    return 0;
+}
+
+extern "C" int asurf_profile_read(int32_t *n_calls, float *fwd_ms_sum, float *bwd_ms_sum) {
+    ASURF_REQUIRE(n_calls && fwd_ms_sum && bwd_ms_sum, ASURF_E_INVALID, "profile_read: null output");
+    float fwd = 0.f, bwd = 0.f;
+    for (int i = 0; i < g_prof.n; ++i) {
+        cudaEvent_t *pe = g_prof.ev + 3 * i;
+        ASURF_CUDA(cudaEventSynchronize(pe[2]));
+        float a = 0.f, b = 0.f;
+        ASURF_CUDA(cudaEventElapsedTime(&a, pe[0], pe[1]));
+        ASURF_CUDA(cudaEventElapsedTime(&b, pe[1], pe[2]));
+        fwd += a;
+        bwd += b;
+    }
+    *n_calls = g_prof.n;
+    *fwd_ms_sum = fwd;
+    *bwd_ms_sum = bwd;
+    g_prof.n = 0;
+    return 0;
+}
+
 extern "C" void asurf_release(void) {
     g_ws_accel.release();
+    g_ws_work.release();
     g_ws_cache.release();
     g_ws_dbg.release();
 }

@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the alpha-Surf hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one training iteration of config C3 on one batch of synthetic rays per GPU:
+fused surf_trav render forward+backward (L2 + entropy + conv-mode losses) -> grid regularisers that exist in this
+build -> RMSprop steps on density / surface / SH for the touched voxels, on a synthetic 512^3 SH-degree-2 shell grid.
+Metric: rays/s, whole job (all ranks).  ``--impl reference`` times the CPU oracle (a port of the reference CUDA
+semantics; the reference has no compiled CPU implementation) on a bounded ray sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rays/sec fwd+bwd (512^3 SH2 surface render)"
+LR = dict(density=1e-2, surface=1e-5, sh=1e-3)
+RMS_BETA, RMS_EPS = 0.95, 1e-8
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx = float(p[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def algorithmic_bytes(st, Q, D, M=64):
+    """compulsory bytes of the reference algorithm for one fused call, from the march counters."""
+    Nv, Nl, Na, S = st["n_steps"], st["n_linked"], st["n_active"], st["n_samples"]
+    cache = 12 * min(S, M * Q)
+    fwd = 16 * Nv + 16 * Nl + 16 * Na + S * 32 * (1 + D) + (24 + 12) * Q + cache
+    bwd = 16 * Nv + 16 * Nl + 16 * Na + S * 32 * (1 + D) + S * 2 * 32 * D + S * 2 * 32 * 2 + 8 * S + (24 + 24) * Q + cache
+    return fwd, bwd
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from alphasurf_b200 import synth
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sg = synth.make_shell_grid(args.reso, basis_dim=9, variant="G", device="cpu")
+    og = oracle.Grid(sg)
+    opts, fused = synth.alphasurf_render_options(), synth.alphasurf_fused_args()
+    sample = args.ref_rays
+    o, d, gt = synth.make_camera_rays(sample, device="cpu")
+    grads = oracle.Grads(og)
+
+    def step():
+        oracle.surf_trav_fused(og, opts, o, d, gt, fused, grads=grads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_note="CPU step = fused render fwd+bwd of a %d-ray sample" % sample),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d rays x %d steps of the same 512^3 workload, fused render fwd+bwd only "
+                                   "(oracle/*.c, OpenMP over rays)" % (sample, args.steps)},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_note=None):
+    c = {"workload": "C3: alpha-Surf surf_trav fused render fwd+bwd + RMSprop(density,surface,sh) step, synthetic "
+                     "%d^3 shell grid G(R) SH deg 2 (D=27), %d rays/step/GPU, options of surface_cuda_syn.yaml"
+                     % (args.reso, args.rays),
+         "grid": "%d^3" % args.reso, "rays_per_step_per_gpu": args.rays, "sh_dim": 27,
+         "l2_policy": "inputs larger than L2 (grid data 2.3 GB); a different ray batch every step",
+         "parallelism": "ray-sharded dp%d, grid replicated" % args.gpus}
+    if sample_note:
+        c["note"] = sample_note
+    return c
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from alphasurf_b200 import capi, synth
+    from alphasurf_b200 import svox2_csrc as C
+    from tests import helpers as H
+    import ctypes
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    Q, D = args.rays, 27
+    sg = synth.make_shell_grid(args.reso, basis_dim=9, variant="G", device="cpu").to(dev)
+    N = sg.capacity
+    opts, fused = synth.alphasurf_render_options(), synth.alphasurf_fused_args()
+    grid = H.fill_grid_spec(C, sg)
+    opt = H.fill_opt(C, opts)
+    G = H.GradSet(sg, dev, with_std=False)
+    gspec = G.spec(C)
+    rms = {k: torch.zeros_like(getattr(sg, k)) for k in ("density", "surface", "sh")}
+    NB = args.batches
+    dev_batches, host_batches = [], []
+    for b in range(NB):
+        o, d, gt = synth.make_camera_rays(Q, device="cpu", seed=synth.SEED + 1000 * rank + b)
+        host_batches.append(tuple(t.pin_memory() for t in (o, d, gt)))
+        dev_batches.append(tuple(t.to(dev) for t in (o, d, gt)))
+    rgb_out = torch.zeros((Q, 3), dtype=torch.float32, device=dev)
+    rgb_host = torch.zeros((Q, 3), dtype=torch.float32).pin_memory()
+    stage = tuple(torch.empty((Q, 3), dtype=torch.float32, device=dev) for _ in range(3))
+    fpos = H.fused_positional(fused)
+    if world > 1:
+        C.set_loss_norm_rays(Q * world)
+    launches = {"n": 0}
+
+    def device_step(o, d, gt):
+        G.mask.zero_()
+        rays = H.fill_rays_spec(C, o, d)
+        C.volume_render_surf_trav_fused(grid, rays, opt, gt, *fpos, rgb_out, gspec)
+        launches["n"] += 2
+        if world > 1:
+            from alphasurf_b200 import dist as adist
+            adist.allreduce_grads(G)
+        C.rmsprop_step(sg.density, rms["density"], G.density, G.mask, RMS_BETA, LR["density"], RMS_EPS, -1e9, LR["density"])
+        C.rmsprop_step(sg.surface, rms["surface"], G.surface, G.mask, RMS_BETA, LR["surface"], RMS_EPS, -1e9, LR["surface"])
+        C.rmsprop_step(sg.sh, rms["sh"], G.sh, G.mask, RMS_BETA, LR["sh"], RMS_EPS, -1e9, LR["sh"])
+        launches["n"] += 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # march counters of batch 0 (outside the timed region) -> algorithmic bytes
+    st = C.render_stats(grid, H.fill_rays_spec(C, dev_batches[0][0], dev_batches[0][1]), opt)
+    fwd_bytes, bwd_bytes = algorithmic_bytes(st, Q, D)
+
+    # ---------------- device-resident timing ----------------
+    for i in range(args.warmup):
+        device_step(*dev_batches[i % NB])
+    L = capi.lib()
+    capi.check(L.asurf_profile_enable(ctypes.c_int32(args.steps)), "profile_enable")
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        device_step(*dev_batches[(args.warmup + i) % NB])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    n_launch = launches["n"]
+    ncalls, fms, bms = ctypes.c_int32(0), ctypes.c_float(0), ctypes.c_float(0)
+    capi.check(L.asurf_profile_read(ctypes.byref(ncalls), ctypes.byref(fms), ctypes.byref(bms)), "profile_read")
+    capi.check(L.asurf_profile_enable(ctypes.c_int32(0)), "profile_disable")
+    fwd_ms = fms.value / max(ncalls.value, 1)
+    bwd_ms = bms.value / max(ncalls.value, 1)
+    ms_step = ms_total / args.steps
+    value = Q * world * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end to end: host buffers in, colours out, through the svox2.csrc-compatible API ----------------
+    def e2e_step(b):
+        ho, hd, hgt = host_batches[b]
+        stage[0].copy_(ho, non_blocking=True)
+        stage[1].copy_(hd, non_blocking=True)
+        stage[2].copy_(hgt, non_blocking=True)
+        device_step(stage[0], stage[1], stage[2])
+        rgb_host.copy_(rgb_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(((rgb_host - hgt) ** 2).mean())  # the mse opt.py logs every step (opt/opt.py:832-860)
+
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i % NB)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step((args.warmup + i) % NB)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = Q * world * args.steps / e2e_s
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    dom = ("backward", bwd_ms, bwd_bytes) if bwd_ms >= fwd_ms else ("forward", fwd_ms, fwd_bytes)
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e9 if dom[1] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom[0])
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args),
+        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                   "samples": clocks["samples"]},
+        "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 3 * Q * 3 * 4, "d2h_bytes_per_step": Q * 3 * 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": n_launch,
+        "roofline": {"bound": "hbm", "kernel": "surf_trav_kernel<%s>" % dom[0], "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom[2], "kernel_ms": dom[1],
+                     "kernels": {"forward_ms": fwd_ms, "backward_ms": bwd_ms, "forward_bytes": fwd_bytes,
+                                 "backward_bytes": bwd_bytes},
+                     "counters_per_ray": {k: st[k] / Q for k in ("n_steps", "n_linked", "n_active", "n_samples")}},
+    }
+    if world == 1 and not args.no_extras:
+        line["cpu_baseline"] = cpu_baseline(args, sg, opts, fused, host_batches[0])
+        ref = reference_cuda_same_gpu(args, sg, opts, fpos, dev_batches, H)
+        if ref is not None:
+            line["reference_cuda_same_gpu"] = ref
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, sg, opts, fused, batch0):
+    """The oracle port on the host cores of this box: bounded sample of the same workload (render fwd+bwd)."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    og = oracle.Grid(sg.to("cpu"))
+    n = args.ref_rays
+    o, d, gt = (t[:n] for t in batch0)
+    grads = oracle.Grads(og)
+    oracle.surf_trav_fused(og, opts, o, d, gt, fused, grads=grads)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        oracle.surf_trav_fused(og, opts, o, d, gt, fused, grads=grads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > args.cpu_seconds or reps >= 200:
+            break
+    return {"value": n * reps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "first %d rays of batch 0, %d repeats (%.1f s), fused render fwd+bwd only, oracle/*.c with OpenMP"
+                      % (n, reps, dt)}
+
+
+def reference_cuda_same_gpu(args, sg, opts, fpos, dev_batches, H):
+    """Extra (not part of the contract): the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same GPU."""
+    import torch
+    try:
+        ref = H.load_reference_cuda()
+    except Exception as e:  # noqa
+        return {"unavailable": repr(e)[:200]}
+    if ref is None:
+        return None
+    Gr = H.GradSet(sg, sg.density.device, with_std=False)
+    grid, opt, gs = H.fill_grid_spec(ref, sg), H.fill_opt(ref, opts), Gr.spec(ref)
+    Q = dev_batches[0][0].shape[0]
+    out = torch.zeros((Q, 3), dtype=torch.float32, device=sg.density.device)
+
+    def call(b):
+        o, d, gt = dev_batches[b % len(dev_batches)]
+        ref.volume_render_surf_trav_fused(grid, H.fill_rays_spec(ref, o, d), opt, gt, *fpos, out, gs)
+
+    for i in range(3):
+        call(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 5
+    for i in range(n):
+        call(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"what": "reference render_ray_kernel + render_ray_backward_kernel (fused call only, no optimizer)",
+            "ms_per_call": ms, "rays_per_s": Q / (ms * 1e-3)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reso", type=int, default=512)
+    ap.add_argument("--rays", type=int, default=65536)
+    ap.add_argument("--batches", type=int, default=8)
+    ap.add_argument("--ref-rays", type=int, default=16384)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline and the reference-CUDA comparison (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

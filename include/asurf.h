@@ -48,6 +48,9 @@ typedef struct {
     /* Optional occupancy pyramid built by asurf_accel_build() for exactly these `links`
      * (NULL: the library builds a transient one for this call). */
     const uint64_t *accel;
+    /* Optional work pyramid built by asurf_work_build() for exactly this grid content (links, density, surface,
+     * level sets) and the render options of the call (NULL: the library builds a transient one per call). */
+    const uint64_t *work;
 } asurf_grid_t;
 
 /* include/data_spec.hpp:168-201 (RenderOptions); bools widened to int32 */
@@ -130,6 +133,12 @@ int asurf_abi_version(void);
 int64_t asurf_accel_words(const int32_t size[3]);            /* number of uint64 words needed */
 int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream);
 
+/* ---- work pyramid (ours): same layout as the occupancy pyramid, bit set iff the voxel can contribute a sample
+ *      under `opt`: all 8 links >= 0, the 8-corner density gate passes (render_lerp_kernel_surf_trav.cu:230-239)
+ *      and a level set lies inside the corner range (:273-277) -- or fake samples are taken everywhere (:423).
+ *      The marcher visits every voxel of the reference DDA but touches grid data only where the bit is set. ---- */
+int asurf_work_build(const asurf_grid_t *grid, const asurf_opt_t *opt, uint64_t *work_out, void *stream);
+
 /* ---- surf_trav renderer ---- */
 /* volume_render_surf_trav, render_lerp_kernel_surf_trav.cu:3596-3654 (forward only; rgb_out (Q,3)) */
 int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
@@ -151,6 +160,10 @@ int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *rays, const 
                       int32_t max_hits, int32_t *hit_count, int32_t *hit_cell, int32_t *hit_kind, float *hit_t,
                       void *stream);
 
+/* test hook: switch the hierarchical empty-block skipping of the marchers off (0) / on (non-zero, default).  Results
+ * must be bit-identical either way; tests/ use it as a full-size property check. */
+void asurf_debug_set_skip(int32_t enabled);
+
 /* ---- optimizer steps, optim_kernel.cu:154-267 ----
  * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */
 int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
@@ -158,6 +171,14 @@ int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int
                        float lr_last, void *stream);
 int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
                    const void *indexer, int64_t n_index, float lr, float lr_last, void *stream);
+
+/* ---- per-kernel timing (ours; feeds bench.py's roofline) ----
+ * After asurf_profile_enable(capacity > 0) every asurf_surf_trav_fused call records CUDA events around its forward
+ * and its backward kernel on the launching stream (up to `capacity` calls are kept).  asurf_profile_read waits for
+ * the recorded events, returns the number of calls and the summed kernel durations in ms, and resets the ring.
+ * asurf_profile_enable(0) switches it off and destroys the events. */
+int asurf_profile_enable(int32_t capacity);
+int asurf_profile_read(int32_t *n_calls, float *fwd_ms_sum, float *bwd_ms_sum);
 
 /* release the library's device workspaces (arena, scratch) */
 void asurf_release(void);

@@ -134,3 +134,34 @@ def test_fused_vs_reference_cuda(name, reso, bd, Q, variant, optfn, fd):
     assert H.rel_err(G2.sh, G2r.sh) < TOL
     assert H.rel_err(G2.density, G2r.density) < TOL
     assert H.rel_err(G2.surface, G2r.surface) < TOL
+
+
+def test_skip_is_exact_at_full_size():
+    """Property check at BASELINE.json's size (512^3, 65536 rays): the hierarchical block skipping must land on exactly
+    the voxels of the voxel-by-voxel DDA -> colours bit-identical, touched masks identical, gradients equal up to
+    atomic order."""
+    from alphasurf_b200 import capi
+    opts, fused = synth.alphasurf_render_options(), synth.alphasurf_fused_args()
+    sg = synth.make_shell_grid(512, basis_dim=9, variant="G").to("cuda")
+    o, d, gt = synth.make_camera_rays(65536, device="cuda")
+    res = []
+    try:
+        for skip in (1, 0):
+            capi.lib().asurf_debug_set_skip(skip)
+            G = H.GradSet(sg, "cuda", with_std=False)
+            rgb = torch.zeros_like(o)
+            ours.volume_render_surf_trav_fused(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d),
+                                               H.fill_opt(ours, opts), gt, *H.fused_positional(fused), rgb, G.spec(ours))
+            cnt, cell, kind, t = ours.debug_trace(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d),
+                                                  H.fill_opt(ours, opts), max_hits=8)
+            torch.cuda.synchronize()
+            res.append((rgb, G, cnt, cell, kind, t))
+    finally:
+        capi.lib().asurf_debug_set_skip(1)
+    a, b = res
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[1].mask, b[1].mask) and int(a[1].mask.sum()) > 0
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4]) and torch.equal(a[5], b[5])
+    assert H.rel_err(a[1].sh, b[1].sh) < 1e-5
+    assert H.rel_err(a[1].surface, b[1].surface) < 1e-5
+    assert H.rel_err(a[1].density, b[1].density) < 1e-5
