@@ -64,7 +64,9 @@ struct DebugP {
     unsigned long long *stats;    // asurf_stats_t
 };
 
-enum { PH_MARCH = 0, PH_ROOTS = 1, PH_FAKE = 2, PH_POST = 3 };
+// lane state: what the lane needs next; phase: where it is inside a work voxel
+enum { ST_IDLE = 0, ST_MARCH = 1, ST_VOXEL = 2, ST_SAMPLE = 3 };
+enum { PH_ENTER = 0, PH_ROOTS = 1, PH_FAKE = 2, PH_POST = 3 };
 
 struct Lane {
     // ray in grid space
@@ -86,8 +88,10 @@ struct Lane {
     double nno[3];       // entry point relative to the voxel
     float nof[3];        // entry point, float
     int root_type, lv_i, j;
-    int phase;
-    bool done, has_sample, has_surf, dn_loaded, fs_ready;
+    int phase, state;
+    bool ray_done, force_fine, has_sample, has_surf, dn_loaded, fs_ready;
+    int64_t ray_id;
+    int n_hits;
     // compositing state
     float logT;
     int intersect_i, sample_i;
@@ -176,7 +180,8 @@ __device__ __forceinline__ void dda_init(const GridP &g, Lane &L) {
     L.word = 0;
     L.w1 = 0;
     L.w2 = 0;
-    L.phase = PH_MARCH;
+    L.force_fine = false;
+    L.state = ST_MARCH;
 }
 
 // ---- exact hierarchical skipping -----------------------------------------------------------------------------------
@@ -202,140 +207,156 @@ __device__ __forceinline__ int axis_after(int v, float o, float d, float T, bool
     return n;
 }
 
-// Skip the empty aligned block of 2^s voxels per side that contains the next voxel.
-// Returns 0: skipped, keep marching; 1: the ray ends inside / at the exit of the block; 2: not skipped (the backward
-// pass must walk the last voxels one by one because of the `t += step_size` quirk, :1935).
-template <bool BWD>
-__device__ __forceinline__ int skip_block(const GridP &g, const asurf_opt_t &opt, Lane &L, int s) {
-    const int lox = (L.nx >> s) << s, loy = (L.ny >> s) << s, loz = (L.nz >> s) << s;
-    const int hix = min(lox + (1 << s), g.size[0] - 1), hiy = min(loy + (1 << s), g.size[1] - 1),
-              hiz = min(loz + (1 << s), g.size[2] - 1);
-    const int Px = (L.dx > 0.f) ? hix : lox, Py = (L.dy > 0.f) ? hiy : loy, Pz = (L.dz > 0.f) ? hiz : loz;
-    const float Tx = plane_t(Px, L.ox, L.dx), Ty = plane_t(Py, L.oy, L.dy), Tz = plane_t(Pz, L.oz, L.dz);
-    const float T = fminf(fminf(Tx, Ty), Tz);
-    if (BWD && !(T + opt.step_size <= L.tmax)) return 2;
-    if (!(T <= L.tmax)) return 1;   // `while (t <= tmax)` fails at a voxel of this (empty) block
-    int nx, ny, nz;
-    if (T == Tx) {
-        nx = (L.dx > 0.f) ? Px : Px - 1;
-        if ((nx < 0) || (nx >= g.size[0] - 1)) return 1;
-        ny = axis_after(L.ny, L.oy, L.dy, T, false, loy, hiy);
-        nz = axis_after(L.nz, L.oz, L.dz, T, false, loz, hiz);
-    } else if (T == Ty) {
-        ny = (L.dy > 0.f) ? Py : Py - 1;
-        if ((ny < 0) || (ny >= g.size[1] - 1)) return 1;
-        nx = axis_after(L.nx, L.ox, L.dx, T, true, lox, hix);
-        nz = axis_after(L.nz, L.oz, L.dz, T, false, loz, hiz);
-    } else {
-        nz = (L.dz > 0.f) ? Pz : Pz - 1;
-        if ((nz < 0) || (nz >= g.size[2] - 1)) return 1;
-        nx = axis_after(L.nx, L.ox, L.dx, T, true, lox, hix);
-        ny = axis_after(L.ny, L.oy, L.dy, T, true, loy, hiy);
-    }
-    L.nx = nx; L.ny = ny; L.nz = nz;
-    L.tfx = plane_t(nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx);
-    L.tfy = plane_t(ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
-    L.tfz = plane_t(nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
-    L.t = T;
-    return 0;
-}
-
 struct Counters {
     unsigned long long steps, linked, active, samples, skips;
 };
 
-// Advance one ray until it has a sample to composite (returns true; the sample is described in L) or the ray
-// is finished (returns false, L.done set).  Follows trace_ray_surf_trav (:86-551) and, with BWD, the loop of
-// trace_ray_surf_trav_backward (:1834-2897) including its `t += step_size` on unlinked voxels (:1935).
+__device__ __forceinline__ void record_hit(const DebugP &dbg, const GridP &g, Lane &L) {
+    if (dbg.hit_count) {
+        if (L.n_hits < dbg.max_hits) {
+            const int64_t o = L.ray_id * dbg.max_hits + L.n_hits;
+            dbg.hit_cell[o] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
+            dbg.hit_kind[o] = (L.fake ? 3 : L.st_id) + 8 * L.intersect_i;
+            dbg.hit_t[o] = L.ts;
+        }
+        ++L.n_hits;
+    }
+}
+
+// One generalized DDA step of a marching lane -- the SAME instruction stream whether the lane walks one voxel (s = 0)
+// or jumps over an empty aligned block of 2^s voxels per side (s = 2, 4, 6), so that the 32 rays of a warp stay
+// converged.  s = 0 reproduces one iteration of the reference loop (:86-221 / :1834-1937) for voxel (nx,ny,nz): on a
+// set bit the lane goes to ST_VOXEL; the backward keeps the reference's `t += step_size` on unlinked voxels (:1935).
 template <bool BWD, bool DEBUG>
-__device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, Lane &L, const CacheP &cache,
-                                        int64_t ray_id, int M, Counters &cnt) {
+__device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &opt, Lane &L, Counters &cnt) {
+    if (!(L.t <= L.tmax)) {   // `while (t <= ray.tmax)`
+        L.state = ST_IDLE;
+        L.ray_done = true;
+        return;
+    }
+    // DEBUG kernels walk the occupancy pyramid (bit = all 8 corner links >= 0) and apply the gates themselves;
+    // the production kernels walk the work pyramid, whose bits already include the gates.
+    const uint64_t *bm = DEBUG ? g.accel : g.work;
+    int s = 0;
+    const int k0 = ((L.nx >> 2) * g.ab1 + (L.ny >> 2)) * g.ab2 + (L.nz >> 2);
+    if (k0 != L.wkey) {   // entering another 4^3 block: consult the pyramid top-down
+        if (g.use_skip && !L.force_fine) {
+            const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
+            if (k2 != L.k2) {
+                L.k2 = k2;
+                L.w2 = __ldg(bm + g.lay.off[2] + k2);
+            }
+            if (L.w2 == 0) {
+                s = 6;
+            } else {
+                const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
+                if (!((L.w2 >> bit1) & 1ull)) {
+                    s = 4;
+                } else {
+                    const int k1 = ((L.nx >> 4) * g.lay.b[1][1] + (L.ny >> 4)) * g.lay.b[1][2] + (L.nz >> 4);
+                    if (k1 != L.k1) {
+                        L.k1 = k1;
+                        L.w1 = __ldg(bm + g.lay.off[1] + k1);
+                    }
+                    const int bit0 = (((L.nx >> 2) & 3) << 4) | (((L.ny >> 2) & 3) << 2) | ((L.nz >> 2) & 3);
+                    if (!((L.w1 >> bit0) & 1ull)) s = 2;
+                }
+            }
+        }
+        if (s == 0) {
+            L.wkey = k0;
+            L.word = __ldg(bm + k0);
+        }
+    }
+    // the block [lo, hi) that is left by this step; for s == 0 it is the voxel itself and T* are its cached t_far
+    const int lox = (L.nx >> s) << s, loy = (L.ny >> s) << s, loz = (L.nz >> s) << s;
+    const int hix = min(lox + (1 << s), g.size[0] - 1), hiy = min(loy + (1 << s), g.size[1] - 1),
+              hiz = min(loz + (1 << s), g.size[2] - 1);
+    const int Px = (L.dx > 0.f) ? hix : lox, Py = (L.dy > 0.f) ? hiy : loy, Pz = (L.dz > 0.f) ? hiz : loz;
+    float Tx = L.tfx, Ty = L.tfy, Tz = L.tfz;
+    if (s) {
+        Tx = plane_t(Px, L.ox, L.dx);
+        Ty = plane_t(Py, L.oy, L.dy);
+        Tz = plane_t(Pz, L.oz, L.dz);
+    }
+    const float T = fminf(fminf(Tx, Ty), Tz);
+    if (s) {
+        if (BWD && !(T + opt.step_size <= L.tmax)) {   // the quirk may end the loop in here: walk voxel by voxel
+            L.force_fine = true;
+            return;
+        }
+        if (!(T <= L.tmax)) {   // `while (t <= tmax)` fails at a voxel of this (empty) block
+            L.state = ST_IDLE;
+            L.ray_done = true;
+            return;
+        }
+    }
+    const int A = (T == Tx) ? 0 : ((T == Ty) ? 1 : 2);   // exit axis; ties go to the lowest axis (:188-197)
+    const int vx = L.nx, vy = L.ny, vz = L.nz;
+    int nx = vx, ny = vy, nz = vz;
+    bool out = false;
+    if (A == 0) {
+        nx = (L.dx > 0.f) ? Px : Px - 1;
+        out = (nx < 0) || (nx >= g.size[0] - 1);
+    } else if (s) {
+        nx = axis_after(vx, L.ox, L.dx, T, true, lox, hix);
+    }
+    if (A == 1) {
+        ny = (L.dy > 0.f) ? Py : Py - 1;
+        out = (ny < 0) || (ny >= g.size[1] - 1);
+    } else if (s) {
+        ny = axis_after(vy, L.oy, L.dy, T, A == 2, loy, hiy);
+    }
+    if (A == 2) {
+        nz = (L.dz > 0.f) ? Pz : Pz - 1;
+        out = (nz < 0) || (nz >= g.size[2] - 1);
+    } else if (s) {
+        nz = axis_after(vz, L.oz, L.dz, T, false, loz, hiz);
+    }
+    if (s && out) {   // the ray leaves the grid through this empty block
+        L.state = ST_IDLE;
+        L.ray_done = true;
+        return;
+    }
+    if (!out) {
+        if (nx != vx) { L.nx = nx; L.tfx = plane_t(nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx); }
+        if (ny != vy) { L.ny = ny; L.tfy = plane_t(ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy); }
+        if (nz != vz) { L.nz = nz; L.tfz = plane_t(nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz); }
+    }
+    L.t = out ? L.tmax + 1.f : T;
+    if (s == 0) {
+        if (DEBUG) ++cnt.steps;
+        const int bit = ((vx & 3) << 4) | ((vy & 3) << 2) | (vz & 3);
+        if ((L.word >> bit) & 1ull) {
+            L.vx = vx; L.vy = vy; L.vz = vz;
+            L.t_far = T;
+            L.state = ST_VOXEL;
+            L.phase = PH_ENTER;
+        } else if (BWD) {
+            // reference quirk (:1935): an UNLINKED voxel adds step_size to t before the loop test.  t is overwritten by
+            // the next step, so this only matters when it ends the loop.
+            if (DEBUG) {
+                L.t += opt.step_size;
+            } else if (!(L.t + opt.step_size <= L.tmax)) {
+                if (!((__ldg(g.accel + k0) >> bit) & 1ull)) L.t += opt.step_size;
+            }
+        }
+    } else if (DEBUG) {
+        ++cnt.skips;
+    }
+}
+
+// Work of a lane inside a voxel whose bit is set: 8-corner loads, level-set / root iteration, fake sample, early stop
+// (trace_ray_surf_trav :212-547, backward :1921-2895).  Runs until the lane has a sample to composite (ST_SAMPLE; the
+// phase is kept so that it resumes behind that sample), returns to marching (ST_MARCH) or ends the ray.
+template <bool BWD, bool DEBUG>
+__device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t &opt, Lane &L, const CacheP &cache,
+                                              int M, Counters &cnt, const DebugP &dbg) {
     const int offy = g.size[2];
     const int64_t offx = (int64_t)g.size[1] * g.size[2];
+    const int64_t ray_id = L.ray_id;
     for (;;) {
-        if (L.phase == PH_MARCH) {
-            if (!(L.t <= L.tmax)) {
-                L.done = true;
-                return false;
-            }
-            if (g.use_skip) {
-                const int k0 = ((L.nx >> 2) * g.ab1 + (L.ny >> 2)) * g.ab2 + (L.nz >> 2);
-                if (k0 != L.wkey) {   // entering another 4^3 block: consult the pyramid top-down
-                    const uint64_t *bm = DEBUG ? g.accel : g.work;
-                    const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
-                    if (k2 != L.k2) {
-                        L.k2 = k2;
-                        L.w2 = __ldg(bm + g.lay.off[2] + k2);
-                    }
-                    int s = 0;
-                    if (L.w2 == 0) {
-                        s = 6;
-                    } else {
-                        const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
-                        if (!((L.w2 >> bit1) & 1ull)) {
-                            s = 4;
-                        } else {
-                            const int k1 = ((L.nx >> 4) * g.lay.b[1][1] + (L.ny >> 4)) * g.lay.b[1][2] + (L.nz >> 4);
-                            if (k1 != L.k1) {
-                                L.k1 = k1;
-                                L.w1 = __ldg(bm + g.lay.off[1] + k1);
-                            }
-                            const int bit0 = (((L.nx >> 2) & 3) << 4) | (((L.ny >> 2) & 3) << 2) | ((L.nz >> 2) & 3);
-                            if (!((L.w1 >> bit0) & 1ull)) s = 2;
-                        }
-                    }
-                    if (s) {
-                        const int r = skip_block<BWD>(g, opt, L, s);
-                        if (r == 1) {
-                            L.done = true;
-                            return false;
-                        }
-                        if (r == 0) {
-                            if (DEBUG) ++cnt.skips;
-                            continue;
-                        }
-                    }
-                }
-            }
-            L.vx = L.nx; L.vy = L.ny; L.vz = L.nz;
-            const float t_far = fminf(fminf(L.tfx, L.tfy), L.tfz);
-            L.t_far = t_far;
-            L.t = t_far;
-            if (t_far == L.tfx) {
-                L.nx += (L.dx > 0.f) ? 1 : -1;
-                if ((L.nx < 0) || (L.nx >= g.size[0] - 1)) L.t = L.tmax + 1.f;
-                else L.tfx = plane_t(L.nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx);
-            } else if (t_far == L.tfy) {
-                L.ny += (L.dy > 0.f) ? 1 : -1;
-                if ((L.ny < 0) || (L.ny >= g.size[1] - 1)) L.t = L.tmax + 1.f;
-                else L.tfy = plane_t(L.ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
-            } else {
-                L.nz += (L.dz > 0.f) ? 1 : -1;
-                if ((L.nz < 0) || (L.nz >= g.size[2] - 1)) L.t = L.tmax + 1.f;
-                else L.tfz = plane_t(L.nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
-            }
-            if (DEBUG) ++cnt.steps;
-            // occupancy: all 8 corner links >= 0  <=>  bit set
-            // DEBUG kernels walk the occupancy bitmap (bit = all 8 corner links >= 0) and apply the gates themselves;
-            // the production kernels walk the work bitmap, whose bit already includes the gates.
-            const int key = ((L.vx >> 2) * g.ab1 + (L.vy >> 2)) * g.ab2 + (L.vz >> 2);
-            if (key != L.wkey) {
-                L.wkey = key;
-                L.word = __ldg((DEBUG ? g.accel : g.work) + key);
-            }
-            const int bit = ((L.vx & 3) << 4) | ((L.vy & 3) << 2) | (L.vz & 3);
-            if (!((L.word >> bit) & 1ull)) {
-                if (BWD) {
-                    // reference quirk (:1935): an UNLINKED voxel adds step_size to t before the loop test.  t is
-                    // overwritten by the next step, so this only matters when it ends the loop.
-                    if (DEBUG) {
-                        L.t += opt.step_size;
-                    } else if (!(L.t + opt.step_size <= L.tmax)) {
-                        if (!((__ldg(g.accel + key) >> bit) & 1ull)) L.t += opt.step_size;
-                    }
-                }
-                continue;
-            }
+        if (L.phase == PH_ENTER) {
             if (DEBUG) ++cnt.linked;
             const int32_t *lp = g.links + (offx * L.vx + (int64_t)offy * L.vy + L.vz);
             L.lk[0] = __ldg(lp);
@@ -351,7 +372,10 @@ __device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, 
                 bool pass = false;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) pass |= !(__ldg(g.density + L.lk[c]) < opt.sigma_thresh);
-                if (!pass) continue;
+                if (!pass) {
+                    L.state = ST_MARCH;
+                    return;
+                }
                 ++cnt.active;
             }
             L.dn_loaded = false;
@@ -459,13 +483,19 @@ __device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, 
                         L.pcnt = -__logf(fmaxf(1.f - rwalpha, 1e-8f));
                         L.weight = __expf(L.logT) * (1.f - __expf(-L.pcnt));
                     }
-                    if (DEBUG) ++cnt.samples;
+                    if (DEBUG) {
+                        ++cnt.samples;
+                        record_hit(dbg, g, L);
+                    }
                     found = true;
                     break;
                 }
                 if (found) break;
             }
-            if (found) return true;
+            if (found) {
+                L.state = ST_SAMPLE;
+                return;
+            }
             L.phase = PH_FAKE;
         }
         if (L.phase == PH_FAKE) {
@@ -531,18 +561,24 @@ __device__ __forceinline__ bool advance(const GridP &g, const asurf_opt_t &opt, 
                         L.pcnt = -1 * __logf(fmaxf(1.f - L.rwalpha, 1e-8f));
                         L.weight = __expf(L.logT) * (1.f - __expf(-L.pcnt));
                     }
-                    if (DEBUG) ++cnt.samples;
-                    return true;
+                    if (DEBUG) {
+                        ++cnt.samples;
+                        record_hit(dbg, g, L);
+                    }
+                    L.state = ST_SAMPLE;
+                    return;
                 }
             }
         }
         // PH_POST: early stop (:544-547 / :2893-2895)
-        L.phase = PH_MARCH;
         if (__expf(L.logT) < opt.stop_thresh) {
             if (!BWD) L.logT = -1e3f;
-            L.done = true;
-            return false;
+            L.state = ST_IDLE;
+            L.ray_done = true;
+        } else {
+            L.state = ST_MARCH;
         }
+        return;
     }
 }
 
@@ -820,18 +856,17 @@ __global__ void __launch_bounds__(CTA_THREADS)
 surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins,
                  const float *__restrict__ dirs, const int64_t Q, float *__restrict__ rgb_out,
                  const float *__restrict__ grad_in, const float *__restrict__ color_cache, const FusedP f,
-                 const CacheP cache, const asurf_grads_t grads, const DebugP dbg) {
+                 const CacheP cache, const asurf_grads_t grads, const DebugP dbg,
+                 unsigned long long *__restrict__ ray_counter) {
     __shared__ float s_sph[CTA_WARPS][32][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t ray_id = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     const int D = g.sh_dim, bd = g.basis_dim;
     const int M = f.M;
 
     Lane L;
-    L.done = true;
-    L.logT = 0.f;
-    L.intersect_i = -1;
-    L.sample_i = 0;
+    L.state = ST_IDLE;
+    L.ray_done = false;
+    L.ray_id = -1;
     float out0 = 0.f, out1 = 0.f, out2 = 0.f;  // FWD: colour; BWD: dL/dRGB
     float accum = 0.f;
     Pre pre;
@@ -839,150 +874,181 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
     cv.sa = cv.sw = cv.st = nullptr;
     cv.n = 0;
     Counters cnt = {0, 0, 0, 0, 0};
-    int n_hits = 0;
+    bool rays_left = true;   // warp-uniform
 
-    if (ray_id < Q) {
-        L.ox = origins[ray_id * 3 + 0]; L.oy = origins[ray_id * 3 + 1]; L.oz = origins[ray_id * 3 + 2];
-        L.dx = dirs[ray_id * 3 + 0]; L.dy = dirs[ray_id * 3 + 1]; L.dz = dirs[ray_id * 3 + 2];
-        eval_sh(bd, L.dx, L.dy, L.dz, s_sph[warp][lane]);  // world-space direction (:3165-3171)
-        float world_step;
-        ray_bounds(g, opt, L, world_step);
-        if (DEBUG && dbg.xf) {
-            float *x = dbg.xf + ray_id * 9;
-            x[0] = L.ox; x[1] = L.oy; x[2] = L.oz; x[3] = L.dx; x[4] = L.dy; x[5] = L.dz;
-            x[6] = L.tmin; x[7] = L.tmax; x[8] = world_step;
-        }
-        if (BWD) {
-            if (f.grad_is_rgb) {  // fused: dL/dRGB from the L2 / L1 mix (:3306-3316)
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float resid = color_cache[ray_id * 3 + i] - grad_in[ray_id * 3 + i];
-                    float gi = resid * f.norm_l2 * f.lambda_l2;
-                    gi += (resid > 0.f) ? (f.norm_l1 * f.lambda_l1) : (-f.norm_l1 * f.lambda_l1);
-                    if (i == 0) out0 = gi; else if (i == 1) out1 = gi; else out2 = gi;
-                }
-            } else {
-                out0 = grad_in[ray_id * 3 + 0]; out1 = grad_in[ray_id * 3 + 1]; out2 = grad_in[ray_id * 3 + 2];
-            }
-            if (M > 0) {
-                cv.sa = cache.sa + ray_id * M; cv.sw = cache.sw + ray_id * M; cv.st = cache.st + ray_id * M;
-                cv.n = cache.n[ray_id];
-            }
-            fused_preamble(cv, pre);
-            accum = fmaf(color_cache[ray_id * 3 + 0], out0,
-                         fmaf(color_cache[ray_id * 3 + 1], out1, color_cache[ray_id * 3 + 2] * out2));
-        }
-        if (!(L.tmin > L.tmax)) {
-            L.done = false;
-            dda_init(g, L);
-        }
-    }
-    __syncwarp();
-
+    // Persistent warp: lanes pull rays from a global counter as they become free, then the warp repeatedly runs the
+    // kind of work most of its lanes are waiting for (march step / voxel work / sample shading / ray set-up).
     for (;;) {
-        bool have = false;
-        if (!L.done) have = advance<BWD, DEBUG>(g, opt, L, cache, ray_id, M, cnt);
-        unsigned pend = __ballot_sync(FULL, have);
-        if (pend == 0) break;
-        if (DEBUG && have && dbg.hit_count) {
-            if (n_hits < dbg.max_hits) {
-                const int64_t o = ray_id * dbg.max_hits + n_hits;
-                dbg.hit_cell[o] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
-                dbg.hit_kind[o] = (L.fake ? 3 : L.st_id) + 8 * L.intersect_i;
-                dbg.hit_t[o] = L.ts;
+        const unsigned m_idle = __ballot_sync(FULL, L.state == ST_IDLE);
+        const unsigned m_march = __ballot_sync(FULL, L.state == ST_MARCH);
+        const unsigned m_vox = __ballot_sync(FULL, L.state == ST_VOXEL);
+        const unsigned m_samp = __ballot_sync(FULL, L.state == ST_SAMPLE);
+        const int n_idle = rays_left ? __popc(m_idle) : 0;
+        const int n_march = __popc(m_march), n_vox = __popc(m_vox), n_samp = __popc(m_samp);
+        if ((n_idle | n_march | n_vox | n_samp) == 0) break;
+
+        if (n_march > 0 && n_march >= n_vox && n_march >= n_samp && n_march >= n_idle) {
+            // ---------------- march: a few generalized DDA steps ----------------
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                if (L.state == ST_MARCH) march_step<BWD, DEBUG>(g, opt, L, cnt);
             }
-            ++n_hits;
-        }
-        float tot_color = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-        while (pend) {
-            const int src = __ffs(pend) - 1;
-            pend &= pend - 1;
-            int lk[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) lk[c] = __shfl_sync(FULL, L.lk[c], src);
-            float pos[3];
-            pos[0] = __shfl_sync(FULL, L.px, src);
-            pos[1] = __shfl_sync(FULL, L.py, src);
-            pos[2] = __shfl_sync(FULL, L.pz, src);
-            float v[8];
-            float lane_color = 0.f;
-            const int kb = (lane < D) ? (lane % bd) : 0;
-            float sph = 0.f;
-            if (lane < D) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = __ldg(g.sh + (int64_t)lk[c] * D + lane);
-                sph = s_sph[warp][src][kb];
-                lane_color = trilerp8(v, pos) * sph;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = 0.f;
-            }
-            const float seg = segment_sum(lane_color, (lane < D) ? kb : 32, bd);
-            const float c0 = __shfl_sync(FULL, seg, 0);
-            const float c1 = __shfl_sync(FULL, seg, bd);
-            const float c2 = __shfl_sync(FULL, seg, 2 * bd);
-            if (!BWD) {
-                if (lane == src) {
-                    out0 += L.weight * fmaxf(c0 + 0.5f, 0.f);
-                    out1 += L.weight * fmaxf(c1 + 0.5f, 0.f);
-                    out2 += L.weight * fmaxf(c2 + 0.5f, 0.f);
+        } else if (n_idle > 0 && n_idle >= n_vox && n_idle >= n_samp) {
+            // ---------------- ray set-up for the free lanes ----------------
+            unsigned long long base = 0;
+            if (lane == __ffs(m_idle) - 1) base = atomicAdd(ray_counter, (unsigned long long)__popc(m_idle));
+            base = __shfl_sync(FULL, base, __ffs(m_idle) - 1);
+            const int64_t ray_id = (int64_t)base + __popc(m_idle & ((1u << lane) - 1u));
+            if (__any_sync(FULL, (L.state == ST_IDLE) && (ray_id >= Q))) rays_left = false;
+            if (L.state == ST_IDLE && ray_id < Q) {
+                L.ray_id = ray_id;
+                L.logT = 0.f;
+                L.intersect_i = -1;
+                L.sample_i = 0;
+                L.n_hits = 0;
+                out0 = out1 = out2 = 0.f;
+                L.ox = origins[ray_id * 3 + 0]; L.oy = origins[ray_id * 3 + 1]; L.oz = origins[ray_id * 3 + 2];
+                L.dx = dirs[ray_id * 3 + 0]; L.dy = dirs[ray_id * 3 + 1]; L.dz = dirs[ray_id * 3 + 2];
+                eval_sh(bd, L.dx, L.dy, L.dz, s_sph[warp][lane]);  // world-space direction (:3165-3171)
+                float world_step;
+                ray_bounds(g, opt, L, world_step);
+                if (DEBUG && dbg.xf) {
+                    float *x = dbg.xf + ray_id * 9;
+                    x[0] = L.ox; x[1] = L.oy; x[2] = L.oz; x[3] = L.dx; x[4] = L.dy; x[5] = L.dz;
+                    x[6] = L.tmin; x[7] = L.tmax; x[8] = world_step;
                 }
-            } else {
-                const float g0 = __shfl_sync(FULL, out0, src);
-                const float g1 = __shfl_sync(FULL, out1, src);
-                const float g2 = __shfl_sync(FULL, out2, src);
-                const float weight = __shfl_sync(FULL, L.weight, src);
-                const float l0 = c0 + 0.5f, l1 = c1 + 0.5f, l2 = c2 + 0.5f;
-                const float t0 = fmaxf(l0, 0.f), t1 = fmaxf(l1, 0.f), t2 = fmaxf(l2, 0.f);
-                float total_color = t0 * g0;  // shuffle order of the reference (:2112-2115): (c0 + c2) + c1
-                total_color += t2 * g2;
-                total_color += t1 * g1;
-                float gacc[3] = {0.f, 0.f, 0.f};
+                if (BWD) {
+                    if (f.grad_is_rgb) {  // fused: dL/dRGB from the L2 / L1 mix (:3306-3316)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float resid = color_cache[ray_id * 3 + i] - grad_in[ray_id * 3 + i];
+                            float gi = resid * f.norm_l2 * f.lambda_l2;
+                            gi += (resid > 0.f) ? (f.norm_l1 * f.lambda_l1) : (-f.norm_l1 * f.lambda_l1);
+                            if (i == 0) out0 = gi; else if (i == 1) out1 = gi; else out2 = gi;
+                        }
+                    } else {
+                        out0 = grad_in[ray_id * 3 + 0]; out1 = grad_in[ray_id * 3 + 1]; out2 = grad_in[ray_id * 3 + 2];
+                    }
+                    cv.n = 0;
+                    if (M > 0) {
+                        cv.sa = cache.sa + ray_id * M; cv.sw = cache.sw + ray_id * M; cv.st = cache.st + ray_id * M;
+                        cv.n = cache.n[ray_id];
+                    }
+                    fused_preamble(cv, pre);
+                    accum = fmaf(color_cache[ray_id * 3 + 0], out0,
+                                 fmaf(color_cache[ray_id * 3 + 1], out1, color_cache[ray_id * 3 + 2] * out2));
+                }
+                if (!(L.tmin > L.tmax)) {
+                    dda_init(g, L);   // -> ST_MARCH
+                } else {
+                    L.ray_done = true;   // misses the grid: background colour / no gradient (:59-65, :1811-1816)
+                }
+            }
+            __syncwarp();
+        } else if (n_vox > 0 && n_vox >= n_samp) {
+            // ---------------- voxel work ----------------
+            if (L.state == ST_VOXEL) voxel_advance<BWD, DEBUG>(g, opt, L, cache, M, cnt, dbg);
+        } else {
+            // ---------------- sample shading: the warp serves its pending lanes one after the other ----------------
+            unsigned pend = m_samp;
+            const bool have = (L.state == ST_SAMPLE);
+            float tot_color = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1;
+                int lk[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) lk[c] = __shfl_sync(FULL, L.lk[c], src);
+                float pos[3];
+                pos[0] = __shfl_sync(FULL, L.px, src);
+                pos[1] = __shfl_sync(FULL, L.py, src);
+                pos[2] = __shfl_sync(FULL, L.pz, src);
+                float v[8];
+                float lane_color = 0.f;
+                const int kb = (lane < D) ? (lane % bd) : 0;
+                float sph = 0.f;
                 if (lane < D) {
-                    const int ch = lane / bd;
-                    const float in01 = (ch == 0) ? ((t0 == l0) ? 1.f : 0.f) : ((ch == 1) ? ((t1 == l1) ? 1.f : 0.f) : ((t2 == l2) ? 1.f : 0.f));
-                    const float gch = (ch == 0) ? g0 : ((ch == 1) ? g1 : g2);
-                    const float grad_common = weight * in01 * gch;
-                    const float curr_grad_color = sph * grad_common;
-                    float w[8];
-                    corner_weights(pos, curr_grad_color, w);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) atomicAdd(grads.grad_sh + (int64_t)lk[c] * D + lane, w[c]);
-                    if (!opt.no_surf_grad_from_sh) trilerp8_pos_grad(v, pos, curr_grad_color, gacc);
+                    for (int c = 0; c < 8; ++c) v[c] = __ldg(g.sh + (int64_t)lk[c] * D + lane);
+                    sph = s_sph[warp][src][kb];
+                    lane_color = trilerp8(v, pos) * sph;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
                 }
-                float sx = 0.f, sy = 0.f, sz = 0.f;
-                if (!opt.no_surf_grad_from_sh) {
-                    sx = __shfl_sync(FULL, warp_sum_down(gacc[0], lane), 0);
-                    sy = __shfl_sync(FULL, warp_sum_down(gacc[1], lane), 0);
-                    sz = __shfl_sync(FULL, warp_sum_down(gacc[2], lane), 0);
+                const float seg = segment_sum(lane_color, (lane < D) ? kb : 32, bd);
+                const float c0 = __shfl_sync(FULL, seg, 0);
+                const float c1 = __shfl_sync(FULL, seg, bd);
+                const float c2 = __shfl_sync(FULL, seg, 2 * bd);
+                if (!BWD) {
+                    if (lane == src) {
+                        out0 += L.weight * fmaxf(c0 + 0.5f, 0.f);
+                        out1 += L.weight * fmaxf(c1 + 0.5f, 0.f);
+                        out2 += L.weight * fmaxf(c2 + 0.5f, 0.f);
+                    }
+                } else {
+                    const float g0 = __shfl_sync(FULL, out0, src);
+                    const float g1 = __shfl_sync(FULL, out1, src);
+                    const float g2 = __shfl_sync(FULL, out2, src);
+                    const float weight = __shfl_sync(FULL, L.weight, src);
+                    const float l0 = c0 + 0.5f, l1 = c1 + 0.5f, l2 = c2 + 0.5f;
+                    const float t0 = fmaxf(l0, 0.f), t1 = fmaxf(l1, 0.f), t2 = fmaxf(l2, 0.f);
+                    float total_color = t0 * g0;  // shuffle order of the reference (:2112-2115): (c0 + c2) + c1
+                    total_color += t2 * g2;
+                    total_color += t1 * g1;
+                    float gacc[3] = {0.f, 0.f, 0.f};
+                    if (lane < D) {
+                        const int ch = lane / bd;
+                        const float in01 = (ch == 0) ? ((t0 == l0) ? 1.f : 0.f)
+                                                     : ((ch == 1) ? ((t1 == l1) ? 1.f : 0.f) : ((t2 == l2) ? 1.f : 0.f));
+                        const float gch = (ch == 0) ? g0 : ((ch == 1) ? g1 : g2);
+                        const float grad_common = weight * in01 * gch;
+                        const float curr_grad_color = sph * grad_common;
+                        float w[8];
+                        corner_weights(pos, curr_grad_color, w);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) atomicAdd(grads.grad_sh + (int64_t)lk[c] * D + lane, w[c]);
+                        if (!opt.no_surf_grad_from_sh) trilerp8_pos_grad(v, pos, curr_grad_color, gacc);
+                    }
+                    float sx = 0.f, sy = 0.f, sz = 0.f;
+                    if (!opt.no_surf_grad_from_sh) {
+                        sx = __shfl_sync(FULL, warp_sum_down(gacc[0], lane), 0);
+                        sy = __shfl_sync(FULL, warp_sum_down(gacc[1], lane), 0);
+                        sz = __shfl_sync(FULL, warp_sum_down(gacc[2], lane), 0);
+                    }
+                    if (lane == src) { tot_color = total_color; gx = sx; gy = sy; gz = sz; }
                 }
-                if (lane == src) { tot_color = total_color; gx = sx; gy = sy; gz = sz; }
+            }
+            if (have) {
+                if (BWD) {
+                    if (!L.fake) finish_real_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color, gx, gy, gz);
+                    else finish_fake_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color);
+                }
+                L.state = ST_VOXEL;   // resume behind the sample
             }
         }
-        if (BWD && have) {
-            if (!L.fake) finish_real_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color, gx, gy, gz);
-            else finish_fake_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color);
+
+        // ---------------- rays that just ended ----------------
+        if (L.ray_done) {
+            L.ray_done = false;
+            L.state = ST_IDLE;
+            const int64_t ray_id = L.ray_id;
+            if (!BWD) {
+                const float bg = __expf(L.logT) * opt.background_brightness;  // a miss keeps logT == 0: pure background
+                rgb_out[ray_id * 3 + 0] = out0 + bg;
+                rgb_out[ray_id * 3 + 1] = out1 + bg;
+                rgb_out[ray_id * 3 + 2] = out2 + bg;
+                if (M > 0) cache.n[ray_id] = L.sample_i;
+            }
+            if (DEBUG && dbg.hit_count) dbg.hit_count[ray_id] = L.n_hits;
         }
     }
-
-    if (ray_id < Q) {
-        if (!BWD) {
-            const float bg = __expf(L.logT) * opt.background_brightness;  // tmin > tmax: logT == 0 -> background
-            rgb_out[ray_id * 3 + 0] = out0 + bg;
-            rgb_out[ray_id * 3 + 1] = out1 + bg;
-            rgb_out[ray_id * 3 + 2] = out2 + bg;
-            if (M > 0) cache.n[ray_id] = L.sample_i;
-        }
-        if (DEBUG) {
-            if (dbg.hit_count) dbg.hit_count[ray_id] = n_hits;
-            if (dbg.stats) {
-                atomicAdd(dbg.stats + 0, cnt.steps);
-                atomicAdd(dbg.stats + 1, cnt.skips);
-                atomicAdd(dbg.stats + 2, cnt.linked);
-                atomicAdd(dbg.stats + 3, cnt.active);
-                atomicAdd(dbg.stats + 4, cnt.samples);
-            }
-        }
+    if (DEBUG && dbg.stats) {
+        atomicAdd(dbg.stats + 0, cnt.steps);
+        atomicAdd(dbg.stats + 1, cnt.skips);
+        atomicAdd(dbg.stats + 2, cnt.linked);
+        atomicAdd(dbg.stats + 3, cnt.active);
+        atomicAdd(dbg.stats + 4, cnt.samples);
     }
 }
 
@@ -993,7 +1059,7 @@ using namespace asurf;
 
 namespace {
 
-Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg;
+Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg, g_ws_ctr;
 
 int g_skip_enabled = 1;  // asurf_debug_set_skip
 
@@ -1062,7 +1128,30 @@ int check_rays(const asurf_rays_t *rays, const asurf_opt_t *opt) {
     return 0;
 }
 
-inline int n_ctas(int64_t Q) { return (int)((Q + CTA_THREADS - 1) / CTA_THREADS); }
+// Persistent grid: about RAYS_PER_LANE rays per lane so that lanes can pick up new rays while their neighbours are
+// still marching, capped at a few resident CTAs per SM for very large batches.
+constexpr int RAYS_PER_LANE = 2;
+inline int n_ctas(int64_t Q) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int64_t want = (Q + (int64_t)CTA_THREADS * RAYS_PER_LANE - 1) / ((int64_t)CTA_THREADS * RAYS_PER_LANE);
+    const int64_t cap = (int64_t)sms * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// zeroed ray counters for the next launches on `st` (two per call: forward, backward)
+int ray_counters(cudaStream_t st, unsigned long long **ctr) {
+    int rc = g_ws_ctr.reserve(2 * sizeof(unsigned long long));
+    if (rc) return rc;
+    ASURF_CUDA(cudaMemsetAsync(g_ws_ctr.ptr, 0, 2 * sizeof(unsigned long long), st));
+    *ctr = (unsigned long long *)g_ws_ctr.ptr;
+    return 0;
+}
 
 }  // namespace
 
@@ -1080,14 +1169,17 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     CacheP cache = {};
     asurf_grads_t grads = {};
     DebugP dbg = {};
+    unsigned long long *ctr = nullptr;
+    rc = ray_counters(st, &ctr);
+    if (rc) return rc;
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
         g.use_skip = 0;   // count every voxel of the reference DDA
         surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg);
+            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr);
     } else {
         surf_trav_kernel<false, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg);
+            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr);
     }
     return check_cuda(cudaGetLastError(), "surf_trav_forward launch");
 }
@@ -1107,8 +1199,11 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     FusedP f = {};
     CacheP cache = {};
     DebugP dbg = {};
+    unsigned long long *ctr = nullptr;
+    rc = ray_counters(st, &ctr);
+    if (rc) return rc;
     surf_trav_kernel<true, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-        g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg);
+        g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg, ctr);
     return check_cuda(cudaGetLastError(), "surf_trav_backward launch");
 }
 
@@ -1167,6 +1262,9 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     DebugP dbg = {};
     FusedP ff = {};
     ff.M = M;
+    unsigned long long *ctr = nullptr;
+    rc = ray_counters(st, &ctr);
+    if (rc) return rc;
     const bool prof = g_prof.cap > 0 && g_prof.n < g_prof.cap;
     cudaEvent_t *pe = prof ? g_prof.ev + 3 * g_prof.n : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
@@ -1175,15 +1273,15 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
         GridP gs = g;
         gs.use_skip = 0;
         surf_trav_kernel<false, true><<<n_ctas(Q), CTA_THREADS, 0, st>>>(gs, *opt, rays->origins, rays->dirs, Q, rgb_out,
-                                                                          nullptr, nullptr, ff, cache, nog, dbg);
+                                                                          nullptr, nullptr, ff, cache, nog, dbg, ctr);
     } else {
         surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
-                                                                           nullptr, nullptr, ff, cache, nog, dbg);
+                                                                           nullptr, nullptr, ff, cache, nog, dbg, ctr);
     }
     DebugP nodbg = {};
     if (prof) cudaEventRecord(pe[1], st);
     surf_trav_kernel<true, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, nullptr, rgb_gt,
-                                                                      rgb_out, f, cache, *grads, nodbg);
+                                                                      rgb_out, f, cache, *grads, nodbg, ctr + 1);
     if (prof) {
         cudaEventRecord(pe[2], st);
         ++g_prof.n;
@@ -1204,8 +1302,12 @@ static int debug_launch(const asurf_grid_t *grid, const asurf_rays_t *rays, cons
     FusedP f = {};
     CacheP cache = {};
     asurf_grads_t grads = {};
+    unsigned long long *ctr = nullptr;
+    rc = ray_counters(st, &ctr);
+    if (rc) return rc;
     surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-        g, *opt, rays->origins, rays->dirs, rays->n_rays, (float *)g_ws_dbg.ptr, nullptr, nullptr, f, cache, grads, dbg);
+        g, *opt, rays->origins, rays->dirs, rays->n_rays, (float *)g_ws_dbg.ptr, nullptr, nullptr, f, cache, grads, dbg,
+        ctr);
     return check_cuda(cudaGetLastError(), "surf_trav debug launch");
 }
 
@@ -1267,4 +1369,5 @@ extern "C" void asurf_release(void) {
     g_ws_work.release();
     g_ws_cache.release();
     g_ws_dbg.release();
+    g_ws_ctr.release();
 }
