@@ -65,12 +65,31 @@ struct DebugP {
 };
 
 // lane state: what the lane needs next; phase: where it is inside a work voxel
+// Output of the pre-march (premarch_kernel): per ray the first PRE_K voxels whose work bit is set, in march order,
+// and where to resume the march if there are more.
+constexpr int PRE_K = 16;
+struct PreP {
+    int32_t *cells;        // (Q, PRE_K) linear voxel index x*Y*Z + y*Z + z
+    int32_t *code;         // (Q,)  bits 0-7 count, 8-15 count visible to the backward loop, 16 continuation,
+                           //       17 backward loop still alive at the continuation, 18 force_fine at the continuation
+    float *cont_t;         // (Q,)  t at the continuation
+    int32_t *cont_vox;     // (Q,)  next voxel at the continuation, 10 bits per axis
+    int32_t *rays;         // compact list of the rays that have any work
+    unsigned long long *n_rays;   // its length (device counter)
+    int enabled;
+};
+
 enum { ST_IDLE = 0, ST_MARCH = 1, ST_VOXEL = 2, ST_SAMPLE = 3 };
 enum { PH_ENTER = 0, PH_ROOTS = 1, PH_FAKE = 2, PH_POST = 3 };
 
 struct Lane {
-    // ray in grid space
+    // ray in grid space; r* = RN(1/d*) for the exact fast divide, slow_div: a direction component is (almost) zero
     float ox, oy, oz, dx, dy, dz, tmin, tmax;
+    float rx, ry, rz;
+    bool slow_div;
+    // pre-marched work-voxel list (premarch_kernel) being consumed, then an optional continuation of the march
+    int list_pos, list_cnt, list_code;
+    bool in_list, bwd_alive;
     // DDA
     int nx, ny, nz;
     float tfx, tfy, tfz, t;
@@ -107,7 +126,22 @@ struct Lane {
     float ts;            // t of the sample
 };
 
-__device__ __forceinline__ float plane_t(int plane, float o, float d) { return ((float)plane - o) / d; }
+// (plane - o) / d rounded exactly like the reference's IEEE divide, from the per-ray reciprocal r = RN(1/d):
+// q = a*r followed by two residual corrections with exact FMA residuals (Markstein's correction step; checked against
+// the true divide on 2.4e9 random (plane, o, d) of this range, including all-ones significands).  Lanes whose
+// direction has an (almost) zero component take the true divide.
+__device__ __forceinline__ float plane_t(int plane, float o, float d, float r, bool slow) {
+    const float a = (float)plane - o;
+    if (slow) return a / d;
+    float q = a * r;
+    float e = fmaf(-d, q, a);
+    q = fmaf(e, r, q);
+    e = fmaf(-d, q, a);
+    return fmaf(e, r, q);
+}
+#define PT_X(L, p) plane_t((p), (L).ox, (L).dx, (L).rx, (L).slow_div)
+#define PT_Y(L, p) plane_t((p), (L).oy, (L).dy, (L).ry, (L).slow_div)
+#define PT_Z(L, p) plane_t((p), (L).oz, (L).dz, (L).rz, (L).slow_div)
 
 __device__ __forceinline__ void load_density(const GridP &g, Lane &L) {
     if (!L.dn_loaded) {
@@ -115,6 +149,13 @@ __device__ __forceinline__ void load_density(const GridP &g, Lane &L) {
         for (int c = 0; c < 8; ++c) L.dn[c] = __ldg(g.density + L.lk[c]);
         L.dn_loaded = true;
     }
+}
+
+__device__ __forceinline__ void div_init(Lane &L) {
+    L.slow_div = !((fabsf(L.dx) >= 1e-18f) && (fabsf(L.dy) >= 1e-18f) && (fabsf(L.dz) >= 1e-18f));
+    L.rx = 1.0f / L.dx;
+    L.ry = 1.0f / L.dy;
+    L.rz = 1.0f / L.dz;
 }
 
 // Ray set-up: world -> grid transform and AABB bounds (ray_find_bounds, include/render_util.cuh:651-701;
@@ -164,6 +205,21 @@ __device__ __forceinline__ void ray_bounds(const GridP &g, const asurf_opt_t &op
             if (L.dz != 0.f) { L.tmin = fmaxf(L.tmin, fminf(t1, t2)); L.tmax = fminf(L.tmax, fmaxf(t1, t2)); }
         }
     }
+    div_init(L);
+}
+
+__device__ __forceinline__ void dda_restart(Lane &L) {   // far-plane times of the next voxel + empty pyramid cache
+    L.tfx = PT_X(L, L.nx + (L.dx > 0.f ? 1 : 0));
+    L.tfy = PT_Y(L, L.ny + (L.dy > 0.f ? 1 : 0));
+    L.tfz = PT_Z(L, L.nz + (L.dz > 0.f ? 1 : 0));
+    L.wkey = -1;
+    L.k1 = -1;
+    L.k2 = -1;
+    L.word = 0;
+    L.w1 = 0;
+    L.w2 = 0;
+    L.in_list = false;
+    L.state = ST_MARCH;
 }
 
 __device__ __forceinline__ void dda_init(const GridP &g, Lane &L) {
@@ -171,40 +227,34 @@ __device__ __forceinline__ void dda_init(const GridP &g, Lane &L) {
     L.nx = min(max((int)fmaf(L.t, L.dx, L.ox), 0), g.size[0] - 2);
     L.ny = min(max((int)fmaf(L.t, L.dy, L.oy), 0), g.size[1] - 2);
     L.nz = min(max((int)fmaf(L.t, L.dz, L.oz), 0), g.size[2] - 2);
-    L.tfx = plane_t(L.nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx);
-    L.tfy = plane_t(L.ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy);
-    L.tfz = plane_t(L.nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz);
-    L.wkey = -1;
-    L.k1 = -1;
-    L.k2 = -1;
-    L.word = 0;
-    L.w1 = 0;
-    L.w2 = 0;
     L.force_fine = false;
-    L.state = ST_MARCH;
+    L.bwd_alive = true;
+    dda_restart(L);
 }
-
 // ---- exact hierarchical skipping -----------------------------------------------------------------------------------
 // The reference DDA is a 3-way merge of the per-axis plane-crossing events ordered by (t, axis): each step takes the
 // smallest t_far, ties going to the lowest axis (:188-197), and every t is the correctly rounded (plane - o) / d.
 // Jumping over an empty aligned block therefore lands on EXACTLY the voxel the voxel-by-voxel DDA would reach, if we
 // (a) find the first event (T, A) that leaves the block and (b) for the other two axes count the planes whose event
 // precedes (T, A) in that order -- estimated from o + T*d and then corrected with the same divides the DDA uses.
-__device__ __forceinline__ bool crossed(int p, float o, float d, float T, bool tie_before) {
-    const float tp = plane_t(p, o, d);
+__device__ __forceinline__ bool crossed(int p, float o, float d, float r, bool slow, float T, bool tie_before) {
+    const float tp = plane_t(p, o, d, r, slow);
     return (tp < T) || ((tp == T) && tie_before);
 }
-__device__ __forceinline__ int axis_after(int v, float o, float d, float T, bool tie_before, int lo, int hi) {
-    if (d > 0.f) {   // crossing plane p enters voxel p
-        int n = min(max((int)floorf(fmaf(T, d, o)), v), hi - 1);
-        while (n < hi - 1 && crossed(n + 1, o, d, T, tie_before)) ++n;
-        while (n > v && !crossed(n, o, d, T, tie_before)) --n;
-        return n;
-    }
-    int n = min(max((int)floorf(fmaf(T, d, o)), lo), v);   // crossing plane p enters voxel p - 1
-    while (n > lo && crossed(n, o, d, T, tie_before)) --n;
-    while (n < v && !crossed(n + 1, o, d, T, tie_before)) ++n;
-    return n;
+// Voxel index on a non-exit axis after the jump.  floor(o + T*d) is within one voxel of the answer (its error is
+// ~1e-4 voxel), so one exact test of the plane above and one of the plane below settle it; straight-line code so
+// that the lanes of a warp stay together.
+__device__ __forceinline__ int axis_after(int v, float o, float d, float r, bool slow, float T, bool tie_before, int lo,
+                                          int hi) {
+    const int est = (int)floorf(fmaf(T, d, o));
+    const bool fwd = d > 0.f;   // fwd: crossing plane p enters voxel p; otherwise it enters voxel p - 1
+    const int n = fwd ? min(max(est, v), hi - 1) : min(max(est, lo), v);
+    const bool cu = crossed(n + 1, o, d, r, slow, T, tie_before);
+    const bool cl = crossed(n, o, d, r, slow, T, tie_before);
+    int delta;
+    if (fwd) delta = ((n < hi - 1) && cu) ? 1 : (((n > v) && !cl) ? -1 : 0);
+    else delta = ((n > lo) && cl) ? -1 : (((n < v) && !cu) ? 1 : 0);
+    return n + delta;
 }
 
 struct Counters {
@@ -223,11 +273,12 @@ __device__ __forceinline__ void record_hit(const DebugP &dbg, const GridP &g, La
     }
 }
 
-// One generalized DDA step of a marching lane -- the SAME instruction stream whether the lane walks one voxel (s = 0)
-// or jumps over an empty aligned block of 2^s voxels per side (s = 2, 4, 6), so that the 32 rays of a warp stay
-// converged.  s = 0 reproduces one iteration of the reference loop (:86-221 / :1834-1937) for voxel (nx,ny,nz): on a
-// set bit the lane goes to ST_VOXEL; the backward keeps the reference's `t += step_size` on unlinked voxels (:1935).
-template <bool BWD, bool DEBUG>
+// One generalized DDA step of a marching lane -- the same instruction stream whether the lane walks one voxel (s = 0)
+// or jumps over an empty aligned block of 2^s voxels per side (s = 4, 6), so that the rays of a warp stay converged.
+// s = 0 reproduces one iteration of the reference loop (:86-221 / :1834-1937) for voxel (nx,ny,nz): on a set bit the
+// lane goes to ST_VOXEL; the backward keeps the reference's `t += step_size` on unlinked voxels (:1935).
+// TRACK (forward pre-march): also follow where the BACKWARD loop would stop because of that quirk (L.bwd_alive).
+template <bool BWD, bool DEBUG, bool TRACK>
 __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &opt, Lane &L, Counters &cnt) {
     if (!(L.t <= L.tmax)) {   // `while (t <= ray.tmax)`
         L.state = ST_IDLE;
@@ -246,22 +297,10 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
                 L.k2 = k2;
                 L.w2 = __ldg(bm + g.lay.off[2] + k2);
             }
-            if (L.w2 == 0) {
-                s = 6;
-            } else {
-                const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
-                if (!((L.w2 >> bit1) & 1ull)) {
-                    s = 4;
-                } else {
-                    const int k1 = ((L.nx >> 4) * g.lay.b[1][1] + (L.ny >> 4)) * g.lay.b[1][2] + (L.nz >> 4);
-                    if (k1 != L.k1) {
-                        L.k1 = k1;
-                        L.w1 = __ldg(bm + g.lay.off[1] + k1);
-                    }
-                    const int bit0 = (((L.nx >> 2) & 3) << 4) | (((L.ny >> 2) & 3) << 2) | ((L.nz >> 2) & 3);
-                    if (!((L.w1 >> bit0) & 1ull)) s = 2;
-                }
-            }
+            const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
+            if (L.w2 == 0) s = 6;
+            else if (!((L.w2 >> bit1) & 1ull)) s = 4;
+            // an empty 4^3 block is walked voxel by voxel: ~5 cheap steps beat one jump
         }
         if (s == 0) {
             L.wkey = k0;
@@ -275,14 +314,14 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
     const int Px = (L.dx > 0.f) ? hix : lox, Py = (L.dy > 0.f) ? hiy : loy, Pz = (L.dz > 0.f) ? hiz : loz;
     float Tx = L.tfx, Ty = L.tfy, Tz = L.tfz;
     if (s) {
-        Tx = plane_t(Px, L.ox, L.dx);
-        Ty = plane_t(Py, L.oy, L.dy);
-        Tz = plane_t(Pz, L.oz, L.dz);
+        Tx = PT_X(L, Px);
+        Ty = PT_Y(L, Py);
+        Tz = PT_Z(L, Pz);
     }
     const float T = fminf(fminf(Tx, Ty), Tz);
     if (s) {
-        if (BWD && !(T + opt.step_size <= L.tmax)) {   // the quirk may end the loop in here: walk voxel by voxel
-            L.force_fine = true;
+        if ((BWD || (TRACK && L.bwd_alive)) && !(T + opt.step_size <= L.tmax)) {
+            L.force_fine = true;   // the backward quirk may end the loop in here: walk voxel by voxel from now on
             return;
         }
         if (!(T <= L.tmax)) {   // `while (t <= tmax)` fails at a voxel of this (empty) block
@@ -294,24 +333,21 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
     const int A = (T == Tx) ? 0 : ((T == Ty) ? 1 : 2);   // exit axis; ties go to the lowest axis (:188-197)
     const int vx = L.nx, vy = L.ny, vz = L.nz;
     int nx = vx, ny = vy, nz = vz;
-    bool out = false;
+    if (s) {   // the other two axes: planes whose crossing precedes the exit event (T, A)
+        nx = axis_after(vx, L.ox, L.dx, L.rx, L.slow_div, T, A > 0, lox, hix);
+        ny = axis_after(vy, L.oy, L.dy, L.ry, L.slow_div, T, A > 1, loy, hiy);
+        nz = axis_after(vz, L.oz, L.dz, L.rz, L.slow_div, T, false, loz, hiz);
+    }
+    bool out;
     if (A == 0) {
         nx = (L.dx > 0.f) ? Px : Px - 1;
         out = (nx < 0) || (nx >= g.size[0] - 1);
-    } else if (s) {
-        nx = axis_after(vx, L.ox, L.dx, T, true, lox, hix);
-    }
-    if (A == 1) {
+    } else if (A == 1) {
         ny = (L.dy > 0.f) ? Py : Py - 1;
         out = (ny < 0) || (ny >= g.size[1] - 1);
-    } else if (s) {
-        ny = axis_after(vy, L.oy, L.dy, T, A == 2, loy, hiy);
-    }
-    if (A == 2) {
+    } else {
         nz = (L.dz > 0.f) ? Pz : Pz - 1;
         out = (nz < 0) || (nz >= g.size[2] - 1);
-    } else if (s) {
-        nz = axis_after(vz, L.oz, L.dz, T, false, loz, hiz);
     }
     if (s && out) {   // the ray leaves the grid through this empty block
         L.state = ST_IDLE;
@@ -319,9 +355,10 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
         return;
     }
     if (!out) {
-        if (nx != vx) { L.nx = nx; L.tfx = plane_t(nx + (L.dx > 0.f ? 1 : 0), L.ox, L.dx); }
-        if (ny != vy) { L.ny = ny; L.tfy = plane_t(ny + (L.dy > 0.f ? 1 : 0), L.oy, L.dy); }
-        if (nz != vz) { L.nz = nz; L.tfz = plane_t(nz + (L.dz > 0.f ? 1 : 0), L.oz, L.dz); }
+        L.nx = nx; L.ny = ny; L.nz = nz;
+        L.tfx = PT_X(L, nx + (L.dx > 0.f ? 1 : 0));
+        L.tfy = PT_Y(L, ny + (L.dy > 0.f ? 1 : 0));
+        L.tfz = PT_Z(L, nz + (L.dz > 0.f ? 1 : 0));
     }
     L.t = out ? L.tmax + 1.f : T;
     if (s == 0) {
@@ -340,10 +377,49 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
             } else if (!(L.t + opt.step_size <= L.tmax)) {
                 if (!((__ldg(g.accel + k0) >> bit) & 1ull)) L.t += opt.step_size;
             }
+        } else if (TRACK) {
+            if (L.bwd_alive && !(L.t + opt.step_size <= L.tmax)) {
+                if (!((__ldg(g.accel + k0) >> bit) & 1ull)) L.bwd_alive = false;   // the backward loop ends here
+            }
         }
     } else if (DEBUG) {
         ++cnt.skips;
     }
+}
+
+// Next unit of work of a lane that consumes a pre-marched list: the next listed voxel, else the continuation of the
+// march, else the ray is finished.
+template <bool BWD>
+__device__ __forceinline__ void next_from_list(const GridP &g, const PreP &pre, Lane &L) {
+    if (L.list_pos < L.list_cnt) {
+        const int32_t cell = __ldg(pre.cells + L.ray_id * PRE_K + L.list_pos);
+        ++L.list_pos;
+        L.vz = cell % g.size[2];
+        const int xy = cell / g.size[2];
+        L.vy = xy % g.size[1];
+        L.vx = xy / g.size[1];
+        const float tfx = PT_X(L, L.vx + (L.dx > 0.f ? 1 : 0));
+        const float tfy = PT_Y(L, L.vy + (L.dy > 0.f ? 1 : 0));
+        const float tfz = PT_Z(L, L.vz + (L.dz > 0.f ? 1 : 0));
+        L.t_far = fminf(fminf(tfx, tfy), tfz);
+        L.state = ST_VOXEL;
+        L.phase = PH_ENTER;
+        return;
+    }
+    const bool cont = ((L.list_code >> 16) & 1) && (!BWD || ((L.list_code >> 17) & 1));
+    if (cont) {
+        const int32_t pv = __ldg(pre.cont_vox + L.ray_id);
+        L.nx = pv & 1023;
+        L.ny = (pv >> 10) & 1023;
+        L.nz = (pv >> 20) & 1023;
+        L.t = __ldg(pre.cont_t + L.ray_id);
+        L.force_fine = (L.list_code >> 18) & 1;
+        L.bwd_alive = true;
+        dda_restart(L);   // -> ST_MARCH, in_list = false
+        return;
+    }
+    L.state = ST_IDLE;
+    L.ray_done = true;
 }
 
 // Work of a lane inside a voxel whose bit is set: 8-corner loads, level-set / root iteration, fake sample, early stop
@@ -351,7 +427,7 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
 // phase is kept so that it resumes behind that sample), returns to marching (ST_MARCH) or ends the ray.
 template <bool BWD, bool DEBUG>
 __device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t &opt, Lane &L, const CacheP &cache,
-                                              int M, Counters &cnt, const DebugP &dbg) {
+                                              int M, Counters &cnt, const DebugP &dbg, const PreP &pre) {
     const int offy = g.size[2];
     const int64_t offx = (int64_t)g.size[1] * g.size[2];
     const int64_t ray_id = L.ray_id;
@@ -373,7 +449,7 @@ __device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t 
 #pragma unroll
                 for (int c = 0; c < 8; ++c) pass |= !(__ldg(g.density + L.lk[c]) < opt.sigma_thresh);
                 if (!pass) {
-                    L.state = ST_MARCH;
+                    L.state = ST_MARCH;   // DEBUG kernels never consume a list
                     return;
                 }
                 ++cnt.active;
@@ -388,9 +464,9 @@ __device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t 
                 L.smin = fminf(L.smin, L.sf[c]);
                 L.smax = fmaxf(L.smax, L.sf[c]);
             }
-            const float tcx = plane_t(L.vx + (L.dx > 0.f ? 0 : 1), L.ox, L.dx);
-            const float tcy = plane_t(L.vy + (L.dy > 0.f ? 0 : 1), L.oy, L.dy);
-            const float tcz = plane_t(L.vz + (L.dz > 0.f ? 0 : 1), L.oz, L.dz);
+            const float tcx = PT_X(L, L.vx + (L.dx > 0.f ? 0 : 1));
+            const float tcy = PT_Y(L, L.vy + (L.dy > 0.f ? 0 : 1));
+            const float tcz = PT_Z(L, L.vz + (L.dz > 0.f ? 0 : 1));
             L.t_close = fmaxf(fmaxf(fmaxf(tcx, tcy), tcz), 0.f);
             L.nof[0] = fmaf(L.t_close, L.dx, L.ox);
             L.nof[1] = fmaf(L.t_close, L.dy, L.oy);
@@ -575,10 +651,79 @@ __device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t 
             if (!BWD) L.logT = -1e3f;
             L.state = ST_IDLE;
             L.ray_done = true;
-        } else {
-            L.state = ST_MARCH;
+            return;
         }
-        return;
+        if (!L.in_list) {
+            L.state = ST_MARCH;
+            return;
+        }
+        next_from_list<BWD>(g, pre, L);
+        if (L.state != ST_VOXEL) return;
+    }
+}
+
+// ---- pre-march: one thread per ray, nothing but the generalized DDA --------------------------------------------------
+// Finds, for every ray, the first PRE_K voxels whose work bit is set (and the state to resume from if there are more),
+// writes the background colour of the rays that have no work at all, and compacts the others into a list for the
+// shading kernels.  Its loop body is march_step only, so the 32 rays of a warp advance in lock step.
+__global__ void __launch_bounds__(256)
+premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                const int64_t Q, const PreP pre, float *__restrict__ rgb_out, int *__restrict__ cache_n) {
+    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Lane L;
+    L.state = ST_IDLE;
+    L.ray_done = false;
+    Counters cnt = {0, 0, 0, 0, 0};
+    int n = 0, n_bwd = 0;
+    bool cont = false;
+    if (ray_id < Q) {
+        L.ox = origins[ray_id * 3 + 0]; L.oy = origins[ray_id * 3 + 1]; L.oz = origins[ray_id * 3 + 2];
+        L.dx = dirs[ray_id * 3 + 0]; L.dy = dirs[ray_id * 3 + 1]; L.dz = dirs[ray_id * 3 + 2];
+        float world_step;
+        ray_bounds(g, opt, L, world_step);
+        if (!(L.tmin > L.tmax)) dda_init(g, L);
+    }
+    while (__any_sync(FULL, L.state == ST_MARCH)) {
+        if (L.state == ST_MARCH) {
+            march_step<false, false, true>(g, opt, L, cnt);
+            if (L.state == ST_VOXEL) {
+                pre.cells[ray_id * PRE_K + n] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
+                ++n;
+                if (L.bwd_alive) ++n_bwd;
+                L.state = ST_MARCH;
+                if (n == PRE_K) {
+                    // resume here unless the loop is over anyway (the shading kernels re-check `t <= tmax`)
+                    cont = true;
+                    L.state = ST_IDLE;
+                }
+            }
+        }
+    }
+    bool has_work = false;
+    if (ray_id < Q) {
+        int code = n | (n_bwd << 8);
+        if (cont) {
+            code |= (1 << 16) | ((L.bwd_alive ? 1 : 0) << 17) | ((L.force_fine ? 1 : 0) << 18);
+            pre.cont_t[ray_id] = L.t;
+            pre.cont_vox[ray_id] = L.nx | (L.ny << 10) | (L.nz << 20);
+        }
+        pre.code[ray_id] = code;
+        has_work = (n > 0);
+        if (!has_work) {
+            if (rgb_out) {   // forward: the ray composites nothing -> background (:59-65, :553-555)
+                const float bg = opt.background_brightness;
+                rgb_out[ray_id * 3 + 0] = bg; rgb_out[ray_id * 3 + 1] = bg; rgb_out[ray_id * 3 + 2] = bg;
+            }
+            if (cache_n) cache_n[ray_id] = 0;
+        }
+    }
+    const unsigned m = __ballot_sync(FULL, has_work);
+    if (m) {
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(pre.n_rays, (unsigned long long)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        if (has_work) pre.rays[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)ray_id;
     }
 }
 
@@ -857,7 +1002,7 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
                  const float *__restrict__ dirs, const int64_t Q, float *__restrict__ rgb_out,
                  const float *__restrict__ grad_in, const float *__restrict__ color_cache, const FusedP f,
                  const CacheP cache, const asurf_grads_t grads, const DebugP dbg,
-                 unsigned long long *__restrict__ ray_counter) {
+                 unsigned long long *__restrict__ ray_counter, const PreP pre) {
     __shared__ float s_sph[CTA_WARPS][32][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = g.sh_dim, bd = g.basis_dim;
@@ -869,12 +1014,14 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
     L.ray_id = -1;
     float out0 = 0.f, out1 = 0.f, out2 = 0.f;  // FWD: colour; BWD: dL/dRGB
     float accum = 0.f;
-    Pre pre;
+    Pre lossc;
     CacheView cv;
     cv.sa = cv.sw = cv.st = nullptr;
     cv.n = 0;
     Counters cnt = {0, 0, 0, 0, 0};
     bool rays_left = true;   // warp-uniform
+    // rays to serve: the compact list of the pre-march, or all Q rays when there was no pre-march
+    const int64_t n_serve = pre.enabled ? (int64_t)*pre.n_rays : Q;
 
     // Persistent warp: lanes pull rays from a global counter as they become free, then the warp repeatedly runs the
     // kind of work most of its lanes are waiting for (march step / voxel work / sample shading / ray set-up).
@@ -891,16 +1038,17 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
             // ---------------- march: a few generalized DDA steps ----------------
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
-                if (L.state == ST_MARCH) march_step<BWD, DEBUG>(g, opt, L, cnt);
+                if (L.state == ST_MARCH) march_step<BWD, DEBUG, false>(g, opt, L, cnt);
             }
         } else if (n_idle > 0 && n_idle >= n_vox && n_idle >= n_samp) {
             // ---------------- ray set-up for the free lanes ----------------
             unsigned long long base = 0;
             if (lane == __ffs(m_idle) - 1) base = atomicAdd(ray_counter, (unsigned long long)__popc(m_idle));
             base = __shfl_sync(FULL, base, __ffs(m_idle) - 1);
-            const int64_t ray_id = (int64_t)base + __popc(m_idle & ((1u << lane) - 1u));
-            if (__any_sync(FULL, (L.state == ST_IDLE) && (ray_id >= Q))) rays_left = false;
-            if (L.state == ST_IDLE && ray_id < Q) {
+            const int64_t serve_id = (int64_t)base + __popc(m_idle & ((1u << lane) - 1u));
+            if (__any_sync(FULL, (L.state == ST_IDLE) && (serve_id >= n_serve))) rays_left = false;
+            if (L.state == ST_IDLE && serve_id < n_serve) {
+                const int64_t ray_id = pre.enabled ? (int64_t)__ldg(pre.rays + serve_id) : serve_id;
                 L.ray_id = ray_id;
                 L.logT = 0.f;
                 L.intersect_i = -1;
@@ -934,20 +1082,26 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
                         cv.sa = cache.sa + ray_id * M; cv.sw = cache.sw + ray_id * M; cv.st = cache.st + ray_id * M;
                         cv.n = cache.n[ray_id];
                     }
-                    fused_preamble(cv, pre);
+                    fused_preamble(cv, lossc);
                     accum = fmaf(color_cache[ray_id * 3 + 0], out0,
                                  fmaf(color_cache[ray_id * 3 + 1], out1, color_cache[ray_id * 3 + 2] * out2));
                 }
-                if (!(L.tmin > L.tmax)) {
-                    dda_init(g, L);   // -> ST_MARCH
-                } else {
+                if (L.tmin > L.tmax) {
                     L.ray_done = true;   // misses the grid: background colour / no gradient (:59-65, :1811-1816)
+                } else if (pre.enabled) {
+                    L.list_code = __ldg(pre.code + ray_id);
+                    L.list_cnt = BWD ? ((L.list_code >> 8) & 255) : (L.list_code & 255);
+                    L.list_pos = 0;
+                    L.in_list = true;
+                    next_from_list<BWD>(g, pre, L);
+                } else {
+                    dda_init(g, L);   // -> ST_MARCH
                 }
             }
             __syncwarp();
         } else if (n_vox > 0 && n_vox >= n_samp) {
             // ---------------- voxel work ----------------
-            if (L.state == ST_VOXEL) voxel_advance<BWD, DEBUG>(g, opt, L, cache, M, cnt, dbg);
+            if (L.state == ST_VOXEL) voxel_advance<BWD, DEBUG>(g, opt, L, cache, M, cnt, dbg, pre);
         } else {
             // ---------------- sample shading: the warp serves its pending lanes one after the other ----------------
             unsigned pend = m_samp;
@@ -1021,8 +1175,8 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
             }
             if (have) {
                 if (BWD) {
-                    if (!L.fake) finish_real_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color, gx, gy, gz);
-                    else finish_fake_bwd(g, opt, f, pre, cv, grads, L, accum, tot_color);
+                    if (!L.fake) finish_real_bwd(g, opt, f, lossc, cv, grads, L, accum, tot_color, gx, gy, gz);
+                    else finish_fake_bwd(g, opt, f, lossc, cv, grads, L, accum, tot_color);
                 }
                 L.state = ST_VOXEL;   // resume behind the sample
             }
@@ -1059,7 +1213,7 @@ using namespace asurf;
 
 namespace {
 
-Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg, g_ws_ctr;
+Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg, g_ws_ctr, g_ws_pre;
 
 int g_skip_enabled = 1;  // asurf_debug_set_skip
 
@@ -1144,13 +1298,34 @@ inline int n_ctas(int64_t Q) {
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
-// zeroed ray counters for the next launches on `st` (two per call: forward, backward)
+// zeroed counters for the next launches on `st`: [0] forward ray fetch, [1] backward ray fetch, [2] compact-list length
 int ray_counters(cudaStream_t st, unsigned long long **ctr) {
-    int rc = g_ws_ctr.reserve(2 * sizeof(unsigned long long));
+    int rc = g_ws_ctr.reserve(4 * sizeof(unsigned long long));
     if (rc) return rc;
-    ASURF_CUDA(cudaMemsetAsync(g_ws_ctr.ptr, 0, 2 * sizeof(unsigned long long), st));
+    ASURF_CUDA(cudaMemsetAsync(g_ws_ctr.ptr, 0, 4 * sizeof(unsigned long long), st));
     *ctr = (unsigned long long *)g_ws_ctr.ptr;
     return 0;
+}
+
+// Runs the pre-march for this call (forward output / cache counts optional) and returns its record.
+int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, unsigned long long *ctr, float *rgb_out,
+             int *cache_n, cudaStream_t st, PreP &pre) {
+    pre = PreP();
+    if (!g_skip_enabled || g.size[0] > 1024 || g.size[1] > 1024 || g.size[2] > 1024) return 0;   // shading kernels march
+    const int64_t Q = rays->n_rays;
+    const size_t per = (size_t)Q * sizeof(int32_t);
+    int rc = g_ws_pre.reserve(per * (PRE_K + 4));
+    if (rc) return rc;
+    char *base = (char *)g_ws_pre.ptr;
+    pre.cells = (int32_t *)base;
+    pre.code = (int32_t *)(base + per * PRE_K);
+    pre.cont_t = (float *)(base + per * (PRE_K + 1));
+    pre.cont_vox = (int32_t *)(base + per * (PRE_K + 2));
+    pre.rays = (int32_t *)(base + per * (PRE_K + 3));
+    pre.n_rays = ctr + 2;
+    pre.enabled = 1;
+    premarch_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, rgb_out, cache_n);
+    return check_cuda(cudaGetLastError(), "premarch launch");
 }
 
 }  // namespace
@@ -1172,14 +1347,17 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     unsigned long long *ctr = nullptr;
     rc = ray_counters(st, &ctr);
     if (rc) return rc;
+    PreP pre = PreP();
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
         g.use_skip = 0;   // count every voxel of the reference DDA
         surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr);
+            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr, pre);
     } else {
+        rc = premarch(g, opt, rays, ctr, rgb_out, nullptr, st, pre);
+        if (rc) return rc;
         surf_trav_kernel<false, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr);
+            g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr, pre);
     }
     return check_cuda(cudaGetLastError(), "surf_trav_forward launch");
 }
@@ -1202,8 +1380,12 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     unsigned long long *ctr = nullptr;
     rc = ray_counters(st, &ctr);
     if (rc) return rc;
+    PreP pre;
+    rc = premarch(g, opt, rays, ctr, nullptr, nullptr, st, pre);
+    if (rc) return rc;
     surf_trav_kernel<true, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
-        g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg, ctr);
+        g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg, ctr + 1,
+        pre);
     return check_cuda(cudaGetLastError(), "surf_trav_backward launch");
 }
 
@@ -1268,20 +1450,25 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     const bool prof = g_prof.cap > 0 && g_prof.n < g_prof.cap;
     cudaEvent_t *pe = prof ? g_prof.ev + 3 * g_prof.n : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
+    PreP pre = PreP(), nopre = PreP();
+    if (!stats_dev) {
+        rc = premarch(g, opt, rays, ctr, rgb_out, cache.n, st, pre);
+        if (rc) return rc;
+    }
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
         GridP gs = g;
         gs.use_skip = 0;
         surf_trav_kernel<false, true><<<n_ctas(Q), CTA_THREADS, 0, st>>>(gs, *opt, rays->origins, rays->dirs, Q, rgb_out,
-                                                                          nullptr, nullptr, ff, cache, nog, dbg, ctr);
+                                                                          nullptr, nullptr, ff, cache, nog, dbg, ctr, nopre);
     } else {
         surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
-                                                                           nullptr, nullptr, ff, cache, nog, dbg, ctr);
+                                                                           nullptr, nullptr, ff, cache, nog, dbg, ctr, pre);
     }
     DebugP nodbg = {};
     if (prof) cudaEventRecord(pe[1], st);
     surf_trav_kernel<true, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, nullptr, rgb_gt,
-                                                                      rgb_out, f, cache, *grads, nodbg, ctr + 1);
+                                                                      rgb_out, f, cache, *grads, nodbg, ctr + 1, pre);
     if (prof) {
         cudaEventRecord(pe[2], st);
         ++g_prof.n;
@@ -1307,7 +1494,7 @@ static int debug_launch(const asurf_grid_t *grid, const asurf_rays_t *rays, cons
     if (rc) return rc;
     surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
         g, *opt, rays->origins, rays->dirs, rays->n_rays, (float *)g_ws_dbg.ptr, nullptr, nullptr, f, cache, grads, dbg,
-        ctr);
+        ctr, PreP());
     return check_cuda(cudaGetLastError(), "surf_trav debug launch");
 }
 
@@ -1370,4 +1557,5 @@ extern "C" void asurf_release(void) {
     g_ws_cache.release();
     g_ws_dbg.release();
     g_ws_ctr.release();
+    g_ws_pre.release();
 }
