@@ -40,6 +40,40 @@ __global__ void __launch_bounds__(256) rmsprop_dense_kernel(float *__restrict__ 
     }
 }
 
+// Row-masked steps: training touches a tiny fraction of the rows (the voxels the batch's samples hit), so scanning all
+// N*C elements for their row's mask byte wastes the launch.  Each warp takes 32 rows, reads their 32 mask bytes in one
+// coalesced load, and then walks only the set rows with the lanes striding over the C channels (coalesced rows).
+template <bool RMS>
+__global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ data, float *__restrict__ rms,
+                                                           float *__restrict__ grad, const uint8_t *__restrict__ mask,
+                                                           int64_t n_rows, int n_cols, float beta, float lr, float eps,
+                                                           float minval, float lr_last) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp0 * 32; base < n_rows; base += n_warps * 32) {
+        const int64_t row = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, row < n_rows && mask[row] != 0);
+        while (m) {
+            const int r = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t off = (base + r) * n_cols;
+            for (int c = lane; c < n_cols; c += 32) {
+                const float l = (c == n_cols - 1) ? lr_last : lr;
+                if (RMS) {
+                    float x = data[off + c], q = rms[off + c], g = grad[off + c];
+                    rmsprop_once(x, q, g, beta, l, eps, minval);
+                    data[off + c] = x;
+                    rms[off + c] = q;
+                } else {
+                    data[off + c] = fmaf(-l, grad[off + c], data[off + c]);
+                }
+                grad[off + c] = 0.f;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) rmsprop_index_kernel(float *__restrict__ data, float *__restrict__ rms,
                                                              float *__restrict__ grad, const int64_t *__restrict__ idx,
                                                              int64_t n_index, int n_cols, float beta, float lr,
@@ -117,8 +151,8 @@ extern "C" int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t 
                                                                          lr, eps, minval, lr_last);
     } else if (indexer_kind == 1) {
         if (n_index == 0 || n_elem == 0) return 0;  // size(0) == 0 -> skip (:189)
-        rmsprop_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer,
-                                                                        n_elem, n_cols, beta, lr, eps, minval, lr_last);
+        masked_rows_kernel<true><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer, n_rows,
+                                                                          n_cols, beta, lr, eps, minval, lr_last);
     } else if (indexer_kind == 2) {
         if (n_index == 0) return 0;
         rmsprop_index_kernel<<<stream_grid(n_index * n_cols), 256, 0, st>>>(data, rms, grad, (const int64_t *)indexer,
@@ -142,8 +176,8 @@ extern "C" int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t 
         sgd_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, nullptr, n_elem, n_cols, lr, lr_last);
     } else if (indexer_kind == 1) {
         if (n_index == 0 || n_elem == 0) return 0;
-        sgd_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, (const uint8_t *)indexer, n_elem, n_cols,
-                                                                    lr, lr_last);
+        masked_rows_kernel<false><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, nullptr, grad, (const uint8_t *)indexer,
+                                                                           n_rows, n_cols, 0.f, lr, 0.f, 0.f, lr_last);
     } else if (indexer_kind == 2) {
         if (n_index == 0) return 0;
         sgd_index_kernel<<<stream_grid(n_index * n_cols), 256, 0, st>>>(data, grad, (const int64_t *)indexer, n_index,

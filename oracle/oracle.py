@@ -211,3 +211,44 @@ def cubic_root_grad(typ, st_id, fs):
     g = np.ones(4, np.float32)
     lib().oracle_cubic_root_grad(C.c_int(typ), C.c_int(st_id), _ptr(fs), _ptr(g))
     return g
+
+
+# ---- optimizer steps: numpy restatement of optim_kernel.cu:15-25 (rmsprop_once) and :97-103 (sgd_once) ----
+def _rows(n_rows, indexer):
+    """indexer as the reference dispatches it (optim_kernel.cu:175-215): None = all rows, bool mask, int64 list."""
+    if indexer is None:
+        return np.arange(n_rows)
+    indexer = np.asarray(indexer)
+    if indexer.dtype == np.bool_:
+        return np.nonzero(indexer)[0]
+    return indexer.astype(np.int64)
+
+
+def rmsprop_step(data, rms, grad, indexer, beta, lr, eps, minval, lr_last):
+    """In place on float32 arrays (N, C).  fmaf is emulated in float64 (exact product, one final rounding)."""
+    if lr_last < 0:
+        lr_last = lr
+    rows = _rows(data.shape[0], indexer)
+    f32 = np.float32
+    g = grad[rows]
+    g2 = (g * g).astype(f32)
+    r = rms[rows]
+    lerp = (np.float64(f32(beta)) * (r - g2).astype(f32).astype(np.float64) + g2.astype(np.float64)).astype(f32)
+    r_new = np.where(r == 0, g2, lerp).astype(f32)
+    lrs = np.full((data.shape[1],), f32(lr), f32)
+    lrs[-1] = f32(lr_last)
+    step = ((lrs[None, :] * g).astype(f32) / (np.sqrt(r_new).astype(f32) + f32(eps)).astype(f32)).astype(f32)
+    data[rows] = np.maximum((data[rows] - step).astype(f32), f32(minval))
+    rms[rows] = r_new
+    grad[rows] = 0
+
+
+def sgd_step(data, grad, indexer, lr, lr_last):
+    if lr_last < 0:
+        lr_last = lr
+    rows = _rows(data.shape[0], indexer)
+    lrs = np.full((data.shape[1],), np.float32(lr), np.float32)
+    lrs[-1] = np.float32(lr_last)
+    d = data[rows].astype(np.float64) - lrs[None, :].astype(np.float64) * grad[rows].astype(np.float64)
+    data[rows] = d.astype(np.float32)
+    grad[rows] = 0

@@ -1,0 +1,41 @@
+"""CPU: the C-ABI library loads and exports every symbol include/asurf.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+from alphasurf_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "asurf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(asurf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared() == sorted(capi.EXPORTS)
+
+
+def test_library_exports_every_symbol():
+    lib = capi.lib()
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert lib.asurf_abi_version() == 1
+    assert isinstance(lib.asurf_last_error(), bytes)
+
+
+def test_accel_words_is_host_only():
+    lib = capi.lib()
+    n = lib.asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
+    assert n == 128 ** 3 + 32 ** 3 + 8 ** 3
+
+
+def test_struct_layouts_match_header():
+    # sizes follow from the field lists in include/asurf.h (natural alignment)
+    assert ctypes.sizeof(capi.OptT) == 17 * 4
+    assert ctypes.sizeof(capi.RaysT) == 24
+    assert ctypes.sizeof(capi.GradsT) == 40
+    assert ctypes.sizeof(capi.GridT) == 8 + 12 + 4 + 8 * 4 + 4 * 3 + 4 + 8 + 12 + 12 + 4 + 4 + 8 + 8
+    assert ctypes.sizeof(capi.FusedT) == 18 * 4 + 8
