@@ -70,6 +70,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.asurf_last_error.restype = C.c_char_p
     L.asurf_accel_words.restype = C.c_int64
+    L.asurf_launch_count.restype = C.c_uint64
     L.asurf_accel_words.argtypes = [C.POINTER(C.c_int32)]
     for name in EXPORTS:
         getattr(L, name)  # fail loudly on a stale library
@@ -81,7 +82,8 @@ def lib():
 EXPORTS = [
     "asurf_last_error", "asurf_abi_version", "asurf_accel_words", "asurf_accel_build", "asurf_work_build", "asurf_surf_trav_forward",
     "asurf_surf_trav_backward", "asurf_surf_trav_fused", "asurf_debug_ray_bounds", "asurf_debug_trace", "asurf_debug_set_skip",
-    "asurf_rmsprop_step", "asurf_sgd_step", "asurf_profile_enable", "asurf_profile_read", "asurf_release",
+    "asurf_rmsprop_step", "asurf_sgd_step", "asurf_tv", "asurf_tv_grad", "asurf_tv_grad_sparse",
+    "asurf_surf_tv_grad_sparse", "asurf_alpha_surf_sparsify_grad_sparse", "asurf_surface_normal_grad_sparse", "asurf_profile_enable", "asurf_profile_read", "asurf_launch_count", "asurf_release",
 ]
 
 

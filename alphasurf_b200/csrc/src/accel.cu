@@ -167,6 +167,7 @@ extern "C" int asurf_work_build(const asurf_grid_t *grid, const asurf_opt_t *opt
                                                            work_out);
     accel_coarsen_kernel<<<div_up(lay.count(1), 128), 128, 0, st>>>(lay, 1, work_out);
     accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, work_out);
+    note_launches(3);
     return check_cuda(cudaGetLastError(), "work_build launch");
 }
 
@@ -183,5 +184,6 @@ extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], ui
     accel_level0_kernel<<<div_up(lay.count(0), 128), 128, 0, st>>>(links, size[0], size[1], size[2], lay, accel_out);
     accel_coarsen_kernel<<<div_up(lay.count(1), 128), 128, 0, st>>>(lay, 1, accel_out);
     accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, accel_out);
+    note_launches(3);
     return check_cuda(cudaGetLastError(), "accel_build launch");
 }

@@ -21,6 +21,14 @@ int check_cuda(cudaError_t e, const char *what) {
     return (int)e;
 }
 
+static unsigned long long g_launches = 0;
+void note_launches(int n) { g_launches += (unsigned long long)n; }
+unsigned long long launches_read(int reset) {
+    const unsigned long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
 int Workspace::reserve(size_t need) {
     int dev = 0;
     ASURF_CUDA(cudaGetDevice(&dev));
@@ -60,3 +68,4 @@ void Workspace::release() {
 
 extern "C" const char *asurf_last_error(void) { return asurf::g_err; }
 extern "C" int asurf_abi_version(void) { return ASURF_ABI_VERSION; }
+extern "C" uint64_t asurf_launch_count(int32_t reset) { return asurf::launches_read(reset); }

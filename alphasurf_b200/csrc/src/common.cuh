@@ -36,6 +36,10 @@ struct Workspace {
     void release();
 };
 
+// ---- launch accounting (asurf_launch_count): every kernel this library enqueues is counted ------------------
+void note_launches(int n);
+unsigned long long launches_read(int reset);
+
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- occupancy pyramid layout (accel.cu) -----------------------------------------------------------------

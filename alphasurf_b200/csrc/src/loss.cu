@@ -1,0 +1,447 @@
+// alphasurf_b200: grid-side regularisers that add their gradient in place (and mark the touched rows).
+//
+// Replaces, from /root/reference/svox2/csrc/loss_kernel.cu:
+//   tv (:1214-1247, kernel :72-117)              tv_grad (:1249-1287, kernel :119-184)
+//   tv_grad_sparse (:1327-1373, kernel :738-807) surf_tv_grad_sparse (:1375-1427, kernel :809-893)
+//   alpha_surf_sparsify_grad_sparse (:1512-1570, kernel :664-734)
+//   surface_normal_grad_sparse (:1572-1622, kernel :397-441 -> add_surface_normal_grad, render_util.cuh:1870-2133)
+//
+// All of them are link-indirected gathers of a handful of scalars per cell followed by a few atomics: HBM / L2 bound,
+// no reuse worth staging.  What this version changes is the execution shape, not the arithmetic: grid-stride loops
+// sized to the SM count with 64-bit element indices (the reference's `int nl` / int thread ids overflow for dense
+// 512^3 x 27), __ldg gathers, and red.global atomics without return values.
+#include "common.cuh"
+
+namespace asurf {
+namespace {
+
+constexpr int LOSS_THREADS = 256;
+
+struct Dims {
+    int sx, sy, sz;
+};
+
+__device__ __forceinline__ void cell_xyz(int64_t xyz, const Dims &d, int &x, int &y, int &z) {
+    z = (int)(xyz % d.sz);
+    const int64_t xy = xyz / d.sz;
+    y = (int)(xy % d.sy);
+    x = (int)(xy / d.sy);
+}
+
+// axis scaling of the finite differences, loss_kernel.cu:22-62 (the NDC branch is commented out there)
+__device__ __forceinline__ void ray_scale(const Dims &d, float *s) {
+    s[0] = d.sx * (1.f / 256.f);
+    s[1] = d.sy * (1.f / 256.f);
+    s[2] = d.sz * (1.f / 256.f);
+}
+
+inline int loss_grid(int64_t n) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int64_t want = (n + LOSS_THREADS - 1) / LOSS_THREADS;
+    const int64_t cap = (int64_t)sms * 32;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ---- dense TV value (tv_kernel) -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LOSS_THREADS) tv_value_kernel(const int32_t *__restrict__ links,
+                                                                 const float *__restrict__ data, int n_cols, Dims d,
+                                                                 int start_dim, int end_dim, float scale, int64_t Q,
+                                                                 int ignore_edge, float *__restrict__ out) {
+    __shared__ float s_part[LOSS_THREADS / 32];
+    const int nch = end_dim - start_dim;
+    float acc = 0.f;
+    float sc[3];
+    ray_scale(d, sc);
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int idx = (int)(tid % nch) + start_dim;
+        const int64_t xyz = tid / nch;
+        const int z = (int)(xyz % (d.sz - 1));
+        const int64_t xy = xyz / (d.sz - 1);
+        const int y = (int)(xy % (d.sy - 1));
+        const int x = (int)(xy / (d.sy - 1));
+        const int64_t p = ((int64_t)x * d.sy + y) * d.sz + z;
+        const int32_t l000 = __ldg(links + p);
+        if (ignore_edge && l000 == 0) continue;   // sic: `== 0` (:89)
+        const int32_t l100 = __ldg(links + p + (int64_t)d.sy * d.sz), l010 = __ldg(links + p + d.sz),
+                      l001 = __ldg(links + p + 1);
+        const float v000 = l000 >= 0 ? __ldg(data + (int64_t)l000 * n_cols + idx) : 0.f;
+        const float nullv = ignore_edge ? v000 : 0.f;
+        const float v100 = l100 >= 0 ? __ldg(data + (int64_t)l100 * n_cols + idx) : nullv;
+        const float v010 = l010 >= 0 ? __ldg(data + (int64_t)l010 * n_cols + idx) : nullv;
+        const float v001 = l001 >= 0 ? __ldg(data + (int64_t)l001 * n_cols + idx) : nullv;
+        const float dx = (v100 - v000) * sc[0], dy = (v010 - v000) * sc[1], dz = (v001 - v000) * sc[2];
+        acc += sqrtf(1e-5f + dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < LOSS_THREADS / 32; ++i) t += s_part[i];
+        atomicAdd(out, t * scale);
+    }
+}
+
+// ---- dense TV gradient (tv_grad_kernel) -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(LOSS_THREADS) tv_grad_dense_kernel(const int32_t *__restrict__ links,
+                                                                      const float *__restrict__ data, int n_cols, Dims d,
+                                                                      int start_dim, int end_dim, float scale, int64_t Q,
+                                                                      int ignore_edge, float *__restrict__ grad) {
+    const int nch = end_dim - start_dim;
+    float sc[3];
+    ray_scale(d, sc);
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int idx = (int)(tid % nch) + start_dim;
+        const int64_t xyz = tid / nch;
+        const int z = (int)(xyz % (d.sz - 1));
+        const int64_t xy = xyz / (d.sz - 1);
+        const int y = (int)(xy % (d.sy - 1));
+        const int x = (int)(xy / (d.sy - 1));
+        const int64_t p = ((int64_t)x * d.sy + y) * d.sz + z;
+        const int32_t l000 = __ldg(links + p);
+        if (ignore_edge && l000 == 0) continue;
+        const int32_t l100 = __ldg(links + p + (int64_t)d.sy * d.sz), l010 = __ldg(links + p + d.sz),
+                      l001 = __ldg(links + p + 1);
+        float v000 = 0.f, v100 = 0.f, v010 = 0.f, v001 = 0.f;
+        if (l000 >= 0) v000 = __ldg(data + (int64_t)l000 * n_cols + idx);
+        if (l100 >= 0) v100 = __ldg(data + (int64_t)l100 * n_cols + idx); else if (ignore_edge) v100 = v000;
+        if (l010 >= 0) v010 = __ldg(data + (int64_t)l010 * n_cols + idx); else if (ignore_edge) v010 = v000;
+        if (l001 >= 0) v001 = __ldg(data + (int64_t)l001 * n_cols + idx); else if (ignore_edge) v001 = v000;
+        float dx = v100 - v000, dy = v010 - v000, dz = v001 - v000;
+        const float idelta = scale * rsqrtf(1e-9f + dx * dx + dy * dy + dz * dz);
+        dx *= sc[0];
+        dy *= sc[1];
+        dz *= sc[2];
+        if (dx != 0.f && l100 >= 0) atomicAdd(grad + (int64_t)l100 * n_cols + idx, dx * idelta);
+        if (dy != 0.f && l010 >= 0) atomicAdd(grad + (int64_t)l010 * n_cols + idx, dy * idelta);
+        if (dz != 0.f && l001 >= 0) atomicAdd(grad + (int64_t)l001 * n_cols + idx, dz * idelta);
+        if (l000 >= 0) atomicAdd(grad + (int64_t)l000 * n_cols + idx, -(dx + dy + dz) * idelta);
+    }
+}
+
+// ---- sparse TV gradient on a list of cells (tv_grad_sparse_kernel / surf_tv_grad_sparse_kernel) -----------------------
+// SURF: missing neighbours take `edge_value`, optional opacity-dependent up-weighting (:863-873).
+template <bool SURF>
+__global__ void __launch_bounds__(LOSS_THREADS)
+tv_grad_sparse_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols,
+                      const float *__restrict__ density, int density_cols, const int32_t *__restrict__ cells, Dims d,
+                      int start_dim, int end_dim, float scale, int64_t Q, int ignore_edge, float edge_value,
+                      int ignore_last_z, int alpha_dependency, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    const int nch = end_dim - start_dim;
+    float sc[3];
+    ray_scale(d, sc);
+    const int64_t offx = (int64_t)d.sy * d.sz;
+    const int offy = d.sz;
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int idx = (int)(tid % nch) + start_dim;
+        const int64_t xyz = __ldg(cells + tid / nch);
+        int x, y, z;
+        cell_xyz(xyz, d, x, y, z);
+        const int32_t *lp = links + xyz;
+        const int32_t l000 = __ldg(lp);
+        if (ignore_edge && l000 == 0) continue;   // sic (:758)
+        const int32_t l001 = ((z + 1 < d.sz) && (!ignore_last_z || z != d.sz - 2)) ? __ldg(lp + 1) : 0;
+        const int32_t l010 = (y + 1 < d.sy) ? __ldg(lp + offy) : 0;
+        const int32_t l100 = (x + 1 < d.sx) ? __ldg(lp + offx) : 0;
+        if (ignore_last_z && z == d.sz - 2) continue;
+        const float missing = SURF ? edge_value : 0.f;
+        const float v000 = l000 >= 0 ? __ldg(data + (int64_t)l000 * n_cols + idx) : missing;
+        const float nullv = ignore_edge ? v000 : missing;
+        const float v001 = l001 >= 0 ? __ldg(data + (int64_t)l001 * n_cols + idx) : nullv;
+        const float v010 = l010 >= 0 ? __ldg(data + (int64_t)l010 * n_cols + idx) : nullv;
+        const float v100 = l100 >= 0 ? __ldg(data + (int64_t)l100 * n_cols + idx) : nullv;
+        float dx = v100 - v000, dy = v010 - v000, dz = v001 - v000;
+        float idelta = scale * rsqrtf(1e-9f + dx * dx + dy * dy + dz * dz);
+        if (SURF && alpha_dependency) {
+            const float a000 = l000 >= 0 ? __ldg(density + (int64_t)l000 * density_cols + idx) : 0.f;
+            const float a001 = l001 >= 0 ? __ldg(density + (int64_t)l001 * density_cols + idx) : 0.f;
+            const float a010 = l010 >= 0 ? __ldg(density + (int64_t)l010 * density_cols + idx) : 0.f;
+            const float a100 = l100 >= 0 ? __ldg(density + (int64_t)l100 * density_cols + idx) : 0.f;
+            const float max_alpha = fmaxf(a000, fmaxf(a001, fmaxf(a010, a100)));
+            if ((double)max_alpha < 0.1) idelta = (float)((double)idelta / fmax((double)(max_alpha * 10), 1e-1));
+        }
+        dx *= sc[0];
+        dy *= sc[1];
+        dz *= sc[2];
+        const float sm = -(dx + dy + dz);
+        if (l000 >= 0 && sm != 0.f) { atomicAdd(grad + (int64_t)l000 * n_cols + idx, sm * idelta); if (mask) mask[l000] = 1; }
+        if (l001 >= 0 && dz != 0.f) { atomicAdd(grad + (int64_t)l001 * n_cols + idx, dz * idelta); if (mask) mask[l001] = 1; }
+        if (l010 >= 0 && dy != 0.f) { atomicAdd(grad + (int64_t)l010 * n_cols + idx, dy * idelta); if (mask) mask[l010] = 1; }
+        if (l100 >= 0 && dx != 0.f) { atomicAdd(grad + (int64_t)l100 * n_cols + idx, dx * idelta); if (mask) mask[l100] = 1; }
+    }
+}
+
+// ---- opacity / surface sparsity (alpha_surf_sparsify_grad_sparse_kernel) -------------------------------------------------
+__global__ void __launch_bounds__(LOSS_THREADS)
+sparsify_kernel(const int32_t *__restrict__ links, const float *__restrict__ alpha, int alpha_cols,
+                const float *__restrict__ surf, int surf_cols, const int32_t *__restrict__ cells, int64_t Q,
+                float scale_alpha, float scale_surf, int surf_decrease, float surf_thresh, float alpha_bound,
+                float surf_bound, uint8_t *__restrict__ mask, float *__restrict__ grad_alpha,
+                float *__restrict__ grad_surf) {
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t l = __ldg(links + __ldg(cells + tid));
+        if (l < 0) continue;
+        if (mask) mask[l] = 1;
+        const float a = __ldg(alpha + (int64_t)l * alpha_cols);
+        const float safe_grad = 1.f / fmaxf(a, 1e-8f);
+        if (a > alpha_bound) atomicAdd(grad_alpha + (int64_t)l * alpha_cols, scale_alpha * safe_grad);
+        const float s = __ldg(surf + (int64_t)l * surf_cols);
+        const bool reg_surf = surf_decrease ? (s > surf_bound) : (s < surf_bound);
+        if (reg_surf && (a < surf_thresh))   // sic: the row offset uses the alpha tensor's width (:729)
+            atomicAdd(grad_surf + (int64_t)l * alpha_cols, surf_decrease ? (scale_surf * safe_grad) : (-scale_surf * safe_grad));
+    }
+}
+
+// ---- surface-normal consistency between a voxel and its +x / +y / +z neighbours (add_surface_normal_grad) -------------
+struct Cell8 {
+    int32_t l[8];
+    float s[8];   // corner k = (dx << 2) | (dy << 1) | dz
+};
+
+__device__ __forceinline__ bool load_cell(const int32_t *__restrict__ links, const float *__restrict__ surf, const Dims &d,
+                                          int x, int y, int z, Cell8 &c) {
+    if (!((x < d.sx - 1) && (y < d.sy - 1) && (z < d.sz - 1))) return false;
+    const int64_t offx = (int64_t)d.sy * d.sz;
+    const int32_t *lp = links + ((int64_t)x * offx + (int64_t)y * d.sz + z);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        c.l[k] = __ldg(lp + (k >> 2) * offx + ((k >> 1) & 1) * d.sz + (k & 1));
+        ok &= (c.l[k] >= 0);
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c.s[k] = __ldg(surf + c.l[k]);
+    return true;
+}
+__device__ __forceinline__ bool cell_empty(const Cell8 &c, float lv) {
+    bool le = true, ge = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        le &= (c.s[k] <= lv);
+        ge &= (c.s[k] >= lv);
+    }
+    return le || ge;
+}
+__device__ __forceinline__ void cell_normal(const Cell8 &c, float *n) {
+    n[0] = ((c.s[4] + c.s[5] + c.s[6] + c.s[7]) - (c.s[0] + c.s[1] + c.s[2] + c.s[3])) / 4;
+    n[1] = ((c.s[2] + c.s[3] + c.s[6] + c.s[7]) - (c.s[0] + c.s[1] + c.s[4] + c.s[5])) / 4;
+    n[2] = ((c.s[1] + c.s[3] + c.s[5] + c.s[7]) - (c.s[0] + c.s[2] + c.s[4] + c.s[6])) / 4;
+}
+__device__ __forceinline__ bool face_connected(float s0, float s1, float s2, float s3, float lv) {
+    return !(((s0 <= lv) && (s1 <= lv) && (s2 <= lv) && (s3 <= lv)) || ((s0 >= lv) && (s1 >= lv) && (s2 >= lv) && (s3 >= lv)));
+}
+// d(normal)/d(8 corners) contracted with g, times scale (_split_add_surface_norm_grad, render_util.cuh:1824-1868)
+__device__ __forceinline__ void scatter_normal_grad(const Cell8 &c, const float *g, float scale, uint8_t *__restrict__ mask,
+                                                    float *__restrict__ grad) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float sx = (k & 4) ? 0.25f : -0.25f, sy = (k & 2) ? 0.25f : -0.25f, sz = (k & 1) ? 0.25f : -0.25f;
+        const float gk = sx * g[0] + sy * g[1] + sz * g[2];
+        const float val = scale * gk;
+        if (val != 0.f) {
+            atomicAdd(grad + c.l[k], val);
+            if (mask) mask[c.l[k]] = 1;
+        }
+    }
+}
+#define NORM3_(v) sqrtf(1e-9f + (v)[0] * (v)[0] + (v)[1] * (v)[1] + (v)[2] * (v)[2])
+#define CUB_(x) ((x) * (x) * (x))
+#define SQR_(x) ((x) * (x))
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+surface_normal_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, const int32_t *__restrict__ cells,
+                      Dims d, int n_rep, int64_t Q, float lv_set, float scale, int con_check, int ignore_empty, int use_l1,
+                      uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t xyz = __ldg(cells + tid / n_rep);
+        int x, y, z;
+        cell_xyz(xyz, d, x, y, z);
+        Cell8 c0;
+        if (!load_cell(links, surf, d, x, y, z, c0)) continue;
+        const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
+        float n0[3];
+        cell_normal(c0, n0);
+        Cell8 cn[3];   // neighbours along x, y, z
+        bool use[3];
+        // order of the reference: z, y, x (:1951-1986); the face shared with the neighbour decides connectivity
+        {
+            bool ok = load_cell(links, surf, d, x, y, z + 1, cn[2]);
+            ok = ok && (!con_check || face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv_set));
+            ok = ok && (!ignore_empty || (!empty000 || !cell_empty(cn[2], lv_set)));
+            use[2] = ok;
+        }
+        {
+            bool ok = load_cell(links, surf, d, x, y + 1, z, cn[1]);
+            ok = ok && (!con_check || face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv_set));
+            ok = ok && (!ignore_empty || (!empty000 || !cell_empty(cn[1], lv_set)));
+            use[1] = ok;
+        }
+        {
+            bool ok = load_cell(links, surf, d, x + 1, y, z, cn[0]);
+            ok = ok && (!con_check || face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv_set));
+            ok = ok && (!ignore_empty || (!empty000 || !cell_empty(cn[0], lv_set)));
+            use[0] = ok;
+        }
+        const int norm_count = (int)use[0] + (int)use[1] + (int)use[2];
+        const float N0 = NORM3_(n0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (!use[i]) continue;
+            float n1[3];
+            cell_normal(cn[i], n1);
+            const float N1 = NORM3_(n1);
+            float d0[3], d1[3];
+            if (use_l1) {
+                const float L[3] = {n0[0] / N0 - n1[0] / N1, n0[1] / N0 - n1[1] / N1, n0[2] / N0 - n1[2] / N1};
+                const float s[3] = {(L[0] > 0.f) ? 1.f : (L[0] == 0.f ? 0.f : -1.f), (L[1] > 0.f) ? 1.f : (L[1] == 0.f ? 0.f : -1.f),
+                                    (L[2] > 0.f) ? 1.f : (L[2] == 0.f ? 0.f : -1.f)};
+                d0[0] = s[0] * (-SQR_(n0[0]) / CUB_(N0) + 1.f / N0) + s[1] * (-n0[0] * n0[1] / CUB_(N0)) + s[2] * (-n0[0] * n0[2] / CUB_(N0));
+                d0[1] = s[0] * (-n0[0] * n0[1] / CUB_(N0)) + s[1] * (-SQR_(n0[1]) / CUB_(N0) + 1.f / N0) + s[2] * (-n0[1] * n0[2] / CUB_(N0));
+                d0[2] = s[0] * (-n0[0] * n0[2] / CUB_(N0)) + s[1] * (-n0[1] * n0[2] / CUB_(N0)) + s[2] * (-SQR_(n0[2]) / CUB_(N0) + 1.f / N0);
+                d1[0] = s[0] * (SQR_(n1[0]) / CUB_(N1) - 1.f / N1) + s[1] * (n1[0] * n1[1] / CUB_(N1)) + s[2] * (n1[0] * n1[2] / CUB_(N1));
+                d1[1] = s[0] * (n1[0] * n1[1] / CUB_(N1)) + s[1] * (SQR_(n1[1]) / CUB_(N1) - 1.f / N1) + s[2] * (n1[1] * n1[2] / CUB_(N1));
+                d1[2] = s[0] * (n1[0] * n1[2] / CUB_(N1)) + s[1] * (n1[1] * n1[2] / CUB_(N1)) + s[2] * (SQR_(n1[2]) / CUB_(N1) - 1.f / N1);
+            } else {
+                const float e0 = n0[0] / N0 - n1[0] / N1, e1 = n0[1] / N0 - n1[1] / N1, e2 = n0[2] / N0 - n1[2] / N1;
+                d0[0] = e0 * (-2.f * SQR_(n0[0]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e1 / CUB_(N0) + -2.f * n0[0] * n0[2] * e2 / CUB_(N0);
+                d0[1] = e1 * (-2.f * SQR_(n0[1]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e0 / CUB_(N0) + -2.f * n0[1] * n0[2] * e2 / CUB_(N0);
+                d0[2] = e2 * (-2.f * SQR_(n0[2]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[2] * e0 / CUB_(N0) + -2.f * n0[1] * n0[2] * e1 / CUB_(N0);
+                d1[0] = e0 * (2.f * SQR_(n1[0]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e1 / CUB_(N1) + 2.f * n1[0] * n1[2] * e2 / CUB_(N1);
+                d1[1] = e1 * (2.f * SQR_(n1[1]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e0 / CUB_(N1) + 2.f * n1[1] * n1[2] * e2 / CUB_(N1);
+                d1[2] = e2 * (2.f * SQR_(n1[2]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[2] * e0 / CUB_(N1) + 2.f * n1[1] * n1[2] * e1 / CUB_(N1);
+            }
+            const float sc = scale * 1.f / norm_count;
+            scatter_normal_grad(c0, d0, sc, mask, grad);
+            scatter_normal_grad(cn[i], d1, sc, mask, grad);
+        }
+    }
+}
+
+int check_common(const int32_t *links, const int32_t size[3], const void *data, const void *grad, const char *who) {
+    ASURF_REQUIRE(links && size && data && grad, ASURF_E_INVALID, "%s: null tensor", who);
+    ASURF_REQUIRE(size[0] >= 1 && size[1] >= 1 && size[2] >= 1, ASURF_E_INVALID, "%s: bad grid size", who);
+    return 0;
+}
+
+}  // namespace
+}  // namespace asurf
+
+using namespace asurf;
+
+extern "C" int asurf_tv(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols, int32_t start_dim,
+                        int32_t end_dim, int32_t ignore_edge, float *out_scalar, void *stream) {
+    int rc = check_common(links, size, data, out_scalar, "tv");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID, "tv: bad channel range");
+    const int64_t nl = (int64_t)(size[0] - 1) * (size[1] - 1) * (size[2] - 1);
+    const int64_t Q = nl * (end_dim - start_dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    ASURF_CUDA(cudaMemsetAsync(out_scalar, 0, sizeof(float), st));
+    if (Q <= 0) return 0;
+    Dims d = {size[0], size[1], size[2]};
+    tv_value_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(links, data, n_cols, d, start_dim, end_dim, 1.f / (float)nl, Q,
+                                                           ignore_edge, out_scalar);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "tv launch");
+}
+
+extern "C" int asurf_tv_grad(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
+                             int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge, float *grad_data,
+                             void *stream) {
+    int rc = check_common(links, size, data, grad_data, "tv_grad");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID, "tv_grad: bad channel range");
+    const int64_t nl = (int64_t)(size[0] - 1) * (size[1] - 1) * (size[2] - 1);
+    const int64_t Q = nl * (end_dim - start_dim);
+    if (Q <= 0) return 0;
+    Dims d = {size[0], size[1], size[2]};
+    tv_grad_dense_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(links, data, n_cols, d, start_dim, end_dim,
+                                                                                   scale / (float)nl, Q, ignore_edge, grad_data);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "tv_grad launch");
+}
+
+extern "C" int asurf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
+                                    const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, int32_t start_dim,
+                                    int32_t end_dim, float scale, int32_t ignore_edge, int32_t ignore_last_z,
+                                    float *grad_data, void *stream) {
+    int rc = check_common(links, size, data, grad_data, "tv_grad_sparse");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID,
+                  "tv_grad_sparse: bad channel range");
+    if (n_cells <= 0) return 0;
+    ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "tv_grad_sparse: null cell list");
+    const int64_t Q = n_cells * (end_dim - start_dim);
+    Dims d = {size[0], size[1], size[2]};
+    tv_grad_sparse_kernel<false><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+        links, data, n_cols, nullptr, 0, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q, ignore_edge, 0.f,
+        ignore_last_z, 0, mask_out, grad_data);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "tv_grad_sparse launch");
+}
+
+extern "C" int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf, int32_t n_cols,
+                                         const float *density, int32_t density_cols, const int32_t *rand_cells,
+                                         int64_t n_cells, uint8_t *mask_out, int32_t start_dim, int32_t end_dim, float scale,
+                                         int32_t ignore_edge, float edge_value, int32_t ignore_last_z,
+                                         int32_t alpha_dependency, float *grad_data, void *stream) {
+    int rc = check_common(links, size, surf, grad_data, "surf_tv_grad_sparse");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID,
+                  "surf_tv_grad_sparse: bad channel range");
+    ASURF_REQUIRE(!alpha_dependency || density, ASURF_E_INVALID, "surf_tv_grad_sparse: alpha_dependency needs the density");
+    if (n_cells <= 0) return 0;
+    ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "surf_tv_grad_sparse: null cell list");
+    const int64_t Q = n_cells * (end_dim - start_dim);
+    Dims d = {size[0], size[1], size[2]};
+    tv_grad_sparse_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+        links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q,
+        ignore_edge, edge_value, ignore_last_z, alpha_dependency, mask_out, grad_data);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "surf_tv_grad_sparse launch");
+}
+
+extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,
+                                                     int32_t alpha_cols, const float *surf, int32_t surf_cols,
+                                                     const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out,
+                                                     float scale_alpha, float scale_surf, int32_t surf_decrease,
+                                                     float surf_thresh, float alpha_bound, float surf_bound,
+                                                     float *grad_alpha, float *grad_surf, void *stream) {
+    int rc = check_common(links, size, alpha, grad_alpha, "alpha_surf_sparsify_grad_sparse");
+    if (rc) return rc;
+    ASURF_REQUIRE(surf && grad_surf, ASURF_E_INVALID, "alpha_surf_sparsify_grad_sparse: null surface tensor");
+    if (n_cells <= 0) return 0;
+    ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "alpha_surf_sparsify_grad_sparse: null cell list");
+    sparsify_kernel<<<loss_grid(n_cells), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+        links, alpha, alpha_cols, surf, surf_cols, rand_cells, n_cells, scale_alpha, scale_surf, surf_decrease, surf_thresh,
+        alpha_bound, surf_bound, mask_out, grad_alpha, grad_surf);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "alpha_surf_sparsify_grad_sparse launch");
+}
+
+extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
+                                                const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
+                                                int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,
+                                                int32_t ignore_empty, int32_t use_l1, float *grad_data, void *stream) {
+    int rc = check_common(links, size, surf, grad_data, "surface_normal_grad_sparse");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim, ASURF_E_INVALID, "surface_normal_grad_sparse: bad channel range");
+    if (n_cells <= 0) return 0;
+    ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "surface_normal_grad_sparse: null cell list");
+    const int n_rep = end_dim - start_dim;   // the reference launches one thread per (cell, channel) and ignores the channel
+    const int64_t Q = n_cells * n_rep;
+    Dims d = {size[0], size[1], size[2]};
+    surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+        links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
+        grad_data);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "surface_normal_grad_sparse launch");
+}

@@ -151,8 +151,13 @@ extern "C" int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t 
                                                                          lr, eps, minval, lr_last);
     } else if (indexer_kind == 1) {
         if (n_index == 0 || n_elem == 0) return 0;  // size(0) == 0 -> skip (:189)
-        masked_rows_kernel<true><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer, n_rows,
-                                                                          n_cols, beta, lr, eps, minval, lr_last);
+        // narrow tensors (density, surface: C = 1) gain nothing from a warp per row: one thread per element instead
+        if (n_cols < 8)
+            rmsprop_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer, n_elem,
+                                                                            n_cols, beta, lr, eps, minval, lr_last);
+        else
+            masked_rows_kernel<true><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer,
+                                                                              n_rows, n_cols, beta, lr, eps, minval, lr_last);
     } else if (indexer_kind == 2) {
         if (n_index == 0) return 0;
         rmsprop_index_kernel<<<stream_grid(n_index * n_cols), 256, 0, st>>>(data, rms, grad, (const int64_t *)indexer,
@@ -161,6 +166,7 @@ extern "C" int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t 
     } else {
         ASURF_REQUIRE(false, ASURF_E_INVALID, "rmsprop_step: bad indexer kind %d", indexer_kind);
     }
+    note_launches(1);
     return check_cuda(cudaGetLastError(), "rmsprop_step launch");
 }
 
@@ -176,8 +182,12 @@ extern "C" int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t 
         sgd_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, nullptr, n_elem, n_cols, lr, lr_last);
     } else if (indexer_kind == 1) {
         if (n_index == 0 || n_elem == 0) return 0;
-        masked_rows_kernel<false><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, nullptr, grad, (const uint8_t *)indexer,
-                                                                           n_rows, n_cols, 0.f, lr, 0.f, 0.f, lr_last);
+        if (n_cols < 8)
+            sgd_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, (const uint8_t *)indexer, n_elem, n_cols,
+                                                                        lr, lr_last);
+        else
+            masked_rows_kernel<false><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, nullptr, grad, (const uint8_t *)indexer,
+                                                                               n_rows, n_cols, 0.f, lr, 0.f, 0.f, lr_last);
     } else if (indexer_kind == 2) {
         if (n_index == 0) return 0;
         sgd_index_kernel<<<stream_grid(n_index * n_cols), 256, 0, st>>>(data, grad, (const int64_t *)indexer, n_index,
@@ -185,5 +195,6 @@ extern "C" int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t 
     } else {
         ASURF_REQUIRE(false, ASURF_E_INVALID, "sgd_step: bad indexer kind %d", indexer_kind);
     }
+    note_launches(1);
     return check_cuda(cudaGetLastError(), "sgd_step launch");
 }

@@ -1325,6 +1325,7 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
     pre.n_rays = ctr + 2;
     pre.enabled = 1;
     premarch_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, rgb_out, cache_n);
+    note_launches(1);
     return check_cuda(cudaGetLastError(), "premarch launch");
 }
 
@@ -1359,6 +1360,7 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
         surf_trav_kernel<false, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
             g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr, pre);
     }
+    note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_trav_forward launch");
 }
 
@@ -1386,6 +1388,7 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     surf_trav_kernel<true, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
         g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg, ctr + 1,
         pre);
+    note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_trav_backward launch");
 }
 
@@ -1473,6 +1476,7 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
         cudaEventRecord(pe[2], st);
         ++g_prof.n;
     }
+    note_launches(2);
     return check_cuda(cudaGetLastError(), "surf_trav_fused launch");
 }
 
@@ -1495,6 +1499,7 @@ static int debug_launch(const asurf_grid_t *grid, const asurf_rays_t *rays, cons
     surf_trav_kernel<false, true><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
         g, *opt, rays->origins, rays->dirs, rays->n_rays, (float *)g_ws_dbg.ptr, nullptr, nullptr, f, cache, grads, dbg,
         ctr, PreP());
+    note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_trav debug launch");
 }
 

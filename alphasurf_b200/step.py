@@ -1,0 +1,166 @@
+"""One alpha-Surf training iteration (config C3 of SURVEY.md 8d) as ``opt/opt.py`` drives it through ``svox2.csrc``.
+
+Host-side mirror of /root/reference/opt/opt.py:800-1125 + the ``SparseGrid`` helpers it calls
+(/root/reference/svox2/svox2.py:3480-3640 ``volume_render_fused``, :4950-5163 and :5690-5724 ``inplace_*_grad``,
+:5972-6100 ``optim_*_step``, :6314-6376 indexers / cell lists).  Every line below is a call into the
+``svox2.csrc``-compatible module; no arithmetic happens in Python.  bench.py times this step; the GPU tests compare it
+with the same sequence run on the UNMODIFIED reference kernels.
+"""
+import numpy as np
+import torch
+
+from . import synth
+
+RMS_BETA, RMS_EPS = 0.95, 1e-8   # opt/util/config_util.py:473 (rms_beta), svox2.py:5972 (epsilon)
+SURFACE_TYPE_SDF = 102
+BASIS_TYPE_SH = 1
+FUSED_ORDER = ["beta_loss", "sparsity_loss", "fused_surf_norm_reg_scale", "fused_surf_norm_reg_con_check",
+               "fused_surf_norm_reg_ignore_empty", "lambda_l2", "lambda_l1", "lambda_l_dist", "lambda_l_entropy",
+               "no_norm_weight_l_entropy", "lambda_l_dist_a", "lambda_l_entropy_a", "lambda_l_samp_dist", "lambda_l_di",
+               "l_di_alpha_thresh", "surf_sparse_alpha_thresh", "lambda_inplace_surf_sparse", "lambda_inwards_norm_loss",
+               "lambda_conv_mode_samp", "l_dist_max_sample"]
+
+
+# ---- SparseGrid._to_cpp / Rays._to_cpp / RenderOptions._to_cpp (svox2.py:6234-6272, :118-128, :57-90) ---------------
+def grid_to_cpp(C, sg):
+    g = C.SparseGridSpec()
+    g.density_data = sg.density
+    g.surface_type = SURFACE_TYPE_SDF
+    g.surface_data = sg.surface
+    g.level_set_data = sg.level_set
+    g.sh_data = sg.sh
+    g.links = sg.links
+    g._offset = sg.offset
+    g._scaling = sg.scaling
+    g.basis_dim = sg.basis_dim
+    g.basis_type = BASIS_TYPE_SH
+    g.fake_sample_std = float(sg.fake_sample_std)
+    g.truncated_vol_render_a = float(sg.truncated_vol_render_a)
+    return g
+
+
+def rays_to_cpp(C, origins, dirs):
+    r = C.RaysSpec()
+    r.origins = origins
+    r.dirs = dirs
+    r.masks = torch.ones((origins.shape[0],), dtype=torch.bool, device=origins.device)
+    return r
+
+
+def opt_to_cpp(C, d):
+    o = C.RenderOptions()
+    for k, v in d.items():
+        if k != "backend":
+            setattr(o, k, v)
+    return o
+
+
+def fused_positional(fd):
+    return [fd[k] for k in FUSED_ORDER]
+
+
+def c3_hyper():
+    """Regulariser / optimizer settings of opt/configs/surface_cuda_syn.yaml (+ config_util defaults)."""
+    return dict(lr_density=1e-2, lr_surface=1e-5, lr_sh=1e-3,
+                lambda_tv_alpha=1e-5, tv_sparsity=0.01,
+                lambda_tv_surface=1e-3, tv_surface_sparsity=1.0, surf_tv_ignore_edge=True, surf_tv_edge_value=-1.0,
+                surf_tv_alpha_dependency=False,
+                lambda_normal_loss=1e-6, norm_surface_sparsity=1.0, norm_con_check=False, norm_ignore_empty=False,
+                lambda_sparsify_alpha=1e-9, lambda_sparsify_surf=0.0, alpha_surf_sparsify_sparsity=0.1,
+                sparsify_surf_decrease=True, sparsify_surf_thresh=0.15, alpha_sparsify_bound=0.0,
+                surf_sparsify_bound=-0.1)
+
+
+class TrainStep:
+    """Grid state + the per-iteration call sequence.  ``C`` is the csrc-compatible module (ours or the reference's)."""
+
+    def __init__(self, C, sg, render_opts=None, fused=None, hyper=None, seed=synth.SEED):
+        self.C, self.sg = C, sg
+        dev = sg.density.device
+        self.dev = dev
+        self.opts = render_opts or synth.alphasurf_render_options()
+        self.fused = fused or synth.alphasurf_fused_args()
+        self.hp = hyper or c3_hyper()
+        self.grad = {k: torch.zeros_like(getattr(sg, k)) for k in ("density", "surface", "sh")}
+        self.rms = {k: torch.zeros_like(getattr(sg, k)) for k in ("density", "surface", "sh")}
+        self.mask = torch.zeros((sg.capacity,), dtype=torch.bool, device=dev)       # sparse_grad_indexer
+        self.mask_sh = torch.zeros((sg.capacity,), dtype=torch.bool, device=dev)    # sparse_sh_grad_indexer
+        self.rng = np.random.RandomState(seed & 0x7fffffff)
+        self.grid_size = sg.links.numel()
+        # _get_rand_cells_non_empty (svox2.py:6354-6376): links never change during training -> computed once
+        self.non_empty = torch.where(sg.links.view(-1) >= 0)[0].int().contiguous()
+        self.grid_spec, self.opt_spec = grid_to_cpp(C, sg), opt_to_cpp(C, self.opts)
+        gs = C.GridOutputGrads()
+        gs.grad_density_out, gs.grad_surface_out, gs.grad_sh_out = self.grad["density"], self.grad["surface"], self.grad["sh"]
+        gs.mask_out = self.mask
+        self.grad_spec = gs
+        self.fpos = fused_positional(self.fused)
+        self.no_mask = torch.empty((0,), dtype=torch.bool, device=dev)
+
+    # ---- cell lists ----------------------------------------------------------------------------------------------
+    def rand_cells(self, frac):           # svox2.py:6335-6352, contiguous=True
+        if frac >= 1.0:
+            return None
+        n = max(int(frac * self.grid_size), 1)
+        start = int(self.rng.randint(0, self.grid_size))
+        arr = torch.arange(start, start + n, dtype=torch.int32, device=self.dev)
+        if start > self.grid_size - n:
+            arr[self.grid_size - n - start:] -= self.grid_size
+        return arr
+
+    def rand_cells_non_empty(self, frac):  # svox2.py:6354-6373, contiguous=True
+        if frac >= 1.0:
+            return self.non_empty
+        ne = self.non_empty.shape[0]
+        n = int(ne * frac)
+        start = int(self.rng.randint(0, ne - n + 1))
+        return self.non_empty[start:start + n]
+
+    # ---- the iteration -----------------------------------------------------------------------------------------------
+    def render(self, origins, dirs, rgb_gt, rgb_out):
+        """volume_render_fused (svox2.py:3480-3640): fresh bool indexer, fused kernel, sh indexer = its copy."""
+        self.mask.zero_()
+        self.C.volume_render_surf_trav_fused(self.grid_spec, rays_to_cpp(self.C, origins, dirs), self.opt_spec, rgb_gt,
+                                             *self.fpos, rgb_out, self.grad_spec)
+        self.mask_sh.copy_(self.mask)
+
+    def step(self, origins, dirs, rgb_gt, rgb_out, between=None):
+        self.render(origins, dirs, rgb_gt, rgb_out)
+        if between is not None:
+            between(self)      # multi-GPU: gradient / mask exchange (alphasurf_b200.dist)
+        self.regularisers()
+        self.optimizer()
+
+    def regularisers(self):
+        C, sg, hp, g = self.C, self.sg, self.hp, self.grad
+        if hp["lambda_tv_alpha"] > 0:      # inplace_tv_grad, opt.py:952-957
+            cells = self.rand_cells(hp["tv_sparsity"])
+            C.tv_grad_sparse(sg.links, sg.density, cells, self.mask, 0, 1, hp["lambda_tv_alpha"], False, 2.0, False,
+                             bool(self.opts["last_sample_opaque"]), -1.0, -1.0, g["density"])
+        if hp["lambda_tv_surface"] > 0:    # inplace_tv_surface_grad, opt.py:959-968
+            cells = self.rand_cells_non_empty(hp["tv_surface_sparsity"])
+            C.surf_tv_grad_sparse(sg.links, sg.surface, sg.density, cells, self.mask, 0, 1, hp["lambda_tv_surface"],
+                                  hp["surf_tv_ignore_edge"], hp["surf_tv_edge_value"], bool(self.opts["last_sample_opaque"]),
+                                  -1.0, -1.0, hp["surf_tv_alpha_dependency"], g["surface"])
+        if hp["lambda_normal_loss"] > 0:   # inplace_surface_normal_grad, opt.py:970-981
+            cells = self.rand_cells_non_empty(hp["norm_surface_sparsity"])
+            C.surface_normal_grad_sparse(sg.links, sg.surface, cells, self.mask, 0.0, 0, 1, hp["lambda_normal_loss"], 0.0,
+                                         -1.0, -1.0, hp["norm_con_check"], hp["norm_ignore_empty"], True, g["surface"])
+        if hp["lambda_sparsify_alpha"] > 0 or hp["lambda_sparsify_surf"] > 0:   # opt.py:1046-1060
+            cells = self.rand_cells_non_empty(hp["alpha_surf_sparsify_sparsity"])
+            C.alpha_surf_sparsify_grad_sparse(sg.links, sg.density, sg.surface, cells, self.mask, hp["lambda_sparsify_alpha"],
+                                              hp["lambda_sparsify_surf"], hp["sparsify_surf_decrease"],
+                                              hp["sparsify_surf_thresh"], hp["alpha_sparsify_bound"],
+                                              hp["surf_sparsify_bound"], g["density"], g["surface"])
+
+    def optimizer(self):
+        """optim_density_step / optim_surface_step / optim_sh_step with the bool indexers (svox2.py:5972-6100).  The
+        reference converts a sparse mask to an index list on the host (a count_nonzero().item() sync per tensor,
+        :6314-6333); the masked kernels here make that conversion unnecessary, the update is the same."""
+        C, sg, hp = self.C, self.sg, self.hp
+        C.rmsprop_step(sg.density, self.rms["density"], self.grad["density"], self.mask, RMS_BETA, hp["lr_density"], RMS_EPS,
+                       -1e9, hp["lr_density"])
+        C.rmsprop_step(sg.surface, self.rms["surface"], self.grad["surface"], self.mask, RMS_BETA, hp["lr_surface"], RMS_EPS,
+                       -1e9, hp["lr_surface"])
+        C.rmsprop_step(sg.sh, self.rms["sh"], self.grad["sh"], self.mask_sh, RMS_BETA, hp["lr_sh"], RMS_EPS, -1e9,
+                       hp["lr_sh"])

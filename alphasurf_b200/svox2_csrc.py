@@ -328,6 +328,106 @@ def sgd_step(data, grad, indexer, lr, lr_last):
             C.c_int64(max(n, 0)), C.c_float(lr), C.c_float(lr_last), capi.current_stream()), "sgd_step")
 
 
+# ---- grid-side regularisers (loss_kernel.cu:1214-1622) ------------------------------------------------------------------
+def _mask_ptr(mask_out):
+    """The reference passes mask_out.data_ptr() when dim() > 0 (:1368); an empty tensor means "no mask"."""
+    _check_input(mask_out, "mask_out")
+    return capi.ptr(mask_out) if (mask_out.dim() > 0 and mask_out.numel() > 0) else None
+
+
+def _check_loss_common(links, data, grad_data=None):
+    _check_input(data, "data")
+    _check_input(links, "links")
+    if grad_data is not None:
+        _check_input(grad_data, "grad_data")
+        if not grad_data.is_floating_point() or grad_data.dim() != 2:
+            raise RuntimeError("grad_data must be a 2-D floating point tensor")
+    if not data.is_floating_point() or links.is_floating_point() or data.dim() != 2 or links.dim() != 3:
+        raise RuntimeError("data must be a 2-D floating point tensor and links a 3-D integer tensor")
+    _check_f32(data, "data")
+    if links.dtype != torch.int32:
+        raise RuntimeError("links must be int32")
+
+
+def _check_cells(rand_cells):
+    _check_input(rand_cells, "rand_cells")
+    if rand_cells.dtype != torch.int32:
+        raise RuntimeError("rand_cells must be int32")
+
+
+def tv(links, data, start_dim, end_dim, use_logalpha, logalpha_delta, ignore_edge, ndc_coeffx, ndc_coeffy):
+    _check_loss_common(links, data)
+    out = torch.zeros((), dtype=data.dtype, device=data.device)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_tv(capi.ptr(links), capi.size3(links.shape), capi.ptr(data), C.c_int32(data.shape[1]),
+                                       C.c_int32(start_dim), C.c_int32(end_dim), C.c_int32(bool(ignore_edge)),
+                                       capi.ptr(out), capi.current_stream()), "tv")
+    return out
+
+
+def tv_grad(links, data, start_dim, end_dim, scale, use_logalpha, logalpha_delta, ignore_edge, ndc_coeffx, ndc_coeffy,
+            grad_data):
+    _check_loss_common(links, data, grad_data)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_tv_grad(capi.ptr(links), capi.size3(links.shape), capi.ptr(data),
+                                            C.c_int32(data.shape[1]), C.c_int32(start_dim), C.c_int32(end_dim),
+                                            C.c_float(scale), C.c_int32(bool(ignore_edge)), capi.ptr(grad_data),
+                                            capi.current_stream()), "tv_grad")
+
+
+def tv_grad_sparse(links, data, rand_cells, mask_out, start_dim, end_dim, scale, use_logalpha, logalpha_delta,
+                   ignore_edge, ignore_last_z, ndc_coeffx, ndc_coeffy, grad_data):
+    _check_loss_common(links, data, grad_data)
+    _check_cells(rand_cells)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_tv_grad_sparse(
+            capi.ptr(links), capi.size3(links.shape), capi.ptr(data), C.c_int32(data.shape[1]), capi.ptr(rand_cells),
+            C.c_int64(rand_cells.shape[0]), _mask_ptr(mask_out), C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale),
+            C.c_int32(bool(ignore_edge)), C.c_int32(bool(ignore_last_z)), capi.ptr(grad_data), capi.current_stream()),
+            "tv_grad_sparse")
+
+
+def surf_tv_grad_sparse(links, data, density_data, rand_cells, mask_out, start_dim, end_dim, scale, ignore_edge,
+                        edge_value, ignore_last_z, ndc_coeffx, ndc_coeffy, alpha_dependency, grad_data):
+    _check_loss_common(links, data, grad_data)
+    _check_input(density_data, "density_data")
+    _check_cells(rand_cells)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_surf_tv_grad_sparse(
+            capi.ptr(links), capi.size3(links.shape), capi.ptr(data), C.c_int32(data.shape[1]), capi.ptr(density_data),
+            C.c_int32(density_data.shape[1]), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]), _mask_ptr(mask_out),
+            C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale), C.c_int32(bool(ignore_edge)), C.c_float(edge_value),
+            C.c_int32(bool(ignore_last_z)), C.c_int32(bool(alpha_dependency)), capi.ptr(grad_data), capi.current_stream()),
+            "surf_tv_grad_sparse")
+
+
+def alpha_surf_sparsify_grad_sparse(links, alpha_data, surf_data, rand_cells, mask_out, scale_alpha, scale_surf,
+                                    surf_sparse_decrease, surf_sparse_thresh, alpha_bound, surf_bound, grad_alpha, grad_surf):
+    _check_loss_common(links, alpha_data, grad_alpha)
+    _check_input(surf_data, "surf_data")
+    _check_input(grad_surf, "grad_surf")
+    _check_cells(rand_cells)
+    with torch.cuda.device(alpha_data.device):
+        capi.check(capi.lib().asurf_alpha_surf_sparsify_grad_sparse(
+            capi.ptr(links), capi.size3(links.shape), capi.ptr(alpha_data), C.c_int32(alpha_data.shape[1]),
+            capi.ptr(surf_data), C.c_int32(surf_data.shape[1]), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]),
+            _mask_ptr(mask_out), C.c_float(scale_alpha), C.c_float(scale_surf), C.c_int32(bool(surf_sparse_decrease)),
+            C.c_float(surf_sparse_thresh), C.c_float(alpha_bound), C.c_float(surf_bound), capi.ptr(grad_alpha),
+            capi.ptr(grad_surf), capi.current_stream()), "alpha_surf_sparsify_grad_sparse")
+
+
+def surface_normal_grad_sparse(links, data, rand_cells, mask_out, lv_set, start_dim, end_dim, scale, eikonal_scale,
+                               ndc_coeffx, ndc_coeffy, con_check, ignore_empty, use_l1, grad_data):
+    _check_loss_common(links, data, grad_data)
+    _check_cells(rand_cells)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_surface_normal_grad_sparse(
+            capi.ptr(links), capi.size3(links.shape), capi.ptr(data), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]),
+            _mask_ptr(mask_out), C.c_float(lv_set), C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale),
+            C.c_int32(bool(con_check)), C.c_int32(bool(ignore_empty)), C.c_int32(bool(use_l1)), capi.ptr(grad_data),
+            capi.current_stream()), "surface_normal_grad_sparse")
+
+
 # ---- test hooks -----------------------------------------------------------------------------------------------------------
 def debug_ray_bounds(grid, rays, opt):
     """(Q,9) grid-space rays as the kernels see them: origin3, dir3, tmin, tmax, world_step."""

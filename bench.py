@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one training iteration of config C3 on one batch of synthetic rays per GPU:
-fused surf_trav render forward+backward (L2 + entropy + conv-mode losses) -> grid regularisers that exist in this
-build -> RMSprop steps on density / surface / SH for the touched voxels, on a synthetic 512^3 SH-degree-2 shell grid.
+fused surf_trav render forward+backward (L2 + entropy + conv-mode losses) -> density TV, surface TV, surface-normal and
+opacity-sparsity regularisers -> RMSprop steps on density / surface / SH for the touched voxels, on a synthetic 512^3 SH-degree-2 shell grid.
 Metric: rays/s, whole job (all ranks).  ``--impl reference`` times the CPU oracle (a port of the reference CUDA
 semantics; the reference has no compiled CPU implementation) on a bounded ray sample of the same workload.
 """
@@ -137,7 +137,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, sample_note=None):
-    c = {"workload": "C3: alpha-Surf surf_trav fused render fwd+bwd + RMSprop(density,surface,sh) step, synthetic "
+    c = {"workload": "C3: alpha-Surf surf_trav fused render fwd+bwd + TV/normal/sparsity regularisers + RMSprop(density,"
+                     "surface,sh) step, synthetic "
                      "%d^3 shell grid G(R) SH deg 2 (D=27), %d rays/step/GPU, options of surface_cuda_syn.yaml"
                      % (args.reso, args.rays),
          "grid": "%d^3" % args.reso, "rays_per_step_per_gpu": args.rays, "sh_dim": 27,
@@ -152,8 +153,8 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from alphasurf_b200 import capi, synth
+    from alphasurf_b200 import step as S
     from alphasurf_b200 import svox2_csrc as C
-    from tests import helpers as H
     import ctypes
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
@@ -161,13 +162,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     Q, D = args.rays, 27
     sg = synth.make_shell_grid(args.reso, basis_dim=9, variant="G", device="cpu").to(dev)
-    N = sg.capacity
-    opts, fused = synth.alphasurf_render_options(), synth.alphasurf_fused_args()
-    grid = H.fill_grid_spec(C, sg)
-    opt = H.fill_opt(C, opts)
-    G = H.GradSet(sg, dev, with_std=False)
-    gspec = G.spec(C)
-    rms = {k: torch.zeros_like(getattr(sg, k)) for k in ("density", "surface", "sh")}
+    ts = S.TrainStep(C, sg)
     NB = args.batches
     dev_batches, host_batches = [], []
     for b in range(NB):
@@ -177,23 +172,31 @@ def run_ours(args, rank, world, local_rank):
     rgb_out = torch.zeros((Q, 3), dtype=torch.float32, device=dev)
     rgb_host = torch.zeros((Q, 3), dtype=torch.float32).pin_memory()
     stage = tuple(torch.empty((Q, 3), dtype=torch.float32, device=dev) for _ in range(3))
-    fpos = H.fused_positional(fused)
+    exchange = None
     if world > 1:
+        from alphasurf_b200 import dist as adist
         C.set_loss_norm_rays(Q * world)
-    launches = {"n": 0}
+        ex = adist.GradExchange(ts)
+        exchange = ex.run
+    L = capi.lib()
+    phase_ev = []   # per step: 4 events (start, after render [+ exchange], after regularisers, after optimizer)
 
-    def device_step(o, d, gt):
-        G.mask.zero_()
-        rays = H.fill_rays_spec(C, o, d)
-        C.volume_render_surf_trav_fused(grid, rays, opt, gt, *fpos, rgb_out, gspec)
-        launches["n"] += 2
-        if world > 1:
-            from alphasurf_b200 import dist as adist
-            adist.allreduce_grads(G)
-        C.rmsprop_step(sg.density, rms["density"], G.density, G.mask, RMS_BETA, LR["density"], RMS_EPS, -1e9, LR["density"])
-        C.rmsprop_step(sg.surface, rms["surface"], G.surface, G.mask, RMS_BETA, LR["surface"], RMS_EPS, -1e9, LR["surface"])
-        C.rmsprop_step(sg.sh, rms["sh"], G.sh, G.mask, RMS_BETA, LR["sh"], RMS_EPS, -1e9, LR["sh"])
-        launches["n"] += 3
+    def device_step(o, d, gt, record=False):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if record:
+            evs[0].record()
+        ts.render(o, d, gt, rgb_out)
+        if exchange is not None:
+            exchange(ts)
+        if record:
+            evs[1].record()
+        ts.regularisers()
+        if record:
+            evs[2].record()
+        ts.optimizer()
+        if record:
+            evs[3].record()
+            phase_ev.append(evs)
 
     def barrier():
         if world > 1:
@@ -208,28 +211,27 @@ def run_ours(args, rank, world, local_rank):
         return x
 
     # march counters of batch 0 (outside the timed region) -> algorithmic bytes
-    st = C.render_stats(grid, H.fill_rays_spec(C, dev_batches[0][0], dev_batches[0][1]), opt)
+    st = C.render_stats(ts.grid_spec, S.rays_to_cpp(C, dev_batches[0][0], dev_batches[0][1]), ts.opt_spec)
     fwd_bytes, bwd_bytes = algorithmic_bytes(st, Q, D)
 
     # ---------------- device-resident timing ----------------
     for i in range(args.warmup):
         device_step(*dev_batches[i % NB])
-    L = capi.lib()
     capi.check(L.asurf_profile_enable(ctypes.c_int32(args.steps)), "profile_enable")
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
-    launches["n"] = 0
+    L.asurf_launch_count(ctypes.c_int32(1))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        device_step(*dev_batches[(args.warmup + i) % NB])
+        device_step(*dev_batches[(args.warmup + i) % NB], record=True)
     ev1.record()
     barrier()
+    n_launch = int(L.asurf_launch_count(ctypes.c_int32(0)))
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    n_launch = launches["n"]
     ncalls, fms, bms = ctypes.c_int32(0), ctypes.c_float(0), ctypes.c_float(0)
     capi.check(L.asurf_profile_read(ctypes.byref(ncalls), ctypes.byref(fms), ctypes.byref(bms)), "profile_read")
     capi.check(L.asurf_profile_enable(ctypes.c_int32(0)), "profile_disable")
@@ -237,6 +239,11 @@ def run_ours(args, rank, world, local_rank):
     bwd_ms = bms.value / max(ncalls.value, 1)
     ms_step = ms_total / args.steps
     value = Q * world * args.steps / (ms_total * 1e-3)
+    phases = {"render_ms": 0.0, "regularisers_ms": 0.0, "optimizer_ms": 0.0}
+    for evs in phase_ev:
+        phases["render_ms"] += evs[0].elapsed_time(evs[1]) / len(phase_ev)
+        phases["regularisers_ms"] += evs[1].elapsed_time(evs[2]) / len(phase_ev)
+        phases["optimizer_ms"] += evs[2].elapsed_time(evs[3]) / len(phase_ev)
 
     # ---------------- end to end: host buffers in, colours out, through the svox2.csrc-compatible API ----------------
     def e2e_step(b):
@@ -280,16 +287,21 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 3 * Q * 3 * 4, "d2h_bytes_per_step": Q * 3 * 4,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": n_launch,
-        "roofline": {"bound": "hbm", "kernel": "surf_trav_kernel<%s>" % dom[0], "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "surf_trav fused render, %s pass (pre-march + shading kernels)" % dom[0],
+                     "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom[2], "kernel_ms": dom[1],
                      "kernels": {"forward_ms": fwd_ms, "backward_ms": bwd_ms, "forward_bytes": fwd_bytes,
-                                 "backward_bytes": bwd_bytes},
+                                 "backward_bytes": bwd_bytes,
+                                 "fused_frac": (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak
+                                 if fwd_ms + bwd_ms > 0 else 0.0},
                      "counters_per_ray": {k: st[k] / Q for k in ("n_steps", "n_linked", "n_active", "n_samples")}},
+        "step_phases": phases,
+        "render_only_rays_per_s": Q * world / ((fwd_ms + bwd_ms) * 1e-3) if fwd_ms + bwd_ms > 0 else None,
     }
     if world == 1 and not args.no_extras:
-        line["cpu_baseline"] = cpu_baseline(args, sg, opts, fused, host_batches[0])
-        ref = reference_cuda_same_gpu(args, sg, opts, fpos, dev_batches, H)
+        line["cpu_baseline"] = cpu_baseline(args, sg, ts.opts, ts.fused, host_batches[0])
+        ref = reference_cuda_same_gpu(args, sg, dev_batches)
         if ref is not None:
             line["reference_cuda_same_gpu"] = ref
     print(json.dumps(line), flush=True)
@@ -317,37 +329,43 @@ def cpu_baseline(args, sg, opts, fused, batch0):
                       % (n, reps, dt)}
 
 
-def reference_cuda_same_gpu(args, sg, opts, fpos, dev_batches, H):
-    """Extra (not part of the contract): the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same GPU."""
+def reference_cuda_same_gpu(args, sg, dev_batches):
+    """Extra (not part of the contract): the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same GPU, driven
+    through the same TrainStep sequence (its own copy of the grid)."""
     import torch
+    from alphasurf_b200 import step as S
+    from tests import helpers as H
     try:
         ref = H.load_reference_cuda()
     except Exception as e:  # noqa
         return {"unavailable": repr(e)[:200]}
     if ref is None:
         return None
-    Gr = H.GradSet(sg, sg.density.device, with_std=False)
-    grid, opt, gs = H.fill_grid_spec(ref, sg), H.fill_opt(ref, opts), Gr.spec(ref)
+    from alphasurf_b200 import synth
+    sg2 = synth.SynthGrid(sg.links, sg.density.clone(), sg.surface.clone(), sg.sh.clone(), sg.level_set, sg.offset,
+                          sg.scaling, sg.basis_dim, sg.fake_sample_std, sg.truncated_vol_render_a, dict(sg.meta))
+    ts = S.TrainStep(ref, sg2)
     Q = dev_batches[0][0].shape[0]
     out = torch.zeros((Q, 3), dtype=torch.float32, device=sg.density.device)
-
-    def call(b):
-        o, d, gt = dev_batches[b % len(dev_batches)]
-        ref.volume_render_surf_trav_fused(grid, H.fill_rays_spec(ref, o, d), opt, gt, *fpos, out, gs)
-
-    for i in range(3):
-        call(i)
+    n, ev = 5, [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for i in range(2):
+        ts.step(*dev_batches[i % len(dev_batches)], out)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n = 5
+    t_render = t_rest = 0.0
     for i in range(n):
-        call(3 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    return {"what": "reference render_ray_kernel + render_ray_backward_kernel (fused call only, no optimizer)",
-            "ms_per_call": ms, "rays_per_s": Q / (ms * 1e-3)}
+        o, d, gt = dev_batches[(2 + i) % len(dev_batches)]
+        ev[0].record()
+        ts.render(o, d, gt, out)
+        ev[1].record()
+        ts.regularisers()
+        ts.optimizer()
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_render += ev[0].elapsed_time(ev[1]) / n
+        t_rest += ev[1].elapsed_time(ev[2]) / n
+    return {"what": "reference svox2.csrc kernels, same C3 step sequence (fused render, regularisers, RMSprop)",
+            "render_ms": t_render, "regularisers_optimizer_ms": t_rest, "ms_per_step": t_render + t_rest,
+            "rays_per_s": Q / ((t_render + t_rest) * 1e-3), "render_only_rays_per_s": Q / (t_render * 1e-3)}
 
 
 def main():

@@ -172,6 +172,37 @@ int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int
 int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
                    const void *indexer, int64_t n_index, float lr, float lr_last, void *stream);
 
+/* ---- grid-side regularisers, loss_kernel.cu (gradients are ADDED into grad_*; mask_out may be NULL) ----
+ * `size` is links' shape; data tensors are (N, n_cols) row-major; rand_cells holds flat x*Y*Z + y*Z + z cell ids. */
+/* tv, loss_kernel.cu:1214-1247: mean over cells and channels [start_dim, end_dim) of sqrt(1e-5 + |grad|^2) -> *out_scalar */
+int asurf_tv(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols, int32_t start_dim,
+             int32_t end_dim, int32_t ignore_edge, float *out_scalar, void *stream);
+/* tv_grad, :1249-1287 (dense) */
+int asurf_tv_grad(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols, int32_t start_dim,
+                  int32_t end_dim, float scale, int32_t ignore_edge, float *grad_data, void *stream);
+/* tv_grad_sparse, :1327-1373 */
+int asurf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
+                         const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, int32_t start_dim,
+                         int32_t end_dim, float scale, int32_t ignore_edge, int32_t ignore_last_z, float *grad_data,
+                         void *stream);
+/* surf_tv_grad_sparse, :1375-1427 */
+int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf, int32_t n_cols,
+                              const float *density, int32_t density_cols, const int32_t *rand_cells, int64_t n_cells,
+                              uint8_t *mask_out, int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
+                              float edge_value, int32_t ignore_last_z, int32_t alpha_dependency, float *grad_data,
+                              void *stream);
+/* alpha_surf_sparsify_grad_sparse, :1512-1570 */
+int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,
+                                          int32_t alpha_cols, const float *surf, int32_t surf_cols,
+                                          const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float scale_alpha,
+                                          float scale_surf, int32_t surf_decrease, float surf_thresh, float alpha_bound,
+                                          float surf_bound, float *grad_alpha, float *grad_surf, void *stream);
+/* surface_normal_grad_sparse, :1572-1622 (eikonal_scale and the ndc coefficients of the reference are unused there) */
+int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
+                                     const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
+                                     int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,
+                                     int32_t ignore_empty, int32_t use_l1, float *grad_data, void *stream);
+
 /* ---- per-kernel timing (ours; feeds bench.py's roofline) ----
  * After asurf_profile_enable(capacity > 0) every asurf_surf_trav_fused call records CUDA events around its forward
  * and its backward kernel on the launching stream (up to `capacity` calls are kept).  asurf_profile_read waits for
@@ -179,6 +210,9 @@ int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t n_cols, int
  * asurf_profile_enable(0) switches it off and destroys the events. */
 int asurf_profile_enable(int32_t capacity);
 int asurf_profile_read(int32_t *n_calls, float *fwd_ms_sum, float *bwd_ms_sum);
+
+/* number of CUDA kernels this library has enqueued since the last reset (bench.py's gpu_launches) */
+uint64_t asurf_launch_count(int32_t reset);
 
 /* release the library's device workspaces (arena, scratch) */
 void asurf_release(void);

@@ -252,3 +252,50 @@ def sgd_step(data, grad, indexer, lr, lr_last):
     d = data[rows].astype(np.float64) - lrs[None, :].astype(np.float64) * grad[rows].astype(np.float64)
     data[rows] = d.astype(np.float32)
     grad[rows] = 0
+
+
+# ---- grid regularisers (oracle_loss.c) --------------------------------------------------------------------------------
+def _sz(links):
+    return (C.c_int32 * 3)(*[int(s) for s in links.shape])
+
+
+def tv(links, data, start_dim, end_dim, ignore_edge):
+    links, data = _np(links, np.int32), _np(data, np.float32)
+    lib().oracle_tv.restype = C.c_float
+    return float(lib().oracle_tv(_ptr(links), _sz(links), _ptr(data), C.c_int(data.shape[1]), C.c_int(start_dim),
+                                 C.c_int(end_dim), C.c_int(int(ignore_edge))))
+
+
+def tv_grad(links, data, start_dim, end_dim, scale, ignore_edge, grad):
+    links, data = _np(links, np.int32), _np(data, np.float32)
+    lib().oracle_tv_grad(_ptr(links), _sz(links), _ptr(data), C.c_int(data.shape[1]), C.c_int(start_dim), C.c_int(end_dim),
+                         C.c_float(scale), C.c_int(int(ignore_edge)), _ptr(grad))
+
+
+def tv_grad_sparse(links, data, density, cells, mask, start_dim, end_dim, scale, ignore_edge, edge_value, ignore_last_z,
+                   alpha_dependency, surf, grad):
+    links, data, cells = _np(links, np.int32), _np(data, np.float32), _np(cells, np.int32)
+    density = _np(density, np.float32)
+    lib().oracle_tv_grad_sparse(_ptr(links), _sz(links), _ptr(data), C.c_int(data.shape[1]), _ptr(density),
+                                C.c_int(0 if density is None else density.shape[1]), _ptr(cells),
+                                C.c_int64(cells.shape[0]), _ptr(mask), C.c_int(start_dim), C.c_int(end_dim),
+                                C.c_float(scale), C.c_int(int(ignore_edge)), C.c_float(edge_value),
+                                C.c_int(int(ignore_last_z)), C.c_int(int(alpha_dependency)), C.c_int(int(surf)), _ptr(grad))
+
+
+def alpha_surf_sparsify(links, alpha, surf, cells, mask, scale_alpha, scale_surf, surf_decrease, surf_thresh, alpha_bound,
+                        surf_bound, grad_alpha, grad_surf):
+    links, alpha, surf, cells = _np(links, np.int32), _np(alpha, np.float32), _np(surf, np.float32), _np(cells, np.int32)
+    lib().oracle_alpha_surf_sparsify(_ptr(links), _ptr(alpha), C.c_int(alpha.shape[1]), _ptr(surf), C.c_int(surf.shape[1]),
+                                     _ptr(cells), C.c_int64(cells.shape[0]), _ptr(mask), C.c_float(scale_alpha),
+                                     C.c_float(scale_surf), C.c_int(int(surf_decrease)), C.c_float(surf_thresh),
+                                     C.c_float(alpha_bound), C.c_float(surf_bound), _ptr(grad_alpha), _ptr(grad_surf))
+
+
+def surface_normal_grad_sparse(links, surf, cells, mask, lv_set, start_dim, end_dim, scale, con_check, ignore_empty, use_l1,
+                               grad):
+    links, surf, cells = _np(links, np.int32), _np(surf, np.float32), _np(cells, np.int32)
+    lib().oracle_surface_normal_grad_sparse(_ptr(links), _sz(links), _ptr(surf), _ptr(cells), C.c_int64(cells.shape[0]),
+                                            _ptr(mask), C.c_float(lv_set), C.c_int(start_dim), C.c_int(end_dim),
+                                            C.c_float(scale), C.c_int(int(con_check)), C.c_int(int(ignore_empty)),
+                                            C.c_int(int(use_l1)), _ptr(grad))

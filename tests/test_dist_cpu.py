@@ -1,0 +1,76 @@
+"""CPU, world_size 2, gloo: the gradient / mask exchange of the ray-sharded data-parallel path (alphasurf_b200.dist).
+Two processes hold different gradients on overlapping touched rows; after the exchange both must hold the sum on the union
+of the rows (what a single process rendering the concatenated batch would have accumulated) and identical masks."""
+import os
+import socket
+import types
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from alphasurf_b200 import dist as adist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _local_state(rank, N, D, touched_frac):
+    g = torch.Generator().manual_seed(100 + rank)
+    mask = torch.rand((N,), generator=g) < touched_frac
+    grad = {"density": torch.randn((N, 1), generator=g), "surface": torch.randn((N, 1), generator=g),
+            "sh": torch.randn((N, D), generator=g)}
+    for k in grad:
+        grad[k][~mask] = 0.0     # a rank only has gradient on rows it touched
+    return types.SimpleNamespace(grad=grad, mask=mask.clone(), mask_sh=mask.clone())
+
+
+def _worker(rank, world, port, N, D, frac, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ts = _local_state(rank, N, D, frac)
+        ex = adist.GradExchange()
+        n = ex.run(ts)
+        # expected: sum over ranks, union of masks
+        states = [_local_state(r, N, D, frac) for r in range(world)]
+        want_mask = torch.stack([s.mask for s in states]).any(0)
+        ok = torch.equal(ts.mask, want_mask) and torch.equal(ts.mask_sh, want_mask) and n == int(want_mask.sum())
+        for k in ("density", "surface", "sh"):
+            want = sum(s.grad[k] for s in states)
+            ok = ok and torch.allclose(ts.grad[k], want, rtol=0, atol=1e-6)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(N, D, frac):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [mp.get_context("spawn").Process(target=_worker, args=(r, world, port, N, D, frac, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_sparse_exchange_world2():
+    _run(5000, 12, 0.02)
+
+
+def test_dense_fallback_world2():
+    _run(2000, 27, 0.6)
+
+
+def test_empty_exchange_world2():
+    _run(1000, 3, 0.0)

@@ -1,0 +1,200 @@
+"""Grid-side regularisers (loss_kernel.cu): our CUDA kernels through the svox2.csrc-compatible API vs the CPU oracle
+(oracle/oracle_loss.c) and vs the UNMODIFIED reference kernels (oracle/_ref) on the same inputs.
+
+Cell lists follow the reference's callers (svox2/svox2.py:4950-5163, :5690-5724): int32 flat cell ids, either a
+contiguous run or a random subset; the mask is the bool "sparse grad indexer" of the grid.
+"""
+import numpy as np
+import pytest
+import torch
+
+from alphasurf_b200 import svox2_csrc as ours
+from alphasurf_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5   # fp32 atomics in a different order; values are otherwise the same formulas
+
+
+def _grid(reso, bd=4, variant="G*", z_order=None):
+    return synth.make_shell_grid(reso, basis_dim=bd, variant=variant, z_order=z_order)
+
+
+def _cells(sg, frac, seed, contiguous):
+    n = sg.links.numel()
+    k = max(int(n * frac), 1)
+    g = torch.Generator().manual_seed(seed)
+    if contiguous:
+        start = int(torch.randint(0, n, (1,), generator=g))
+        c = (torch.arange(start, start + k) % n)
+    else:
+        c = torch.randint(0, n, (k,), generator=g)
+    return c.to(torch.int32)
+
+
+def _close(a, b, what):
+    e = H.rel_err(a.cpu(), torch.as_tensor(b))
+    assert e < TOL, (what, e)
+
+
+@pytest.mark.parametrize("reso,ignore_edge", [(24, False), (24, True), (33, True)])
+def test_tv_and_tv_grad_dense(reso, ignore_edge):
+    from oracle import oracle
+    sg = _grid(reso)
+    links, sh = sg.links.cuda(), sg.sh.cuda()
+    D = sh.shape[1]
+    tv = ours.tv(links, sh, 1, D, False, 2.0, ignore_edge, -1.0, -1.0)
+    want = oracle.tv(sg.links, sg.sh, 1, D, ignore_edge)
+    assert abs(float(tv) - want) < 1e-5 * abs(want)
+    grad = torch.zeros_like(sh)
+    ours.tv_grad(links, sh, 1, D, 0.37, False, 2.0, ignore_edge, -1.0, -1.0, grad)
+    g_o = np.zeros(tuple(sg.sh.shape), np.float32)
+    oracle.tv_grad(sg.links, sg.sh, 1, D, 0.37, ignore_edge, g_o)
+    _close(grad, g_o, "tv_grad")
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        g_r = torch.zeros_like(sh)
+        ref.tv_grad(links, sh, 1, D, 0.37, False, 2.0, ignore_edge, -1.0, -1.0, g_r)
+        _close(grad, g_r.cpu(), "tv_grad vs reference CUDA")
+        tv_r = ref.tv(links, sh, 1, D, False, 2.0, ignore_edge, -1.0, -1.0)
+        assert abs(float(tv) - float(tv_r)) < 1e-5 * abs(float(tv_r))
+
+
+@pytest.mark.parametrize("what", ["density", "sh"])
+@pytest.mark.parametrize("contiguous", [True, False])
+@pytest.mark.parametrize("ignore_edge,ignore_last_z", [(False, False), (True, False), (False, True)])
+def test_tv_grad_sparse(what, contiguous, ignore_edge, ignore_last_z):
+    from oracle import oracle
+    sg = _grid(28)
+    data_c = sg.density if what == "density" else sg.sh
+    s, e = (0, 1) if what == "density" else (1, data_c.shape[1])
+    cells_c = _cells(sg, 0.3, 5, contiguous)
+    links, data, cells = sg.links.cuda(), data_c.cuda(), cells_c.cuda()
+    grad = torch.zeros_like(data)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.tv_grad_sparse(links, data, cells, mask, s, e, 0.81, False, 2.0, ignore_edge, ignore_last_z, -1.0, -1.0, grad)
+    g_o = np.zeros(tuple(data_c.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.tv_grad_sparse(sg.links, data_c, None, cells_c, m_o, s, e, 0.81, ignore_edge, 0.0, ignore_last_z, False, False, g_o)
+    _close(grad, g_o, "tv_grad_sparse")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        g_r, m_r = torch.zeros_like(data), torch.zeros_like(mask)
+        ref.tv_grad_sparse(links, data, cells, m_r, s, e, 0.81, False, 2.0, ignore_edge, ignore_last_z, -1.0, -1.0, g_r)
+        _close(grad, g_r.cpu(), "tv_grad_sparse vs reference CUDA")
+        assert torch.equal(mask, m_r)
+
+
+def test_tv_grad_sparse_without_mask():
+    """An empty mask tensor means "no mask" (loss_kernel.cu:1368)."""
+    sg = _grid(20)
+    links, data, cells = sg.links.cuda(), sg.density.cuda(), _cells(sg, 0.5, 1, False).cuda()
+    g1, g2 = torch.zeros_like(data), torch.zeros_like(data)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.tv_grad_sparse(links, data, cells, mask, 0, 1, 1.0, False, 2.0, False, False, -1.0, -1.0, g1)
+    ours.tv_grad_sparse(links, data, cells, torch.empty((0,), dtype=torch.bool, device="cuda"), 0, 1, 1.0, False, 2.0,
+                        False, False, -1.0, -1.0, g2)
+    assert H.rel_err(g1, g2) < TOL
+    assert int(mask.sum()) > 0
+
+
+@pytest.mark.parametrize("alpha_dependency", [False, True])
+@pytest.mark.parametrize("ignore_edge,edge_value", [(True, -1.0), (False, -1.0), (False, 0.5)])
+def test_surf_tv_grad_sparse(alpha_dependency, ignore_edge, edge_value):
+    from oracle import oracle
+    sg = _grid(28, variant="G")
+    dens_c = sg.density * 0.2   # so that some max-alpha values fall under the 0.1 up-weighting threshold
+    cells_c = _cells(sg, 1.0, 3, True)
+    links, surf, dens, cells = sg.links.cuda(), sg.surface.cuda(), dens_c.cuda(), cells_c.cuda()
+    grad = torch.zeros_like(surf)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.surf_tv_grad_sparse(links, surf, dens, cells, mask, 0, 1, 1e-3, ignore_edge, edge_value, False, -1.0, -1.0,
+                             alpha_dependency, grad)
+    g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.tv_grad_sparse(sg.links, sg.surface, dens_c, cells_c, m_o, 0, 1, 1e-3, ignore_edge, edge_value, False,
+                          alpha_dependency, True, g_o)
+    _close(grad, g_o, "surf_tv_grad_sparse")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        g_r, m_r = torch.zeros_like(surf), torch.zeros_like(mask)
+        ref.surf_tv_grad_sparse(links, surf, dens, cells, m_r, 0, 1, 1e-3, ignore_edge, edge_value, False, -1.0, -1.0,
+                                alpha_dependency, g_r)
+        _close(grad, g_r.cpu(), "surf_tv_grad_sparse vs reference CUDA")
+        assert torch.equal(mask, m_r)
+
+
+@pytest.mark.parametrize("surf_decrease", [False, True])
+def test_alpha_surf_sparsify(surf_decrease):
+    from oracle import oracle
+    sg = _grid(28, variant="G")
+    dens_c = sg.density - 0.45   # mix of positive / negative raw alpha around the bounds
+    cells_c = _cells(sg, 0.4, 9, False)
+    links, surf, dens, cells = sg.links.cuda(), sg.surface.cuda(), dens_c.cuda(), cells_c.cuda()
+    ga, gs = torch.zeros_like(dens), torch.zeros_like(surf)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    args = (1e-3, 2e-3, surf_decrease, 0.15, 0.0, -0.1)
+    ours.alpha_surf_sparsify_grad_sparse(links, dens, surf, cells, mask, *args, ga, gs)
+    ga_o, gs_o = np.zeros(tuple(dens_c.shape), np.float32), np.zeros(tuple(sg.surface.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.alpha_surf_sparsify(sg.links, dens_c, sg.surface, cells_c, m_o, *args, ga_o, gs_o)
+    _close(ga, ga_o, "sparsify grad_alpha")
+    _close(gs, gs_o, "sparsify grad_surf")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        ga_r, gs_r, m_r = torch.zeros_like(dens), torch.zeros_like(surf), torch.zeros_like(mask)
+        ref.alpha_surf_sparsify_grad_sparse(links, dens, surf, cells, m_r, *args, ga_r, gs_r)
+        _close(ga, ga_r.cpu(), "sparsify grad_alpha vs reference CUDA")
+        _close(gs, gs_r.cpu(), "sparsify grad_surf vs reference CUDA")
+        assert torch.equal(mask, m_r)
+
+
+@pytest.mark.parametrize("con_check,ignore_empty,use_l1", [(False, False, True), (True, False, False), (True, True, True),
+                                                          (False, True, False)])
+def test_surface_normal_grad_sparse(con_check, ignore_empty, use_l1):
+    from oracle import oracle
+    sg = _grid(28, variant="G*")
+    cells_c = _cells(sg, 1.0, 2, True)
+    links, surf, cells = sg.links.cuda(), sg.surface.cuda(), cells_c.cuda()
+    lv = float(sg.level_set[0])
+    grad = torch.zeros_like(surf)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.surface_normal_grad_sparse(links, surf, cells, mask, lv, 0, 1, 1e-2, 0.0, -1.0, -1.0, con_check, ignore_empty,
+                                    use_l1, grad)
+    g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.surface_normal_grad_sparse(sg.links, sg.surface, cells_c, m_o, lv, 0, 1, 1e-2, con_check, ignore_empty, use_l1, g_o)
+    _close(grad, g_o, "surface_normal_grad_sparse")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        g_r, m_r = torch.zeros_like(surf), torch.zeros_like(mask)
+        ref.surface_normal_grad_sparse(links, surf, cells, m_r, lv, 0, 1, 1e-2, 0.0, -1.0, -1.0, con_check, ignore_empty,
+                                       use_l1, g_r)
+        _close(grad, g_r.cpu(), "surface_normal_grad_sparse vs reference CUDA")
+        assert torch.equal(mask, m_r)
+
+
+def test_loss_kernels_at_full_size_properties():
+    """512^3-sized property checks: the sparse TV gradient over ALL cells equals the dense TV gradient (same formula,
+    scale/nl vs scale/n_cells normalisation accounted for), and gradients of a constant field vanish."""
+    R = 256
+    sg = synth.make_shell_grid(R, basis_dim=1, variant="G").to("cuda")
+    n = sg.links.numel()
+    # cells of the dense kernel: x,y,z < R-1
+    ar = torch.arange(R - 1, device="cuda", dtype=torch.int32)
+    cells = ((ar[:, None, None] * R + ar[None, :, None]) * R + ar[None, None, :]).reshape(-1).contiguous()
+    g_d, g_s = torch.zeros_like(sg.density), torch.zeros_like(sg.density)
+    ours.tv_grad(sg.links, sg.density, 0, 1, 1.0, False, 2.0, False, -1.0, -1.0, g_d)
+    ours.tv_grad_sparse(sg.links, sg.density, cells, torch.empty((0,), dtype=torch.bool, device="cuda"), 0, 1, 1.0, False,
+                        2.0, False, False, -1.0, -1.0, g_s)
+    assert H.rel_err(g_s, g_d) < 1e-4
+    const = torch.full_like(sg.density, 0.7)
+    g_c = torch.zeros_like(const)
+    ours.tv_grad_sparse(sg.links, const, cells, torch.empty((0,), dtype=torch.bool, device="cuda"), 0, 1, 1.0, False, 2.0,
+                        True, False, -1.0, -1.0, g_c)
+    assert float(g_c.abs().max()) == 0.0
+    assert n == R ** 3

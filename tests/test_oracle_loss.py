@@ -1,0 +1,106 @@
+"""CPU: the loss oracle (oracle/oracle_loss.c) against an independent vectorised restatement of the same formulas
+(loss_kernel.cu:119-184, :664-807) and against its own size-independent properties.  The reference ships neither
+vectors nor a CPU implementation of these kernels; tests/test_loss_gpu.py pins the oracle on the UNMODIFIED reference
+kernels on the GPU box."""
+import numpy as np
+import torch
+
+from alphasurf_b200 import synth
+from oracle import oracle
+
+
+def _tv_grad_torch(links, data, start, end, scale, ignore_edge):
+    """Dense TV gradient with autograd-free tensor algebra (float64 accumulate)."""
+    X, Y, Z = links.shape
+    sc = [s / 256.0 for s in (X, Y, Z)]
+    nl = (X - 1) * (Y - 1) * (Z - 1)
+    l000 = links[:-1, :-1, :-1].long()
+    nbr = [links[1:, :-1, :-1].long(), links[:-1, 1:, :-1].long(), links[:-1, :-1, 1:].long()]
+    grad = torch.zeros(data.shape, dtype=torch.float64)
+    for idx in range(start, end):
+        col = data[:, idx]
+        v000 = torch.where(l000 >= 0, col[l000.clamp_min(0)], torch.zeros(()))
+        skip = (l000 == 0) if ignore_edge else torch.zeros_like(l000, dtype=torch.bool)
+        d = []
+        for l in nbr:
+            v = torch.where(l >= 0, col[l.clamp_min(0)], v000 if ignore_edge else torch.zeros(()))
+            d.append(v - v000)
+        idelta = (scale / np.float32(nl)) * torch.rsqrt(1e-9 + d[0] ** 2 + d[1] ** 2 + d[2] ** 2)
+        idelta = torch.where(skip, torch.zeros(()), idelta)
+        tot = torch.zeros_like(idelta)
+        for a in range(3):
+            da = d[a] * sc[a]
+            tot = tot + da
+            ok = (nbr[a] >= 0) & (da != 0)
+            grad[:, idx].index_add_(0, nbr[a][ok], (da * idelta)[ok].double())
+        ok = l000 >= 0
+        grad[:, idx].index_add_(0, l000[ok], (-(tot) * idelta)[ok].double())
+    return grad
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_tv_grad_dense_matches_tensor_restatement():
+    sg = synth.make_shell_grid(20, basis_dim=4, variant="G*")
+    for ignore_edge in (False, True):
+        g = np.zeros(tuple(sg.sh.shape), np.float32)
+        oracle.tv_grad(sg.links, sg.sh, 1, 5, 0.5, ignore_edge, g)
+        want = _tv_grad_torch(sg.links, sg.sh, 1, 5, 0.5, ignore_edge)
+        assert _rel(g, want.numpy()) < 1e-5
+        assert np.abs(g[:, 0]).max() == 0 and np.abs(g[:, 5:]).max() == 0   # only channels [1, 5) are touched
+
+
+def test_sparse_over_all_cells_equals_dense():
+    sg = synth.make_shell_grid(18, basis_dim=1, variant="G")
+    R = 18
+    ar = np.arange(R - 1)
+    cells = ((ar[:, None, None] * R + ar[None, :, None]) * R + ar[None, None, :]).reshape(-1).astype(np.int32)
+    gd, gs = np.zeros(tuple(sg.density.shape), np.float32), np.zeros(tuple(sg.density.shape), np.float32)
+    oracle.tv_grad(sg.links, sg.density, 0, 1, 1.0, False, gd)
+    mask = np.zeros((sg.capacity,), np.uint8)
+    oracle.tv_grad_sparse(sg.links, sg.density, None, cells, mask, 0, 1, 1.0, False, 0.0, False, False, False, gs)
+    assert _rel(gs, gd) < 1e-6
+    assert mask.sum() > 0 and set(np.nonzero(mask)[0]) >= set(np.nonzero(gs[:, 0])[0])
+
+
+def test_tv_value_and_constant_field():
+    # fully linked 8^3 grid holding a constant: every difference is 0 -> tv = sqrt(1e-5) over the cells whose link != 0
+    R = 8
+    links = torch.arange(R ** 3, dtype=torch.int32).reshape(R, R, R)
+    const = np.full((R ** 3, 1), 0.25, np.float32)
+    nl = (R - 1) ** 3
+    assert abs(oracle.tv(links, const, 0, 1, False) - np.sqrt(np.float32(1e-5))) < 1e-7
+    assert abs(oracle.tv(links, const, 0, 1, True) - np.sqrt(np.float32(1e-5)) * (nl - 1) / nl) < 1e-7   # link 0 is skipped (sic)
+    g = np.zeros_like(const)
+    cells = np.arange(R ** 3, dtype=np.int32)
+    oracle.tv_grad_sparse(links, const, None, cells, None, 0, 1, 1.0, True, 0.0, False, False, False, g)
+    assert np.abs(g).max() == 0
+    # a linear ramp along z: |dz| = slope everywhere, gradient cancels in the interior
+    ramp = (np.arange(R ** 3) % R).astype(np.float32).reshape(-1, 1) * 0.5
+    tv = oracle.tv(links, ramp, 0, 1, False)
+    assert abs(tv - np.sqrt(np.float32(1e-5) + (0.5 * R / 256.0) ** 2)) < 1e-6
+
+
+def test_sparsify_matches_tensor_restatement():
+    sg = synth.make_shell_grid(16, basis_dim=1, variant="G")
+    gen = torch.Generator().manual_seed(3)
+    cells = torch.randint(0, sg.links.numel(), (5000,), generator=gen).to(torch.int32)
+    alpha = (sg.density - 0.45).numpy()
+    surf = sg.surface.numpy()
+    ga, gs = np.zeros_like(alpha), np.zeros_like(surf)
+    mask = np.zeros((sg.capacity,), np.uint8)
+    oracle.alpha_surf_sparsify(sg.links, alpha, surf, cells, mask, 1e-3, 2e-3, False, 0.15, 0.0, -0.1, ga, gs)
+    l = sg.links.reshape(-1)[cells.long()].numpy()
+    l = l[l >= 0]
+    want_a, want_s = np.zeros(alpha.shape[0], np.float64), np.zeros(alpha.shape[0], np.float64)
+    a = alpha[l, 0]
+    safe = 1.0 / np.maximum(a, np.float32(1e-8))
+    np.add.at(want_a, l[a > 0.0], 1e-3 * safe[a > 0.0])
+    sel = (surf[l, 0] < -0.1) & (a < 0.15)
+    np.add.at(want_s, l[sel], -2e-3 * safe[sel])
+    assert _rel(ga[:, 0], want_a) < 1e-5
+    assert _rel(gs[:, 0], want_s) < 1e-5 or (np.abs(want_s).max() == 0 and np.abs(gs).max() == 0)
+    assert np.array_equal(np.nonzero(mask)[0], np.unique(l))

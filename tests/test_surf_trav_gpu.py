@@ -129,15 +129,20 @@ def test_fused_vs_reference_cuda(name, reso, bd, Q, variant, optfn, fd):
                                           H.fill_opt(ours, opts), gout, out_r, G2.spec(ours))
     ref.volume_render_surf_trav_backward(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts),
                                          gout, out_r, G2r.spec(ref))
-    # atomic-order nondeterminism of the reference itself (run it again): added to the tolerance
-    G3r = H.GradSet(sg, "cuda")
-    ref.volume_render_surf_trav_backward(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts),
-                                         gout, out_r, G3r.spec(ref))
+    # atomic-order nondeterminism of the reference itself (three more runs): added to the tolerance
+    noise = {"sh": 0.0, "density": 0.0, "surface": 0.0}
+    for _ in range(3):
+        G3r = H.GradSet(sg, "cuda")
+        ref.volume_render_surf_trav_backward(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d),
+                                             H.fill_opt(ref, opts), gout, out_r, G3r.spec(ref))
+        for k in noise:
+            noise[k] = max(noise[k], H.rel_err(getattr(G3r, k), getattr(G2r, k)))
     torch.cuda.synchronize()
     assert torch.equal(G2.mask, G2r.mask)
-    assert H.rel_err(G2.sh, G2r.sh) < TOL + 2 * H.rel_err(G3r.sh, G2r.sh)
-    assert H.rel_err(G2.density, G2r.density) < TOL + 2 * H.rel_err(G3r.density, G2r.density)
-    assert H.rel_err(G2.surface, G2r.surface) < TOL + 2 * H.rel_err(G3r.surface, G2r.surface)
+    assert H.rel_err(G2.sh, G2r.sh) < TOL + 3 * noise["sh"]
+    assert H.rel_err(G2.density, G2r.density) < TOL + 3 * noise["density"]
+    e_surf = H.rel_err(G2.surface, G2r.surface)
+    assert e_surf < TOL + 3 * noise["surface"], (e_surf, noise)
 
 
 def test_skip_is_exact_at_full_size():
