@@ -325,6 +325,229 @@ surface_normal_kernel(const int32_t *__restrict__ links, const float *__restrict
     }
 }
 
+// ---- the same loss for the common case of one thread per cell (n_rep == 1), run-aggregated -------------------------------
+// The callers' cell lists are runs of consecutive flat ids (a contiguous window, or every stored cell in z-fastest order),
+// so the 32 cells of a warp are mostly z-neighbours.  A cell and its +x / +y / +z neighbours touch the 20 vertices
+// (x..x+2, y..y+2, z..z+2) \ {i = 2 and j = 2}: 8 vertex columns along z with up to 3 vertices each.  Per column each lane
+// loads only its k = 0 vertex (link + scalar) and takes k = 1, 2 from the next lanes of its run; the <= 48 gradient
+// contributions of the reference thread (6 cells x 8 corners, render_util.cuh:1824-1868) are first summed per vertex in
+// registers, then passed down the run (vertex z + 1 of lane L is vertex z of lane L + 1), so that a lane issues ONE
+// red.global.add per column (8 per cell instead of 48) and the run's last lane flushes the two trailing vertices.
+// Same contributions as the reference; only the fp32 summation order differs (it is unordered atomics there).
+__device__ __forceinline__ void load_vertex(const int32_t *__restrict__ links, const float *__restrict__ surf, const Dims &d,
+                                            int x, int y, int z, int32_t &l, float &s) {
+    l = -1;
+    s = 0.f;
+    if (x < d.sx && y < d.sy && z < d.sz) {
+        l = __ldg(links + (((int64_t)x * d.sy + y) * d.sz + z));
+        if (l >= 0) s = __ldg(surf + l);
+    }
+}
+
+// column index of vertex offset (i, j) in {0,1,2}^2 \ {(2,2)}
+__device__ __forceinline__ constexpr int ncol(int i, int j) { return (i == 2) ? 6 + j : ((j == 2) ? 4 + i : 2 * i + j); }
+
+struct NormalAcc {
+    float a[8][3];
+    unsigned touched;   // bit col * 3 + k
+};
+
+// corner (ci, cj, ck) of the cell at offset (OI, OJ, OK) from the thread's cell
+template <int OI, int OJ, int OK>
+__device__ __forceinline__ void cell_from_columns(const int32_t (&lk)[8][3], const float (&sv)[8][3], Cell8 &c, bool &ok) {
+    ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int col = ncol(OI + (k >> 2), OJ + ((k >> 1) & 1));
+        c.l[k] = lk[col][OK + (k & 1)];
+        c.s[k] = sv[col][OK + (k & 1)];
+        ok &= (c.l[k] >= 0);
+    }
+}
+
+template <int OI, int OJ, int OK>
+__device__ __forceinline__ void accumulate_normal_grad(const float *g, float scale, NormalAcc &A) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float sx = (k & 4) ? 0.25f : -0.25f, sy = (k & 2) ? 0.25f : -0.25f, sz = (k & 1) ? 0.25f : -0.25f;
+        const float val = scale * (sx * g[0] + sy * g[1] + sz * g[2]);
+        const int col = ncol(OI + (k >> 2), OJ + ((k >> 1) & 1)), kk = OK + (k & 1);
+        if (val != 0.f) {
+            A.a[col][kk] += val;
+            A.touched |= 1u << (col * 3 + kk);
+        }
+    }
+}
+
+// d(loss)/d(normal of cell 0) and d(loss)/d(normal of the neighbour).  add_surface_normal_grad (render_util.cuh:1987-2110)
+// expands d(n/|n|)/dn = (I - nh nh^T)/|n| term by term with ~30 divisions per pair; contracted with the loss direction s
+// (sign(nh0 - nh1) for L1, 2 (nh0 - nh1) for L2) it is  d0 = (s - nh0 (s.nh0)) / N0,  d1 = -(s - nh1 (s.nh1)) / N1.
+// nh = n / N uses the reference's true divisions so that sign() sees the same operands.
+__device__ __forceinline__ void normal_pair_grad(const float *nh0, float rN0, const float *nh1, float rN1, int use_l1,
+                                                 float *d0, float *d1) {
+    const float L[3] = {nh0[0] - nh1[0], nh0[1] - nh1[1], nh0[2] - nh1[2]};
+    float s[3];
+    if (use_l1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s[a] = (L[a] > 0.f) ? 1.f : (L[a] == 0.f ? 0.f : -1.f);
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s[a] = 2.f * L[a];
+    }
+    const float dot0 = s[0] * nh0[0] + s[1] * nh0[1] + s[2] * nh0[2];
+    const float dot1 = s[0] * nh1[0] + s[1] * nh1[1] + s[2] * nh1[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        d0[a] = (s[a] - nh0[a] * dot0) * rN0;
+        d1[a] = -(s[a] - nh1[a] * dot1) * rN1;
+    }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS)
+surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf,
+                           const int32_t *__restrict__ cells, Dims d, int64_t Q, float lv_set, float scale, int con_check,
+                           int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp0 * 32; base < Q; base += n_warps * 32) {
+        const bool act = (base + lane) < Q;
+        const int64_t id = act ? (int64_t)__ldg(cells + base + lane) : -2;
+        int x = 0, y = 0, z = 0;
+        if (act) cell_xyz(id, d, x, y, z);
+        const int64_t id_next = __shfl_down_sync(FULLM, id, 1);
+        const bool has_next = act && (lane < 31) && (id_next == id + 1) && (z + 1 < d.sz);
+        const bool has_prev = (__shfl_up_sync(FULLM, (int)has_next, 1) != 0) && (lane > 0);
+
+        // ---- vertex columns: k = 0 from memory, k = 1, 2 from the following lanes of the run (or memory at its end) ----
+        int32_t lk[8][3];
+        float sv[8][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (i == 2 && j == 2) continue;
+                const int c = ncol(i, j);
+                lk[c][0] = -1;
+                sv[c][0] = 0.f;
+                if (act) load_vertex(links, surf, d, x + i, y + j, z, lk[c][0], sv[c][0]);
+            }
+#pragma unroll
+        for (int k = 1; k < 3; ++k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int32_t ln = __shfl_down_sync(FULLM, lk[c][k - 1], 1);
+                const float sn = __shfl_down_sync(FULLM, sv[c][k - 1], 1);
+                lk[c][k] = ln;
+                sv[c][k] = sn;
+            }
+            if (!has_next) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (i == 2 && j == 2) continue;
+                        const int c = ncol(i, j);
+                        lk[c][k] = -1;
+                        sv[c][k] = 0.f;
+                        if (act && (k == 1 || (i < 2 && j < 2))) load_vertex(links, surf, d, x + i, y + j, z + k, lk[c][k], sv[c][k]);
+                    }
+            }
+        }
+
+        // ---- the reference thread's arithmetic on the four cells ----
+        NormalAcc A;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) A.a[c][0] = A.a[c][1] = A.a[c][2] = 0.f;
+        A.touched = 0u;
+        Cell8 c0;
+        bool ok0;
+        cell_from_columns<0, 0, 0>(lk, sv, c0, ok0);
+        if (act && ok0) {
+            const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
+            float n0[3];
+            cell_normal(c0, n0);
+            Cell8 cz, cy, cx;
+            bool uz, uy, ux;
+            cell_from_columns<0, 0, 1>(lk, sv, cz, uz);
+            cell_from_columns<0, 1, 0>(lk, sv, cy, uy);
+            cell_from_columns<1, 0, 0>(lk, sv, cx, ux);
+            uz = uz && (!con_check || face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv_set));
+            uz = uz && (!ignore_empty || (!empty000 || !cell_empty(cz, lv_set)));
+            uy = uy && (!con_check || face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv_set));
+            uy = uy && (!ignore_empty || (!empty000 || !cell_empty(cy, lv_set)));
+            ux = ux && (!con_check || face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv_set));
+            ux = ux && (!ignore_empty || (!empty000 || !cell_empty(cx, lv_set)));
+            const int norm_count = (int)ux + (int)uy + (int)uz;
+            const float N0 = NORM3_(n0);
+            const float nh0[3] = {n0[0] / N0, n0[1] / N0, n0[2] / N0};
+            const float rN0 = 1.f / N0;
+            const float sc = scale * 1.f / norm_count;
+            float n1[3], d0[3], d1[3];
+            if (ux) {   // the reference loops i = 0 (x), 1 (y), 2 (z)
+                cell_normal(cx, n1);
+                const float N1 = NORM3_(n1);
+                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
+                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                accumulate_normal_grad<0, 0, 0>(d0, sc, A);
+                accumulate_normal_grad<1, 0, 0>(d1, sc, A);
+            }
+            if (uy) {
+                cell_normal(cy, n1);
+                const float N1 = NORM3_(n1);
+                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
+                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                accumulate_normal_grad<0, 0, 0>(d0, sc, A);
+                accumulate_normal_grad<0, 1, 0>(d1, sc, A);
+            }
+            if (uz) {
+                cell_normal(cz, n1);
+                const float N1 = NORM3_(n1);
+                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
+                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                accumulate_normal_grad<0, 0, 0>(d0, sc, A);
+                accumulate_normal_grad<0, 0, 1>(d1, sc, A);
+            }
+        }
+
+        // ---- pass the k = 2 and k = 1 sums down the run, then one atomic per column ----
+        {
+            const unsigned tw = __shfl_up_sync(FULLM, A.touched, 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float t = __shfl_up_sync(FULLM, A.a[c][2], 1);
+                if (has_prev) {
+                    A.a[c][1] += t;
+                    A.touched |= ((tw >> (c * 3 + 2)) & 1u) << (c * 3 + 1);
+                }
+            }
+        }
+        {
+            const unsigned tw = __shfl_up_sync(FULLM, A.touched, 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float t = __shfl_up_sync(FULLM, A.a[c][1], 1);
+                if (has_prev) {
+                    A.a[c][0] += t;
+                    A.touched |= ((tw >> (c * 3 + 1)) & 1u) << (c * 3 + 0);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k > 0 && has_next) continue;   // handed to the next lane
+                if ((A.touched >> (c * 3 + k)) & 1u) {
+                    atomicAdd(grad + lk[c][k], A.a[c][k]);
+                    if (mask) mask[lk[c][k]] = 1;
+                }
+            }
+        }
+    }
+}
+
 int check_common(const int32_t *links, const int32_t size[3], const void *data, const void *grad, const char *who) {
     ASURF_REQUIRE(links && size && data && grad, ASURF_E_INVALID, "%s: null tensor", who);
     ASURF_REQUIRE(size[0] >= 1 && size[1] >= 1 && size[2] >= 1, ASURF_E_INVALID, "%s: bad grid size", who);
@@ -439,9 +662,14 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
     const int n_rep = end_dim - start_dim;   // the reference launches one thread per (cell, channel) and ignores the channel
     const int64_t Q = n_cells * n_rep;
     Dims d = {size[0], size[1], size[2]};
-    surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-        links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-        grad_data);
+    if (n_rep == 1)
+        surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+            links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
+            grad_data);
+    else
+        surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+            links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1,
+            mask_out, grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surface_normal_grad_sparse launch");
 }

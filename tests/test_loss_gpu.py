@@ -56,8 +56,11 @@ def test_tv_and_tv_grad_dense(reso, ignore_edge):
         g_r = torch.zeros_like(sh)
         ref.tv_grad(links, sh, 1, D, 0.37, False, 2.0, ignore_edge, -1.0, -1.0, g_r)
         _close(grad, g_r.cpu(), "tv_grad vs reference CUDA")
-        tv_r = ref.tv(links, sh, 1, D, False, 2.0, ignore_edge, -1.0, -1.0)
-        assert abs(float(tv) - float(tv_r)) < 1e-5 * abs(float(tv_r))
+        if not ignore_edge:
+            # with ignore_edge the reference kernel returns early BEFORE its cub::BlockReduce (loss_kernel.cu:89, :113):
+            # exited threads leave stale partials in the reduction and its value is not reproducible (seen: 2 % off)
+            tv_r = ref.tv(links, sh, 1, D, False, 2.0, ignore_edge, -1.0, -1.0)
+            assert abs(float(tv) - float(tv_r)) < 1e-5 * abs(float(tv_r))
 
 
 @pytest.mark.parametrize("what", ["density", "sh"])
