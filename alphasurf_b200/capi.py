@@ -74,6 +74,8 @@ def lib():
     L.asurf_accel_words.argtypes = [C.POINTER(C.c_int32)]
     for name in EXPORTS:
         getattr(L, name)  # fail loudly on a stale library
+    if os.environ.get("ASURF_WAVE") == "0":   # debugging knob: persistent shading kernels only
+        L.asurf_debug_set_wave(C.c_int32(0))
     _LIB = L
     return L
 
@@ -81,7 +83,7 @@ def lib():
 # every symbol include/asurf.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "asurf_last_error", "asurf_abi_version", "asurf_accel_words", "asurf_accel_build", "asurf_work_build", "asurf_surf_trav_forward",
-    "asurf_surf_trav_backward", "asurf_surf_trav_fused", "asurf_debug_ray_bounds", "asurf_debug_trace", "asurf_debug_set_skip",
+    "asurf_surf_trav_backward", "asurf_surf_trav_fused", "asurf_debug_ray_bounds", "asurf_debug_trace", "asurf_debug_set_skip", "asurf_debug_set_wave",
     "asurf_rmsprop_step", "asurf_sgd_step", "asurf_tv", "asurf_tv_grad", "asurf_tv_grad_sparse",
     "asurf_surf_tv_grad_sparse", "asurf_alpha_surf_sparsify_grad_sparse", "asurf_surface_normal_grad_sparse", "asurf_profile_enable", "asurf_profile_read", "asurf_launch_count", "asurf_release",
 ]

@@ -67,16 +67,25 @@ struct DebugP {
 // lane state: what the lane needs next; phase: where it is inside a work voxel
 // Output of the pre-march (premarch_kernel): per ray the first PRE_K voxels whose work bit is set, in march order,
 // and where to resume the march if there are more.
-constexpr int PRE_K = 16;
+constexpr int PRE_K_MAX = 128;   // list capacity per ray (PreP::K <= PRE_K_MAX; the count is stored in 8 bits)
 struct PreP {
-    int32_t *cells;        // (Q, PRE_K) linear voxel index x*Y*Z + y*Z + z
+    int32_t *cells;        // (Q, K) linear voxel index x*Y*Z + y*Z + z
+    int K;                 // list capacity per ray
     int32_t *code;         // (Q,)  bits 0-7 count, 8-15 count visible to the backward loop, 16 continuation,
                            //       17 backward loop still alive at the continuation, 18 force_fine at the continuation
     float *cont_t;         // (Q,)  t at the continuation
     int32_t *cont_vox;     // (Q,)  next voxel at the continuation, 10 bits per axis
-    int32_t *rays;         // compact list of the rays that have any work
+    int32_t *rays;         // compact list of the rays the persistent shading kernels serve
     unsigned long long *n_rays;   // its length (device counter)
     int enabled;
+    // wavefront path (see "wavefront kernels" below): rays whose whole march fits the list ("short" rays)
+    int wave;                     // 1: short rays go to the wavefront kernels, `rays` holds only the long ones
+    int32_t *rays_short;          // compact list of short rays
+    unsigned long long *n_short;  // its length
+    int32_t *item_base;           // (Q,) first entry of the ray's voxels in the compact item queue
+    int32_t *itemq;               // compact item queue: ray_id * K + k  (-1: slot of a ray that did not fit)
+    int64_t item_cap;             // capacity of the item queue; rays that do not fit stay with the persistent kernels
+    unsigned long long *n_items;  // its length
 };
 
 enum { ST_IDLE = 0, ST_MARCH = 1, ST_VOXEL = 2, ST_SAMPLE = 3 };
@@ -392,7 +401,7 @@ __device__ __forceinline__ void march_step(const GridP &g, const asurf_opt_t &op
 template <bool BWD>
 __device__ __forceinline__ void next_from_list(const GridP &g, const PreP &pre, Lane &L) {
     if (L.list_pos < L.list_cnt) {
-        const int32_t cell = __ldg(pre.cells + L.ray_id * PRE_K + L.list_pos);
+        const int32_t cell = __ldg(pre.cells + L.ray_id * pre.K + L.list_pos);
         ++L.list_pos;
         L.vz = cell % g.size[2];
         const int xy = cell / g.size[2];
@@ -688,11 +697,11 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
         if (L.state == ST_MARCH) {
             march_step<false, false, true>(g, opt, L, cnt);
             if (L.state == ST_VOXEL) {
-                pre.cells[ray_id * PRE_K + n] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
+                pre.cells[ray_id * pre.K + n] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
                 ++n;
                 if (L.bwd_alive) ++n_bwd;
                 L.state = ST_MARCH;
-                if (n == PRE_K) {
+                if (n == pre.K) {
                     // resume here unless the loop is over anyway (the shading kernels re-check `t <= tmax`)
                     cont = true;
                     L.state = ST_IDLE;
@@ -718,12 +727,45 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
             if (cache_n) cache_n[ray_id] = 0;
         }
     }
-    const unsigned m = __ballot_sync(FULL, has_work);
+    // short rays (whole march listed, and room left in the item queue) feed the wavefront kernels, the others the
+    // persistent shading kernels
+    const bool want_short = has_work && pre.wave && !cont;
+    bool is_short = false;
+    const unsigned mw = __ballot_sync(FULL, want_short);
+    if (mw) {
+        // item queue: the ray's n voxels get consecutive entries (exclusive prefix over the warp + one atomic)
+        int incl = want_short ? n : 0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += o;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        unsigned long long ibase = 0;
+        if (lane == 0) ibase = atomicAdd(pre.n_items, (unsigned long long)total);
+        ibase = __shfl_sync(FULL, ibase, 0);
+        if (want_short) {
+            const int64_t first = (int64_t)ibase + incl - n;
+            is_short = (first + n <= pre.item_cap);
+            if (is_short) pre.item_base[ray_id] = (int32_t)first;
+            for (int k = 0; k < n; ++k)
+                if (first + k < pre.item_cap) pre.itemq[first + k] = is_short ? (int32_t)(ray_id * pre.K + k) : -1;
+        }
+    }
+    const bool is_long = has_work && !is_short;
+    const unsigned m = __ballot_sync(FULL, is_long);
     if (m) {
         unsigned long long base = 0;
         if (lane == __ffs(m) - 1) base = atomicAdd(pre.n_rays, (unsigned long long)__popc(m));
         base = __shfl_sync(FULL, base, __ffs(m) - 1);
-        if (has_work) pre.rays[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)ray_id;
+        if (is_long) pre.rays[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)ray_id;
+    }
+    const unsigned ms = __ballot_sync(FULL, is_short);
+    if (ms) {
+        unsigned long long base = 0;
+        if (lane == __ffs(ms) - 1) base = atomicAdd(pre.n_short, (unsigned long long)__popc(ms));
+        base = __shfl_sync(FULL, base, __ffs(ms) - 1);
+        if (is_short) pre.rays_short[base + __popc(ms & ((1u << lane) - 1u))] = (int32_t)ray_id;
     }
 }
 
@@ -1022,6 +1064,10 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
     bool rays_left = true;   // warp-uniform
     // rays to serve: the compact list of the pre-march, or all Q rays when there was no pre-march
     const int64_t n_serve = pre.enabled ? (int64_t)*pre.n_rays : Q;
+    // Rays in flight per warp: with few rays to serve (the long rays left over by the wavefront path) they are spread
+    // over all warps instead of being packed 32 to a warp, where they would serialise each other's divergent work.
+    const int64_t total_warps = (int64_t)gridDim.x * CTA_WARPS;
+    const int quota = (int)min((int64_t)32, max((int64_t)1, (n_serve + total_warps - 1) / total_warps));
 
     // Persistent warp: lanes pull rays from a global counter as they become free, then the warp repeatedly runs the
     // kind of work most of its lanes are waiting for (march step / voxel work / sample shading / ray set-up).
@@ -1030,7 +1076,8 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
         const unsigned m_march = __ballot_sync(FULL, L.state == ST_MARCH);
         const unsigned m_vox = __ballot_sync(FULL, L.state == ST_VOXEL);
         const unsigned m_samp = __ballot_sync(FULL, L.state == ST_SAMPLE);
-        const int n_idle = rays_left ? __popc(m_idle) : 0;
+        const int can_take = rays_left ? max(0, min(__popc(m_idle), quota - (32 - __popc(m_idle)))) : 0;
+        const int n_idle = can_take;
         const int n_march = __popc(m_march), n_vox = __popc(m_vox), n_samp = __popc(m_samp);
         if ((n_idle | n_march | n_vox | n_samp) == 0) break;
 
@@ -1043,11 +1090,13 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
         } else if (n_idle > 0 && n_idle >= n_vox && n_idle >= n_samp) {
             // ---------------- ray set-up for the free lanes ----------------
             unsigned long long base = 0;
-            if (lane == __ffs(m_idle) - 1) base = atomicAdd(ray_counter, (unsigned long long)__popc(m_idle));
+            if (lane == __ffs(m_idle) - 1) base = atomicAdd(ray_counter, (unsigned long long)can_take);
             base = __shfl_sync(FULL, base, __ffs(m_idle) - 1);
-            const int64_t serve_id = (int64_t)base + __popc(m_idle & ((1u << lane) - 1u));
-            if (__any_sync(FULL, (L.state == ST_IDLE) && (serve_id >= n_serve))) rays_left = false;
-            if (L.state == ST_IDLE && serve_id < n_serve) {
+            const int rank = __popc(m_idle & ((1u << lane) - 1u));
+            const bool take = (L.state == ST_IDLE) && (rank < can_take);
+            const int64_t serve_id = (int64_t)base + rank;
+            if (__any_sync(FULL, take && (serve_id >= n_serve))) rays_left = false;
+            if (take && serve_id < n_serve) {
                 const int64_t ray_id = pre.enabled ? (int64_t)__ldg(pre.rays + serve_id) : serve_id;
                 L.ray_id = ray_id;
                 L.logT = 0.f;
@@ -1206,12 +1255,17 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
     }
 }
 
+#include "surf_wave.inl"
+
 }  // namespace
 }  // namespace asurf
 
 using namespace asurf;
 
 namespace {
+
+Workspace g_ws_wave;
+int g_wave_enabled = 1;  // asurf_debug_set_wave
 
 Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg, g_ws_ctr, g_ws_pre;
 
@@ -1298,11 +1352,12 @@ inline int n_ctas(int64_t Q) {
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
-// zeroed counters for the next launches on `st`: [0] forward ray fetch, [1] backward ray fetch, [2] compact-list length
+// zeroed counters for the next launches on `st`: [0] forward ray fetch, [1] backward ray fetch, [2] long-ray list length,
+// [3] short-ray list length, [4] item queue length, [5] hit queue length
 int ray_counters(cudaStream_t st, unsigned long long **ctr) {
-    int rc = g_ws_ctr.reserve(4 * sizeof(unsigned long long));
+    int rc = g_ws_ctr.reserve(8 * sizeof(unsigned long long));
     if (rc) return rc;
-    ASURF_CUDA(cudaMemsetAsync(g_ws_ctr.ptr, 0, 4 * sizeof(unsigned long long), st));
+    ASURF_CUDA(cudaMemsetAsync(g_ws_ctr.ptr, 0, 8 * sizeof(unsigned long long), st));
     *ctr = (unsigned long long *)g_ws_ctr.ptr;
     return 0;
 }
@@ -1313,20 +1368,86 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
     pre = PreP();
     if (!g_skip_enabled || g.size[0] > 1024 || g.size[1] > 1024 || g.size[2] > 1024) return 0;   // shading kernels march
     const int64_t Q = rays->n_rays;
+    // list capacity per ray: as long as the buffers stay moderate (a grazing ray through a thin sheet lists ~100 voxels)
+    int K = PRE_K_MAX;
+    while (K > 16 && (int64_t)Q * K > ((int64_t)1 << 27)) K >>= 1;
+    const int64_t item_cap = Q * 6 + 4096;
     const size_t per = (size_t)Q * sizeof(int32_t);
-    int rc = g_ws_pre.reserve(per * (PRE_K + 4));
+    int rc = g_ws_pre.reserve(per * (K + 6) + (size_t)item_cap * sizeof(int32_t));
     if (rc) return rc;
     char *base = (char *)g_ws_pre.ptr;
     pre.cells = (int32_t *)base;
-    pre.code = (int32_t *)(base + per * PRE_K);
-    pre.cont_t = (float *)(base + per * (PRE_K + 1));
-    pre.cont_vox = (int32_t *)(base + per * (PRE_K + 2));
-    pre.rays = (int32_t *)(base + per * (PRE_K + 3));
+    pre.K = K;
+    pre.code = (int32_t *)(base + per * K);
+    pre.cont_t = (float *)(base + per * (K + 1));
+    pre.cont_vox = (int32_t *)(base + per * (K + 2));
+    pre.rays = (int32_t *)(base + per * (K + 3));
+    pre.rays_short = (int32_t *)(base + per * (K + 4));
+    pre.item_base = (int32_t *)(base + per * (K + 5));
+    pre.itemq = (int32_t *)(base + per * (K + 6));
+    pre.item_cap = item_cap;
     pre.n_rays = ctr + 2;
+    pre.n_short = ctr + 3;
+    pre.n_items = ctr + 4;
     pre.enabled = 1;
+    pre.wave = (g_wave_enabled && g.level_set_num == 1) ? 1 : 0;
     premarch_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, rgb_out, cache_n);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "premarch launch");
+}
+
+// ---- wavefront path: buffers for the item queue and the stage launches -----------------------------------
+inline int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+inline int wave_grid(int64_t want_threads, int threads, int ctas_per_sm) {
+    const int64_t want = (want_threads + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+int wave_buffers(const PreP &pre, unsigned long long *ctr, WaveP &wv) {
+    const size_t n = (size_t)pre.item_cap;
+    const size_t b_items = n * sizeof(ItemRec), b_hits = n * WAVE_ENT * sizeof(HitRec), b_q = n * WAVE_ENT * sizeof(int32_t);
+    int rc = g_ws_wave.reserve(b_items + b_hits + b_q);
+    if (rc) return rc;
+    char *base = (char *)g_ws_wave.ptr;
+    wv.items = (ItemRec *)base;
+    wv.hits = (HitRec *)(base + b_items);
+    wv.hitq = (int32_t *)(base + b_items + b_hits);
+    wv.n_hits = ctr + 5;
+    return 0;
+}
+
+// eval -> colour -> composite for the short rays (rgb_out may be NULL: backward-only rematerialisation)
+int wave_forward(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, const PreP &pre, const WaveP &wv,
+                 const CacheP &cache, int M, float *rgb_out, cudaStream_t st) {
+    const int64_t Q = rays->n_rays;
+    FusedP nof = {};
+    asurf_grads_t nog = {};
+    wave_eval_kernel<<<wave_grid(Q * 2, 128, 16), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv);
+    wave_wide_kernel<false><<<wave_grid(Q * 32, 128, 16), 128, 0, st>>>(g, *opt, rays->dirs, pre, wv, nullptr, nullptr, nof, nog);
+    wave_composite_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, pre, wv, cache, M, rgb_out);
+    note_launches(3);
+    return check_cuda(cudaGetLastError(), "wavefront forward launch");
+}
+
+int wave_backward(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, const PreP &pre, const WaveP &wv,
+                  const float *grad_in, const float *color_cache, const FusedP &f, const CacheP &cache,
+                  const asurf_grads_t &grads, cudaStream_t st) {
+    const int64_t Q = rays->n_rays;
+    wave_wide_kernel<true><<<wave_grid(Q * 32, 128, 16), 128, 0, st>>>(g, *opt, rays->dirs, pre, wv, grad_in, color_cache, f, grads);
+    wave_bwd_scalar_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv, grad_in,
+                                                                  color_cache, f, cache, grads);
+    note_launches(2);
+    return check_cuda(cudaGetLastError(), "wavefront backward launch");
 }
 
 }  // namespace
@@ -1357,6 +1478,13 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     } else {
         rc = premarch(g, opt, rays, ctr, rgb_out, nullptr, st, pre);
         if (rc) return rc;
+        if (pre.wave) {
+            WaveP wv;
+            rc = wave_buffers(pre, ctr, wv);
+            if (rc) return rc;
+            rc = wave_forward(g, opt, rays, pre, wv, cache, 0, rgb_out, st);
+            if (rc) return rc;
+        }
         surf_trav_kernel<false, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
             g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr, pre);
     }
@@ -1385,6 +1513,15 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     PreP pre;
     rc = premarch(g, opt, rays, ctr, nullptr, nullptr, st, pre);
     if (rc) return rc;
+    if (pre.wave) {   // rematerialise the short rays' samples, then their backward
+        WaveP wv;
+        rc = wave_buffers(pre, ctr, wv);
+        if (rc) return rc;
+        rc = wave_forward(g, opt, rays, pre, wv, cache, 0, nullptr, st);
+        if (rc) return rc;
+        rc = wave_backward(g, opt, rays, pre, wv, grad_out, color_cache, f, cache, *grads, st);
+        if (rc) return rc;
+    }
     surf_trav_kernel<true, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
         g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg, ctr + 1,
         pre);
@@ -1454,6 +1591,7 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     cudaEvent_t *pe = prof ? g_prof.ev + 3 * g_prof.n : nullptr;
     if (prof) cudaEventRecord(pe[0], st);
     PreP pre = PreP(), nopre = PreP();
+    WaveP wv = WaveP();
     if (!stats_dev) {
         rc = premarch(g, opt, rays, ctr, rgb_out, cache.n, st, pre);
         if (rc) return rc;
@@ -1465,11 +1603,21 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
         surf_trav_kernel<false, true><<<n_ctas(Q), CTA_THREADS, 0, st>>>(gs, *opt, rays->origins, rays->dirs, Q, rgb_out,
                                                                           nullptr, nullptr, ff, cache, nog, dbg, ctr, nopre);
     } else {
+        if (pre.wave) {
+            rc = wave_buffers(pre, ctr, wv);
+            if (rc) return rc;
+            rc = wave_forward(g, opt, rays, pre, wv, cache, M, rgb_out, st);
+            if (rc) return rc;
+        }
         surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
                                                                            nullptr, nullptr, ff, cache, nog, dbg, ctr, pre);
     }
     DebugP nodbg = {};
     if (prof) cudaEventRecord(pe[1], st);
+    if (pre.wave) {
+        rc = wave_backward(g, opt, rays, pre, wv, rgb_gt, rgb_out, f, cache, *grads, st);
+        if (rc) return rc;
+    }
     surf_trav_kernel<true, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, nullptr, rgb_gt,
                                                                       rgb_out, f, cache, *grads, nodbg, ctr + 1, pre);
     if (prof) {
@@ -1525,6 +1673,7 @@ extern "C" int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *r
 }
 
 extern "C" void asurf_debug_set_skip(int32_t enabled) { g_skip_enabled = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_wave(int32_t enabled) { g_wave_enabled = enabled ? 1 : 0; }
 
 extern "C" int asurf_profile_enable(int32_t capacity) {
     for (int i = 0; i < 3 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
@@ -1563,4 +1712,5 @@ extern "C" void asurf_release(void) {
     g_ws_dbg.release();
     g_ws_ctr.release();
     g_ws_pre.release();
+    g_ws_wave.release();
 }

@@ -164,6 +164,11 @@ int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *rays, const 
  * must be bit-identical either way; tests/ use it as a full-size property check. */
 void asurf_debug_set_skip(int32_t enabled);
 
+/* test hook: route every ray through the persistent shading kernels (0) instead of sending the rays whose march fits the
+ * pre-march list through the wavefront kernels (non-zero, default).  Colours must be bit-identical either way, gradients
+ * equal up to atomic order. */
+void asurf_debug_set_wave(int32_t enabled);
+
 /* ---- optimizer steps, optim_kernel.cu:154-267 ----
  * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */
 int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,
