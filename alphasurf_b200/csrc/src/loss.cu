@@ -367,15 +367,16 @@ __device__ __forceinline__ void cell_from_columns(const int32_t (&lk)[8][3], con
 
 template <int OI, int OJ, int OK>
 __device__ __forceinline__ void accumulate_normal_grad(const float *g, float scale, NormalAcc &A) {
+    // val(corner) = scale * (+-g0 +-g1 +-g2) / 4: the 8 sign combinations from a 2-level butterfly
+    const float q = 0.25f * scale;
+    const float a0 = q * g[0], a1 = q * g[1], a2 = q * g[2];
+    const float u[4] = {-a0 - a1, -a0 + a1, a0 - a1, a0 + a1};   // index (i << 1) | j
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float sx = (k & 4) ? 0.25f : -0.25f, sy = (k & 2) ? 0.25f : -0.25f, sz = (k & 1) ? 0.25f : -0.25f;
-        const float val = scale * (sx * g[0] + sy * g[1] + sz * g[2]);
+        const float val = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
         const int col = ncol(OI + (k >> 2), OJ + ((k >> 1) & 1)), kk = OK + (k & 1);
-        if (val != 0.f) {
-            A.a[col][kk] += val;
-            A.touched |= 1u << (col * 3 + kk);
-        }
+        A.a[col][kk] += val;                                       // adding an exact 0 changes nothing
+        A.touched |= (val != 0.f ? 1u : 0u) << (col * 3 + kk);     // but only non-zero contributions mark the row
     }
 }
 
@@ -415,7 +416,13 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
         const bool act = (base + lane) < Q;
         const int64_t id = act ? (int64_t)__ldg(cells + base + lane) : -2;
         int x = 0, y = 0, z = 0;
-        if (act) cell_xyz(id, d, x, y, z);
+        if (act) {   // flat ids are < 2^31: 32-bit divisions
+            const unsigned uid = (unsigned)id;
+            const unsigned xy = uid / (unsigned)d.sz;
+            z = (int)(uid - xy * (unsigned)d.sz);
+            x = (int)(xy / (unsigned)d.sy);
+            y = (int)(xy - (unsigned)x * (unsigned)d.sy);
+        }
         const int64_t id_next = __shfl_down_sync(FULLM, id, 1);
         const bool has_next = act && (lane < 31) && (id_next == id + 1) && (z + 1 < d.sz);
         const bool has_prev = (__shfl_up_sync(FULLM, (int)has_next, 1) != 0) && (lane > 0);
@@ -431,7 +438,11 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
                 const int c = ncol(i, j);
                 lk[c][0] = -1;
                 sv[c][0] = 0.f;
-                if (act) load_vertex(links, surf, d, x + i, y + j, z, lk[c][0], sv[c][0]);
+                if (act && (x + i < d.sx) && (y + j < d.sy)) {
+                    const int32_t l = __ldg(links + (id + (int64_t)i * d.sy * d.sz + j * d.sz));
+                    lk[c][0] = l;
+                    if (l >= 0) sv[c][0] = __ldg(surf + l);
+                }
             }
 #pragma unroll
         for (int k = 1; k < 3; ++k) {

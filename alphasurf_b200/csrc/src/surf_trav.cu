@@ -89,6 +89,8 @@ struct PreP {
 };
 
 enum { ST_IDLE = 0, ST_MARCH = 1, ST_VOXEL = 2, ST_SAMPLE = 3 };
+enum { PM_DONE = 0, PM_LOOKUP = 1, PM_JUMP = 2, PM_FINE = 3 };   // pre-march phases
+constexpr int PM_FINE_STEPS = 6;
 enum { PH_ENTER = 0, PH_ROOTS = 1, PH_FAKE = 2, PH_POST = 3 };
 
 struct Lane {
@@ -693,18 +695,128 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
         ray_bounds(g, opt, L, world_step);
         if (!(L.tmin > L.tmax)) dda_init(g, L);
     }
-    while (__any_sync(FULL, L.state == ST_MARCH)) {
-        if (L.state == ST_MARCH) {
-            march_step<false, false, true>(g, opt, L, cnt);
-            if (L.state == ST_VOXEL) {
-                pre.cells[ray_id * pre.K + n] = (int32_t)(((int64_t)L.vx * g.size[1] + L.vy) * g.size[2] + L.vz);
-                ++n;
-                if (L.bwd_alive) ++n_bwd;
-                L.state = ST_MARCH;
-                if (n == pre.K) {
-                    // resume here unless the loop is over anyway (the shading kernels re-check `t <= tmax`)
-                    cont = true;
-                    L.state = ST_IDLE;
+    // The march runs in three warp-wide phases per round so that lanes doing the same kind of step execute together:
+    // LOOKUP (which pyramid level is empty around the next voxel), JUMP (leave an empty 16^3 / 64^3 block: ~200
+    // instructions) and FINE (a few voxel-by-voxel steps inside the cached 4^3 word: ~40 instructions each).  The
+    // arithmetic of each step is that of march_step<false, false, true>.
+    int mode = (L.state == ST_MARCH) ? PM_LOOKUP : PM_DONE;
+    int jump_s = 0;
+    const uint64_t *bm = g.work;
+    while (__any_sync(FULL, mode != PM_DONE)) {
+        // ---------------- LOOKUP ----------------
+        if (mode == PM_LOOKUP) {
+            if (!(L.t <= L.tmax)) {
+                mode = PM_DONE;
+            } else {
+                int s = 0;
+                if (g.use_skip && !L.force_fine) {
+                    const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
+                    if (k2 != L.k2) {
+                        L.k2 = k2;
+                        L.w2 = __ldg(bm + g.lay.off[2] + k2);
+                    }
+                    const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
+                    if (L.w2 == 0) s = 6;
+                    else if (!((L.w2 >> bit1) & 1ull)) s = 4;
+                }
+                if (s == 0) {
+                    const int k0 = ((L.nx >> 2) * g.ab1 + (L.ny >> 2)) * g.ab2 + (L.nz >> 2);
+                    L.wkey = k0;
+                    L.word = __ldg(bm + k0);
+                    mode = PM_FINE;
+                } else {
+                    jump_s = s;
+                    mode = PM_JUMP;
+                }
+            }
+        }
+        // ---------------- JUMP over an empty aligned block of 2^s voxels per side ----------------
+        if (__any_sync(FULL, mode == PM_JUMP)) {
+            if (mode == PM_JUMP) {
+                const int sft = jump_s;
+                const int lox = (L.nx >> sft) << sft, loy = (L.ny >> sft) << sft, loz = (L.nz >> sft) << sft;
+                const int hix = min(lox + (1 << sft), g.size[0] - 1), hiy = min(loy + (1 << sft), g.size[1] - 1),
+                          hiz = min(loz + (1 << sft), g.size[2] - 1);
+                const int Px = (L.dx > 0.f) ? hix : lox, Py = (L.dy > 0.f) ? hiy : loy, Pz = (L.dz > 0.f) ? hiz : loz;
+                const float Tx = PT_X(L, Px), Ty = PT_Y(L, Py), Tz = PT_Z(L, Pz);
+                const float T = fminf(fminf(Tx, Ty), Tz);
+                if (L.bwd_alive && !(T + opt.step_size <= L.tmax)) {
+                    L.force_fine = true;   // the backward quirk may end the loop in here: voxel by voxel from now on
+                    mode = PM_LOOKUP;
+                } else if (!(T <= L.tmax)) {
+                    mode = PM_DONE;        // `while (t <= tmax)` fails at a voxel of this (empty) block
+                } else {
+                    const int A = (T == Tx) ? 0 : ((T == Ty) ? 1 : 2);
+                    int nx = axis_after(L.nx, L.ox, L.dx, L.rx, L.slow_div, T, A > 0, lox, hix);
+                    int ny = axis_after(L.ny, L.oy, L.dy, L.ry, L.slow_div, T, A > 1, loy, hiy);
+                    int nz = axis_after(L.nz, L.oz, L.dz, L.rz, L.slow_div, T, false, loz, hiz);
+                    bool out;
+                    if (A == 0) {
+                        nx = (L.dx > 0.f) ? Px : Px - 1;
+                        out = (nx < 0) || (nx >= g.size[0] - 1);
+                    } else if (A == 1) {
+                        ny = (L.dy > 0.f) ? Py : Py - 1;
+                        out = (ny < 0) || (ny >= g.size[1] - 1);
+                    } else {
+                        nz = (L.dz > 0.f) ? Pz : Pz - 1;
+                        out = (nz < 0) || (nz >= g.size[2] - 1);
+                    }
+                    if (out) {
+                        mode = PM_DONE;    // the ray leaves the grid through this empty block
+                    } else {
+                        L.nx = nx; L.ny = ny; L.nz = nz;
+                        L.tfx = PT_X(L, nx + (L.dx > 0.f ? 1 : 0));
+                        L.tfy = PT_Y(L, ny + (L.dy > 0.f ? 1 : 0));
+                        L.tfz = PT_Z(L, nz + (L.dz > 0.f ? 1 : 0));
+                        L.t = T;
+                        mode = PM_LOOKUP;
+                    }
+                }
+            }
+        }
+        // ---------------- FINE: voxel-by-voxel steps inside the cached 4^3 word ----------------
+#pragma unroll 1
+        for (int it = 0; it < PM_FINE_STEPS; ++it) {
+            if (!__any_sync(FULL, mode == PM_FINE)) break;
+            if (mode == PM_FINE) {
+                if (!(L.t <= L.tmax)) {
+                    mode = PM_DONE;
+                } else {
+                    const float T = fminf(fminf(L.tfx, L.tfy), L.tfz);
+                    const int vx = L.nx, vy = L.ny, vz = L.nz;
+                    bool out;
+                    int moved;   // old ^ new coordinate of the exit axis
+                    if (T == L.tfx) {
+                        const int nn = vx + ((L.dx > 0.f) ? 1 : -1);
+                        out = (nn < 0) || (nn >= g.size[0] - 1);
+                        moved = vx ^ nn;
+                        if (!out) { L.nx = nn; L.tfx = PT_X(L, nn + (L.dx > 0.f ? 1 : 0)); }
+                    } else if (T == L.tfy) {
+                        const int nn = vy + ((L.dy > 0.f) ? 1 : -1);
+                        out = (nn < 0) || (nn >= g.size[1] - 1);
+                        moved = vy ^ nn;
+                        if (!out) { L.ny = nn; L.tfy = PT_Y(L, nn + (L.dy > 0.f ? 1 : 0)); }
+                    } else {
+                        const int nn = vz + ((L.dz > 0.f) ? 1 : -1);
+                        out = (nn < 0) || (nn >= g.size[2] - 1);
+                        moved = vz ^ nn;
+                        if (!out) { L.nz = nn; L.tfz = PT_Z(L, nn + (L.dz > 0.f ? 1 : 0)); }
+                    }
+                    L.t = out ? L.tmax + 1.f : T;
+                    const int bit = ((vx & 3) << 4) | ((vy & 3) << 2) | (vz & 3);
+                    if ((L.word >> bit) & 1ull) {
+                        pre.cells[ray_id * pre.K + n] = (int32_t)(((int64_t)vx * g.size[1] + vy) * g.size[2] + vz);
+                        ++n;
+                        if (L.bwd_alive) ++n_bwd;
+                        if (n == pre.K) {
+                            cont = true;   // resume here (the shading kernels re-check `t <= tmax`)
+                            mode = PM_DONE;
+                        }
+                    } else if (L.bwd_alive && !(L.t + opt.step_size <= L.tmax)) {
+                        // backward quirk (:1935): an UNLINKED voxel this close to tmax ends the backward loop
+                        if (!((__ldg(g.accel + L.wkey) >> bit) & 1ull)) L.bwd_alive = false;
+                    }
+                    if (mode == PM_FINE && (out || (moved >> 2))) mode = out ? PM_DONE : PM_LOOKUP;
                 }
             }
         }
@@ -1273,9 +1385,10 @@ int g_skip_enabled = 1;  // asurf_debug_set_skip
 
 // per-kernel timing ring (asurf_profile_*)
 struct ProfRing {
-    cudaEvent_t *ev = nullptr;  // 3 events per call: start, mid, end
+    cudaEvent_t *ev = nullptr;  // PROF_EV events per call: start, work pyramid, pre-march, forward, backward
     int cap = 0, n = 0;
 } g_prof;
+constexpr int PROF_EV = 5;
 
 int make_grid(const asurf_grid_t *grid, const asurf_opt_t *opt, bool need_work, cudaStream_t st, GridP &g) {
     ASURF_REQUIRE(grid, ASURF_E_INVALID, "surf_trav: null grid");
@@ -1543,9 +1656,13 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     if (Q == 0) return 0;
     ASURF_REQUIRE(rgb_gt && rgb_out, ASURF_E_INVALID, "surf_trav_fused: null colour tensor");
     ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "surf_trav_fused: null gradient buffer");
+    const bool prof = g_prof.cap > 0 && g_prof.n < g_prof.cap;
+    cudaEvent_t *pe = prof ? g_prof.ev + PROF_EV * g_prof.n : nullptr;
+    if (prof) cudaEventRecord(pe[0], st);
     GridP g;
     rc = make_grid(grid, opt, true, st, g);
     if (rc) return rc;
+    if (prof) cudaEventRecord(pe[1], st);
     const int M = fu->l_dist_max_sample;
     CacheP cache = {};
     if (M > 0) {
@@ -1587,15 +1704,13 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     unsigned long long *ctr = nullptr;
     rc = ray_counters(st, &ctr);
     if (rc) return rc;
-    const bool prof = g_prof.cap > 0 && g_prof.n < g_prof.cap;
-    cudaEvent_t *pe = prof ? g_prof.ev + 3 * g_prof.n : nullptr;
-    if (prof) cudaEventRecord(pe[0], st);
     PreP pre = PreP(), nopre = PreP();
     WaveP wv = WaveP();
     if (!stats_dev) {
         rc = premarch(g, opt, rays, ctr, rgb_out, cache.n, st, pre);
         if (rc) return rc;
     }
+    if (prof) cudaEventRecord(pe[2], st);
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
         GridP gs = g;
@@ -1613,7 +1728,7 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
                                                                            nullptr, nullptr, ff, cache, nog, dbg, ctr, pre);
     }
     DebugP nodbg = {};
-    if (prof) cudaEventRecord(pe[1], st);
+    if (prof) cudaEventRecord(pe[3], st);
     if (pre.wave) {
         rc = wave_backward(g, opt, rays, pre, wv, rgb_gt, rgb_out, f, cache, *grads, st);
         if (rc) return rc;
@@ -1621,7 +1736,7 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     surf_trav_kernel<true, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, nullptr, rgb_gt,
                                                                       rgb_out, f, cache, *grads, nodbg, ctr + 1, pre);
     if (prof) {
-        cudaEventRecord(pe[2], st);
+        cudaEventRecord(pe[4], st);
         ++g_prof.n;
     }
     note_launches(2);
@@ -1676,32 +1791,40 @@ extern "C" void asurf_debug_set_skip(int32_t enabled) { g_skip_enabled = enabled
 extern "C" void asurf_debug_set_wave(int32_t enabled) { g_wave_enabled = enabled ? 1 : 0; }
 
 extern "C" int asurf_profile_enable(int32_t capacity) {
-    for (int i = 0; i < 3 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
+    for (int i = 0; i < PROF_EV * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
     delete[] g_prof.ev;
     g_prof = ProfRing();
     if (capacity <= 0) return 0;
-    g_prof.ev = new cudaEvent_t[3 * (size_t)capacity];
-    for (int i = 0; i < 3 * capacity; ++i) ASURF_CUDA(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.ev = new cudaEvent_t[PROF_EV * (size_t)capacity];
+    for (int i = 0; i < PROF_EV * capacity; ++i) ASURF_CUDA(cudaEventCreate(&g_prof.ev[i]));
     g_prof.cap = capacity;
+    return 0;
+}
+
+extern "C" int asurf_profile_read_stages(int32_t *n_calls, float *stage_ms_sum) {
+    ASURF_REQUIRE(n_calls && stage_ms_sum, ASURF_E_INVALID, "profile_read_stages: null output");
+    for (int k = 0; k < PROF_EV - 1; ++k) stage_ms_sum[k] = 0.f;
+    for (int i = 0; i < g_prof.n; ++i) {
+        cudaEvent_t *pe = g_prof.ev + PROF_EV * i;
+        ASURF_CUDA(cudaEventSynchronize(pe[PROF_EV - 1]));
+        for (int k = 0; k < PROF_EV - 1; ++k) {
+            float a = 0.f;
+            ASURF_CUDA(cudaEventElapsedTime(&a, pe[k], pe[k + 1]));
+            stage_ms_sum[k] += a;
+        }
+    }
+    *n_calls = g_prof.n;
+    g_prof.n = 0;
     return 0;
 }
 
 extern "C" int asurf_profile_read(int32_t *n_calls, float *fwd_ms_sum, float *bwd_ms_sum) {
     ASURF_REQUIRE(n_calls && fwd_ms_sum && bwd_ms_sum, ASURF_E_INVALID, "profile_read: null output");
-    float fwd = 0.f, bwd = 0.f;
-    for (int i = 0; i < g_prof.n; ++i) {
-        cudaEvent_t *pe = g_prof.ev + 3 * i;
-        ASURF_CUDA(cudaEventSynchronize(pe[2]));
-        float a = 0.f, b = 0.f;
-        ASURF_CUDA(cudaEventElapsedTime(&a, pe[0], pe[1]));
-        ASURF_CUDA(cudaEventElapsedTime(&b, pe[1], pe[2]));
-        fwd += a;
-        bwd += b;
-    }
-    *n_calls = g_prof.n;
-    *fwd_ms_sum = fwd;
-    *bwd_ms_sum = bwd;
-    g_prof.n = 0;
+    float st[PROF_EV - 1];
+    int rc = asurf_profile_read_stages(n_calls, st);
+    if (rc) return rc;
+    *fwd_ms_sum = st[0] + st[1] + st[2];
+    *bwd_ms_sum = st[3];
     return 0;
 }
 

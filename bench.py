@@ -232,11 +232,12 @@ def run_ours(args, rank, world, local_rank):
     n_launch = int(L.asurf_launch_count(ctypes.c_int32(0)))
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    ncalls, fms, bms = ctypes.c_int32(0), ctypes.c_float(0), ctypes.c_float(0)
-    capi.check(L.asurf_profile_read(ctypes.byref(ncalls), ctypes.byref(fms), ctypes.byref(bms)), "profile_read")
+    ncalls, stages = ctypes.c_int32(0), (ctypes.c_float * 4)()
+    capi.check(L.asurf_profile_read_stages(ctypes.byref(ncalls), stages), "profile_read_stages")
     capi.check(L.asurf_profile_enable(ctypes.c_int32(0)), "profile_disable")
-    fwd_ms = fms.value / max(ncalls.value, 1)
-    bwd_ms = bms.value / max(ncalls.value, 1)
+    stage_ms = [v / max(ncalls.value, 1) for v in stages]
+    fwd_ms = stage_ms[0] + stage_ms[1] + stage_ms[2]    # work pyramid build + pre-march + forward shading
+    bwd_ms = stage_ms[3]
     ms_step = ms_total / args.steps
     value = Q * world * args.steps / (ms_total * 1e-3)
     phases = {"render_ms": 0.0, "regularisers_ms": 0.0, "optimizer_ms": 0.0}
@@ -291,7 +292,10 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom[2], "kernel_ms": dom[1],
-                     "kernels": {"forward_ms": fwd_ms, "backward_ms": bwd_ms, "forward_bytes": fwd_bytes,
+                     "kernels": {"forward_ms": fwd_ms, "backward_ms": bwd_ms,
+                                 "stages_ms": {"work_pyramid": stage_ms[0], "premarch": stage_ms[1],
+                                               "forward_shading": stage_ms[2], "backward": stage_ms[3]},
+                                 "forward_bytes": fwd_bytes,
                                  "backward_bytes": bwd_bytes,
                                  "fused_frac": (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak
                                  if fwd_ms + bwd_ms > 0 else 0.0},

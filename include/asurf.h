@@ -210,11 +210,13 @@ int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3]
 
 /* ---- per-kernel timing (ours; feeds bench.py's roofline) ----
  * After asurf_profile_enable(capacity > 0) every asurf_surf_trav_fused call records CUDA events around its forward
- * and its backward kernel on the launching stream (up to `capacity` calls are kept).  asurf_profile_read waits for
+ * (work pyramid build, pre-march, shading) and its backward pass on the launching stream (up to `capacity` calls are kept).  asurf_profile_read waits for
  * the recorded events, returns the number of calls and the summed kernel durations in ms, and resets the ring.
  * asurf_profile_enable(0) switches it off and destroys the events. */
 int asurf_profile_enable(int32_t capacity);
 int asurf_profile_read(int32_t *n_calls, float *fwd_ms_sum, float *bwd_ms_sum);
+/* same, split by stage: [0] work pyramid build, [1] pre-march, [2] forward shading, [3] backward (4 floats) */
+int asurf_profile_read_stages(int32_t *n_calls, float *stage_ms_sum);
 
 /* number of CUDA kernels this library has enqueued since the last reset (bench.py's gpu_launches) */
 uint64_t asurf_launch_count(int32_t reset);
