@@ -74,74 +74,127 @@ __global__ void __launch_bounds__(128) accel_coarsen_kernel(AccelLayout lay, int
     buf[lay.off[level] + w] = word;
 }
 
-// Work bitmap, level 0: one warp per 4x4x4-cell block.  The 5x5x5 vertices of the block are staged once in shared
-// memory (surface scalar + raw density), then each lane classifies two cells.
-constexpr int WORK_WARPS = 8;
-__global__ void __launch_bounds__(WORK_WARPS * 32)
-work_level0_kernel(const int32_t *__restrict__ links, const float *__restrict__ density,
-                   const float *__restrict__ surface, const float *__restrict__ level_set, int level_set_num,
-                   float sigma_thresh, int every_voxel, int sx, int sy, int sz, AccelLayout lay,
-                   const uint64_t *__restrict__ occ, uint64_t *__restrict__ out) {
-    __shared__ float s_surf[WORK_WARPS][128];
-    __shared__ float s_dens[WORK_WARPS][128];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n_words = lay.count(0);
-    for (int64_t w = (int64_t)blockIdx.x * WORK_WARPS + warp; w < n_words; w += (int64_t)gridDim.x * WORK_WARPS) {
-        const uint64_t o = occ[w];
-        if (o == 0) {
-            if (lane == 0) out[w] = 0;
-            continue;
-        }
-        const int bz = (int)(w % lay.b[0][2]);
-        const int by = (int)((w / lay.b[0][2]) % lay.b[0][1]);
-        const int bx = (int)(w / ((int64_t)lay.b[0][2] * lay.b[0][1]));
-        __syncwarp();
+// Work bitmap, levels 0 and 1 in one pass: one CTA per non-empty 16^3-cell block (= one level-1 word), walking the list
+// of such blocks that asurf_accel_build leaves behind the occupancy pyramid.  The block's 17^3 vertices (surface scalar +
+// raw density through `links`) are staged once in shared memory -- 1.2x the block's own vertices, against 1.95x for a 5^3
+// halo per 4^3 block -- with many independent gathers in flight per thread; then each warp classifies 8 of the 64 4^3
+// sub-blocks.  Words of blocks without linked cells are cleared by a memset before the launch.
+constexpr int WB_THREADS = 256;
+constexpr int WB_V = 17;
+__global__ void __launch_bounds__(WB_THREADS)
+work_block16_kernel(const int32_t *__restrict__ links, const float *__restrict__ density,
+                    const float *__restrict__ surface, const float *__restrict__ level_set, int level_set_num,
+                    float sigma_thresh, int every_voxel, int sx, int sy, int sz, AccelLayout lay,
+                    const uint64_t *__restrict__ occ, uint64_t *__restrict__ out) {
+    __shared__ float s_surf[WB_V * WB_V * WB_V];
+    __shared__ float s_dens[WB_V * WB_V * WB_V];
+    __shared__ unsigned s_l1[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_active = (int64_t)occ[lay.off[3]];
+    const uint32_t *active = (const uint32_t *)(occ + lay.off[3] + 1);
+    constexpr int NV = WB_V * WB_V * WB_V;
+    for (int64_t it = blockIdx.x; it < n_active; it += gridDim.x) {
+        __syncthreads();   // the shared buffers of the previous block are free
+        const int64_t w1 = active[it];
+        const int cz = (int)(w1 % lay.b[1][2]);
+        const int cy = (int)((w1 / lay.b[1][2]) % lay.b[1][1]);
+        const int cx = (int)(w1 / ((int64_t)lay.b[1][2] * lay.b[1][1]));
+        if (tid < 2) s_l1[tid] = 0u;
+        const int x0 = cx * 16, y0 = cy * 16, z0 = cz * 16;
+        // stage the vertices: batches of 4 independent link loads, then 8 independent gathers
+        for (int vb = tid; vb < NV; vb += 4 * WB_THREADS) {
+            int32_t l[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int v = lane + 32 * r;
-            if (v < 125) {
-                const int x = bx * 4 + v / 25, y = by * 4 + (v / 5) % 5, z = bz * 4 + v % 5;
-                float sv = 0.f, dv = 0.f;
-                if (x < sx && y < sy && z < sz) {
-                    const int32_t l = links[((int64_t)x * sy + y) * sz + z];
-                    if (l >= 0) {
-                        sv = surface[l];
-                        dv = density[l];
+            for (int r = 0; r < 4; ++r) {
+                const int v = vb + r * WB_THREADS;
+                l[r] = -1;
+                if (v < NV) {
+                    const int x = x0 + v / (WB_V * WB_V), y = y0 + (v / WB_V) % WB_V, z = z0 + v % WB_V;
+                    if (x < sx && y < sy && z < sz) l[r] = __ldg(links + (((int64_t)x * sy + y) * sz + z));
+                }
+            }
+            float sv[4], dv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                sv[r] = 0.f;
+                dv[r] = 0.f;
+                if (l[r] >= 0) {
+                    sv[r] = __ldg(surface + l[r]);
+                    dv[r] = __ldg(density + l[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int v = vb + r * WB_THREADS;
+                if (v < NV) {
+                    s_surf[v] = sv[r];
+                    s_dens[v] = dv[r];
+                }
+            }
+        }
+        __syncthreads();
+        unsigned long long l1bits = 0;   // lane 0 of each warp collects the non-empty sub-blocks it produced
+        for (int sb = warp * 8; sb < warp * 8 + 8; ++sb) {
+            const int i = sb >> 4, j = (sb >> 2) & 3, k = sb & 3;
+            const int bx = cx * 4 + i, by = cy * 4 + j, bz = cz * 4 + k;
+            if (!(bx < lay.b[0][0] && by < lay.b[0][1] && bz < lay.b[0][2])) continue;
+            const int64_t k0 = ((int64_t)bx * lay.b[0][1] + by) * lay.b[0][2] + bz;
+            const uint64_t o = occ[k0];
+            if (o == 0) continue;   // the word was cleared by the memset
+            unsigned bits[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                bool work = false;
+                if ((o >> c) & 1ull) {
+                    const int vx = i * 4 + (c >> 4), vy = j * 4 + ((c >> 2) & 3), vz = k * 4 + (c & 3);
+                    const int base = (vx * WB_V + vy) * WB_V + vz;
+                    float smin = INFINITY, smax = -INFINITY;
+                    bool gate = false;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int idx = base + (q >> 2) * WB_V * WB_V + ((q >> 1) & 1) * WB_V + (q & 1);
+                        const float sv = s_surf[idx];
+                        smin = fminf(smin, sv);
+                        smax = fmaxf(smax, sv);
+                        gate |= !(s_dens[idx] < sigma_thresh);
                     }
+                    bool has_surf = every_voxel != 0;
+                    for (int q = 0; q < level_set_num && !has_surf; ++q) {
+                        const float lv = level_set[q];
+                        has_surf = !((lv < smin) || (lv > smax));
+                    }
+                    work = gate && has_surf;
                 }
-                s_surf[warp][v] = sv;
-                s_dens[warp][v] = dv;
+                bits[h] = __ballot_sync(0xffffffffu, work);
+            }
+            const uint64_t word = (uint64_t)bits[0] | ((uint64_t)bits[1] << 32);
+            if (lane == 0) {
+                out[k0] = word;
+                if (word != 0) l1bits |= 1ull << sb;
             }
         }
-        __syncwarp();
-        unsigned bits[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = lane + 32 * h;
-            bool work = false;
-            if ((o >> c) & 1ull) {
-                const int base = (c >> 4) * 25 + ((c >> 2) & 3) * 5 + (c & 3);
-                float smin = INFINITY, smax = -INFINITY;
-                bool gate = false;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int idx = base + (k >> 2) * 25 + ((k >> 1) & 1) * 5 + (k & 1);
-                    const float sv = s_surf[warp][idx];
-                    smin = fminf(smin, sv);
-                    smax = fmaxf(smax, sv);
-                    gate |= !(s_dens[warp][idx] < sigma_thresh);
-                }
-                bool has_surf = every_voxel != 0;
-                for (int i = 0; i < level_set_num && !has_surf; ++i) {
-                    const float lv = level_set[i];
-                    has_surf = !((lv < smin) || (lv > smax));
-                }
-                work = gate && has_surf;
-            }
-            bits[h] = __ballot_sync(0xffffffffu, work);
+        if (lane == 0 && l1bits != 0) {
+            atomicOr(&s_l1[0], (unsigned)(l1bits & 0xffffffffull));
+            atomicOr(&s_l1[1], (unsigned)(l1bits >> 32));
         }
-        if (lane == 0) out[w] = (uint64_t)bits[0] | ((uint64_t)bits[1] << 32);
+        __syncthreads();
+        if (tid == 0) out[lay.off[1] + w1] = (uint64_t)s_l1[0] | ((uint64_t)s_l1[1] << 32);
     }
+}
+
+// After the three pyramid levels the occupancy buffer holds the list of non-empty level-1 (16^3) blocks:
+// word off[3] = their number, then their indices as uint32 (2 per word).  The work-pyramid build walks this list.
+__global__ void __launch_bounds__(256) accel_list1_kernel(AccelLayout lay, uint64_t *__restrict__ buf) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = (w < lay.count(1)) && (buf[lay.off[1] + w] != 0);
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd((unsigned long long *)(buf + lay.off[3]), (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (on) ((uint32_t *)(buf + lay.off[3] + 1))[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)w;
 }
 
 }  // namespace
@@ -158,22 +211,22 @@ extern "C" int asurf_work_build(const asurf_grid_t *grid, const asurf_opt_t *opt
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t want = (lay.count(0) + WORK_WARPS - 1) / WORK_WARPS;
-    const int blocks = (int)(want < (int64_t)sms * 32 ? want : (int64_t)sms * 32);
     const int every_voxel = (opt->surf_fake_sample && !opt->limited_fake_sample) ? 1 : 0;
-    work_level0_kernel<<<blocks, WORK_WARPS * 32, 0, st>>>(grid->links, grid->density, grid->surface, grid->level_set,
-                                                           grid->level_set_num, opt->sigma_thresh, every_voxel,
-                                                           grid->size[0], grid->size[1], grid->size[2], lay, grid->accel,
-                                                           work_out);
-    accel_coarsen_kernel<<<div_up(lay.count(1), 128), 128, 0, st>>>(lay, 1, work_out);
+    // words of blocks without linked cells stay zero: clear levels 0 and 1, then visit the non-empty 16^3 blocks only
+    ASURF_CUDA(cudaMemsetAsync(work_out, 0, (size_t)lay.off[2] * sizeof(uint64_t), st));
+    const int64_t n1 = lay.count(1);
+    const int ctas = (int)(n1 < (int64_t)sms * 5 ? n1 : (int64_t)sms * 5);
+    work_block16_kernel<<<ctas, WB_THREADS, 0, st>>>(grid->links, grid->density, grid->surface, grid->level_set,
+                                                     grid->level_set_num, opt->sigma_thresh, every_voxel, grid->size[0],
+                                                     grid->size[1], grid->size[2], lay, grid->accel, work_out);
     accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, work_out);
-    note_launches(3);
+    note_launches(2);
     return check_cuda(cudaGetLastError(), "work_build launch");
 }
 
 extern "C" int64_t asurf_accel_words(const int32_t size[3]) {
     AccelLayout lay(size);
-    return lay.off[3];
+    return lay.off[3] + 1 + (lay.count(1) + 1) / 2;   // pyramid + list of non-empty level-1 blocks
 }
 
 extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream) {
@@ -184,6 +237,8 @@ extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], ui
     accel_level0_kernel<<<div_up(lay.count(0), 128), 128, 0, st>>>(links, size[0], size[1], size[2], lay, accel_out);
     accel_coarsen_kernel<<<div_up(lay.count(1), 128), 128, 0, st>>>(lay, 1, accel_out);
     accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, accel_out);
-    note_launches(3);
+    ASURF_CUDA(cudaMemsetAsync(accel_out + lay.off[3], 0, sizeof(uint64_t), st));
+    accel_list1_kernel<<<div_up(lay.count(1), 256), 256, 0, st>>>(lay, accel_out);
+    note_launches(4);
     return check_cuda(cudaGetLastError(), "accel_build launch");
 }

@@ -1423,7 +1423,7 @@ int make_grid(const asurf_grid_t *grid, const asurf_opt_t *opt, bool need_work, 
     if (grid->accel) {
         g.accel = grid->accel;
     } else {
-        int rc = g_ws_accel.reserve((size_t)lay.off[3] * sizeof(uint64_t));
+        int rc = g_ws_accel.reserve((size_t)asurf_accel_words(grid->size) * sizeof(uint64_t));
         if (rc) return rc;
         rc = asurf_accel_build(grid->links, grid->size, (uint64_t *)g_ws_accel.ptr, st);
         if (rc) return rc;
