@@ -1526,28 +1526,31 @@ inline int wave_grid(int64_t want_threads, int threads, int ctas_per_sm) {
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
-int wave_buffers(const PreP &pre, unsigned long long *ctr, WaveP &wv) {
+int wave_buffers(const PreP &pre, int64_t Q, unsigned long long *ctr, WaveP &wv) {
     const size_t n = (size_t)pre.item_cap;
     const size_t b_items = n * sizeof(ItemRec), b_hits = n * WAVE_ENT * sizeof(HitRec), b_q = n * WAVE_ENT * sizeof(int32_t);
-    int rc = g_ws_wave.reserve(b_items + b_hits + b_q);
+    const size_t b_pre = (size_t)Q * sizeof(Pre);
+    int rc = g_ws_wave.reserve(b_items + b_hits + b_q + b_pre);
     if (rc) return rc;
     char *base = (char *)g_ws_wave.ptr;
     wv.items = (ItemRec *)base;
     wv.hits = (HitRec *)(base + b_items);
     wv.hitq = (int32_t *)(base + b_items + b_hits);
+    wv.ray_pre = (Pre *)(base + b_items + b_hits + b_q);
     wv.n_hits = ctr + 5;
     return 0;
 }
 
 // eval -> colour -> composite for the short rays (rgb_out may be NULL: backward-only rematerialisation)
 int wave_forward(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, const PreP &pre, const WaveP &wv,
-                 const CacheP &cache, int M, float *rgb_out, cudaStream_t st) {
+                 const CacheP &cache, int M, float *rgb_out, const float *grad_in, const float *color_cache,
+                 const FusedP &f, cudaStream_t st) {
     const int64_t Q = rays->n_rays;
     FusedP nof = {};
     asurf_grads_t nog = {};
     wave_eval_kernel<<<wave_grid(Q * 2, 128, 16), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv);
     wave_wide_kernel<false><<<wave_grid(Q * 32, 128, 16), 128, 0, st>>>(g, *opt, rays->dirs, pre, wv, nullptr, nullptr, nof, nog);
-    wave_composite_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, pre, wv, cache, M, rgb_out);
+    wave_composite_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, pre, wv, cache, M, rgb_out, grad_in, color_cache, f);
     note_launches(3);
     return check_cuda(cudaGetLastError(), "wavefront forward launch");
 }
@@ -1557,8 +1560,8 @@ int wave_backward(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *ra
                   const asurf_grads_t &grads, cudaStream_t st) {
     const int64_t Q = rays->n_rays;
     wave_wide_kernel<true><<<wave_grid(Q * 32, 128, 16), 128, 0, st>>>(g, *opt, rays->dirs, pre, wv, grad_in, color_cache, f, grads);
-    wave_bwd_scalar_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv, grad_in,
-                                                                  color_cache, f, cache, grads);
+    wave_bwd_hit_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv, grad_in,
+                                                               color_cache, f, cache, grads);
     note_launches(2);
     return check_cuda(cudaGetLastError(), "wavefront backward launch");
 }
@@ -1593,9 +1596,9 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
         if (rc) return rc;
         if (pre.wave) {
             WaveP wv;
-            rc = wave_buffers(pre, ctr, wv);
+            rc = wave_buffers(pre, rays->n_rays, ctr, wv);
             if (rc) return rc;
-            rc = wave_forward(g, opt, rays, pre, wv, cache, 0, rgb_out, st);
+            rc = wave_forward(g, opt, rays, pre, wv, cache, 0, rgb_out, nullptr, nullptr, f, st);
             if (rc) return rc;
         }
         surf_trav_kernel<false, false><<<n_ctas(rays->n_rays), CTA_THREADS, 0, st>>>(
@@ -1628,9 +1631,9 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     if (rc) return rc;
     if (pre.wave) {   // rematerialise the short rays' samples, then their backward
         WaveP wv;
-        rc = wave_buffers(pre, ctr, wv);
+        rc = wave_buffers(pre, rays->n_rays, ctr, wv);
         if (rc) return rc;
-        rc = wave_forward(g, opt, rays, pre, wv, cache, 0, nullptr, st);
+        rc = wave_forward(g, opt, rays, pre, wv, cache, 0, nullptr, grad_out, color_cache, f, st);
         if (rc) return rc;
         rc = wave_backward(g, opt, rays, pre, wv, grad_out, color_cache, f, cache, *grads, st);
         if (rc) return rc;
@@ -1719,9 +1722,9 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
                                                                           nullptr, nullptr, ff, cache, nog, dbg, ctr, nopre);
     } else {
         if (pre.wave) {
-            rc = wave_buffers(pre, ctr, wv);
+            rc = wave_buffers(pre, rays->n_rays, ctr, wv);
             if (rc) return rc;
-            rc = wave_forward(g, opt, rays, pre, wv, cache, M, rgb_out, st);
+            rc = wave_forward(g, opt, rays, pre, wv, cache, M, rgb_out, rgb_gt, nullptr, f, st);
             if (rc) return rc;
         }
         surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,

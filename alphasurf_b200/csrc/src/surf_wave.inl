@@ -11,7 +11,8 @@
 //   wave_composite  thread per ray: the sequential part (intersect_i, truncated re-weighting, log-transmittance,
 //                   sample caches, early stop, colour; :370-547) in forward AND backward arithmetic (:2097-2101)
 //   wave_bwd_wide   warp per sample: SH gradient scatter + d(colour)/d(position) (:2212-2263)
-//   wave_bwd_scalar thread per ray: everything the reference does on lane 0 (:2137-2448, :2590-2866)
+//   wave_bwd_hit    thread per sample: everything the reference does on lane 0 (:2137-2448, :2590-2866), started from the
+//                   loop state the composite stage left in the sample record
 //
 // Entry order per ray = (listed voxel, root index), i.e. the order trace_ray_surf_trav meets them.
 
@@ -33,7 +34,9 @@ struct HitRec {               // per entry
     float weight_f, weight_b; // compositing weight in forward / backward arithmetic
     float gx, gy, gz;         // d(colour loss)/d(position) from the SH part
     int32_t live_b;           // the backward loop reaches this entry
-    int32_t pad;
+    // state of the backward loop when it reaches this entry (written by the composite stage)
+    float accum_b, logT_b;
+    int32_t isect_b, sample_b;
 };
 
 struct WaveP {
@@ -41,6 +44,7 @@ struct WaveP {
     HitRec *hits;
     int32_t *hitq;                 // compact queue of sample entries: item index * 4 + entry
     unsigned long long *n_hits;
+    Pre *ray_pre;                  // (Q,) per-ray constants of the fused losses (fused_preamble)
 };
 
 __device__ __forceinline__ int ent_kind(int32_t n_ent, int e) { return (n_ent >> (8 + 8 * e)) & 3; }
@@ -166,7 +170,7 @@ wave_eval_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
                     h.c0 = h.c1 = h.c2 = 0.f;
                     h.weight_f = h.weight_b = 0.f;
                     h.gx = h.gy = h.gz = 0.f;
-                    h.live_b = 0; h.pad = 0;
+                    h.live_b = 0; h.accum_b = 0.f; h.logT_b = 0.f; h.isect_b = 0; h.sample_b = 0;
                     hr[n_ent] = h;
                     n_samp |= (samp ? 1 : 0) << n_ent;
                     packed |= ((samp ? ENT_SAMPLE : ENT_COUNT) | (j << 2)) << (8 + 8 * n_ent);
@@ -210,7 +214,7 @@ wave_eval_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
                     h.c0 = h.c1 = h.c2 = 0.f;
                     h.weight_f = h.weight_b = 0.f;
                     h.gx = h.gy = h.gz = 0.f;
-                    h.live_b = 0; h.pad = 0;
+                    h.live_b = 0; h.accum_b = 0.f; h.logT_b = 0.f; h.isect_b = 0; h.sample_b = 0;
                     hr[0] = h;
                     it.surf_miu = surf_miu;
                     it.surf_std = surf_std;
@@ -339,9 +343,13 @@ wave_wide_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
 }
 
 // ---- stage 3: thread per ray, the sequential compositing ---------------------------------------------------------------------
+// Forward: colours, sample caches.  With a gradient source (grad_in != NULL) it also walks the backward loop's scalar
+// recurrences -- accum (:1795-1797, :2118), log-transmittance, intersect_i, cache index -- and leaves their value AT each
+// entry in the entry's record, plus the per-ray loss constants, so that the backward of every entry can run on its own.
 __global__ void __launch_bounds__(128)
 wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, const WaveP wv, const CacheP cache, int M,
-                      float *__restrict__ rgb_out) {
+                      float *__restrict__ rgb_out, const float *__restrict__ grad_in,
+                      const float *__restrict__ color_cache, const FusedP f) {
     const int64_t n_short = (int64_t)*pre.n_short;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_short; s += (int64_t)gridDim.x * blockDim.x) {
         const int64_t ray_id = __ldg(pre.rays_short + s);
@@ -384,6 +392,8 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
                     out2 += wf * fmaxf(hr->c2 + 0.5f, 0.f);
                 }
                 if (alive_b) {
+                    hr->logT_b = logT_b;
+                    hr->isect_b = intersect_i;
                     const float pcnt = -__logf(fmaxf(1.f - rwalpha, 1e-8f));
                     wb = __expf(logT_b) * (1.f - __expf(-pcnt));
                     logT_b -= pcnt;
@@ -399,34 +409,94 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
             }
             if (alive_b && (__expf(logT_b) < opt.stop_thresh)) alive_b = false;
         }
+        const float bg = __expf(logT) * opt.background_brightness;
+        float cc[3] = {out0 + bg, out1 + bg, out2 + bg};
         if (rgb_out) {
-            const float bg = __expf(logT) * opt.background_brightness;
-            rgb_out[ray_id * 3 + 0] = out0 + bg;
-            rgb_out[ray_id * 3 + 1] = out1 + bg;
-            rgb_out[ray_id * 3 + 2] = out2 + bg;
+            rgb_out[ray_id * 3 + 0] = cc[0];
+            rgb_out[ray_id * 3 + 1] = cc[1];
+            rgb_out[ray_id * 3 + 2] = cc[2];
             if (M > 0) cache.n[ray_id] = sample_i;
+        }
+        if (grad_in == nullptr) continue;
+        // ---- the backward loop's recurrences ----
+        if (color_cache) {
+            cc[0] = color_cache[ray_id * 3 + 0]; cc[1] = color_cache[ray_id * 3 + 1]; cc[2] = color_cache[ray_id * 3 + 2];
+        }
+        float gi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (f.grad_is_rgb) {   // fused: dL/dRGB from the L2 / L1 mix (:3306-3316)
+                const float resid = cc[i] - grad_in[ray_id * 3 + i];
+                gi[i] = resid * f.norm_l2 * f.lambda_l2;
+                gi[i] += (resid > 0.f) ? (f.norm_l1 * f.lambda_l1) : (-f.norm_l1 * f.lambda_l1);
+            } else {
+                gi[i] = grad_in[ray_id * 3 + i];
+            }
+        }
+        CacheView cv;
+        cv.sa = cv.sw = cv.st = nullptr;
+        cv.n = 0;
+        if (M > 0) {
+            cv.sa = cache.sa + ray_id * M; cv.sw = cache.sw + ray_id * M; cv.st = cache.st + ray_id * M;
+            cv.n = rgb_out ? sample_i : cache.n[ray_id];
+        }
+        Pre lossc;
+        fused_preamble(cv, lossc);
+        wv.ray_pre[ray_id] = lossc;
+        float accum = fmaf(cc[0], gi[0], fmaf(cc[1], gi[1], cc[2] * gi[2]));
+        int sample_b = 0;
+        bool live = true;
+        for (int k = 0; k < n_bwd && live; ++k) {
+            const int32_t ne = wv.items[base + k].n_ent;
+            const int cnt = ne & 255;
+            for (int e = 0; e < cnt; ++e) {
+                const int kind = ent_kind(ne, e);
+                if (kind == ENT_COUNT) continue;
+                HitRec *hr = wv.hits + (base + k) * WAVE_ENT + e;
+                if (!hr->live_b) { live = false; break; }
+                hr->accum_b = accum;
+                hr->sample_b = sample_b;
+                const float l0 = hr->c0 + 0.5f, l1 = hr->c1 + 0.5f, l2 = hr->c2 + 0.5f;
+                float total_color = fmaxf(l0, 0.f) * gi[0];   // shuffle order of the reference (:2112-2115): (c0 + c2) + c1
+                total_color += fmaxf(l2, 0.f) * gi[2];
+                total_color += fmaxf(l1, 0.f) * gi[1];
+                accum -= hr->weight_b * total_color;
+                if ((kind == ENT_SAMPLE || opt.fake_sample_l_dist) && (sample_b < M - 1)) sample_b += 1;
+            }
         }
     }
 }
 
-// ---- stage 5: thread per ray, the scalar part of the backward -----------------------------------------------------------------
+// ---- stage 5: thread per sample, the scalar part of its backward (the reference's lane-0 code, :2137-2448, :2590-2866) --------
 __global__ void __launch_bounds__(128)
-wave_bwd_scalar_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins,
-                       const float *__restrict__ dirs, const PreP pre, const WaveP wv, const float *__restrict__ grad_in,
-                       const float *__restrict__ color_cache, const FusedP f, const CacheP cache,
-                       const asurf_grads_t grads) {
-    const int64_t n_short = (int64_t)*pre.n_short;
+wave_bwd_hit_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins,
+                    const float *__restrict__ dirs, const PreP pre, const WaveP wv, const float *__restrict__ grad_in,
+                    const float *__restrict__ color_cache, const FusedP f, const CacheP cache,
+                    const asurf_grads_t grads) {
+    const int64_t n_hits = (int64_t)*wv.n_hits;
     const int M = f.M;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_short; s += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t ray_id = __ldg(pre.rays_short + s);
-        const int32_t code = __ldg(pre.code + ray_id);
-        const int n_bwd = (code >> 8) & 255;
-        const int64_t base = __ldg(pre.item_base + ray_id);
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t hc = __ldg(wv.hitq + h);
+        const int64_t t = hc >> 2;
+        const int e = hc & 3;
+        const HitRec hr = wv.hits[t * WAVE_ENT + e];
+        if (!hr.live_b) continue;
+        const int32_t code = __ldg(pre.itemq + t);
+        const int64_t ray_id = code / pre.K;
+        const ItemRec it = wv.items[t];
+        const int kind = ent_kind(it.n_ent, e);
         Lane L;
         wave_ray(g, opt, origins, dirs, ray_id, L);
-        L.logT = 0.f;
-        L.intersect_i = -1;
-        L.sample_i = 0;
+        wave_voxel(g, __ldg(pre.cells + code), L);
+        wave_links(g, L);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) L.sf[c] = __ldg(g.surface + L.lk[c]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) L.dn[c] = __ldg(g.density + L.lk[c]);
+        L.fs[0] = it.fs[0]; L.fs[1] = it.fs[1]; L.fs[2] = it.fs[2]; L.fs[3] = it.fs[3];
+        L.root_type = it.root_type;
+        L.surf_miu = it.surf_miu;
+        L.surf_std = it.surf_std;
         float g0, g1, g2;
         if (f.grad_is_rgb) {
             float gi[3];
@@ -447,57 +517,33 @@ wave_bwd_scalar_kernel(const GridP g, const asurf_opt_t opt, const float *__rest
             cv.sa = cache.sa + ray_id * M; cv.sw = cache.sw + ray_id * M; cv.st = cache.st + ray_id * M;
             cv.n = cache.n[ray_id];
         }
-        Pre lossc;
-        fused_preamble(cv, lossc);
-        float accum = fmaf(color_cache[ray_id * 3 + 0], g0, fmaf(color_cache[ray_id * 3 + 1], g1, color_cache[ray_id * 3 + 2] * g2));
-        for (int k = 0; k < n_bwd; ++k) {
-            const int64_t t = base + k;
-            const ItemRec it = wv.items[t];
-            const int cnt = it.n_ent & 255;
-            bool loaded = false;
-            for (int e = 0; e < cnt; ++e) {
-                const int kind = ent_kind(it.n_ent, e);
-                if (kind != ENT_FAKE) ++L.intersect_i;
-                if (kind == ENT_COUNT) continue;
-                const HitRec hr = wv.hits[t * WAVE_ENT + e];
-                if (!loaded) {
-                    wave_voxel(g, __ldg(pre.cells + ray_id * pre.K + k), L);
-                    wave_links(g, L);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) L.sf[c] = __ldg(g.surface + L.lk[c]);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) L.dn[c] = __ldg(g.density + L.lk[c]);
-                    L.fs[0] = it.fs[0]; L.fs[1] = it.fs[1]; L.fs[2] = it.fs[2]; L.fs[3] = it.fs[3];
-                    L.root_type = it.root_type;
-                    L.surf_miu = it.surf_miu;
-                    L.surf_std = it.surf_std;
-                    loaded = true;
-                }
-                L.px = hr.px; L.py = hr.py; L.pz = hr.pz;
-                L.ts = hr.ts;
-                L.raw_alpha = hr.raw_alpha;
-                L.alpha = hr.alpha;
-                L.trunc_rw_ = opt.truncated_vol_render ? trunc_rw(L.intersect_i, g.trunc_a, opt.trunc_vol_weight_min) : 1.f;
-                L.fake = (kind == ENT_FAKE);
-                if (!L.fake) {
-                    L.st_id = ent_root(it.n_ent, e);
-                    L.rwalpha = L.alpha * L.trunc_rw_;
-                    L.pcnt = -__logf(fmaxf(1.f - L.rwalpha, 1e-8f));
-                } else {
-                    L.reweight = hr.reweight;
-                    L.fake_dist = hr.fake_dist;
-                    L.rwalpha = L.alpha * L.reweight * L.trunc_rw_;
-                    L.pcnt = -1 * __logf(fmaxf(1.f - L.rwalpha, 1e-8f));
-                }
-                L.weight = __expf(L.logT) * (1.f - __expf(-L.pcnt));
-                const float l0 = hr.c0 + 0.5f, l1 = hr.c1 + 0.5f, l2 = hr.c2 + 0.5f;
-                float total_color = fmaxf(l0, 0.f) * g0;   // shuffle order of the reference (:2112-2115): (c0 + c2) + c1
-                total_color += fmaxf(l2, 0.f) * g2;
-                total_color += fmaxf(l1, 0.f) * g1;
-                if (!L.fake) finish_real_bwd(g, opt, f, lossc, cv, grads, L, accum, total_color, hr.gx, hr.gy, hr.gz);
-                else finish_fake_bwd(g, opt, f, lossc, cv, grads, L, accum, total_color);
-            }
-            if (__expf(L.logT) < opt.stop_thresh) break;
+        const Pre lossc = wv.ray_pre[ray_id];
+        L.logT = hr.logT_b;
+        L.intersect_i = hr.isect_b;
+        L.sample_i = hr.sample_b;
+        float accum = hr.accum_b;
+        L.px = hr.px; L.py = hr.py; L.pz = hr.pz;
+        L.ts = hr.ts;
+        L.raw_alpha = hr.raw_alpha;
+        L.alpha = hr.alpha;
+        L.trunc_rw_ = opt.truncated_vol_render ? trunc_rw(L.intersect_i, g.trunc_a, opt.trunc_vol_weight_min) : 1.f;
+        L.fake = (kind == ENT_FAKE);
+        if (!L.fake) {
+            L.st_id = ent_root(it.n_ent, e);
+            L.rwalpha = L.alpha * L.trunc_rw_;
+            L.pcnt = -__logf(fmaxf(1.f - L.rwalpha, 1e-8f));
+        } else {
+            L.reweight = hr.reweight;
+            L.fake_dist = hr.fake_dist;
+            L.rwalpha = L.alpha * L.reweight * L.trunc_rw_;
+            L.pcnt = -1 * __logf(fmaxf(1.f - L.rwalpha, 1e-8f));
         }
+        L.weight = __expf(L.logT) * (1.f - __expf(-L.pcnt));
+        const float l0 = hr.c0 + 0.5f, l1 = hr.c1 + 0.5f, l2 = hr.c2 + 0.5f;
+        float total_color = fmaxf(l0, 0.f) * g0;   // shuffle order of the reference (:2112-2115): (c0 + c2) + c1
+        total_color += fmaxf(l2, 0.f) * g2;
+        total_color += fmaxf(l1, 0.f) * g1;
+        if (!L.fake) finish_real_bwd(g, opt, f, lossc, cv, grads, L, accum, total_color, hr.gx, hr.gy, hr.gz);
+        else finish_fake_bwd(g, opt, f, lossc, cv, grads, L, accum, total_color);
     }
 }
