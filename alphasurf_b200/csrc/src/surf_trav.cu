@@ -90,7 +90,7 @@ struct PreP {
 
 enum { ST_IDLE = 0, ST_MARCH = 1, ST_VOXEL = 2, ST_SAMPLE = 3 };
 enum { PM_DONE = 0, PM_LOOKUP = 1, PM_JUMP = 2, PM_FINE = 3 };   // pre-march phases
-constexpr int PM_FINE_STEPS = 6;
+constexpr int PM_FINE_STEPS = 16, PM_JUMP_STEPS = 3;
 enum { PH_ENTER = 0, PH_ROOTS = 1, PH_FAKE = 2, PH_POST = 3 };
 
 struct Lane {
@@ -695,43 +695,47 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
         ray_bounds(g, opt, L, world_step);
         if (!(L.tmin > L.tmax)) dda_init(g, L);
     }
-    // The march runs in three warp-wide phases per round so that lanes doing the same kind of step execute together:
-    // LOOKUP (which pyramid level is empty around the next voxel), JUMP (leave an empty 16^3 / 64^3 block: ~200
-    // instructions) and FINE (a few voxel-by-voxel steps inside the cached 4^3 word: ~40 instructions each).  The
+    // The march runs in warp-wide phases so that lanes doing the same kind of step execute together: a JUMP phase
+    // (look up which pyramid level is empty around the next voxel, leave empty 16^3 / 64^3 blocks: ~250 instructions per
+    // jump) repeated while lanes keep jumping, then a FINE phase (voxel-by-voxel steps inside non-empty 16^3 blocks,
+    // branch-free, ~40 instructions each, re-loading the 4^3 word when the lane crosses into the next one).  The
     // arithmetic of each step is that of march_step<false, false, true>.
     int mode = (L.state == ST_MARCH) ? PM_LOOKUP : PM_DONE;
     int jump_s = 0;
     const uint64_t *bm = g.work;
-    while (__any_sync(FULL, mode != PM_DONE)) {
-        // ---------------- LOOKUP ----------------
-        if (mode == PM_LOOKUP) {
-            if (!(L.t <= L.tmax)) {
-                mode = PM_DONE;
-            } else {
-                int s = 0;
-                if (g.use_skip && !L.force_fine) {
-                    const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
-                    if (k2 != L.k2) {
-                        L.k2 = k2;
-                        L.w2 = __ldg(bm + g.lay.off[2] + k2);
-                    }
-                    const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
-                    if (L.w2 == 0) s = 6;
-                    else if (!((L.w2 >> bit1) & 1ull)) s = 4;
-                }
-                if (s == 0) {
-                    const int k0 = ((L.nx >> 2) * g.ab1 + (L.ny >> 2)) * g.ab2 + (L.nz >> 2);
-                    L.wkey = k0;
-                    L.word = __ldg(bm + k0);
-                    mode = PM_FINE;
-                } else {
-                    jump_s = s;
-                    mode = PM_JUMP;
-                }
+    const int sgx = (L.dx > 0.f) ? 1 : -1, sgy = (L.dy > 0.f) ? 1 : -1, sgz = (L.dz > 0.f) ? 1 : -1;
+    // pyramid decision for the voxel (nx,ny,nz): FINE with its 4^3 word loaded, or JUMP over an empty block
+    auto lookup = [&]() {
+        int s = 0;
+        if (g.use_skip && !L.force_fine) {
+            const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
+            if (k2 != L.k2) {
+                L.k2 = k2;
+                L.w2 = __ldg(bm + g.lay.off[2] + k2);
             }
+            const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
+            if (L.w2 == 0) s = 6;
+            else if (!((L.w2 >> bit1) & 1ull)) s = 4;
         }
-        // ---------------- JUMP over an empty aligned block of 2^s voxels per side ----------------
-        if (__any_sync(FULL, mode == PM_JUMP)) {
+        if (s == 0) {
+            const int k0 = ((L.nx >> 2) * g.ab1 + (L.ny >> 2)) * g.ab2 + (L.nz >> 2);
+            L.wkey = k0;
+            L.word = __ldg(bm + k0);
+            mode = PM_FINE;
+        } else {
+            jump_s = s;
+            mode = PM_JUMP;
+        }
+    };
+    while (__any_sync(FULL, mode != PM_DONE)) {
+        // ---------------- JUMP phase ----------------
+#pragma unroll 1
+        for (int jt = 0; jt < PM_JUMP_STEPS; ++jt) {
+            if (mode == PM_LOOKUP) {
+                if (!(L.t <= L.tmax)) mode = PM_DONE;
+                else lookup();
+            }
+            if (!__any_sync(FULL, mode == PM_JUMP)) break;
             if (mode == PM_JUMP) {
                 const int sft = jump_s;
                 const int lox = (L.nx >> sft) << sft, loy = (L.ny >> sft) << sft, loz = (L.nz >> sft) << sft;
@@ -750,18 +754,12 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                     int nx = axis_after(L.nx, L.ox, L.dx, L.rx, L.slow_div, T, A > 0, lox, hix);
                     int ny = axis_after(L.ny, L.oy, L.dy, L.ry, L.slow_div, T, A > 1, loy, hiy);
                     int nz = axis_after(L.nz, L.oz, L.dz, L.rz, L.slow_div, T, false, loz, hiz);
-                    bool out;
-                    if (A == 0) {
-                        nx = (L.dx > 0.f) ? Px : Px - 1;
-                        out = (nx < 0) || (nx >= g.size[0] - 1);
-                    } else if (A == 1) {
-                        ny = (L.dy > 0.f) ? Py : Py - 1;
-                        out = (ny < 0) || (ny >= g.size[1] - 1);
-                    } else {
-                        nz = (L.dz > 0.f) ? Pz : Pz - 1;
-                        out = (nz < 0) || (nz >= g.size[2] - 1);
-                    }
-                    if (out) {
+                    nx = (A == 0) ? ((L.dx > 0.f) ? Px : Px - 1) : nx;
+                    ny = (A == 1) ? ((L.dy > 0.f) ? Py : Py - 1) : ny;
+                    nz = (A == 2) ? ((L.dz > 0.f) ? Pz : Pz - 1) : nz;
+                    const int na = (A == 0) ? nx : ((A == 1) ? ny : nz);
+                    const int lim = (A == 0) ? g.size[0] : ((A == 1) ? g.size[1] : g.size[2]);
+                    if ((na < 0) || (na >= lim - 1)) {
                         mode = PM_DONE;    // the ray leaves the grid through this empty block
                     } else {
                         L.nx = nx; L.ny = ny; L.nz = nz;
@@ -774,7 +772,7 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                 }
             }
         }
-        // ---------------- FINE: voxel-by-voxel steps inside the cached 4^3 word ----------------
+        // ---------------- FINE phase: voxel-by-voxel steps inside non-empty 16^3 blocks ----------------
 #pragma unroll 1
         for (int it = 0; it < PM_FINE_STEPS; ++it) {
             if (!__any_sync(FULL, mode == PM_FINE)) break;
@@ -784,23 +782,23 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                 } else {
                     const float T = fminf(fminf(L.tfx, L.tfy), L.tfz);
                     const int vx = L.nx, vy = L.ny, vz = L.nz;
-                    bool out;
-                    int moved;   // old ^ new coordinate of the exit axis
-                    if (T == L.tfx) {
-                        const int nn = vx + ((L.dx > 0.f) ? 1 : -1);
-                        out = (nn < 0) || (nn >= g.size[0] - 1);
-                        moved = vx ^ nn;
-                        if (!out) { L.nx = nn; L.tfx = PT_X(L, nn + (L.dx > 0.f ? 1 : 0)); }
-                    } else if (T == L.tfy) {
-                        const int nn = vy + ((L.dy > 0.f) ? 1 : -1);
-                        out = (nn < 0) || (nn >= g.size[1] - 1);
-                        moved = vy ^ nn;
-                        if (!out) { L.ny = nn; L.tfy = PT_Y(L, nn + (L.dy > 0.f ? 1 : 0)); }
-                    } else {
-                        const int nn = vz + ((L.dz > 0.f) ? 1 : -1);
-                        out = (nn < 0) || (nn >= g.size[2] - 1);
-                        moved = vz ^ nn;
-                        if (!out) { L.nz = nn; L.tfz = PT_Z(L, nn + (L.dz > 0.f ? 1 : 0)); }
+                    // exit axis (ties go to the lowest axis, :188-197); everything below is select-based
+                    const bool ax = (T == L.tfx), ay = (!ax) && (T == L.tfy);
+                    const int m_old = ax ? vx : (ay ? vy : vz);
+                    const int sg = ax ? sgx : (ay ? sgy : sgz);
+                    const int lim = ax ? g.size[0] : (ay ? g.size[1] : g.size[2]);
+                    const int m_new = m_old + sg;
+                    const bool out = (m_new < 0) || (m_new >= lim - 1);
+                    const float oa = ax ? L.ox : (ay ? L.oy : L.oz), da = ax ? L.dx : (ay ? L.dy : L.dz),
+                                ra = ax ? L.rx : (ay ? L.ry : L.rz);
+                    const float tnew = plane_t(m_new + (sg > 0 ? 1 : 0), oa, da, ra, L.slow_div);
+                    if (!out) {
+                        L.nx = ax ? m_new : vx;
+                        L.ny = ay ? m_new : vy;
+                        L.nz = (ax || ay) ? vz : m_new;
+                        L.tfx = ax ? tnew : L.tfx;
+                        L.tfy = ay ? tnew : L.tfy;
+                        L.tfz = (ax || ay) ? L.tfz : tnew;
                     }
                     L.t = out ? L.tmax + 1.f : T;
                     const int bit = ((vx & 3) << 4) | ((vy & 3) << 2) | (vz & 3);
@@ -816,7 +814,10 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                         // backward quirk (:1935): an UNLINKED voxel this close to tmax ends the backward loop
                         if (!((__ldg(g.accel + L.wkey) >> bit) & 1ull)) L.bwd_alive = false;
                     }
-                    if (mode == PM_FINE && (out || (moved >> 2))) mode = out ? PM_DONE : PM_LOOKUP;
+                    if (mode == PM_FINE) {
+                        if (out) mode = PM_DONE;
+                        else if ((m_old ^ m_new) >> 2) lookup();   // next 4^3 block: new word, or an empty block to jump
+                    }
                 }
             }
         }

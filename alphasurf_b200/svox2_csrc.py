@@ -471,3 +471,28 @@ def render_stats(grid, rays, opt):
                    "render_stats")
     v = st.tolist()
     return dict(n_steps=v[0], n_skips=v[1], n_linked=v[2], n_active=v[3], n_samples=v[4])
+
+
+# ---- entry points of svox2.cpp that are outside the hot path ----------------------------------
+# They exist so that `hasattr(_C, name)` probes of the reference behave (svox2/utils.py:36 requires `sample_grid`), and
+# raise instead of silently doing nothing: there is no fallback implementation in this package.
+def _not_on_hot_path(name):
+    def fn(*args, **kwargs):
+        raise NotImplementedError("svox2.csrc.%s is outside the B200 hot path of alphasurf_b200 (SURVEY.md 8f)" % name)
+    fn.__name__ = name
+    return fn
+
+
+for _name in ("sample_grid", "sample_grid_backward", "sample_grid_sh_surf", "sample_grid_raw_alpha", "cubic_extract_iso_pts",
+              "volume_render_expected_term_surf_trav", "volume_render_mode_term_surf_trav",
+              "volume_render_sigma_thresh_surf_trav", "volume_render_alpha_surf_trav", "extract_pts_surf_trav",
+              "render_normal_surf_trav", "volume_render_expected_term", "volume_render_mode_term", "volume_render_med_term",
+              "volume_render_sigma_thresh", "dilate", "accel_dist_prop", "grid_weight_render", "sparse_grid_weight_render",
+              "sparse_grid_visbility_render_surf", "sparse_grid_mask_render", "surface_normal_grad",
+              "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
+              "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
+              "volume_render_nvol", "volume_render_nvol_backward", "volume_render_nvol_fused", "volume_render_svox1",
+              "volume_render_svox1_backward", "volume_render_svox1_fused", "test_cubic_root_grad"):
+    if _name not in globals():
+        globals()[_name] = _not_on_hot_path(_name)
+del _name
