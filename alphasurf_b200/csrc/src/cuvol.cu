@@ -1,0 +1,438 @@
+// alphasurf_b200: the Plenoxels "cuvol" volume renderer (forward, backward, fused, image) for sm_100a.
+//
+// Replaces volume_render_cuvol / _backward / _fused / _image of
+// /root/reference/svox2/csrc/render_lerp_kernel_cuvol.cu:1120-1354 (kernels :762-919, marchers trace_ray_cuvol :30-125 and
+// trace_ray_cuvol_backward :371-535, skipping compute_skip_dist include/render_util.cuh:286-368).
+//
+// Semantics are the reference's sample by sample: t advances by step_size (or by ceil(skip/step)*step over an empty
+// block announced by a negative link), every sample gathers 8 links + 8 densities, and where sigma > sigma_thresh the
+// 8 x D SH coefficients.  The execution differs:
+//   * one warp per ray (the SH gather is warp-wide), but the DENSITY phase runs a batch of 8 consecutive sample
+//     positions at once on lanes 0..7 -- their t are produced by the same repeated `t += step` additions, so they are
+//     the reference's positions exactly; samples behind the first skipping one are discarded and the batch restarts
+//     at the skip target.  That puts 8 x (1 + 8 + 8) independent gathers in flight per warp instead of one dependent
+//     chain per sample.
+//   * per-ray scalars live in registers (no shared SingleRaySpec), channel sums use the reference's
+//     HeadSegmentedSum add order, gradients leave as coalesced red.global.add (27 consecutive floats per corner row).
+#include "common.cuh"
+#include "surf_math.cuh"
+
+namespace asurf {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CV_THREADS = 128;
+constexpr int CV_WARPS = CV_THREADS / 32;
+constexpr int CV_BATCH = 8;
+
+struct CvGrid {
+    const int32_t *links;
+    const float *density, *sh;
+    int size[3];
+    int basis_dim, sh_dim;
+    float offset[3], scaling[3];
+};
+
+struct CvCam {          // include/data_spec.hpp:124-137 (CameraSpec), c2w row-major 3x4
+    float c2w[12];
+    float fx, fy, cx, cy;
+    int width, height;
+};
+
+struct CvRay {
+    float o[3], d[3];
+    float tmin, tmax, world_step;
+};
+
+// ray_find_bounds (include/render_util.cuh:651-701) + transform_coord (cuda_util.cuh:63-69); AABB clip only
+__device__ __forceinline__ void cv_ray_bounds(const CvGrid &g, const asurf_opt_t &opt, CvRay &r) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r.o[i] = fmaf(r.o[i], g.scaling[i], g.offset[i]);
+        r.d[i] *= g.scaling[i];
+    }
+    const float delta_scale = rnorm3df(r.d[0], r.d[1], r.d[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.d[i] *= delta_scale;
+    r.world_step = delta_scale * opt.step_size;
+    r.tmin = opt.near_clip / r.world_step * opt.step_size;
+    r.tmax = 2e3f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float inv = (float)(1.0 / (double)r.d[i]);
+        const float t1 = (-0.5f - r.o[i]) * inv, t2 = ((float)g.size[i] - 0.5f - r.o[i]) * inv;
+        if (r.d[i] != 0.f) {
+            r.tmin = fmaxf(r.tmin, fminf(t1, t2));
+            r.tmax = fminf(r.tmax, fmaxf(t1, t2));
+        }
+    }
+}
+
+// compute_skip_dist (include/render_util.cuh:286-368) for the voxel l, interpolation offsets pos
+__device__ __forceinline__ float cv_skip_dist(const CvRay &r, const int *l, const float *pos, int32_t link_val) {
+    if (link_val >= -1) return 0.f;
+    const uint32_t dist = (uint32_t)(-link_val);
+    const uint32_t shift = dist - 1;
+    const uint32_t side = (uint32_t)((float)(1 << shift) - 1.f);
+    float tmin = 0.f, tmax = 1e9f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int ul = ((l[i] >> shift) << shift);
+        ul -= l[i];
+        const float invdir = (float)(1.0 / (double)r.d[i]);
+        const float t1 = ((float)ul - pos[i] + 0.f) * invdir;
+        const float t2 = ((float)(ul + side) - pos[i] + 0.f) * invdir;
+        if (r.d[i] != 0.f) {
+            tmin = fmaxf(tmin, fminf(t1, t2));
+            if (fmaxf(t1, t2) < tmax) tmax = fmaxf(t1, t2);
+        }
+    }
+    if (tmin > 0.f) return 0.f;
+    return tmax;
+}
+
+// cam2world_ray (include/render_util.cuh:599-617), no NDC
+__device__ __forceinline__ void cv_cam_ray(const CvCam &cam, int ix, int iy, float *o, float *d) {
+    float x = ((float)ix + 0.5f - cam.cx) / cam.fx;
+    float y = ((float)iy + 0.5f - cam.cy) / cam.fy;
+    float z = sqrtf((float)((double)(x * x + y * y) + 1.0));
+    x /= z; y /= z; z = 1.0f / z;
+    d[0] = cam.c2w[0] * x + cam.c2w[1] * y + cam.c2w[2] * z;
+    d[1] = cam.c2w[4] * x + cam.c2w[5] * y + cam.c2w[6] * z;
+    d[2] = cam.c2w[8] * x + cam.c2w[9] * y + cam.c2w[10] * z;
+    o[0] = cam.c2w[3]; o[1] = cam.c2w[7]; o[2] = cam.c2w[11];
+}
+
+__device__ __forceinline__ float cv_segment_sum(float v, int pos_in_seg, int bd) {   // HeadSegmentedSum order
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+        const float o = __shfl_down_sync(FULL, v, off);
+        if (pos_in_seg + off < bd) v += o;
+    }
+    return v;
+}
+
+struct CvSample {      // lane-private result of the density phase (lanes 0..CV_BATCH-1)
+    float t, sigma, skip;
+    float pos[3];
+    int lk[8];
+    bool in_range;
+};
+
+// One sample position on the calling lane: voxel, skip test, 8 links, trilinear sigma (trace_ray_cuvol :57-84).
+__device__ __forceinline__ void cv_density_phase(const CvGrid &g, const CvRay &r, CvSample &s) {
+    int l[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float p = fmaf(s.t, r.d[j], r.o[j]);
+        p = fminf(fmaxf(p, 0.f), (float)g.size[j] - 1.f);
+        l[j] = min((int)p, g.size[j] - 2);
+        s.pos[j] = p - (float)l[j];
+    }
+    const int offy = g.size[2];
+    const int64_t offx = (int64_t)g.size[1] * g.size[2];
+    const int32_t *lp = g.links + (offx * l[0] + (int64_t)offy * l[1] + l[2]);
+    s.lk[0] = __ldg(lp);
+    s.skip = cv_skip_dist(r, l, s.pos, s.lk[0]);
+    s.lk[1] = __ldg(lp + 1);
+    s.lk[2] = __ldg(lp + offy);
+    s.lk[3] = __ldg(lp + offy + 1);
+    s.lk[4] = __ldg(lp + offx);
+    s.lk[5] = __ldg(lp + offx + 1);
+    s.lk[6] = __ldg(lp + offx + offy);
+    s.lk[7] = __ldg(lp + offx + offy + 1);
+    float dn[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dn[c] = (s.lk[c] >= 0) ? __ldg(g.density + s.lk[c]) : 0.f;
+    s.sigma = trilerp8(dn, s.pos);
+}
+
+// BWD = false: colour;  BWD = true: gradients.  IMAGE: rays from the camera (forward only).
+template <bool BWD, bool IMAGE>
+__global__ void __launch_bounds__(CV_THREADS)
+cuvol_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+             const CvCam cam, const int64_t Q, float *__restrict__ rgb_out, float *__restrict__ log_transmit_out,
+             const float *__restrict__ grad_in, const float *__restrict__ color_cache, int grad_is_rgb, float norm_factor,
+             const float *__restrict__ log_transmit_in, float beta_loss, float sparsity_loss, const asurf_grads_t grads) {
+    __shared__ float s_sph[CV_WARPS][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray_id >= Q) return;
+    const int D = g.sh_dim, bd = g.basis_dim;
+    CvRay r;
+    float wd[3];
+    if (IMAGE) {
+        cv_cam_ray(cam, (int)(ray_id % cam.width), (int)(ray_id / cam.width), r.o, r.d);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            r.o[i] = origins[ray_id * 3 + i];
+            r.d[i] = dirs[ray_id * 3 + i];
+        }
+    }
+    wd[0] = r.d[0]; wd[1] = r.d[1]; wd[2] = r.d[2];
+    if (lane == 0) eval_sh(bd, wd[0], wd[1], wd[2], s_sph[warp]);   // world-space direction
+    __syncwarp();
+    cv_ray_bounds(g, opt, r);
+    const int kb = (lane < D) ? (lane % bd) : 0;
+    const float sph = (lane < D) ? s_sph[warp][kb] : 0.f;
+
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, accum = 0.f;
+    if (BWD) {
+        if (grad_is_rgb) {   // fused: grad_in is rgb_gt (:873-880)
+            g0 = (color_cache[ray_id * 3 + 0] - grad_in[ray_id * 3 + 0]) * norm_factor;
+            g1 = (color_cache[ray_id * 3 + 1] - grad_in[ray_id * 3 + 1]) * norm_factor;
+            g2 = (color_cache[ray_id * 3 + 2] - grad_in[ray_id * 3 + 2]) * norm_factor;
+        } else {
+            g0 = grad_in[ray_id * 3 + 0]; g1 = grad_in[ray_id * 3 + 1]; g2 = grad_in[ray_id * 3 + 2];
+        }
+        accum = fmaf(color_cache[ray_id * 3 + 0], g0, fmaf(color_cache[ray_id * 3 + 1], g1, color_cache[ray_id * 3 + 2] * g2));
+        if (beta_loss > 0.f) {
+            const float transmit_in = __expf(log_transmit_in ? log_transmit_in[ray_id] : 0.f);
+            beta_loss *= (1 - transmit_in / (1 - transmit_in + 1e-3));
+            accum += beta_loss;
+        }
+    }
+    float out0 = 0.f, out1 = 0.f, out2 = 0.f;
+    float log_transmit = 0.f;
+    if (r.tmin > r.tmax) {
+        if (!BWD && lane == 0) {
+            rgb_out[ray_id * 3 + 0] = opt.background_brightness;
+            rgb_out[ray_id * 3 + 1] = opt.background_brightness;
+            rgb_out[ray_id * 3 + 2] = opt.background_brightness;
+            if (log_transmit_out) log_transmit_out[ray_id] = 0.f;
+        }
+        return;
+    }
+    float t = r.tmin;
+    bool stop = false;
+    while (!stop && (t <= r.tmax)) {
+        // ---- density phase: lanes 0..7 take the next 8 sample positions t, t+step, (t+step)+step, ... ----
+        CvSample s;
+        s.t = t;
+        for (int i = 0; i < lane && i < CV_BATCH - 1; ++i) s.t += opt.step_size;
+        s.in_range = (lane < CV_BATCH) && (s.t <= r.tmax);
+        s.sigma = 0.f;
+        s.skip = 0.f;
+        if (s.in_range) cv_density_phase(g, r, s);
+        const unsigned m_in = __ballot_sync(FULL, s.in_range);
+        const unsigned m_skip = __ballot_sync(FULL, s.in_range && (s.skip >= opt.step_size));
+        // samples up to (excluding) the first skipping one are the reference's samples
+        const int n_in = __popc(m_in);
+        const int first_skip = m_skip ? (__ffs(m_skip) - 1) : n_in;
+        for (int i = 0; i < first_skip; ++i) {
+            const float sigma = __shfl_sync(FULL, s.sigma, i);
+            const float ts = __shfl_sync(FULL, s.t, i);
+            float world_step = r.world_step;
+            if (opt.last_sample_opaque && ts + opt.step_size > r.tmax) {
+                world_step = 1e9f;
+                r.world_step = 1e9f;   // sticky, as in the reference (:85-87)
+            }
+            if (sigma > opt.sigma_thresh) {
+                int lk[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) lk[c] = __shfl_sync(FULL, s.lk[c], i);
+                float pos[3];
+                pos[0] = __shfl_sync(FULL, s.pos[0], i);
+                pos[1] = __shfl_sync(FULL, s.pos[1], i);
+                pos[2] = __shfl_sync(FULL, s.pos[2], i);
+                float v[8];
+                float lane_color = 0.f;
+                if (lane < D) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = (lk[c] >= 0) ? __ldg(g.sh + (int64_t)lk[c] * D + lane) : 0.f;
+                    lane_color = trilerp8(v, pos) * sph;
+                }
+                const float pcnt = world_step * sigma;
+                const float weight = __expf(log_transmit) * (1.f - __expf(-pcnt));
+                log_transmit -= pcnt;
+                const float seg = cv_segment_sum(lane_color, (lane < D) ? kb : 32, bd);
+                const float c0 = __shfl_sync(FULL, seg, 0);
+                const float c1 = __shfl_sync(FULL, seg, bd);
+                const float c2 = __shfl_sync(FULL, seg, 2 * bd);
+                if (!BWD) {
+                    out0 += weight * fmaxf(c0 + 0.5f, 0.f);
+                    out1 += weight * fmaxf(c1 + 0.5f, 0.f);
+                    out2 += weight * fmaxf(c2 + 0.5f, 0.f);
+                    if (__expf(log_transmit) < opt.stop_thresh) {
+                        log_transmit = -1e3f;
+                        stop = true;
+                        break;
+                    }
+                } else {
+                    const float l0 = c0 + 0.5f, l1 = c1 + 0.5f, l2 = c2 + 0.5f;
+                    const float t0 = fmaxf(l0, 0.f), t1 = fmaxf(l1, 0.f), t2 = fmaxf(l2, 0.f);
+                    float total_color = t0 * g0;   // (c0 + c2) + c1, the reference's shuffle order (:466-469)
+                    total_color += t2 * g2;
+                    total_color += t1 * g1;
+                    if (lane < D) {
+                        const int ch = lane / bd;
+                        const float in01 = (ch == 0) ? ((t0 == l0) ? 1.f : 0.f)
+                                                     : ((ch == 1) ? ((t1 == l1) ? 1.f : 0.f) : ((t2 == l2) ? 1.f : 0.f));
+                        const float gch = (ch == 0) ? g0 : ((ch == 1) ? g1 : g2);
+                        const float curr_grad_color = sph * (weight * in01 * gch);
+                        float w[8];
+                        corner_weights(pos, curr_grad_color, w);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (lk[c] >= 0) atomicAdd(grads.grad_sh + (int64_t)lk[c] * D + lane, w[c]);
+                    }
+                    accum -= weight * total_color;
+                    float curr_grad_sigma = world_step * (total_color * __expf(log_transmit) - accum);
+                    if (sparsity_loss > 0.f) curr_grad_sigma += sparsity_loss * (4 * sigma / (1 + 2 * (sigma * sigma)));
+                    {   // density scatter: corner c on lane c (trilerp_backward_cuvol_one_density, render_util.cuh:124-154)
+                        float w[8];
+                        corner_weights(pos, curr_grad_sigma, w);
+                        if (lane < 8) {
+                            float wc = w[0];
+                            int lc = lk[0];
+#pragma unroll
+                            for (int c = 1; c < 8; ++c)
+                                if (lane == c) { wc = w[c]; lc = lk[c]; }
+                            if (lc >= 0) {
+                                atomicAdd(grads.grad_density + lc, wc);
+                                if (grads.mask) grads.mask[lc] = 1;
+                            }
+                        }
+                    }
+                    if (__expf(log_transmit) < opt.stop_thresh) {
+                        stop = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (stop) break;
+        // ---- next batch start: behind the last sample, or at the skip target ----
+        if (m_skip && first_skip < n_in) {
+            const float ts = __shfl_sync(FULL, s.t, first_skip);
+            const float sk = __shfl_sync(FULL, s.skip, first_skip);
+            t = ts + ceilf(sk / opt.step_size) * opt.step_size;
+        } else if (n_in > 0) {
+            t = __shfl_sync(FULL, s.t, n_in - 1) + opt.step_size;
+        } else {
+            break;
+        }
+    }
+    if (!BWD && lane == 0) {
+        const float bg = __expf(log_transmit) * opt.background_brightness;
+        rgb_out[ray_id * 3 + 0] = out0 + bg;
+        rgb_out[ray_id * 3 + 1] = out1 + bg;
+        rgb_out[ray_id * 3 + 2] = out2 + bg;
+        if (log_transmit_out) log_transmit_out[ray_id] = log_transmit;
+    }
+}
+
+Workspace g_ws_lt;
+
+int cv_make_grid(const asurf_grid_t *grid, CvGrid &g, const char *who) {
+    ASURF_REQUIRE(grid, ASURF_E_INVALID, "%s: null grid", who);
+    ASURF_REQUIRE(grid->links && grid->density && grid->sh, ASURF_E_INVALID, "%s: null grid tensor", who);
+    ASURF_REQUIRE(grid->size[0] >= 2 && grid->size[1] >= 2 && grid->size[2] >= 2, ASURF_E_INVALID, "%s: grid smaller than 2^3", who);
+    ASURF_REQUIRE(grid->basis_dim == 1 || grid->basis_dim == 4 || grid->basis_dim == 9, ASURF_E_UNSUPPORTED,
+                  "%s: basis_dim %d not supported (SH with 1, 4 or 9 functions)", who, grid->basis_dim);
+    ASURF_REQUIRE(grid->sh_dim == 3 * grid->basis_dim, ASURF_E_INVALID, "%s: sh_dim must be 3*basis_dim", who);
+    g.links = grid->links;
+    g.density = grid->density;
+    g.sh = grid->sh;
+    for (int i = 0; i < 3; ++i) {
+        g.size[i] = grid->size[i];
+        g.offset[i] = grid->offset[i];
+        g.scaling[i] = grid->scaling[i];
+    }
+    g.basis_dim = grid->basis_dim;
+    g.sh_dim = grid->sh_dim;
+    return 0;
+}
+
+inline int cv_blocks(int64_t Q) { return (int)((Q * 32 + CV_THREADS - 1) / CV_THREADS); }
+
+}  // namespace
+}  // namespace asurf
+
+using namespace asurf;
+
+extern "C" int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, float *rgb_out,
+                                   float *log_transmit_out, void *stream) {
+    ASURF_REQUIRE(rays && opt && rgb_out, ASURF_E_INVALID, "cuvol_forward: null argument");
+    ASURF_REQUIRE(!opt->use_spheric_clip, ASURF_E_UNSUPPORTED, "cuvol_forward: spheric clip is not on the hot path");
+    const int64_t Q = rays->n_rays;
+    if (Q <= 0) return 0;
+    CvGrid g;
+    int rc = cv_make_grid(grid, g, "cuvol_forward");
+    if (rc) return rc;
+    asurf_grads_t nog = {};
+    CvCam cam = {};
+    cuvol_kernel<false, false><<<cv_blocks(Q), CV_THREADS, 0, (cudaStream_t)stream>>>(
+        g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, log_transmit_out, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "cuvol_forward launch");
+}
+
+extern "C" int asurf_cuvol_image(const asurf_grid_t *grid, const float *c2w_host, float fx, float fy, float cx, float cy,
+                                 int32_t width, int32_t height, const asurf_opt_t *opt, float *rgb_out, void *stream) {
+    ASURF_REQUIRE(c2w_host && opt && rgb_out, ASURF_E_INVALID, "cuvol_image: null argument");
+    ASURF_REQUIRE(!opt->use_spheric_clip, ASURF_E_UNSUPPORTED, "cuvol_image: spheric clip is not on the hot path");
+    const int64_t Q = (int64_t)width * height;
+    if (Q <= 0) return 0;
+    CvGrid g;
+    int rc = cv_make_grid(grid, g, "cuvol_image");
+    if (rc) return rc;
+    asurf_grads_t nog = {};
+    CvCam cam;
+    for (int i = 0; i < 12; ++i) cam.c2w[i] = c2w_host[i];
+    cam.fx = fx; cam.fy = fy; cam.cx = cx; cam.cy = cy;
+    cam.width = width; cam.height = height;
+    cuvol_kernel<false, true><<<cv_blocks(Q), CV_THREADS, 0, (cudaStream_t)stream>>>(
+        g, *opt, nullptr, nullptr, cam, Q, rgb_out, nullptr, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "cuvol_image launch");
+}
+
+extern "C" int asurf_cuvol_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                    const float *grad_out, const float *color_cache, const asurf_grads_t *grads,
+                                    void *stream) {
+    ASURF_REQUIRE(rays && opt && grad_out && color_cache && grads, ASURF_E_INVALID, "cuvol_backward: null argument");
+    ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "cuvol_backward: null gradient buffer");
+    ASURF_REQUIRE(!opt->use_spheric_clip, ASURF_E_UNSUPPORTED, "cuvol_backward: spheric clip is not on the hot path");
+    const int64_t Q = rays->n_rays;
+    if (Q <= 0) return 0;
+    CvGrid g;
+    int rc = cv_make_grid(grid, g, "cuvol_backward");
+    if (rc) return rc;
+    CvCam cam = {};
+    cuvol_kernel<true, false><<<cv_blocks(Q), CV_THREADS, 0, (cudaStream_t)stream>>>(
+        g, *opt, rays->origins, rays->dirs, cam, Q, nullptr, nullptr, grad_out, color_cache, 0, 0.f, nullptr, 0.f, 0.f, *grads);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "cuvol_backward launch");
+}
+
+extern "C" int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                 const float *rgb_gt, float beta_loss, float sparsity_loss, int64_t norm_rays, float *rgb_out,
+                                 const asurf_grads_t *grads, void *stream) {
+    ASURF_REQUIRE(rays && opt && rgb_gt && rgb_out && grads, ASURF_E_INVALID, "cuvol_fused: null argument");
+    ASURF_REQUIRE(grads->grad_density && grads->grad_sh, ASURF_E_INVALID, "cuvol_fused: null gradient buffer");
+    ASURF_REQUIRE(!opt->use_spheric_clip, ASURF_E_UNSUPPORTED, "cuvol_fused: spheric clip is not on the hot path");
+    const int64_t Q = rays->n_rays;
+    if (Q <= 0) return 0;
+    CvGrid g;
+    int rc = cv_make_grid(grid, g, "cuvol_fused");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *lt = nullptr;
+    if (beta_loss > 0.f) {   // the backward needs the forward's final log-transmittance (:1291-1296)
+        rc = g_ws_lt.reserve((size_t)Q * sizeof(float));
+        if (rc) return rc;
+        lt = (float *)g_ws_lt.ptr;
+    }
+    const int64_t qn = norm_rays > 0 ? norm_rays : Q;
+    asurf_grads_t nog = {};
+    CvCam cam = {};
+    cuvol_kernel<false, false><<<cv_blocks(Q), CV_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, lt,
+                                                                    nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
+    cuvol_kernel<true, false><<<cv_blocks(Q), CV_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, cam, Q, nullptr, nullptr,
+                                                                   rgb_gt, rgb_out, 1, 2.f / (float)(3 * (int)qn), lt,
+                                                                   beta_loss / (float)qn, sparsity_loss, *grads);
+    note_launches(2);
+    return check_cuda(cudaGetLastError(), "cuvol_fused launch");
+}

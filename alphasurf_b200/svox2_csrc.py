@@ -182,7 +182,7 @@ def accel_for(links: torch.Tensor) -> torch.Tensor:
     return acc
 
 
-def _grid_t(grid: SparseGridSpec, need_surface=True):
+def _grid_t(grid: SparseGridSpec, need_surface=True, need_accel=True):
     g = capi.GridT()
     g.links = grid.links.data_ptr()
     g.size[:] = [int(s) for s in grid.links.shape]
@@ -199,8 +199,8 @@ def _grid_t(grid: SparseGridSpec, need_surface=True):
     g.scaling[:] = [float(v) for v in grid._scaling.tolist()]
     g.fake_sample_std = float(grid.fake_sample_std)
     g.truncated_vol_render_a = float(grid.truncated_vol_render_a)
-    acc = accel_for(grid.links)
-    g.accel = acc.data_ptr()
+    acc = accel_for(grid.links) if need_accel else None
+    g.accel = acc.data_ptr() if need_accel else None
     return g, acc
 
 
@@ -285,6 +285,61 @@ def volume_render_surf_trav_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_l
                                                     capi.ptr(rgb_gt), C.byref(f), capi.ptr(rgb_out),
                                                     C.byref(_grads_t(grads)), None, capi.current_stream()),
                    "volume_render_surf_trav_fused")
+
+
+# ---- Plenoxels renderer (render_lerp_kernel_cuvol.cu:1120-1354) -----------------------------------------------------------
+def volume_render_cuvol(grid, rays, opt):
+    _check_grid(grid)
+    _check_rays(rays)
+    out = torch.empty_like(rays.origins)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid, need_accel=False)
+        capi.check(capi.lib().asurf_cuvol_forward(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                  capi.ptr(out), None, capi.current_stream()), "volume_render_cuvol")
+    return out
+
+
+def volume_render_cuvol_image(grid, cam, opt):
+    _check_grid(grid)
+    _check_input(cam.c2w, "c2w")
+    if cam.ndc_coeffx > 0.0:
+        raise NotImplementedError("NDC cameras are outside the B200 hot path")
+    out = torch.empty((int(cam.height), int(cam.width), 3), dtype=grid.sh_data.dtype, device=grid.sh_data.device)
+    c2w = (C.c_float * 12)(*[float(v) for v in cam.c2w[:3, :4].reshape(-1).tolist()])
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid, need_accel=False)
+        capi.check(capi.lib().asurf_cuvol_image(C.byref(g), c2w, C.c_float(cam.fx), C.c_float(cam.fy), C.c_float(cam.cx),
+                                                C.c_float(cam.cy), C.c_int32(int(cam.width)), C.c_int32(int(cam.height)),
+                                                C.byref(capi.make_opt(opt)), capi.ptr(out), capi.current_stream()),
+                   "volume_render_cuvol_image")
+    return out
+
+
+def volume_render_cuvol_backward(grid, rays, opt, grad_out, color_cache, grads):
+    _check_grid(grid)
+    _check_rays(rays)
+    _check_grads(grads)
+    _check_input(grad_out, "grad_out")
+    _check_input(color_cache, "color_cache")
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid, need_accel=False)
+        capi.check(capi.lib().asurf_cuvol_backward(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                   capi.ptr(grad_out), capi.ptr(color_cache), C.byref(_grads_t(grads)),
+                                                   capi.current_stream()), "volume_render_cuvol_backward")
+
+
+def volume_render_cuvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss, rgb_out, grads):
+    _check_input(rgb_gt, "rgb_gt")
+    _check_input(rgb_out, "rgb_out")
+    _check_grid(grid)
+    _check_rays(rays)
+    _check_grads(grads)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid, need_accel=False)
+        capi.check(capi.lib().asurf_cuvol_fused(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                capi.ptr(rgb_gt), C.c_float(beta_loss), C.c_float(sparsity_loss),
+                                                C.c_int64(_NORM_RAYS or 0), capi.ptr(rgb_out), C.byref(_grads_t(grads)),
+                                                capi.current_stream()), "volume_render_cuvol_fused")
 
 
 # ---- optimizer steps (optim_kernel.cu:154-267) -------------------------------------------------------------------------

@@ -169,6 +169,22 @@ void asurf_debug_set_skip(int32_t enabled);
  * equal up to atomic order. */
 void asurf_debug_set_wave(int32_t enabled);
 
+/* ---- Plenoxels "cuvol" renderer, render_lerp_kernel_cuvol.cu:1120-1354 (grid->surface / level_set / accel / work unused;
+ *      links may hold the negative skip codes written by accel_dist_prop) ---- */
+/* volume_render_cuvol, :1120-1160 (rgb_out (Q,3); log_transmit_out (Q,) or NULL) */
+int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, float *rgb_out,
+                        float *log_transmit_out, void *stream);
+/* volume_render_cuvol_image, :1162-1209: rays of a pinhole camera (c2w: 12 host floats, row-major 3x4), rgb_out (H,W,3) */
+int asurf_cuvol_image(const asurf_grid_t *grid, const float *c2w_host, float fx, float fy, float cx, float cy, int32_t width,
+                      int32_t height, const asurf_opt_t *opt, float *rgb_out, void *stream);
+/* volume_render_cuvol_backward, :1211-1270 */
+int asurf_cuvol_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, const float *grad_out,
+                         const float *color_cache, const asurf_grads_t *grads, void *stream);
+/* volume_render_cuvol_fused, :1272-1354 (norm_rays: 0 = this call's Q, see asurf_fused_t.norm_rays) */
+int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, const float *rgb_gt,
+                      float beta_loss, float sparsity_loss, int64_t norm_rays, float *rgb_out, const asurf_grads_t *grads,
+                      void *stream);
+
 /* ---- optimizer steps, optim_kernel.cu:154-267 ----
  * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */
 int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,

@@ -52,5 +52,38 @@ def main():
         print(name, "rgb mean", float(res["rgb"].mean()), "N", sg.capacity)
 
 
+CUVOL_CASES = [
+    # name, reso, basis_dim, n_rays, seed
+    ("l0_cuvol_sh1_r24", 24, 4, 96, 11),
+    ("l0_cuvol_sh2_r20", 20, 9, 64, 12),
+]
+
+
+def cuvol_options():
+    """Plenoxels options the L0 renderer honours (it has no sigma / stop thresholds and no skipping)."""
+    o = synth.alphasurf_render_options()
+    o.update(backend="cuvol", sigma_thresh=0.0, stop_thresh=0.0)
+    return o
+
+
+def main_cuvol():
+    assert ref_l0.available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    for name, reso, bd, nr, seed in CUVOL_CASES:
+        sg = synth.make_shell_grid(reso, basis_dim=bd, variant="G", seed=synth.SEED + seed, z_order=False, sigma_density=True)
+        o, d, gt = synth.make_camera_rays(nr, seed=synth.SEED + 10 * seed, cam_radius=2.2)
+        opts = cuvol_options()
+        res = ref_l0.render_l0_cuvol(sg, opts, o, d, gt)
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"),
+            links=sg.links.numpy(), density=sg.density.numpy(), sh=sg.sh.numpy(), offset=sg.offset.numpy(),
+            scaling=sg.scaling.numpy(), basis_dim=np.int32(bd), origins=o.numpy(), dirs=d.numpy(), rgb_gt=gt.numpy(),
+            rgb=res["rgb"].numpy(), grad_density=res["grad_density"].numpy(), grad_sh=res["grad_sh"].numpy(),
+            opts=np.array(repr(opts)))
+        print(name, "rgb mean", float(res["rgb"].mean()), "N", sg.capacity)
+
+
 if __name__ == "__main__":
-    main()
+    if "--cuvol-only" not in sys.argv:
+        main()
+    main_cuvol()

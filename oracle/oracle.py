@@ -299,3 +299,40 @@ def surface_normal_grad_sparse(links, surf, cells, mask, lv_set, start_dim, end_
                                             _ptr(mask), C.c_float(lv_set), C.c_int(start_dim), C.c_int(end_dim),
                                             C.c_float(scale), C.c_int(int(con_check)), C.c_int(int(ignore_empty)),
                                             C.c_int(int(use_l1)), _ptr(grad))
+
+
+# ---- Plenoxels cuvol renderer (oracle_cuvol.c) ---------------------------------------------------------------------------
+def cuvol_forward(grid: Grid, opt: dict, origins, dirs, xf=None, want_log_transmit=False):
+    o, d, xf = _np(origins, np.float32), _np(dirs, np.float32), _np(xf, np.float32)
+    Q = o.shape[0]
+    out = np.zeros((Q, 3), np.float32)
+    lt = np.zeros((Q,), np.float32)
+    lib().oracle_cuvol_forward(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q), _ptr(out),
+                               _ptr(lt))
+    return (out, lt) if want_log_transmit else out
+
+
+def cuvol_backward(grid: Grid, opt: dict, origins, dirs, grad_out, color_cache, xf=None, grads: Grads = None):
+    o, d, xf = _np(origins, np.float32), _np(dirs, np.float32), _np(xf, np.float32)
+    go, cc = _np(grad_out, np.float32), _np(color_cache, np.float32)
+    grads = grads or Grads(grid, with_std=False)
+    lib().oracle_cuvol_backward(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(o.shape[0]),
+                                _ptr(go), _ptr(cc), C.c_int(0), C.c_float(0.0), None, C.c_float(0.0), C.c_float(0.0),
+                                C.byref(grads.c))
+    return grads
+
+
+def cuvol_fused(grid: Grid, opt: dict, origins, dirs, rgb_gt, beta_loss=0.0, sparsity_loss=0.0, xf=None, grads: Grads = None,
+                q_norm=None):
+    """volume_render_cuvol_fused (render_lerp_kernel_cuvol.cu:1272-1354): forward, then backward of the MSE."""
+    o, d, xf = _np(origins, np.float32), _np(dirs, np.float32), _np(xf, np.float32)
+    gt = _np(rgb_gt, np.float32)
+    Q = o.shape[0]
+    qn = Q if q_norm is None else int(q_norm)
+    out, lt = cuvol_forward(grid, opt, o, d, xf=xf, want_log_transmit=True)
+    grads = grads or Grads(grid, with_std=False)
+    norm = np.float32(2.0) / np.float32(3 * qn)
+    lib().oracle_cuvol_backward(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q), _ptr(gt),
+                                _ptr(out), C.c_int(1), C.c_float(norm), _ptr(lt) if beta_loss > 0 else None,
+                                C.c_float(np.float32(beta_loss) / np.float32(qn)), C.c_float(sparsity_loss), C.byref(grads.c))
+    return out, grads

@@ -94,3 +94,34 @@ def render_l0(sg, opt: dict, origins, dirs, run_backward=True, lambda_l_entropy=
         res.update(grad_density=z(grid.density_data), grad_sh=z(grid.sh_data), grad_surface=z(grid.surface_data),
                    grad_fake_sample_std=z(grid.fake_sample_std))
     return res
+
+
+def render_l0_cuvol(sg, opt: dict, origins, dirs, rgb_gt=None):
+    """Plenoxels flavour: SparseGrid.volume_render(use_kernel=False) -> _volume_render_gradcheck_lerp
+    (svox2/svox2.py:1215-1441) on a grid WITHOUT a surface; backward of mean((rgb - rgb_gt)^2), the loss the fused CUDA
+    call differentiates (render_lerp_kernel_cuvol.cu:873-880)."""
+    svox2 = import_reference()
+    R = sg.links.shape[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        grid = svox2.SparseGrid(reso=R, center=[0.0, 0.0, 0.0], radius=[1.0, 1.0, 1.0], basis_dim=sg.basis_dim,
+                                use_z_order=False, device="cpu", background_nlayers=0, basis_type=svox2.BASIS_TYPE_SH,
+                                surface_type=svox2.SURFACE_TYPE_NONE, use_sphere_bound=False, use_octree=False)
+    grid.links = sg.links.clone().cpu()
+    grid.capacity = sg.capacity
+    grid.density_data = torch.nn.Parameter(sg.density.clone().cpu())
+    grid.sh_data = torch.nn.Parameter(sg.sh.clone().cpu())
+    for k, v in opt.items():
+        if hasattr(grid.opt, k):
+            setattr(grid.opt, k, v)
+    grid.opt.backend = "cuvol"
+    rays = svox2.Rays(origins.clone().cpu(), dirs.clone().cpu())
+    with cpu_tensor_redirect(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rgb = grid.volume_render(rays, use_kernel=False)["rgb"]
+    res = {"rgb": rgb.detach().float()}
+    if rgb_gt is not None:
+        loss = ((rgb - rgb_gt.cpu()) ** 2).mean()
+        loss.backward()
+        res.update(grad_density=grid.density_data.grad.detach().float(), grad_sh=grid.sh_data.grad.detach().float())
+    return res
