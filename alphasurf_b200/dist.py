@@ -17,13 +17,21 @@ import torch.distributed as dist
 
 
 class GradExchange:
-    """Sum density / surface / SH gradients of the touched rows and OR the touched masks over all ranks."""
+    """Sum density / surface / SH gradients of the touched rows and OR the touched masks over all ranks.
+
+    Two-phase use (what TrainStep / bench.py do): ``begin`` right after the fused render -- OR the masks, pack the touched
+    rows into one bucket, clear them in the gradient tensors and start the all-reduce asynchronously -- then the grid
+    regularisers run (they add identical values on every rank into the cleared rows, so they must not travel), and ``end``
+    before the optimizer waits for the collective and adds the reduced render gradients back.  The NCCL transfer overlaps
+    the regulariser kernels.  ``run`` does both phases back to back.
+    """
 
     def __init__(self, ts=None, group=None, dense_threshold=0.25):
         self.group = group
         self.dense_threshold = dense_threshold   # above this touched fraction the dense all-reduce is cheaper
         self.bucket = None
         self.last_rows = 0
+        self._pending = None
 
     def _bucket(self, n, width, like):
         if self.bucket is None or self.bucket.shape[0] < n or self.bucket.shape[1] != width or self.bucket.device != like.device:
@@ -31,29 +39,50 @@ class GradExchange:
             self.bucket = torch.empty((cap, width), dtype=like.dtype, device=like.device)
         return self.bucket[:n]
 
-    def run(self, ts):
+    def begin(self, ts):
         """``ts``: object with ``grad`` = {density (N,1), surface (N,1), sh (N,D)}, ``mask`` and ``mask_sh`` (N,) bool."""
         g = ts.grad
         mask_u8 = ts.mask.view(torch.uint8)
         dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group)
+        ts.mask_sh.copy_(ts.mask)
         N = ts.mask.shape[0]
         rows = torch.nonzero(ts.mask).flatten()          # identical on every rank (host sync: the count)
         n = int(rows.shape[0])
         self.last_rows = n
+        if n == 0:
+            self._pending = None
+            return 0
         if n > self.dense_threshold * N:
             for k in ("density", "surface", "sh"):
                 dist.all_reduce(g[k], op=dist.ReduceOp.SUM, group=self.group)
-        elif n > 0:
-            D = g["sh"].shape[1]
-            buf = self._bucket(n, 2 + D, g["sh"])
-            buf[:, 0] = g["density"].view(-1)[rows]
-            buf[:, 1] = g["surface"].view(-1)[rows]
-            buf[:, 2:] = g["sh"][rows]
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            g["density"].index_copy_(0, rows, buf[:, 0:1])
-            g["surface"].index_copy_(0, rows, buf[:, 1:2])
-            g["sh"].index_copy_(0, rows, buf[:, 2:])
-        ts.mask_sh.copy_(ts.mask)
+            self._pending = None
+            return n
+        D = g["sh"].shape[1]
+        buf = self._bucket(n, 2 + D, g["sh"])
+        buf[:, 0] = g["density"].view(-1)[rows]
+        buf[:, 1] = g["surface"].view(-1)[rows]
+        buf[:, 2:] = g["sh"][rows]
+        g["density"].view(-1).index_fill_(0, rows, 0.0)
+        g["surface"].view(-1).index_fill_(0, rows, 0.0)
+        g["sh"].index_fill_(0, rows, 0.0)
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending = (work, rows, buf)
+        return n
+
+    def end(self, ts):
+        if self._pending is None:
+            return
+        work, rows, buf = self._pending
+        self._pending = None
+        work.wait()
+        g = ts.grad
+        g["density"].view(-1).index_add_(0, rows, buf[:, 0])
+        g["surface"].view(-1).index_add_(0, rows, buf[:, 1])
+        g["sh"].index_add_(0, rows, buf[:, 2:])
+
+    def run(self, ts):
+        n = self.begin(ts)
+        self.end(ts)
         return n
 
 

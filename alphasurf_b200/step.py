@@ -124,11 +124,15 @@ class TrainStep:
                                              *self.fpos, rgb_out, self.grad_spec)
         self.mask_sh.copy_(self.mask)
 
-    def step(self, origins, dirs, rgb_gt, rgb_out, between=None):
+    def step(self, origins, dirs, rgb_gt, rgb_out, exchange=None):
+        """``exchange``: alphasurf_b200.dist.GradExchange for the ray-sharded multi-GPU step (its all-reduce overlaps the
+        regularisers)."""
         self.render(origins, dirs, rgb_gt, rgb_out)
-        if between is not None:
-            between(self)      # multi-GPU: gradient / mask exchange (alphasurf_b200.dist)
+        if exchange is not None:
+            exchange.begin(self)
         self.regularisers()
+        if exchange is not None:
+            exchange.end(self)
         self.optimizer()
 
     def regularisers(self):

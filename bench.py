@@ -176,8 +176,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         from alphasurf_b200 import dist as adist
         C.set_loss_norm_rays(Q * world)
-        ex = adist.GradExchange(ts)
-        exchange = ex.run
+        exchange = adist.GradExchange(ts)
     L = capi.lib()
     phase_ev = []   # per step: 4 events (start, after render [+ exchange], after regularisers, after optimizer)
 
@@ -187,10 +186,12 @@ def run_ours(args, rank, world, local_rank):
             evs[0].record()
         ts.render(o, d, gt, rgb_out)
         if exchange is not None:
-            exchange(ts)
+            exchange.begin(ts)    # mask OR + packed touched rows, all-reduce in flight during the regularisers
         if record:
             evs[1].record()
         ts.regularisers()
+        if exchange is not None:
+            exchange.end(ts)
         if record:
             evs[2].record()
         ts.optimizer()
