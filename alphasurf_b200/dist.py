@@ -59,12 +59,19 @@ class GradExchange:
             return n
         D = g["sh"].shape[1]
         buf = self._bucket(n, 2 + D, g["sh"])
-        buf[:, 0] = g["density"].view(-1)[rows]
-        buf[:, 1] = g["surface"].view(-1)[rows]
-        buf[:, 2:] = g["sh"][rows]
-        g["density"].view(-1).index_fill_(0, rows, 0.0)
-        g["surface"].view(-1).index_fill_(0, rows, 0.0)
-        g["sh"].index_fill_(0, rows, 0.0)
+        if buf.is_cuda:    # one kernel: rows -> bucket, rows cleared (asurf_rows_pack)
+            from . import capi
+            import ctypes as C
+            capi.check(capi.lib().asurf_rows_pack(capi.ptr(rows), C.c_int64(n), capi.ptr(g["density"]), capi.ptr(g["surface"]),
+                                                  capi.ptr(g["sh"]), C.c_int32(D), capi.ptr(buf), C.c_int32(1),
+                                                  capi.current_stream(buf.device)), "rows_pack")
+        else:              # host tensors (gloo tests of the protocol)
+            buf[:, 0] = g["density"].view(-1)[rows]
+            buf[:, 1] = g["surface"].view(-1)[rows]
+            buf[:, 2:] = g["sh"][rows]
+            g["density"].view(-1).index_fill_(0, rows, 0.0)
+            g["surface"].view(-1).index_fill_(0, rows, 0.0)
+            g["sh"].index_fill_(0, rows, 0.0)
         work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._pending = (work, rows, buf)
         return n
@@ -76,9 +83,16 @@ class GradExchange:
         self._pending = None
         work.wait()
         g = ts.grad
-        g["density"].view(-1).index_add_(0, rows, buf[:, 0])
-        g["surface"].view(-1).index_add_(0, rows, buf[:, 1])
-        g["sh"].index_add_(0, rows, buf[:, 2:])
+        if buf.is_cuda:
+            from . import capi
+            import ctypes as C
+            capi.check(capi.lib().asurf_rows_unpack_add(capi.ptr(rows), C.c_int64(rows.shape[0]), capi.ptr(g["density"]),
+                                                        capi.ptr(g["surface"]), capi.ptr(g["sh"]), C.c_int32(g["sh"].shape[1]),
+                                                        capi.ptr(buf), capi.current_stream(buf.device)), "rows_unpack_add")
+        else:
+            g["density"].view(-1).index_add_(0, rows, buf[:, 0])
+            g["surface"].view(-1).index_add_(0, rows, buf[:, 1])
+            g["sh"].index_add_(0, rows, buf[:, 2:])
 
     def run(self, ts):
         n = self.begin(ts)

@@ -130,7 +130,7 @@ int asurf_abi_version(void);
 
 /* ---- occupancy pyramid (ours; the reference marches voxel by voxel with USE_ACC_SKIP=false,
  *      render_lerp_kernel_surf_trav.cu:31) ---- */
-int64_t asurf_accel_words(const int32_t size[3]);            /* number of uint64 words needed */
+int64_t asurf_accel_words(const int32_t size[3]);            /* number of uint64 words needed (3 levels + block list) */
 int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream);
 
 /* ---- work pyramid (ours): same layout as the occupancy pyramid, bit set iff the voxel can contribute a sample
@@ -223,6 +223,15 @@ int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3]
                                      const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
                                      int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,
                                      int32_t ignore_empty, int32_t use_l1, float *grad_data, void *stream);
+
+/* ---- multi-GPU gradient exchange helpers (ours; alphasurf_b200/dist.py) ----
+ * rows: device int64 (n_rows,), ascending row indices touched on some rank; bucket: device (n_rows, 2 + sh_dim) floats,
+ * row = [density.grad, surface.grad, sh.grad...].  pack copies the rows into the bucket (and clears them in the gradient
+ * tensors when clear_rows != 0); unpack_add adds the (all-reduced) bucket back. */
+int asurf_rows_pack(const int64_t *rows, int64_t n_rows, float *grad_density, float *grad_surface, float *grad_sh,
+                    int32_t sh_dim, float *bucket, int32_t clear_rows, void *stream);
+int asurf_rows_unpack_add(const int64_t *rows, int64_t n_rows, float *grad_density, float *grad_surface, float *grad_sh,
+                          int32_t sh_dim, const float *bucket, void *stream);
 
 /* ---- per-kernel timing (ours; feeds bench.py's roofline) ----
  * After asurf_profile_enable(capacity > 0) every asurf_surf_trav_fused call records CUDA events around its forward

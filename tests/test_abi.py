@@ -29,7 +29,8 @@ def test_library_exports_every_symbol():
 def test_accel_words_is_host_only():
     lib = capi.lib()
     n = lib.asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
-    assert n == 128 ** 3 + 32 ** 3 + 8 ** 3
+    # three pyramid levels + the list of non-empty 16^3 blocks (count word + uint32 ids, 2 per word)
+    assert n == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2
 
 
 def test_struct_layouts_match_header():
