@@ -183,6 +183,18 @@ work_block16_kernel(const int32_t *__restrict__ links, const float *__restrict__
     }
 }
 
+// number of vertices with a link >= 0 (kept behind the block list; the regularisers use it to recognise the list of all
+// stored vertices)
+__global__ void __launch_bounds__(256) count_stored_kernel(const int32_t *__restrict__ links, int64_t n,
+                                                            unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += (links[i] >= 0) ? 1ull : 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // After the three pyramid levels the occupancy buffer holds the list of non-empty level-1 (16^3) blocks:
 // word off[3] = their number, then their indices as uint32 (2 per word).  The work-pyramid build walks this list.
 __global__ void __launch_bounds__(256) accel_list1_kernel(AccelLayout lay, uint64_t *__restrict__ buf) {
@@ -226,7 +238,7 @@ extern "C" int asurf_work_build(const asurf_grid_t *grid, const asurf_opt_t *opt
 
 extern "C" int64_t asurf_accel_words(const int32_t size[3]) {
     AccelLayout lay(size);
-    return lay.off[3] + 1 + (lay.count(1) + 1) / 2;   // pyramid + list of non-empty level-1 blocks
+    return lay.off[3] + 1 + (lay.count(1) + 1) / 2 + 1;   // pyramid + list of non-empty level-1 blocks + stored-vertex count
 }
 
 extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream) {
@@ -239,6 +251,9 @@ extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], ui
     accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, accel_out);
     ASURF_CUDA(cudaMemsetAsync(accel_out + lay.off[3], 0, sizeof(uint64_t), st));
     accel_list1_kernel<<<div_up(lay.count(1), 256), 256, 0, st>>>(lay, accel_out);
-    note_launches(4);
+    uint64_t *n_stored = accel_out + lay.off[3] + 1 + (lay.count(1) + 1) / 2;
+    ASURF_CUDA(cudaMemsetAsync(n_stored, 0, sizeof(uint64_t), st));
+    count_stored_kernel<<<148 * 8, 256, 0, st>>>(links, (int64_t)size[0] * size[1] * size[2], (unsigned long long *)n_stored);
+    note_launches(5);
     return check_cuda(cudaGetLastError(), "accel_build launch");
 }

@@ -407,8 +407,10 @@ __device__ __forceinline__ void normal_pair_grad(const float *nh0, float rN0, co
 __global__ void __launch_bounds__(LOSS_THREADS)
 surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf,
                            const int32_t *__restrict__ cells, Dims d, int64_t Q, float lv_set, float scale, int con_check,
-                           int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+                           int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad,
+                           const int *__restrict__ tile_flag) {
     constexpr unsigned FULLM = 0xffffffffu;
+    if (tile_flag && *tile_flag) return;   // the list is every stored vertex: surface_normal_tile_kernel does the work
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -559,6 +561,167 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
     }
 }
 
+// ---- the same loss when the list is "every stored vertex" (norm_surface_sparsity = 1, the alpha-Surf training config) ------
+// Then the work is dense over the occupied part of the grid: one CTA per non-empty 16^3-cell block (the block list behind
+// the occupancy pyramid), the block's 18^3 vertices (link + scalar) staged once in shared memory, each thread handling 16
+// cells, the <= 48 contributions per cell accumulated with shared-memory atomics, and ONE red.global.add per touched
+// vertex of the tile at the end (~1.4 per cell instead of 48).  cells_cover_check_kernel proves on the device that the
+// list really is the ascending enumeration of all stored vertices; each of the two kernels (tile / list) returns at once
+// when the flag says the other one applies, so no host synchronisation is needed.
+constexpr int NT_V = 18;
+constexpr int NT_NV = NT_V * NT_V * NT_V;
+constexpr int NT_THREADS = 256;
+constexpr size_t NT_SMEM = (size_t)NT_NV * (4 + 4 + 4 + 1);
+
+__global__ void __launch_bounds__(256)
+cells_cover_check_kernel(const int32_t *__restrict__ links, const int32_t *__restrict__ cells, int64_t n_cells,
+                         const uint64_t *__restrict__ accel, AccelLayout lay, int *__restrict__ flag) {
+    // flag starts at 1; cleared when the list is not exactly the ascending list of all vertices with link >= 0
+    const int64_t n_stored = (int64_t)accel[lay.off[3] + 1 + (lay.count(1) + 1) / 2];
+    if (n_cells != n_stored) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
+        return;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = __ldg(cells + i);
+        const bool ok = (c >= 0) && (__ldg(links + c) >= 0) && (i == 0 || __ldg(cells + i - 1) < c);
+        if (!ok) *flag = 0;
+    }
+}
+
+__device__ __forceinline__ void tile_cell(const int32_t *s_link, const float *s_surf, int cx, int cy, int cz, Cell8 &c, bool &ok) {
+    ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int v = ((cx + (k >> 2)) * NT_V + (cy + ((k >> 1) & 1))) * NT_V + (cz + (k & 1));
+        c.l[k] = s_link[v];
+        c.s[k] = s_surf[v];
+        ok &= (c.l[k] >= 0);
+    }
+}
+
+__device__ __forceinline__ void tile_scatter(float *s_grad, uint8_t *s_touch, int cx, int cy, int cz, const float *g, float scale) {
+    const float q = 0.25f * scale;
+    const float a0 = q * g[0], a1 = q * g[1], a2 = q * g[2];
+    const float u[4] = {-a0 - a1, -a0 + a1, a0 - a1, a0 + a1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float val = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
+        if (val != 0.f) {
+            const int v = ((cx + (k >> 2)) * NT_V + (cy + ((k >> 1) & 1))) * NT_V + (cz + (k & 1));
+            atomicAdd(s_grad + v, val);
+            s_touch[v] = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT_THREADS)
+surface_normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, Dims d,
+                           const uint64_t *__restrict__ accel, AccelLayout lay, const int *__restrict__ flag, float lv_set,
+                           float scale, int con_check, int ignore_empty, int use_l1, uint8_t *__restrict__ mask,
+                           float *__restrict__ grad) {
+    if (*flag == 0) return;   // not the full enumeration: the list kernel does the work
+    extern __shared__ unsigned char nt_smem[];
+    int32_t *s_link = (int32_t *)nt_smem;
+    float *s_surf = (float *)(nt_smem + (size_t)NT_NV * 4);
+    float *s_grad = (float *)(nt_smem + (size_t)NT_NV * 8);
+    uint8_t *s_touch = (uint8_t *)(nt_smem + (size_t)NT_NV * 12);
+    const int tid = threadIdx.x;
+    const int64_t n_active = (int64_t)accel[lay.off[3]];
+    const uint32_t *active = (const uint32_t *)(accel + lay.off[3] + 1);
+    for (int64_t it = blockIdx.x; it < n_active; it += gridDim.x) {
+        __syncthreads();
+        const int64_t w1 = active[it];
+        const int bz = (int)(w1 % lay.b[1][2]);
+        const int by = (int)((w1 / lay.b[1][2]) % lay.b[1][1]);
+        const int bx = (int)(w1 / ((int64_t)lay.b[1][2] * lay.b[1][1]));
+        const int x0 = bx * 16, y0 = by * 16, z0 = bz * 16;
+        for (int vb = tid; vb < NT_NV; vb += 4 * NT_THREADS) {
+            int32_t l[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int v = vb + r * NT_THREADS;
+                l[r] = -1;
+                if (v < NT_NV) {
+                    const int x = x0 + v / (NT_V * NT_V), y = y0 + (v / NT_V) % NT_V, z = z0 + v % NT_V;
+                    if (x < d.sx && y < d.sy && z < d.sz) l[r] = __ldg(links + (((int64_t)x * d.sy + y) * d.sz + z));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int v = vb + r * NT_THREADS;
+                if (v < NT_NV) {
+                    s_link[v] = l[r];
+                    s_surf[v] = (l[r] >= 0) ? __ldg(surf + l[r]) : 0.f;
+                    s_grad[v] = 0.f;
+                    s_touch[v] = 0;
+                }
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < 4096; c += NT_THREADS) {
+            const int cx = c >> 8, cy = (c >> 4) & 15, cz = c & 15;
+            Cell8 c0;
+            bool ok0;
+            tile_cell(s_link, s_surf, cx, cy, cz, c0, ok0);
+            if (!ok0) continue;
+            const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
+            float n0[3];
+            cell_normal(c0, n0);
+            Cell8 cz1, cy1, cx1;
+            bool uz, uy, ux;
+            tile_cell(s_link, s_surf, cx, cy, cz + 1, cz1, uz);
+            tile_cell(s_link, s_surf, cx, cy + 1, cz, cy1, uy);
+            tile_cell(s_link, s_surf, cx + 1, cy, cz, cx1, ux);
+            uz = uz && (!con_check || face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv_set));
+            uz = uz && (!ignore_empty || (!empty000 || !cell_empty(cz1, lv_set)));
+            uy = uy && (!con_check || face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv_set));
+            uy = uy && (!ignore_empty || (!empty000 || !cell_empty(cy1, lv_set)));
+            ux = ux && (!con_check || face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv_set));
+            ux = ux && (!ignore_empty || (!empty000 || !cell_empty(cx1, lv_set)));
+            const int norm_count = (int)ux + (int)uy + (int)uz;
+            if (norm_count == 0) continue;
+            const float N0 = NORM3_(n0);
+            const float nh0[3] = {n0[0] / N0, n0[1] / N0, n0[2] / N0};
+            const float rN0 = 1.f / N0;
+            const float sc = scale * 1.f / norm_count;
+            float n1[3], d0[3], d1[3];
+            if (ux) {
+                cell_normal(cx1, n1);
+                const float N1 = NORM3_(n1);
+                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
+                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                tile_scatter(s_grad, s_touch, cx, cy, cz, d0, sc);
+                tile_scatter(s_grad, s_touch, cx + 1, cy, cz, d1, sc);
+            }
+            if (uy) {
+                cell_normal(cy1, n1);
+                const float N1 = NORM3_(n1);
+                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
+                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                tile_scatter(s_grad, s_touch, cx, cy, cz, d0, sc);
+                tile_scatter(s_grad, s_touch, cx, cy + 1, cz, d1, sc);
+            }
+            if (uz) {
+                cell_normal(cz1, n1);
+                const float N1 = NORM3_(n1);
+                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
+                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                tile_scatter(s_grad, s_touch, cx, cy, cz, d0, sc);
+                tile_scatter(s_grad, s_touch, cx, cy, cz + 1, d1, sc);
+            }
+        }
+        __syncthreads();
+        for (int v = tid; v < NT_NV; v += NT_THREADS) {
+            if (s_touch[v]) {
+                const int32_t l = s_link[v];
+                atomicAdd(grad + l, s_grad[v]);
+                if (mask) mask[l] = 1;
+            }
+        }
+    }
+}
+
 int check_common(const int32_t *links, const int32_t size[3], const void *data, const void *grad, const char *who) {
     ASURF_REQUIRE(links && size && data && grad, ASURF_E_INVALID, "%s: null tensor", who);
     ASURF_REQUIRE(size[0] >= 1 && size[1] >= 1 && size[2] >= 1, ASURF_E_INVALID, "%s: bad grid size", who);
@@ -661,10 +824,13 @@ extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const
     return check_cuda(cudaGetLastError(), "alpha_surf_sparsify_grad_sparse launch");
 }
 
+static Workspace g_ws_flag;
+
 extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                                 const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
                                                 int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,
-                                                int32_t ignore_empty, int32_t use_l1, float *grad_data, void *stream) {
+                                                int32_t ignore_empty, int32_t use_l1, float *grad_data,
+                                                const uint64_t *accel, void *stream) {
     int rc = check_common(links, size, surf, grad_data, "surface_normal_grad_sparse");
     if (rc) return rc;
     ASURF_REQUIRE(end_dim > start_dim, ASURF_E_INVALID, "surface_normal_grad_sparse: bad channel range");
@@ -673,11 +839,35 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
     const int n_rep = end_dim - start_dim;   // the reference launches one thread per (cell, channel) and ignores the channel
     const int64_t Q = n_cells * n_rep;
     Dims d = {size[0], size[1], size[2]};
-    if (n_rep == 1)
-        surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+    if (n_rep == 1) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int *flag = nullptr;
+        AccelLayout lay(size);
+        // a list that may be "every stored vertex" (at least a tenth of the grid): let the device decide which kernel runs
+        if (accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 && size[2] >= 16) {
+            rc = g_ws_flag.reserve(sizeof(int));
+            if (rc) return rc;
+            static bool attr_set = false;
+            if (!attr_set) {
+                ASURF_CUDA(cudaFuncSetAttribute(surface_normal_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
+                attr_set = true;
+            }
+            int one = 1;
+            ASURF_CUDA(cudaMemcpyAsync(g_ws_flag.ptr, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+            cells_cover_check_kernel<<<loss_grid(n_cells), 256, 0, st>>>(links, rand_cells, n_cells, accel, lay, (int *)g_ws_flag.ptr);
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            surface_normal_tile_kernel<<<sms * 2, NT_THREADS, NT_SMEM, st>>>(links, surf, d, accel, lay, (const int *)g_ws_flag.ptr,
+                                                                            lv_set, scale / (float)(int)n_cells, con_check,
+                                                                            ignore_empty, use_l1, mask_out, grad_data);
+            flag = (const int *)g_ws_flag.ptr;
+            note_launches(2);
+        }
+        surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
             links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-            grad_data);
-    else
+            grad_data, flag);
+    } else
         surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
             links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1,
             mask_out, grad_data);

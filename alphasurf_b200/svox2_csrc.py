@@ -480,7 +480,7 @@ def surface_normal_grad_sparse(links, data, rand_cells, mask_out, lv_set, start_
             capi.ptr(links), capi.size3(links.shape), capi.ptr(data), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]),
             _mask_ptr(mask_out), C.c_float(lv_set), C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale),
             C.c_int32(bool(con_check)), C.c_int32(bool(ignore_empty)), C.c_int32(bool(use_l1)), capi.ptr(grad_data),
-            capi.current_stream()), "surface_normal_grad_sparse")
+            capi.ptr(accel_for(links)), capi.current_stream()), "surface_normal_grad_sparse")
 
 
 # ---- test hooks -----------------------------------------------------------------------------------------------------------

@@ -218,11 +218,14 @@ int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t si
                                           const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float scale_alpha,
                                           float scale_surf, int32_t surf_decrease, float surf_thresh, float alpha_bound,
                                           float surf_bound, float *grad_alpha, float *grad_surf, void *stream);
-/* surface_normal_grad_sparse, :1572-1622 (eikonal_scale and the ndc coefficients of the reference are unused there) */
+/* surface_normal_grad_sparse, :1572-1622 (eikonal_scale and the ndc coefficients of the reference are unused there).
+ * accel: optional occupancy buffer of `links` (asurf_accel_build); with it, a list that enumerates every stored vertex is
+ * processed by a dense tiled kernel instead of cell by cell (same result up to summation order). */
 int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                      const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
                                      int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,
-                                     int32_t ignore_empty, int32_t use_l1, float *grad_data, void *stream);
+                                     int32_t ignore_empty, int32_t use_l1, float *grad_data, const uint64_t *accel,
+                                     void *stream);
 
 /* ---- multi-GPU gradient exchange helpers (ours; alphasurf_b200/dist.py) ----
  * rows: device int64 (n_rows,), ascending row indices touched on some rank; bucket: device (n_rows, 2 + sh_dim) floats,

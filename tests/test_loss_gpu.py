@@ -202,3 +202,35 @@ def test_loss_kernels_at_full_size_properties():
                         True, False, -1.0, -1.0, g_c)
     assert float(g_c.abs().max()) == 0.0
     assert n == R ** 3
+
+
+@pytest.mark.parametrize("reso,variant,z_order", [(40, "G*", None), (64, "G", None), (33, "G*", False)])
+@pytest.mark.parametrize("con_check,ignore_empty,use_l1", [(False, False, True), (True, True, False)])
+def test_surface_normal_all_stored_cells_tile_path(reso, variant, z_order, con_check, ignore_empty, use_l1):
+    """norm_surface_sparsity = 1: the list is every stored vertex in ascending order (svox2.py:6354-6361); the library
+    recognises it on the device and runs the dense tiled kernel.  Same result as the oracle / the reference kernel, and as
+    our list kernel on a permuted copy of the list (which cannot take the tile path)."""
+    from oracle import oracle
+    sg = _grid(reso, variant=variant, z_order=z_order)
+    cells_c = torch.where(sg.links.view(-1) >= 0)[0].int()
+    links, surf, cells = sg.links.cuda(), sg.surface.cuda(), cells_c.cuda()
+    lv = float(sg.level_set[0])
+    args = (lv, 0, 1, 1e-2, 0.0, -1.0, -1.0, con_check, ignore_empty, use_l1)
+    grad = torch.zeros_like(surf)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.surface_normal_grad_sparse(links, surf, cells, mask, *args, grad)
+    g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.surface_normal_grad_sparse(sg.links, sg.surface, cells_c, m_o, lv, 0, 1, 1e-2, con_check, ignore_empty, use_l1, g_o)
+    _close(grad, g_o, "normal loss, tile path vs oracle")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+    perm = cells[torch.randperm(cells.shape[0], device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))]
+    g_p, m_p = torch.zeros_like(surf), torch.zeros_like(mask)
+    ours.surface_normal_grad_sparse(links, surf, perm.contiguous(), m_p, *args, g_p)
+    assert H.rel_err(grad, g_p) < TOL and torch.equal(mask, m_p)
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        g_r, m_r = torch.zeros_like(surf), torch.zeros_like(mask)
+        ref.surface_normal_grad_sparse(links, surf, cells, m_r, *args, g_r)
+        _close(grad, g_r.cpu(), "normal loss, tile path vs reference CUDA")
+        assert torch.equal(mask, m_r)
