@@ -564,7 +564,7 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
 // ---- the same loss when the list is "every stored vertex" (norm_surface_sparsity = 1, the alpha-Surf training config) ------
 // Then the work is dense over the occupied part of the grid: one CTA per non-empty 16^3-cell block (the block list behind
 // the occupancy pyramid), the block's 18^3 vertices (link + scalar) staged once in shared memory, each thread handling 16
-// cells, the <= 48 contributions per cell accumulated with shared-memory atomics, and ONE red.global.add per touched
+// cells, the <= 48 contributions per cell accumulated in shared memory (27 conflict-free colour rounds, no atomics), and ONE red.global.add per touched
 // vertex of the tile at the end (~1.4 per cell instead of 48).  cells_cover_check_kernel proves on the device that the
 // list really is the ascending enumeration of all stored vertices; each of the two kernels (tile / list) returns at once
 // when the flag says the other one applies, so no host synchronisation is needed.
@@ -607,9 +607,9 @@ __device__ __forceinline__ void tile_scatter(float *s_grad, uint8_t *s_touch, in
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float val = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
-        if (val != 0.f) {
+        if (val != 0.f) {   // plain read-modify-write: cells processed together are >= 3 apart on every axis
             const int v = ((cx + (k >> 2)) * NT_V + (cy + ((k >> 1) & 1))) * NT_V + (cz + (k & 1));
-            atomicAdd(s_grad + v, val);
+            s_grad[v] += val;
             s_touch[v] = 1;
         }
     }
@@ -659,8 +659,12 @@ surface_normal_tile_kernel(const int32_t *__restrict__ links, const float *__res
             }
         }
         __syncthreads();
-        for (int c = tid; c < 4096; c += NT_THREADS) {
-            const int cx = c >> 8, cy = (c >> 4) & 15, cz = c & 15;
+        // 27 colours: cells with the same (cx, cy, cz) mod 3 touch disjoint vertex sets (a cell writes vertices
+        // [c, c + 2]^3), so each colour round needs no atomics; 6^3 = 216 cells per round on 256 threads
+        for (int colour = 0; colour < 27; ++colour) {
+            if (colour) __syncthreads();
+            const int cx = 3 * (tid / 36) + colour / 9, cy = 3 * ((tid / 6) % 6) + (colour / 3) % 3, cz = 3 * (tid % 6) + colour % 3;
+            if (tid >= 216 || cx >= 16 || cy >= 16 || cz >= 16) continue;
             Cell8 c0;
             bool ok0;
             tile_cell(s_link, s_surf, cx, cy, cz, c0, ok0);
@@ -825,6 +829,11 @@ extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const
 }
 
 static Workspace g_ws_flag;
+// The dense tiled variant of the normal loss is exact but, as measured on B200 (profiles/r1_ncu_full_normal_tile.txt), not
+// faster than the run-aggregated list kernel (2.2 ms vs 1.3 ms at 512^3): both are instruction-bound on the 48 corner
+// contributions per cell.  It stays behind this switch (tests exercise both) until its per-cell normals are shared.
+static int g_normal_tile = 0;
+extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_normal_tile = enabled ? 1 : 0; }
 
 extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                                 const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
@@ -844,7 +853,8 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
         const int *flag = nullptr;
         AccelLayout lay(size);
         // a list that may be "every stored vertex" (at least a tenth of the grid): let the device decide which kernel runs
-        if (accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 && size[2] >= 16) {
+        if (g_normal_tile && accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 &&
+            size[2] >= 16) {
             rc = g_ws_flag.reserve(sizeof(int));
             if (rc) return rc;
             static bool attr_set = false;

@@ -169,6 +169,10 @@ void asurf_debug_set_skip(int32_t enabled);
  * equal up to atomic order. */
 void asurf_debug_set_wave(int32_t enabled);
 
+/* test hook: let surface_normal_grad_sparse take its dense tiled kernel when the list enumerates every stored vertex
+ * (0, default: always the run-aggregated list kernel).  Same result either way up to summation order. */
+void asurf_debug_set_normal_tile(int32_t enabled);
+
 /* ---- Plenoxels "cuvol" renderer, render_lerp_kernel_cuvol.cu:1120-1354 (grid->surface / level_set / accel / work unused;
  *      links may hold the negative skip codes written by accel_dist_prop) ---- */
 /* volume_render_cuvol, :1120-1160 (rgb_out (Q,3); log_transmit_out (Q,) or NULL) */

@@ -218,7 +218,12 @@ def test_surface_normal_all_stored_cells_tile_path(reso, variant, z_order, con_c
     args = (lv, 0, 1, 1e-2, 0.0, -1.0, -1.0, con_check, ignore_empty, use_l1)
     grad = torch.zeros_like(surf)
     mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
-    ours.surface_normal_grad_sparse(links, surf, cells, mask, *args, grad)
+    from alphasurf_b200 import capi
+    capi.lib().asurf_debug_set_normal_tile(1)
+    try:
+        ours.surface_normal_grad_sparse(links, surf, cells, mask, *args, grad)
+    finally:
+        capi.lib().asurf_debug_set_normal_tile(0)
     g_o = np.zeros(tuple(sg.surface.shape), np.float32)
     m_o = np.zeros((sg.capacity,), np.uint8)
     oracle.surface_normal_grad_sparse(sg.links, sg.surface, cells_c, m_o, lv, 0, 1, 1e-2, con_check, ignore_empty, use_l1, g_o)
