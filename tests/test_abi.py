@@ -29,8 +29,8 @@ def test_library_exports_every_symbol():
 def test_accel_words_is_host_only():
     lib = capi.lib()
     n = lib.asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
-    # three pyramid levels + the list of non-empty 16^3 blocks (count word + uint32 ids, 2 per word)
-    assert n == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2
+    # three pyramid levels + the list of non-empty 16^3 blocks (count word + uint32 ids, 2 per word) + stored-vertex count
+    assert n == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2 + 1
 
 
 def test_struct_layouts_match_header():
