@@ -26,12 +26,16 @@ class GradExchange:
     the regulariser kernels.  ``run`` does both phases back to back.
     """
 
-    def __init__(self, ts=None, group=None, dense_threshold=0.25):
+    def __init__(self, ts=None, group=None, dense_threshold=0.25, shard_regularisers=True):
         self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.shard_regularisers = shard_regularisers   # end() also sums the cell-sharded regulariser gradients
         self.dense_threshold = dense_threshold   # above this touched fraction the dense all-reduce is cheaper
         self.bucket = None
         self.last_rows = 0
         self._pending = None
+        self._hold = None
 
     def _bucket(self, n, width, like):
         if self.bucket is None or self.bucket.shape[0] < n or self.bucket.shape[1] != width or self.bucket.device != like.device:
@@ -56,6 +60,10 @@ class GradExchange:
             for k in ("density", "surface", "sh"):
                 dist.all_reduce(g[k], op=dist.ReduceOp.SUM, group=self.group)
             self._pending = None
+            if self.shard_regularisers and self.world > 1:   # keep the summed render part out of end()'s dense sum
+                self._hold = (g["density"].clone(), g["surface"].clone())
+                g["density"].zero_()
+                g["surface"].zero_()
             return n
         D = g["sh"].shape[1]
         buf = self._bucket(n, 2 + D, g["sh"])
@@ -77,12 +85,22 @@ class GradExchange:
         return n
 
     def end(self, ts):
+        g = ts.grad
+        if self.shard_regularisers and self.world > 1:
+            # the regularisers ran on this rank's share of the cells: sum the shards (they touch every stored row, so
+            # this exchange is dense) and OR the masks they set
+            dist.all_reduce(ts.mask.view(torch.uint8), op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(g["density"], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(g["surface"], op=dist.ReduceOp.SUM, group=self.group)
+            if self._hold is not None:
+                g["density"].add_(self._hold[0])
+                g["surface"].add_(self._hold[1])
+                self._hold = None
         if self._pending is None:
             return
         work, rows, buf = self._pending
         self._pending = None
         work.wait()
-        g = ts.grad
         if buf.is_cuda:
             from . import capi
             import ctypes as C

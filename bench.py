@@ -50,7 +50,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -189,9 +189,11 @@ def run_ours(args, rank, world, local_rank):
             exchange.begin(ts)    # mask OR + packed touched rows, all-reduce in flight during the regularisers
         if record:
             evs[1].record()
-        ts.regularisers()
         if exchange is not None:
+            ts.regularisers(exchange.rank, exchange.world)   # cell-sharded; end() sums the shards
             exchange.end(ts)
+        else:
+            ts.regularisers()
         if record:
             evs[2].record()
         ts.optimizer()

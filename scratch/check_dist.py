@@ -17,6 +17,7 @@ rgb = torch.zeros((Ql, 3), device=dev)
 ts.render(o[sl].contiguous(), d[sl].contiguous(), gt[sl].contiguous(), rgb)
 ex = adist.GradExchange(ts)
 n = ex.begin(ts)
+ts.regularisers(ex.rank, ex.world)
 ex.end(ts)
 torch.cuda.synchronize()
 res = {}
@@ -25,6 +26,7 @@ if rank == 0:
     ts1 = S.TrainStep(C, sg)
     rgb1 = torch.zeros((Qg, 3), device=dev)
     ts1.render(o, d, gt, rgb1)
+    ts1.regularisers()
     torch.cuda.synchronize()
     rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
     res = {"world": world, "rows_exchanged": n, "mask_equal": bool(torch.equal(ts.mask, ts1.mask)),

@@ -36,7 +36,7 @@ def _worker(rank, world, port, N, D, frac, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ts = _local_state(rank, N, D, frac)
-        ex = adist.GradExchange()
+        ex = adist.GradExchange(shard_regularisers=False)   # protocol of the sparse render-gradient exchange alone
         n = ex.run(ts)
         # expected: sum over ranks, union of masks
         states = [_local_state(r, N, D, frac) for r in range(world)]
@@ -74,3 +74,60 @@ def test_dense_fallback_world2():
 
 def test_empty_exchange_world2():
     _run(1000, 3, 0.0)
+
+
+def _worker_sharded(rank, world, port, N, D, frac, ret):
+    """full protocol: sparse exchange of the render gradients around cell-sharded regularisers"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def reg(r):   # what rank r's share of the regularisers adds: rows [r*N/world, (r+1)*N/world)
+            g = torch.Generator().manual_seed(500 + r)
+            lo, hi = (N * r) // world, (N * (r + 1)) // world
+            dd, ds = torch.zeros((N, 1)), torch.zeros((N, 1))
+            dd[lo:hi] = torch.randn((hi - lo, 1), generator=g)
+            ds[lo:hi] = torch.randn((hi - lo, 1), generator=g)
+            m = torch.zeros((N,), dtype=torch.bool)
+            m[lo:hi] = True
+            return dd, ds, m
+        ts = _local_state(rank, N, D, frac)
+        ex = adist.GradExchange()
+        ex.begin(ts)
+        dd, ds, m = reg(rank)
+        ts.grad["density"] += dd
+        ts.grad["surface"] += ds
+        ts.mask |= m
+        ex.end(ts)
+        states = [_local_state(r, N, D, frac) for r in range(world)]
+        regs = [reg(r) for r in range(world)]
+        ok = torch.equal(ts.mask, torch.ones((N,), dtype=torch.bool))
+        ok = ok and torch.equal(ts.mask_sh, torch.stack([s.mask for s in states]).any(0))
+        ok = ok and torch.allclose(ts.grad["density"], sum(s.grad["density"] for s in states) + sum(x[0] for x in regs), atol=1e-6)
+        ok = ok and torch.allclose(ts.grad["surface"], sum(s.grad["surface"] for s in states) + sum(x[1] for x in regs), atol=1e-6)
+        ok = ok and torch.allclose(ts.grad["sh"], sum(s.grad["sh"] for s in states), atol=1e-6)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_sharded(N, D, frac):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [mp.get_context("spawn").Process(target=_worker_sharded, args=(r, world, port, N, D, frac, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_sharded_regularisers_sparse_world2():
+    _run_sharded(4000, 12, 0.03)
+
+
+def test_sharded_regularisers_dense_world2():
+    _run_sharded(1500, 27, 0.7)
