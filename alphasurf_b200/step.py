@@ -151,8 +151,8 @@ class TrainStep:
         C, sg, hp, g = self.C, self.sg, self.hp, self.grad
         hp = dict(hp)
         sh_ = lambda cells: self._shard(cells, rank, world)
-        for k in ("lambda_tv_alpha", "lambda_tv_surface", "lambda_normal_loss", "lambda_sparsify_alpha", "lambda_sparsify_surf"):
-            hp[k] = hp[k] / world
+        for k in ("lambda_tv_alpha", "lambda_tv_surface", "lambda_normal_loss"):
+            hp[k] = hp[k] / world       # the sparsity loss is NOT normalised by the list length (loss_kernel.cu:1555-1558)
         if hp["lambda_tv_alpha"] > 0:      # inplace_tv_grad, opt.py:952-957
             cells = sh_(self.rand_cells(hp["tv_sparsity"]))
             C.tv_grad_sparse(sg.links, sg.density, cells, self.mask, 0, 1, hp["lambda_tv_alpha"], False, 2.0, False,
