@@ -209,7 +209,180 @@ __global__ void __launch_bounds__(256) accel_list1_kernel(AccelLayout lay, uint6
     if (on) ((uint32_t *)(buf + lay.off[3] + 1))[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)w;
 }
 
+// ---- incremental maintenance of the work pyramid across calls -------------------------------------------------------------
+// A voxel's work bit is a function of its 8 corner vertices through three per-vertex predicates only:
+// (surface < lv), (surface > lv) [smin <= lv <= smax  <=>  not all corners > lv and not all < lv] and (density >= sigma_thresh).
+// Training changes every stored value a little every step, but those predicates flip for a handful of vertices.  So the
+// library keeps, per grid, the class byte of every data row; each call re-reads surface / density once, in row order
+// (coalesced, 8 B per row instead of 1.2 x 12 B per vertex through `links`), and re-derives -- from the actual data -- only
+// the <= 8 voxels around each vertex whose class changed.  The cache validates itself against the data on every call;
+// links / options changes are caught by the key (pointers, options, generation of the occupancy buffer).
+__global__ void __launch_bounds__(256)
+inverse_links_kernel(const int32_t *__restrict__ links, int64_t n_vertices, int32_t *__restrict__ inv) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t l = links[i];
+        if (l >= 0) inv[l] = (int32_t)i;
+    }
+}
+
+__device__ __forceinline__ uint8_t vertex_class(float s, float dn, float lv, float sigma_thresh) {
+    return (uint8_t)((s < lv ? 1 : 0) | (s > lv ? 2 : 0) | (!(dn < sigma_thresh) ? 4 : 0));
+}
+
+// INIT: fill the class bytes.  Otherwise: compare, update, and list the rows whose class changed.
+template <bool INIT>
+__global__ void __launch_bounds__(256)
+class_scan_kernel(const float *__restrict__ surface, const float *__restrict__ density, int64_t n_rows,
+                  const float *__restrict__ level_set, float sigma_thresh, uint8_t *__restrict__ cls,
+                  int32_t *__restrict__ changed, unsigned long long *__restrict__ n_changed) {
+    const int lane = threadIdx.x & 31;
+    const float lv = __ldg(level_set);   // read on the device every call: a changed level set is just more changed classes
+    for (int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; r0 < n_rows; r0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = r0 + lane;
+        bool diff = false;
+        if (r < n_rows) {
+            const uint8_t c = vertex_class(surface[r], density[r], lv, sigma_thresh);
+            if (INIT) {
+                cls[r] = c;
+            } else if (c != cls[r]) {
+                cls[r] = c;
+                diff = true;
+            }
+        }
+        if (!INIT) {
+            const unsigned m = __ballot_sync(0xffffffffu, diff);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(n_changed, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (diff) changed[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
+            }
+        }
+    }
+}
+
+// 8 threads per changed row: thread k re-derives the voxel whose corner k is the changed vertex.
+__global__ void __launch_bounds__(256)
+work_patch_kernel(const int32_t *__restrict__ links, const float *__restrict__ density, const float *__restrict__ surface,
+                  const float *__restrict__ level_set, float sigma_thresh, int sx, int sy, int sz, AccelLayout lay,
+                  const uint64_t *__restrict__ occ,
+                  const int32_t *__restrict__ inv, const int32_t *__restrict__ changed,
+                  const unsigned long long *__restrict__ n_changed, uint64_t *__restrict__ work) {
+    const int64_t n = (int64_t)*n_changed * 8;
+    const float lv = __ldg(level_set);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t flat = inv[changed[i >> 3]];
+        const int k = (int)(i & 7);
+        const int vz = flat % sz, vy = (flat / sz) % sy, vx = flat / (sz * sy);
+        const int x = vx - (k >> 2), y = vy - ((k >> 1) & 1), z = vz - (k & 1);
+        if (x < 0 || y < 0 || z < 0 || x >= sx - 1 || y >= sy - 1 || z >= sz - 1) continue;
+        const int64_t k0 = ((int64_t)(x >> 2) * lay.b[0][1] + (y >> 2)) * lay.b[0][2] + (z >> 2);
+        const int bit = ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
+        if (!((occ[k0] >> bit) & 1ull)) continue;   // not all 8 links: never a work voxel
+        float smin = INFINITY, smax = -INFINITY;
+        bool gate = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int32_t l = links[((int64_t)(x + (q >> 2)) * sy + (y + ((q >> 1) & 1))) * sz + (z + (q & 1))];
+            const float sv = surface[l];
+            smin = fminf(smin, sv);
+            smax = fmaxf(smax, sv);
+            gate |= !(density[l] < sigma_thresh);
+        }
+        const bool w = gate && !((lv < smin) || (lv > smax));
+        if (w) atomicOr((unsigned long long *)(work + k0), 1ull << bit);
+        else atomicAnd((unsigned long long *)(work + k0), ~(1ull << bit));
+    }
+}
+
+struct WorkCache {
+    Workspace work, cls, inv, changed, ctr;
+    const void *links = nullptr, *surface = nullptr, *density = nullptr, *accel = nullptr;
+    int32_t size[3] = {0, 0, 0};
+    int64_t capacity = 0;
+    float sigma_thresh = 0.f;
+    unsigned long long accel_gen = 0;
+    bool valid = false;
+} g_wc;
+
+unsigned long long g_accel_gen = 0;          // bumped by every asurf_accel_build
+const void *g_accel_last[16] = {nullptr};    // occupancy buffers built by this library and their generation
+unsigned long long g_accel_last_gen[16] = {0};
+
+unsigned long long accel_generation(const void *accel) {
+    for (int i = 0; i < 16; ++i)
+        if (g_accel_last[i] == accel) return g_accel_last_gen[i];
+    return 0;   // unknown buffer: never cached
+}
+
 }  // namespace
+
+// Work pyramid for the render call: incremental when the grid is the one of the previous call, full build otherwise.
+int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out) {
+    AccelLayout lay(grid->size);
+    const bool every_voxel = opt->surf_fake_sample && !opt->limited_fake_sample;
+    const unsigned long long gen = accel_generation(grid->accel);
+    const bool cacheable = gen != 0 && grid->level_set_num == 1 && !every_voxel && grid->capacity > 0 &&
+                           (int64_t)grid->size[0] * grid->size[1] * grid->size[2] < ((int64_t)1 << 31);
+    int rc = g_wc.work.reserve((size_t)lay.off[3] * sizeof(uint64_t));
+    if (rc) return rc;
+    uint64_t *work = (uint64_t *)g_wc.work.ptr;
+    *work_out = work;
+    const bool hit = cacheable && g_wc.valid && g_wc.links == grid->links && g_wc.surface == grid->surface &&
+                     g_wc.density == grid->density && g_wc.accel == grid->accel && g_wc.accel_gen == gen &&
+                     g_wc.capacity == grid->capacity && g_wc.size[0] == grid->size[0] && g_wc.size[1] == grid->size[1] &&
+                     g_wc.size[2] == grid->size[2] && g_wc.sigma_thresh == opt->sigma_thresh;
+    const int64_t N = grid->capacity;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int scan_blocks = (int)((N + 255) / 256 < (int64_t)sms * 16 ? (N + 255) / 256 : (int64_t)sms * 16);
+    if (hit) {
+        unsigned long long *ctr = (unsigned long long *)g_wc.ctr.ptr;
+        ASURF_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+        class_scan_kernel<false><<<scan_blocks, 256, 0, st>>>(grid->surface, grid->density, N, grid->level_set, opt->sigma_thresh,
+                                                              (uint8_t *)g_wc.cls.ptr, (int32_t *)g_wc.changed.ptr, ctr);
+        work_patch_kernel<<<sms * 4, 256, 0, st>>>(grid->links, grid->density, grid->surface, grid->level_set, opt->sigma_thresh,
+                                                   grid->size[0], grid->size[1], grid->size[2], lay, grid->accel,
+                                                   (const int32_t *)g_wc.inv.ptr, (const int32_t *)g_wc.changed.ptr, ctr, work);
+        accel_coarsen_kernel<<<div_up(lay.count(1), 128), 128, 0, st>>>(lay, 1, work);
+        accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, work);
+        note_launches(4);
+        return check_cuda(cudaGetLastError(), "work pyramid update");
+    }
+    g_wc.valid = false;
+    rc = asurf_work_build(grid, opt, work, st);
+    if (rc || !cacheable) return rc;
+    // start a cache for this grid: class bytes, row -> vertex map
+    rc = g_wc.cls.reserve((size_t)N);
+    if (!rc) rc = g_wc.inv.reserve((size_t)N * sizeof(int32_t));
+    if (!rc) rc = g_wc.changed.reserve((size_t)N * sizeof(int32_t));
+    if (!rc) rc = g_wc.ctr.reserve(sizeof(unsigned long long));
+    if (rc) return rc;
+    const int64_t nv = (int64_t)grid->size[0] * grid->size[1] * grid->size[2];
+    inverse_links_kernel<<<sms * 16, 256, 0, st>>>(grid->links, nv, (int32_t *)g_wc.inv.ptr);
+    class_scan_kernel<true><<<scan_blocks, 256, 0, st>>>(grid->surface, grid->density, N, grid->level_set, opt->sigma_thresh,
+                                                         (uint8_t *)g_wc.cls.ptr, nullptr, nullptr);
+    note_launches(2);
+    g_wc.links = grid->links; g_wc.surface = grid->surface; g_wc.density = grid->density; g_wc.accel = grid->accel;
+    g_wc.accel_gen = gen; g_wc.capacity = N; g_wc.sigma_thresh = opt->sigma_thresh;
+    for (int i = 0; i < 3; ++i) g_wc.size[i] = grid->size[i];
+    g_wc.valid = true;
+    return check_cuda(cudaGetLastError(), "work pyramid cache init");
+}
+
+int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st) {
+    ASURF_REQUIRE(g_wc.work.ptr && (size_t)words * sizeof(uint64_t) <= g_wc.work.bytes, ASURF_E_INVALID,
+                  "work cache: nothing cached / size mismatch");
+    return check_cuda(cudaMemcpyAsync(out, g_wc.work.ptr, (size_t)words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st),
+                      "work cache copy");
+}
+
+void work_cache_release() {
+    g_wc.work.release(); g_wc.cls.release(); g_wc.inv.release(); g_wc.changed.release(); g_wc.ctr.release();
+    g_wc.valid = false;
+}
+
 }  // namespace asurf
 
 using namespace asurf;
@@ -244,6 +417,14 @@ extern "C" int64_t asurf_accel_words(const int32_t size[3]) {
 extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream) {
     ASURF_REQUIRE(links && accel_out, ASURF_E_INVALID, "accel_build: null pointer");
     ASURF_REQUIRE(size[0] >= 2 && size[1] >= 2 && size[2] >= 2, ASURF_E_INVALID, "accel_build: grid smaller than 2^3");
+    {   // a new generation for this buffer: work pyramids cached for an older content of the address are dropped
+        ++g_accel_gen;
+        int slot = (int)(g_accel_gen % 16);
+        for (int i = 0; i < 16; ++i)
+            if (g_accel_last[i] == (const void *)accel_out) slot = i;
+        g_accel_last[slot] = (const void *)accel_out;
+        g_accel_last_gen[slot] = g_accel_gen;
+    }
     AccelLayout lay(size);
     cudaStream_t st = (cudaStream_t)stream;
     accel_level0_kernel<<<div_up(lay.count(0), 128), 128, 0, st>>>(links, size[0], size[1], size[2], lay, accel_out);
@@ -257,3 +438,8 @@ extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], ui
     note_launches(5);
     return check_cuda(cudaGetLastError(), "accel_build launch");
 }
+
+extern "C" int asurf_debug_work_cache_copy(uint64_t *out, int64_t words, void *stream) {
+    return work_cache_copy(out, words, (cudaStream_t)stream);
+}
+extern "C" int32_t asurf_debug_work_cache_valid(void) { return g_wc.valid ? 1 : 0; }

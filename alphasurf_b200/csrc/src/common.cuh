@@ -40,6 +40,11 @@ struct Workspace {
 void note_launches(int n);
 unsigned long long launches_read(int reset);
 
+// work pyramid of a render call (accel.cu): incremental update of a cached pyramid when the grid is unchanged
+int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out);
+void work_cache_release();
+int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st);
+
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- occupancy pyramid layout (accel.cu) -----------------------------------------------------------------

@@ -1432,13 +1432,12 @@ int make_grid(const asurf_grid_t *grid, const asurf_opt_t *opt, bool need_work, 
     }
     g.work = grid->work;
     if (need_work && !grid->work) {
-        int rc = g_ws_work.reserve((size_t)lay.off[3] * sizeof(uint64_t));
-        if (rc) return rc;
         asurf_grid_t tmp = *grid;
         tmp.accel = g.accel;
-        rc = asurf_work_build(&tmp, opt, (uint64_t *)g_ws_work.ptr, st);
+        const uint64_t *w = nullptr;
+        int rc = work_pyramid_for_call(&tmp, opt, st, &w);
         if (rc) return rc;
-        g.work = (const uint64_t *)g_ws_work.ptr;
+        g.work = w;
     }
     return 0;
 }
@@ -1835,6 +1834,7 @@ extern "C" int asurf_profile_read(int32_t *n_calls, float *fwd_ms_sum, float *bw
 extern "C" void asurf_release(void) {
     g_ws_accel.release();
     g_ws_work.release();
+    work_cache_release();
     g_ws_cache.release();
     g_ws_dbg.release();
     g_ws_ctr.release();

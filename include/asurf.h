@@ -169,6 +169,12 @@ void asurf_debug_set_skip(int32_t enabled);
  * equal up to atomic order. */
 void asurf_debug_set_wave(int32_t enabled);
 
+/* test hooks: the work pyramid the library keeps between render calls on the same grid (updated incrementally from the
+ * vertices whose level-set side / density gate changed).  copy: the pyramid used by the last render call (device buffer
+ * of asurf_accel_words-sized pyramid part, i.e. the first three levels); valid: whether a cache exists. */
+int asurf_debug_work_cache_copy(uint64_t *out, int64_t words, void *stream);
+int32_t asurf_debug_work_cache_valid(void);
+
 /* test hook: let surface_normal_grad_sparse take its dense tiled kernel when the list enumerates every stored vertex
  * (0, default: always the run-aggregated list kernel).  Same result either way up to summation order. */
 void asurf_debug_set_normal_tile(int32_t enabled);

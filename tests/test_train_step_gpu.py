@@ -61,3 +61,44 @@ def test_train_step_full_size_smoke():
     assert int(ts.mask.sum()) > sg.capacity // 2                 # surface TV / normal loss run over every stored cell
     for k in ("density", "surface", "sh"):
         assert bool(torch.isfinite(getattr(sg, k)).all())
+
+
+def test_incremental_work_pyramid_equals_full_rebuild():
+    """Across training steps the library updates its cached work pyramid only around the vertices whose level-set side or
+    density gate changed; after every render call it must equal a pyramid built from scratch on the same data, bit for bit.
+    Large learning rates make many vertices change side per step."""
+    import ctypes as C
+    from alphasurf_b200 import capi
+    L = capi.lib()
+    for variant, reso in (("G", 96), ("G*", 64)):
+        sg = synth.make_shell_grid(reso, basis_dim=9, variant=variant).to("cuda")
+        hp = S.c3_hyper()
+        hp.update(lr_surface=3e-2, lr_density=0.2)
+        ts = S.TrainStep(ours, sg, hyper=hp)
+        Q = 8192
+        out = torch.zeros((Q, 3), device="cuda")
+        words = (reso // 4 + (1 if (reso - 1) % 4 else 0)) ** 3      # generous: only the first `n3` words are compared
+        n3 = L.asurf_accel_words(capi.size3(sg.links.shape))
+        cached = torch.zeros((n3,), dtype=torch.int64, device="cuda")
+        full = torch.zeros((n3,), dtype=torch.int64, device="cuda")
+        n_changed_total = 0
+        prev = None
+        for it in range(5):
+            o, d, gt = synth.make_camera_rays(Q, device="cuda", seed=300 + it)
+            ts.render(o, d, gt, out)
+            assert L.asurf_debug_work_cache_valid() == 1
+            # size of the three pyramid levels
+            from alphasurf_b200.svox2_csrc import accel_for, _grid_t
+            g, keep = _grid_t(ts.grid_spec)
+            lay_words = n3 - 2 - (((reso + 14) // 16) ** 3 + 1) // 2      # accel_words = levels + 1 + ids/2 + 1
+            capi.check(L.asurf_debug_work_cache_copy(capi.ptr(cached), C.c_int64(lay_words), capi.current_stream()), "copy")
+            capi.check(L.asurf_work_build(C.byref(g), C.byref(capi.make_opt(ts.opt_spec)), capi.ptr(full),
+                                          capi.current_stream()), "work_build")
+            torch.cuda.synchronize()
+            assert torch.equal(cached[:lay_words], full[:lay_words]), (variant, it)
+            if prev is not None:
+                n_changed_total += int((prev != full[:lay_words]).sum())
+            prev = full[:lay_words].clone()
+            ts.regularisers()
+            ts.optimizer()
+        assert n_changed_total > 0, "the steps were supposed to move the level set through some voxels"
