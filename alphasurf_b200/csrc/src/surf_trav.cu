@@ -673,28 +673,19 @@ __device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t 
     }
 }
 
-// ---- pre-march: one thread per ray, nothing but the generalized DDA --------------------------------------------------
-// Finds, for every ray, the first PRE_K voxels whose work bit is set (and the state to resume from if there are more),
-// writes the background colour of the rays that have no work at all, and compacts the others into a list for the
-// shading kernels.  Its loop body is march_step only, so the 32 rays of a warp advance in lock step.
-__global__ void __launch_bounds__(256)
-premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
-                const int64_t Q, const PreP pre, float *__restrict__ rgb_out, int *__restrict__ cache_n) {
-    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    Lane L;
-    L.state = ST_IDLE;
-    L.ray_done = false;
-    Counters cnt = {0, 0, 0, 0, 0};
-    int n = 0, n_bwd = 0;
-    bool cont = false;
-    if (ray_id < Q) {
-        L.ox = origins[ray_id * 3 + 0]; L.oy = origins[ray_id * 3 + 1]; L.oz = origins[ray_id * 3 + 2];
-        L.dx = dirs[ray_id * 3 + 0]; L.dy = dirs[ray_id * 3 + 1]; L.dz = dirs[ray_id * 3 + 2];
-        float world_step;
-        ray_bounds(g, opt, L, world_step);
-        if (!(L.tmin > L.tmax)) dda_init(g, L);
-    }
+// ---- pre-march: nothing but the generalized DDA ------------------------------------------------------------------------
+// Finds, for every ray, the voxels whose work bit is set, in march order (up to PreP::K, with the state to resume from if
+// there are more), writes the background colour of the rays that have no work at all, and compacts the others into queues
+// for the shading kernels.  Two shapes: one thread per ray (premarch_kernel), or -- for large batches -- one thread per
+// (ray, 64-voxel slab along the ray's dominant axis) followed by a per-ray merge (premarch_seg_kernel +
+// premarch_merge_kernel): 8x more, 8x shorter independent marches, because the DDA state at a slab boundary follows
+// exactly from the boundary crossing event (same rule as the block jumps).
+
+// The march of one lane from its current DDA state until the ray ends, the list is full (cont), or -- axisA >= 0 -- the
+// voxel coordinate on axisA leaves [slab_lo, slab_hi].
+__device__ __forceinline__ void premarch_march(const GridP &g, const asurf_opt_t &opt, Lane &L, int32_t *__restrict__ out_cells,
+                                               int out_cap, int &n, int &n_bwd, bool &cont, int axisA, int slab_lo,
+                                               int slab_hi) {
     // The march runs in warp-wide phases so that lanes doing the same kind of step execute together: a JUMP phase
     // (look up which pyramid level is empty around the next voxel, leave empty 16^3 / 64^3 blocks: ~250 instructions per
     // jump) repeated while lanes keep jumping, then a FINE phase (voxel-by-voxel steps inside non-empty 16^3 blocks,
@@ -768,6 +759,10 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                         L.tfz = PT_Z(L, nz + (L.dz > 0.f ? 1 : 0));
                         L.t = T;
                         mode = PM_LOOKUP;
+                        if (axisA >= 0) {   // segmented march: the item ends when the ray leaves its slab
+                            const int na2 = (axisA == 0) ? nx : ((axisA == 1) ? ny : nz);
+                            if (na2 < slab_lo || na2 > slab_hi) mode = PM_DONE;
+                        }
                     }
                 }
             }
@@ -803,10 +798,10 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                     L.t = out ? L.tmax + 1.f : T;
                     const int bit = ((vx & 3) << 4) | ((vy & 3) << 2) | (vz & 3);
                     if ((L.word >> bit) & 1ull) {
-                        pre.cells[ray_id * pre.K + n] = (int32_t)(((int64_t)vx * g.size[1] + vy) * g.size[2] + vz);
+                        out_cells[n] = (int32_t)(((int64_t)vx * g.size[1] + vy) * g.size[2] + vz);
                         ++n;
                         if (L.bwd_alive) ++n_bwd;
-                        if (n == pre.K) {
+                        if (n == out_cap) {
                             cont = true;   // resume here (the shading kernels re-check `t <= tmax`)
                             mode = PM_DONE;
                         }
@@ -815,15 +810,24 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
                         if (!((__ldg(g.accel + L.wkey) >> bit) & 1ull)) L.bwd_alive = false;
                     }
                     if (mode == PM_FINE) {
+                        const int na2 = (axisA == 0) ? L.nx : ((axisA == 1) ? L.ny : L.nz);
                         if (out) mode = PM_DONE;
+                        else if (axisA >= 0 && (na2 < slab_lo || na2 > slab_hi)) mode = PM_DONE;   // left the item's slab
                         else if ((m_old ^ m_new) >> 2) lookup();   // next 4^3 block: new word, or an empty block to jump
                     }
                 }
             }
         }
     }
+}
+
+// Per-ray epilogue: list header, background for rays without work, short / long classification and the compact queues.
+__device__ __forceinline__ void premarch_finish(const GridP &g, const asurf_opt_t &opt, const PreP &pre, const Lane &L,
+                                                int64_t ray_id, bool valid, int n, int n_bwd, bool cont,
+                                                float *__restrict__ rgb_out, int *__restrict__ cache_n) {
+    const int lane = threadIdx.x & 31;
     bool has_work = false;
-    if (ray_id < Q) {
+    if (valid) {
         int code = n | (n_bwd << 8);
         if (cont) {
             code |= (1 << 16) | ((L.bwd_alive ? 1 : 0) << 17) | ((L.force_fine ? 1 : 0) << 18);
@@ -831,7 +835,7 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
             pre.cont_vox[ray_id] = L.nx | (L.ny << 10) | (L.nz << 20);
         }
         pre.code[ray_id] = code;
-        has_work = (n > 0);
+        has_work = (n > 0) || cont;
         if (!has_work) {
             if (rgb_out) {   // forward: the ray composites nothing -> background (:59-65, :553-555)
                 const float bg = opt.background_brightness;
@@ -880,6 +884,136 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
         base = __shfl_sync(FULL, base, __ffs(ms) - 1);
         if (is_short) pre.rays_short[base + __popc(ms & ((1u << lane) - 1u))] = (int32_t)ray_id;
     }
+}
+
+__device__ __forceinline__ void premarch_ray_setup(const GridP &g, const asurf_opt_t &opt, const float *__restrict__ origins,
+                                                   const float *__restrict__ dirs, int64_t ray_id, Lane &L) {
+    L.ox = origins[ray_id * 3 + 0]; L.oy = origins[ray_id * 3 + 1]; L.oz = origins[ray_id * 3 + 2];
+    L.dx = dirs[ray_id * 3 + 0]; L.dy = dirs[ray_id * 3 + 1]; L.dz = dirs[ray_id * 3 + 2];
+    float world_step;
+    ray_bounds(g, opt, L, world_step);
+    if (!(L.tmin > L.tmax)) dda_init(g, L);
+}
+
+__global__ void __launch_bounds__(256)
+premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                const int64_t Q, const PreP pre, float *__restrict__ rgb_out, int *__restrict__ cache_n) {
+    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Lane L;
+    L.state = ST_IDLE;
+    L.ray_done = false;
+    int n = 0, n_bwd = 0;
+    bool cont = false;
+    if (ray_id < Q) premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
+    premarch_march(g, opt, L, pre.cells + (ray_id < Q ? ray_id : 0) * pre.K, pre.K, n, n_bwd, cont, -1, 0, 0);
+    premarch_finish(g, opt, pre, L, ray_id, ray_id < Q, n, n_bwd, cont, rgb_out, cache_n);
+}
+
+// ---- segmented pre-march ---------------------------------------------------------------------------------------------------
+constexpr int SEG_K = 64;        // list capacity of one (ray, slab) item
+constexpr int SEG_SLAB = 64;     // slab thickness in voxels (aligned: the 64^3 pyramid blocks never straddle slabs)
+struct SegP {
+    int32_t *cells;   // (Q, NS, SEG_K)
+    int32_t *meta;    // (Q, NS): count | visible-to-backward count << 8 | alive at the end << 16 | overflow << 17
+    int NS;
+};
+
+__device__ __forceinline__ int dominant_axis(const Lane &L) {
+    const float ax = fabsf(L.dx), ay = fabsf(L.dy), az = fabsf(L.dz);
+    return (ax >= ay && ax >= az) ? 0 : ((ay >= az) ? 1 : 2);
+}
+
+__global__ void __launch_bounds__(256)
+premarch_seg_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                    const int64_t Q, const SegP seg) {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ray_id = item / seg.NS;
+    const int s = (int)(item - ray_id * seg.NS);   // s-th slab the ray visits
+    Lane L;
+    L.state = ST_IDLE;
+    L.ray_done = false;
+    int n = 0, n_bwd = 0;
+    bool cont = false;
+    int A = 0, slab_lo = 0, slab_hi = 0;
+    const bool in_range = ray_id < Q;
+    if (in_range) {
+        premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
+        if (L.state == ST_MARCH) {
+            A = dominant_axis(L);
+            const float oA = (A == 0) ? L.ox : ((A == 1) ? L.oy : L.oz), dA = (A == 0) ? L.dx : ((A == 1) ? L.dy : L.dz),
+                        rA = (A == 0) ? L.rx : ((A == 1) ? L.ry : L.rz);
+            const int v0A = (A == 0) ? L.nx : ((A == 1) ? L.ny : L.nz);
+            const int sizeA = g.size[A];
+            const int sign = (dA > 0.f) ? 1 : -1;
+            const int j = v0A / SEG_SLAB + s * sign;
+            slab_lo = j * SEG_SLAB;
+            slab_hi = slab_lo + SEG_SLAB - 1;
+            if (j < 0 || slab_lo > sizeA - 2) {
+                L.state = ST_IDLE;   // no such slab on this ray
+            } else if (s > 0) {
+                // DDA state right after the ray crosses into the slab: the event (T, A) and, for the other axes, the planes
+                // whose crossing precedes it in the DDA's (t, axis) order -- the landing rule of the block jumps
+                const int P = (sign > 0) ? slab_lo : slab_lo + SEG_SLAB;
+                const float T = plane_t(P, oA, dA, rA, L.slow_div);
+                bool ok = true;
+#pragma unroll
+                for (int B = 0; B < 3; ++B) {   // the march ends at the first step out of [0, size - 2] on any axis
+                    if (B == A) continue;
+                    const float oB = (B == 0) ? L.ox : ((B == 1) ? L.oy : L.oz), dB = (B == 0) ? L.dx : ((B == 1) ? L.dy : L.dz),
+                                rB = (B == 0) ? L.rx : ((B == 1) ? L.ry : L.rz);
+                    const float te = plane_t(dB > 0.f ? g.size[B] - 1 : 0, oB, dB, rB, L.slow_div);
+                    if ((te < T) || ((te == T) && (B < A))) ok = false;
+                }
+                const int nA = (sign > 0) ? P : P - 1;
+                if (!ok || nA < 0 || nA > sizeA - 2) {
+                    L.state = ST_IDLE;
+                } else {
+                    const int nx = (A == 0) ? nA : axis_after(L.nx, L.ox, L.dx, L.rx, L.slow_div, T, false, 0, g.size[0] - 1);
+                    const int ny = (A == 1) ? nA : axis_after(L.ny, L.oy, L.dy, L.ry, L.slow_div, T, A > 1, 0, g.size[1] - 1);
+                    const int nz = (A == 2) ? nA : axis_after(L.nz, L.oz, L.dz, L.rz, L.slow_div, T, A > 2, 0, g.size[2] - 1);
+                    L.nx = nx; L.ny = ny; L.nz = nz;
+                    L.t = T;
+                    dda_restart(L);
+                }
+            }
+        }
+    }
+    premarch_march(g, opt, L, seg.cells + (in_range ? item : 0) * SEG_K, SEG_K, n, n_bwd, cont, A, slab_lo, slab_hi);
+    if (in_range) seg.meta[item] = n | (n_bwd << 8) | ((L.bwd_alive ? 1 : 0) << 16) | ((cont ? 1 : 0) << 17);
+}
+
+__global__ void __launch_bounds__(256)
+premarch_merge_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                      const int64_t Q, const PreP pre, const SegP seg, float *__restrict__ rgb_out, int *__restrict__ cache_n) {
+    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Lane L;
+    L.state = ST_IDLE;
+    L.ray_done = false;
+    int n = 0, n_bwd = 0;
+    bool cont = false;
+    if (ray_id < Q) {
+        bool alive = true, too_long = false;
+        for (int s = 0; s < seg.NS && !too_long; ++s) {
+            const int32_t m = seg.meta[ray_id * seg.NS + s];
+            const int c = m & 255;
+            if (((m >> 17) & 1) || (n + c > pre.K)) {
+                too_long = true;
+                break;
+            }
+            const int32_t *src = seg.cells + (ray_id * seg.NS + s) * SEG_K;
+            for (int k = 0; k < c; ++k) pre.cells[ray_id * pre.K + n + k] = src[k];
+            n += c;
+            if (alive) n_bwd += (m >> 8) & 255;
+            if (!((m >> 16) & 1)) alive = false;
+        }
+        if (too_long) {   // more work voxels than the lists hold: the persistent kernels march this ray from its start
+            premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
+            n = 0;
+            n_bwd = 0;
+            cont = true;
+        }
+    }
+    premarch_finish(g, opt, pre, L, ray_id, ray_id < Q, n, n_bwd, cont, rgb_out, cache_n);
 }
 
 // Sum of `bd` consecutive lanes starting at a segment head, same add order as the reference's
@@ -1377,8 +1511,9 @@ using namespace asurf;
 
 namespace {
 
-Workspace g_ws_wave;
+Workspace g_ws_wave, g_ws_seg;
 int g_wave_enabled = 1;  // asurf_debug_set_wave
+int g_seg_enabled = 1;   // asurf_debug_set_seg
 
 Workspace g_ws_accel, g_ws_work, g_ws_cache, g_ws_dbg, g_ws_ctr, g_ws_pre;
 
@@ -1504,6 +1639,25 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
     pre.n_items = ctr + 4;
     pre.enabled = 1;
     pre.wave = (g_wave_enabled && g.level_set_num == 1) ? 1 : 0;
+    const int maxsz = g.size[0] > g.size[1] ? (g.size[0] > g.size[2] ? g.size[0] : g.size[2])
+                                            : (g.size[1] > g.size[2] ? g.size[1] : g.size[2]);
+    const int NS = (maxsz + SEG_SLAB - 1) / SEG_SLAB;
+    if (g_seg_enabled && Q >= 8192 && NS >= 2 && NS <= 16 && (int64_t)Q * NS * SEG_K <= ((int64_t)1 << 29)) {
+        // large batch: one thread per (ray, slab) item, then a per-ray merge
+        SegP seg;
+        seg.NS = NS;
+        const size_t b_cells = (size_t)Q * NS * SEG_K * sizeof(int32_t), b_meta = (size_t)Q * NS * sizeof(int32_t);
+        rc = g_ws_seg.reserve(b_cells + b_meta);
+        if (rc) return rc;
+        seg.cells = (int32_t *)g_ws_seg.ptr;
+        seg.meta = (int32_t *)((char *)g_ws_seg.ptr + b_cells);
+        const int64_t n_items = Q * NS;
+        premarch_seg_kernel<<<(int)((n_items + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, seg);
+        premarch_merge_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, seg, rgb_out,
+                                                                      cache_n);
+        note_launches(2);
+        return check_cuda(cudaGetLastError(), "segmented premarch launch");
+    }
     premarch_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, rgb_out, cache_n);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "premarch launch");
@@ -1792,6 +1946,7 @@ extern "C" int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *r
 
 extern "C" void asurf_debug_set_skip(int32_t enabled) { g_skip_enabled = enabled ? 1 : 0; }
 extern "C" void asurf_debug_set_wave(int32_t enabled) { g_wave_enabled = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_seg(int32_t enabled) { g_seg_enabled = enabled ? 1 : 0; }
 
 extern "C" int asurf_profile_enable(int32_t capacity) {
     for (int i = 0; i < PROF_EV * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);
@@ -1840,4 +1995,5 @@ extern "C" void asurf_release(void) {
     g_ws_ctr.release();
     g_ws_pre.release();
     g_ws_wave.release();
+    g_ws_seg.release();
 }

@@ -219,3 +219,35 @@ def test_wavefront_path_equals_persistent_path(name, reso, bd, Q, variant, optfn
             assert H.rel_err(getattr(ga, k), getattr(gb, k)) < 2e-5, k
         if ga.std is not None:
             assert H.rel_err(ga.std, gb.std) < 2e-5 or float(gb.std.abs().max()) == 0.0
+
+
+SEG_CASES = [("G-512", 512, "G", 65536, synth.alphasurf_render_options), ("G-200", 200, "G", 16384, synth.parity_render_options),
+             ("G*-128", 128, "G*", 8192, synth.alphasurf_render_options)]
+
+
+@pytest.mark.parametrize("name,reso,variant,Q,optfn", SEG_CASES, ids=[c[0] for c in SEG_CASES])
+def test_segmented_premarch_equals_whole_ray_premarch(name, reso, variant, Q, optfn):
+    """Large batches march every ray as independent (ray, 64-voxel slab) items whose start state is derived from the slab
+    boundary crossing; the listed voxels -- hence colours (bit-identical), masks and gradients -- must be those of the
+    thread-per-ray march.  G* lists more voxels than fit (fallback to the persistent kernels from the ray start)."""
+    from alphasurf_b200 import capi
+    opts, fused = optfn(), synth.alphasurf_fused_args()
+    sg = synth.make_shell_grid(reso, basis_dim=9, variant=variant).to("cuda")
+    o, d, gt = synth.make_camera_rays(Q, device="cuda", seed=21)
+    res = []
+    try:
+        for seg in (1, 0):
+            capi.lib().asurf_debug_set_seg(seg)
+            G = H.GradSet(sg, "cuda")
+            rgb = torch.zeros_like(o)
+            ours.volume_render_surf_trav_fused(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d),
+                                               H.fill_opt(ours, opts), gt, *H.fused_positional(fused), rgb, G.spec(ours))
+            torch.cuda.synchronize()
+            res.append((rgb, G))
+    finally:
+        capi.lib().asurf_debug_set_seg(1)
+    a, b = res
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[1].mask, b[1].mask) and int(a[1].mask.sum()) > 0
+    for k in ("sh", "density", "surface"):
+        assert H.rel_err(getattr(a[1], k), getattr(b[1], k)) < 1e-5, k
