@@ -676,16 +676,13 @@ __device__ __forceinline__ void voxel_advance(const GridP &g, const asurf_opt_t 
 // ---- pre-march: nothing but the generalized DDA ------------------------------------------------------------------------
 // Finds, for every ray, the voxels whose work bit is set, in march order (up to PreP::K, with the state to resume from if
 // there are more), writes the background colour of the rays that have no work at all, and compacts the others into queues
-// for the shading kernels.  Two shapes: one thread per ray (premarch_kernel), or -- for large batches -- one thread per
-// (ray, 64-voxel slab along the ray's dominant axis) followed by a per-ray merge (premarch_seg_kernel +
-// premarch_merge_kernel): 8x more, 8x shorter independent marches, because the DDA state at a slab boundary follows
-// exactly from the boundary crossing event (same rule as the block jumps).
+// for the shading kernels.  Two shapes: one thread per ray (premarch_kernel), or -- for large batches -- the two-level
+// march below (premarch_coarse_kernel / premarch_fine_kernel / premarch_merge_kernel).
 
-// The march of one lane from its current DDA state until the ray ends, the list is full (cont), or -- axisA >= 0 -- the
-// voxel coordinate on axisA leaves [slab_lo, slab_hi].
+// The march of one lane from its current DDA state until the ray ends, the list is full (cont), or -- box_shift > 0 -- the
+// ray leaves the aligned block of 2^box_shift voxels per side it started in.
 __device__ __forceinline__ void premarch_march(const GridP &g, const asurf_opt_t &opt, Lane &L, int32_t *__restrict__ out_cells,
-                                               int out_cap, int &n, int &n_bwd, bool &cont, int axisA, int slab_lo,
-                                               int slab_hi) {
+                                               int out_cap, int &n, int &n_bwd, bool &cont, int box_shift) {
     // The march runs in warp-wide phases so that lanes doing the same kind of step execute together: a JUMP phase
     // (look up which pyramid level is empty around the next voxel, leave empty 16^3 / 64^3 blocks: ~250 instructions per
     // jump) repeated while lanes keep jumping, then a FINE phase (voxel-by-voxel steps inside non-empty 16^3 blocks,
@@ -759,10 +756,6 @@ __device__ __forceinline__ void premarch_march(const GridP &g, const asurf_opt_t
                         L.tfz = PT_Z(L, nz + (L.dz > 0.f ? 1 : 0));
                         L.t = T;
                         mode = PM_LOOKUP;
-                        if (axisA >= 0) {   // segmented march: the item ends when the ray leaves its slab
-                            const int na2 = (axisA == 0) ? nx : ((axisA == 1) ? ny : nz);
-                            if (na2 < slab_lo || na2 > slab_hi) mode = PM_DONE;
-                        }
                     }
                 }
             }
@@ -810,9 +803,8 @@ __device__ __forceinline__ void premarch_march(const GridP &g, const asurf_opt_t
                         if (!((__ldg(g.accel + L.wkey) >> bit) & 1ull)) L.bwd_alive = false;
                     }
                     if (mode == PM_FINE) {
-                        const int na2 = (axisA == 0) ? L.nx : ((axisA == 1) ? L.ny : L.nz);
                         if (out) mode = PM_DONE;
-                        else if (axisA >= 0 && (na2 < slab_lo || na2 > slab_hi)) mode = PM_DONE;   // left the item's slab
+                        else if (box_shift && ((m_old ^ m_new) >> box_shift)) mode = PM_DONE;   // left the item's block
                         else if ((m_old ^ m_new) >> 2) lookup();   // next 4^3 block: new word, or an empty block to jump
                     }
                 }
@@ -905,86 +897,162 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
     int n = 0, n_bwd = 0;
     bool cont = false;
     if (ray_id < Q) premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
-    premarch_march(g, opt, L, pre.cells + (ray_id < Q ? ray_id : 0) * pre.K, pre.K, n, n_bwd, cont, -1, 0, 0);
+    premarch_march(g, opt, L, pre.cells + (ray_id < Q ? ray_id : 0) * pre.K, pre.K, n, n_bwd, cont, 0);
     premarch_finish(g, opt, pre, L, ray_id, ray_id < Q, n, n_bwd, cont, rgb_out, cache_n);
 }
 
-// ---- segmented pre-march ---------------------------------------------------------------------------------------------------
-constexpr int SEG_K = 64;        // list capacity of one (ray, slab) item
-constexpr int SEG_SLAB = 64;     // slab thickness in voxels (aligned: the 64^3 pyramid blocks never straddle slabs)
-struct SegP {
-    int32_t *cells;   // (Q, NS, SEG_K)
-    int32_t *meta;    // (Q, NS): count | visible-to-backward count << 8 | alive at the end << 16 | overflow << 17
-    int NS;
+// ---- two-level pre-march -----------------------------------------------------------------------------------------------------
+// coarse: thread per ray, block jumps ONLY -- every 16^3 / 64^3 block is left with the exact landing rule whether it is empty
+//         or not (the rule does not depend on the block's content); a non-empty 16^3 block (or any block in the last
+//         step_size of the ray, where the backward's early exit has to be tracked voxel by voxel) is queued as an item
+//         (ray, entry voxel, entry t).  All lanes of a warp do the same kind of step.
+// fine:   thread per item, voxel-by-voxel steps inside that one block, listing its work voxels.  Items are homogeneous
+//         (<= 46 steps), so warps stay full -- the long fine stretches of grazing rays no longer hold 31 other rays up.
+// merge:  thread per ray, concatenates its items' lists in order and runs the per-ray epilogue.
+constexpr int CI_MAX = 24;       // items per ray (non-empty 16^3 blocks it crosses); more -> the ray goes to the persistent kernels
+constexpr int FI_K = 32;         // work voxels listed per item
+struct TwoP {
+    int32_t *ray_items;          // (Q, CI_MAX, 2): packed voxel (10 bits per axis), t bits
+    int32_t *ray_nitems;         // (Q,) number of items, or -1 when there were more than CI_MAX
+    int32_t *item_first;         // (Q,) first entry of the ray's items in the item queue
+    int32_t *fq;                 // fine-item queue: ray_id * CI_MAX + i
+    unsigned long long *n_fq;
+    int32_t *fi_cells;           // (Q * CI_MAX budget, FI_K) indexed by queue position
+    int32_t *fi_meta;            // count | visible-to-backward count << 8 | alive at the end << 16 | overflow << 17
+    int64_t fq_cap;
 };
 
-__device__ __forceinline__ int dominant_axis(const Lane &L) {
-    const float ax = fabsf(L.dx), ay = fabsf(L.dy), az = fabsf(L.dz);
-    return (ax >= ay && ax >= az) ? 0 : ((ay >= az) ? 1 : 2);
+__global__ void __launch_bounds__(256)
+premarch_coarse_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                       const int64_t Q, const TwoP tw) {
+    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Lane L;
+    L.state = ST_IDLE;
+    L.ray_done = false;
+    if (ray_id < Q) premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
+    const uint64_t *bm = g.work;
+    int n_items = 0;
+    bool tail = false;   // within step_size of tmax: every further block becomes an item (backward quirk, :1935)
+    bool active = (L.state == ST_MARCH);
+    while (__any_sync(FULL, active)) {
+        if (active) {
+            if (!(L.t <= L.tmax)) {
+                active = false;
+            } else {
+                int sft = 4;
+                bool emit = tail || !g.use_skip;
+                if (g.use_skip) {
+                    const int k2 = ((L.nx >> 6) * g.lay.b[2][1] + (L.ny >> 6)) * g.lay.b[2][2] + (L.nz >> 6);
+                    if (k2 != L.k2) {
+                        L.k2 = k2;
+                        L.w2 = __ldg(bm + g.lay.off[2] + k2);
+                    }
+                    const int bit1 = (((L.nx >> 4) & 3) << 4) | (((L.ny >> 4) & 3) << 2) | ((L.nz >> 4) & 3);
+                    if (L.w2 == 0) sft = tail ? 4 : 6;
+                    else if ((L.w2 >> bit1) & 1ull) emit = true;
+                }
+                const int lox = (L.nx >> sft) << sft, loy = (L.ny >> sft) << sft, loz = (L.nz >> sft) << sft;
+                const int hix = min(lox + (1 << sft), g.size[0] - 1), hiy = min(loy + (1 << sft), g.size[1] - 1),
+                          hiz = min(loz + (1 << sft), g.size[2] - 1);
+                const int Px = (L.dx > 0.f) ? hix : lox, Py = (L.dy > 0.f) ? hiy : loy, Pz = (L.dz > 0.f) ? hiz : loz;
+                const float Tx = PT_X(L, Px), Ty = PT_Y(L, Py), Tz = PT_Z(L, Pz);
+                const float T = fminf(fminf(Tx, Ty), Tz);
+                if (!tail && !(T + opt.step_size <= L.tmax)) {
+                    tail = true;       // re-evaluate this position with 16^3 granularity and an item
+                } else {
+                    if (emit) {
+                        if (n_items < CI_MAX) {
+                            tw.ray_items[(ray_id * CI_MAX + n_items) * 2 + 0] = L.nx | (L.ny << 10) | (L.nz << 20);
+                            tw.ray_items[(ray_id * CI_MAX + n_items) * 2 + 1] = __float_as_int(L.t);
+                        }
+                        ++n_items;
+                    }
+                    if (!(T <= L.tmax)) {
+                        active = false;    // `while (t <= tmax)` fails inside this block (the item, if any, handles it)
+                    } else {
+                        const int A = (T == Tx) ? 0 : ((T == Ty) ? 1 : 2);
+                        int nx = axis_after(L.nx, L.ox, L.dx, L.rx, L.slow_div, T, A > 0, lox, hix);
+                        int ny = axis_after(L.ny, L.oy, L.dy, L.ry, L.slow_div, T, A > 1, loy, hiy);
+                        int nz = axis_after(L.nz, L.oz, L.dz, L.rz, L.slow_div, T, false, loz, hiz);
+                        nx = (A == 0) ? ((L.dx > 0.f) ? Px : Px - 1) : nx;
+                        ny = (A == 1) ? ((L.dy > 0.f) ? Py : Py - 1) : ny;
+                        nz = (A == 2) ? ((L.dz > 0.f) ? Pz : Pz - 1) : nz;
+                        const int na = (A == 0) ? nx : ((A == 1) ? ny : nz);
+                        const int lim = (A == 0) ? g.size[0] : ((A == 1) ? g.size[1] : g.size[2]);
+                        if ((na < 0) || (na >= lim - 1)) {
+                            active = false;   // the ray leaves the grid through this block
+                        } else {
+                            L.nx = nx; L.ny = ny; L.nz = nz;
+                            L.t = T;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // queue the items: a ray's items get consecutive queue entries
+    const bool ok = (ray_id < Q) && (n_items > 0) && (n_items <= CI_MAX);
+    int incl = ok ? n_items : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += o;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    unsigned long long base = 0;
+    if (total) {
+        if (lane == 0) base = atomicAdd(tw.n_fq, (unsigned long long)total);
+        base = __shfl_sync(FULL, base, 0);
+    }
+    if (ray_id < Q) {
+        int32_t ni = (n_items > CI_MAX) ? -1 : n_items;
+        if (ok) {
+            const int64_t first = (int64_t)base + incl - n_items;
+            if (first + n_items <= tw.fq_cap) {
+                tw.item_first[ray_id] = (int32_t)first;
+                for (int i = 0; i < n_items; ++i) tw.fq[first + i] = (int32_t)(ray_id * CI_MAX + i);
+            } else {
+                ni = -1;   // queue full: the persistent kernels march this ray
+                for (int i = 0; i < n_items; ++i)
+                    if (first + i < tw.fq_cap) tw.fq[first + i] = -1;
+            }
+        }
+        tw.ray_nitems[ray_id] = ni;
+    }
 }
 
 __global__ void __launch_bounds__(256)
-premarch_seg_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
-                    const int64_t Q, const SegP seg) {
-    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t ray_id = item / seg.NS;
-    const int s = (int)(item - ray_id * seg.NS);   // s-th slab the ray visits
+premarch_fine_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                     const TwoP tw) {
+    const int64_t n_all = (int64_t)*tw.n_fq;
+    const int64_t n_fq = n_all < tw.fq_cap ? n_all : tw.fq_cap;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Lane L;
     L.state = ST_IDLE;
     L.ray_done = false;
     int n = 0, n_bwd = 0;
     bool cont = false;
-    int A = 0, slab_lo = 0, slab_hi = 0;
-    const bool in_range = ray_id < Q;
-    if (in_range) {
-        premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
-        if (L.state == ST_MARCH) {
-            A = dominant_axis(L);
-            const float oA = (A == 0) ? L.ox : ((A == 1) ? L.oy : L.oz), dA = (A == 0) ? L.dx : ((A == 1) ? L.dy : L.dz),
-                        rA = (A == 0) ? L.rx : ((A == 1) ? L.ry : L.rz);
-            const int v0A = (A == 0) ? L.nx : ((A == 1) ? L.ny : L.nz);
-            const int sizeA = g.size[A];
-            const int sign = (dA > 0.f) ? 1 : -1;
-            const int j = v0A / SEG_SLAB + s * sign;
-            slab_lo = j * SEG_SLAB;
-            slab_hi = slab_lo + SEG_SLAB - 1;
-            if (j < 0 || slab_lo > sizeA - 2) {
-                L.state = ST_IDLE;   // no such slab on this ray
-            } else if (s > 0) {
-                // DDA state right after the ray crosses into the slab: the event (T, A) and, for the other axes, the planes
-                // whose crossing precedes it in the DDA's (t, axis) order -- the landing rule of the block jumps
-                const int P = (sign > 0) ? slab_lo : slab_lo + SEG_SLAB;
-                const float T = plane_t(P, oA, dA, rA, L.slow_div);
-                bool ok = true;
-#pragma unroll
-                for (int B = 0; B < 3; ++B) {   // the march ends at the first step out of [0, size - 2] on any axis
-                    if (B == A) continue;
-                    const float oB = (B == 0) ? L.ox : ((B == 1) ? L.oy : L.oz), dB = (B == 0) ? L.dx : ((B == 1) ? L.dy : L.dz),
-                                rB = (B == 0) ? L.rx : ((B == 1) ? L.ry : L.rz);
-                    const float te = plane_t(dB > 0.f ? g.size[B] - 1 : 0, oB, dB, rB, L.slow_div);
-                    if ((te < T) || ((te == T) && (B < A))) ok = false;
-                }
-                const int nA = (sign > 0) ? P : P - 1;
-                if (!ok || nA < 0 || nA > sizeA - 2) {
-                    L.state = ST_IDLE;
-                } else {
-                    const int nx = (A == 0) ? nA : axis_after(L.nx, L.ox, L.dx, L.rx, L.slow_div, T, false, 0, g.size[0] - 1);
-                    const int ny = (A == 1) ? nA : axis_after(L.ny, L.oy, L.dy, L.ry, L.slow_div, T, A > 1, 0, g.size[1] - 1);
-                    const int nz = (A == 2) ? nA : axis_after(L.nz, L.oz, L.dz, L.rz, L.slow_div, T, A > 2, 0, g.size[2] - 1);
-                    L.nx = nx; L.ny = ny; L.nz = nz;
-                    L.t = T;
-                    dda_restart(L);
-                }
-            }
-        }
+    const int32_t code = (q < n_fq) ? __ldg(tw.fq + q) : -1;
+    if (code >= 0) {
+        const int64_t ray_id = code / CI_MAX;
+        premarch_ray_setup(g, opt, origins, dirs, ray_id, L);   // bounds + reciprocals (the start voxel is overwritten)
+        const int32_t pv = tw.ray_items[(int64_t)code * 2 + 0];
+        L.nx = pv & 1023;
+        L.ny = (pv >> 10) & 1023;
+        L.nz = (pv >> 20) & 1023;
+        L.t = __int_as_float(tw.ray_items[(int64_t)code * 2 + 1]);
+        L.force_fine = true;   // inside the item's block every voxel is visited
+        L.bwd_alive = true;
+        dda_restart(L);
     }
-    premarch_march(g, opt, L, seg.cells + (in_range ? item : 0) * SEG_K, SEG_K, n, n_bwd, cont, A, slab_lo, slab_hi);
-    if (in_range) seg.meta[item] = n | (n_bwd << 8) | ((L.bwd_alive ? 1 : 0) << 16) | ((cont ? 1 : 0) << 17);
+    premarch_march(g, opt, L, tw.fi_cells + (code >= 0 ? q : 0) * FI_K, FI_K, n, n_bwd, cont, 4);
+    if (code >= 0) tw.fi_meta[q] = n | (n_bwd << 8) | ((L.bwd_alive ? 1 : 0) << 16) | ((cont ? 1 : 0) << 17);
 }
 
 __global__ void __launch_bounds__(256)
 premarch_merge_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
-                      const int64_t Q, const PreP pre, const SegP seg, float *__restrict__ rgb_out, int *__restrict__ cache_n) {
+                      const int64_t Q, const PreP pre, const TwoP tw, float *__restrict__ rgb_out, int *__restrict__ cache_n) {
     const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Lane L;
     L.state = ST_IDLE;
@@ -992,21 +1060,23 @@ premarch_merge_kernel(const GridP g, const asurf_opt_t opt, const float *__restr
     int n = 0, n_bwd = 0;
     bool cont = false;
     if (ray_id < Q) {
-        bool alive = true, too_long = false;
-        for (int s = 0; s < seg.NS && !too_long; ++s) {
-            const int32_t m = seg.meta[ray_id * seg.NS + s];
+        const int ni = tw.ray_nitems[ray_id];
+        bool alive = true, too_long = (ni < 0);
+        const int64_t first = (ni > 0) ? (int64_t)tw.item_first[ray_id] : 0;
+        for (int i = 0; i < ni && !too_long; ++i) {
+            const int32_t m = tw.fi_meta[first + i];
             const int c = m & 255;
             if (((m >> 17) & 1) || (n + c > pre.K)) {
                 too_long = true;
                 break;
             }
-            const int32_t *src = seg.cells + (ray_id * seg.NS + s) * SEG_K;
+            const int32_t *src = tw.fi_cells + (first + i) * FI_K;
             for (int k = 0; k < c; ++k) pre.cells[ray_id * pre.K + n + k] = src[k];
             n += c;
             if (alive) n_bwd += (m >> 8) & 255;
             if (!((m >> 16) & 1)) alive = false;
         }
-        if (too_long) {   // more work voxels than the lists hold: the persistent kernels march this ray from its start
+        if (too_long) {   // more work than the lists hold: the persistent kernels march this ray from its start
             premarch_ray_setup(g, opt, origins, dirs, ray_id, L);
             n = 0;
             n_bwd = 0;
@@ -1601,7 +1671,7 @@ inline int n_ctas(int64_t Q) {
 }
 
 // zeroed counters for the next launches on `st`: [0] forward ray fetch, [1] backward ray fetch, [2] long-ray list length,
-// [3] short-ray list length, [4] item queue length, [5] hit queue length
+// [3] short-ray list length, [4] item queue length, [5] hit queue length, [6] fine-item queue length of the pre-march
 int ray_counters(cudaStream_t st, unsigned long long **ctr) {
     int rc = g_ws_ctr.reserve(8 * sizeof(unsigned long long));
     if (rc) return rc;
@@ -1639,24 +1709,28 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
     pre.n_items = ctr + 4;
     pre.enabled = 1;
     pre.wave = (g_wave_enabled && g.level_set_num == 1) ? 1 : 0;
-    const int maxsz = g.size[0] > g.size[1] ? (g.size[0] > g.size[2] ? g.size[0] : g.size[2])
-                                            : (g.size[1] > g.size[2] ? g.size[1] : g.size[2]);
-    const int NS = (maxsz + SEG_SLAB - 1) / SEG_SLAB;
-    if (g_seg_enabled && Q >= 8192 && NS >= 2 && NS <= 16 && (int64_t)Q * NS * SEG_K <= ((int64_t)1 << 29)) {
-        // large batch: one thread per (ray, slab) item, then a per-ray merge
-        SegP seg;
-        seg.NS = NS;
-        const size_t b_cells = (size_t)Q * NS * SEG_K * sizeof(int32_t), b_meta = (size_t)Q * NS * sizeof(int32_t);
-        rc = g_ws_seg.reserve(b_cells + b_meta);
+    if (g_seg_enabled && g.use_skip && Q >= 8192 && Q * CI_MAX < ((int64_t)1 << 31)) {
+        // large batch: coarse (block jumps, thread per ray) -> fine (thread per non-empty 16^3 block crossed) -> merge
+        TwoP tw;
+        tw.fq_cap = Q * 8 + 4096;
+        const size_t b_items = (size_t)Q * CI_MAX * 2 * sizeof(int32_t), b_q = (size_t)Q * sizeof(int32_t),
+                     b_fq = (size_t)tw.fq_cap * sizeof(int32_t), b_cells = (size_t)tw.fq_cap * FI_K * sizeof(int32_t);
+        rc = g_ws_seg.reserve(b_items + 2 * b_q + 2 * b_fq + b_cells);
         if (rc) return rc;
-        seg.cells = (int32_t *)g_ws_seg.ptr;
-        seg.meta = (int32_t *)((char *)g_ws_seg.ptr + b_cells);
-        const int64_t n_items = Q * NS;
-        premarch_seg_kernel<<<(int)((n_items + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, seg);
-        premarch_merge_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, seg, rgb_out,
+        char *sb = (char *)g_ws_seg.ptr;
+        tw.ray_items = (int32_t *)sb;
+        tw.ray_nitems = (int32_t *)(sb + b_items);
+        tw.item_first = (int32_t *)(sb + b_items + b_q);
+        tw.fq = (int32_t *)(sb + b_items + 2 * b_q);
+        tw.fi_meta = (int32_t *)(sb + b_items + 2 * b_q + b_fq);
+        tw.fi_cells = (int32_t *)(sb + b_items + 2 * b_q + 2 * b_fq);
+        tw.n_fq = ctr + 6;
+        premarch_coarse_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, tw);
+        premarch_fine_kernel<<<(int)((tw.fq_cap + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, tw);
+        premarch_merge_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, tw, rgb_out,
                                                                       cache_n);
-        note_launches(2);
-        return check_cuda(cudaGetLastError(), "segmented premarch launch");
+        note_launches(3);
+        return check_cuda(cudaGetLastError(), "two-level premarch launch");
     }
     premarch_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, rgb_out, cache_n);
     note_launches(1);

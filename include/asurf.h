@@ -169,8 +169,8 @@ void asurf_debug_set_skip(int32_t enabled);
  * equal up to atomic order. */
 void asurf_debug_set_wave(int32_t enabled);
 
-/* test hook: segmented pre-march (one thread per (ray, 64-voxel slab), used for batches >= 8192 rays) off (0) / on
- * (non-zero, default).  The listed voxels must be identical either way. */
+/* test hook: two-level pre-march (block jumps per ray, then one thread per non-empty 16^3 block crossed; used for batches
+ * >= 8192 rays) off (0) / on (non-zero, default).  The listed voxels must be identical either way. */
 void asurf_debug_set_seg(int32_t enabled);
 
 /* test hooks: the work pyramid the library keeps between render calls on the same grid (updated incrementally from the

@@ -226,10 +226,10 @@ SEG_CASES = [("G-512", 512, "G", 65536, synth.alphasurf_render_options), ("G-200
 
 
 @pytest.mark.parametrize("name,reso,variant,Q,optfn", SEG_CASES, ids=[c[0] for c in SEG_CASES])
-def test_segmented_premarch_equals_whole_ray_premarch(name, reso, variant, Q, optfn):
-    """Large batches march every ray as independent (ray, 64-voxel slab) items whose start state is derived from the slab
-    boundary crossing; the listed voxels -- hence colours (bit-identical), masks and gradients -- must be those of the
-    thread-per-ray march.  G* lists more voxels than fit (fallback to the persistent kernels from the ray start)."""
+def test_two_level_premarch_equals_whole_ray_premarch(name, reso, variant, Q, optfn):
+    """Large batches use the two-level pre-march (block jumps per ray, then one thread per non-empty 16^3 block crossed,
+    entered in the state the jump rule gives); the listed voxels -- hence colours (bit-identical), masks and gradients --
+    must be those of the thread-per-ray march.  G* lists more voxels than fit (fallback to the persistent kernels)."""
     from alphasurf_b200 import capi
     opts, fused = optfn(), synth.alphasurf_fused_args()
     sg = synth.make_shell_grid(reso, basis_dim=9, variant=variant).to("cuda")
