@@ -909,8 +909,8 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
 // fine:   thread per item, voxel-by-voxel steps inside that one block, listing its work voxels.  Items are homogeneous
 //         (<= 46 steps), so warps stay full -- the long fine stretches of grazing rays no longer hold 31 other rays up.
 // merge:  thread per ray, concatenates its items' lists in order and runs the per-ray epilogue.
-constexpr int CI_MAX = 24;       // items per ray (non-empty 16^3 blocks it crosses); more -> the ray goes to the persistent kernels
-constexpr int FI_K = 32;         // work voxels listed per item
+constexpr int CI_MAX = 40;       // items per ray (non-empty 16^3 blocks it crosses); more -> the ray goes to the persistent kernels
+constexpr int FI_K = 48;         // work voxels listed per item (a ray crosses at most 46 voxels of a 16^3 block)
 struct TwoP {
     int32_t *ray_items;          // (Q, CI_MAX, 2): packed voxel (10 bits per axis), t bits
     int32_t *ray_nitems;         // (Q,) number of items, or -1 when there were more than CI_MAX
@@ -2021,6 +2021,10 @@ extern "C" int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *r
 extern "C" void asurf_debug_set_skip(int32_t enabled) { g_skip_enabled = enabled ? 1 : 0; }
 extern "C" void asurf_debug_set_wave(int32_t enabled) { g_wave_enabled = enabled ? 1 : 0; }
 extern "C" void asurf_debug_set_seg(int32_t enabled) { g_seg_enabled = enabled ? 1 : 0; }
+extern "C" int asurf_debug_counters(uint64_t *out8) {   // synchronises: queue lengths of the last render call
+    ASURF_REQUIRE(out8 && g_ws_ctr.ptr, ASURF_E_INVALID, "debug_counters: nothing to read");
+    return check_cuda(cudaMemcpy(out8, g_ws_ctr.ptr, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost), "debug_counters");
+}
 
 extern "C" int asurf_profile_enable(int32_t capacity) {
     for (int i = 0; i < PROF_EV * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]);

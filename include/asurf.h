@@ -173,6 +173,10 @@ void asurf_debug_set_wave(int32_t enabled);
  * >= 8192 rays) off (0) / on (non-zero, default).  The listed voxels must be identical either way. */
 void asurf_debug_set_seg(int32_t enabled);
 
+/* test hook (synchronises): the 8 device counters of the last render call -- [0],[1] ray fetch cursors of the persistent
+ * kernels, [2] long rays, [3] short rays, [4] (ray, voxel) items, [5] samples, [6] fine items of the pre-march. */
+int asurf_debug_counters(uint64_t *out8);
+
 /* test hooks: the work pyramid the library keeps between render calls on the same grid (updated incrementally from the
  * vertices whose level-set side / density gate changed).  copy: the pyramid used by the last render call (device buffer
  * of asurf_accel_words-sized pyramid part, i.e. the first three levels); valid: whether a cache exists. */
