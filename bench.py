@@ -36,55 +36,63 @@ def measured_peak():
 
 
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period; the timed region of
+    the default run lasts ~50 ms, too short for `nvidia-smi -lms`), with the nvidia-smi one-shot query as a fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = False
+        self._thread = None
+        self._nvml = None
+
+    def _loop(self):
+        n = self._nvml
+        try:
+            h = n.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            while not self._stop:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                try:
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
+        except Exception:
+            pass
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            import threading
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+            time.sleep(0.02)
         except Exception:
-            self.proc = None
+            self._nvml = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, reasons, mx = [], set(), None
-        try:
-            for line in open(self.path):
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1]))
-                    mx = float(p[2])
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml thread, 5 ms period"}
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+        if not self.samples:   # fallback: one nvidia-smi query right after the timed region
+            try:
+                q = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in q.strip().split(",")[:2]]
+                self.samples, self.max_mhz = [a], b
+                out["source"] = "nvidia-smi query after the timed region"
+            except Exception:
+                return out
+        sm = sorted(self.samples)
+        out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(sm))
         return out
 
 
@@ -287,8 +295,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args),
-        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                   "samples": clocks["samples"]},
+        "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 3 * Q * 3 * 4, "d2h_bytes_per_step": Q * 3 * 4,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": n_launch,
