@@ -1757,14 +1757,15 @@ inline int wave_grid(int64_t want_threads, int threads, int ctas_per_sm) {
 int wave_buffers(const PreP &pre, int64_t Q, unsigned long long *ctr, WaveP &wv) {
     const size_t n = (size_t)pre.item_cap;
     const size_t b_items = n * sizeof(ItemRec), b_hits = n * WAVE_ENT * sizeof(HitRec), b_q = n * WAVE_ENT * sizeof(int32_t);
-    const size_t b_pre = (size_t)Q * sizeof(Pre);
-    int rc = g_ws_wave.reserve(b_items + b_hits + b_q + b_pre);
+    const size_t b_pre = (size_t)Q * sizeof(Pre), b_mask = (size_t)Q * 4 * sizeof(uint32_t);
+    int rc = g_ws_wave.reserve(b_items + b_hits + b_q + b_pre + b_mask);
     if (rc) return rc;
     char *base = (char *)g_ws_wave.ptr;
     wv.items = (ItemRec *)base;
     wv.hits = (HitRec *)(base + b_items);
     wv.hitq = (int32_t *)(base + b_items + b_hits);
     wv.ray_pre = (Pre *)(base + b_items + b_hits + b_q);
+    wv.ray_mask = (uint32_t *)(base + b_items + b_hits + b_q + b_pre);
     wv.n_hits = ctr + 5;
     return 0;
 }
@@ -1776,6 +1777,7 @@ int wave_forward(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *ray
     const int64_t Q = rays->n_rays;
     FusedP nof = {};
     asurf_grads_t nog = {};
+    ASURF_CUDA(cudaMemsetAsync(wv.ray_mask, 0, (size_t)Q * 4 * sizeof(uint32_t), st));
     wave_eval_kernel<<<wave_grid(Q * 2, 128, 16), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv);
     wave_wide_kernel<false><<<wave_grid(Q * 32, 128, 16), 128, 0, st>>>(g, *opt, rays->dirs, pre, wv, nullptr, nullptr, nof, nog);
     wave_composite_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, pre, wv, cache, M, rgb_out, grad_in, color_cache, f);

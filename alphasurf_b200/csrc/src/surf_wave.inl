@@ -45,6 +45,7 @@ struct WaveP {
     int32_t *hitq;                 // compact queue of sample entries: item index * 4 + entry
     unsigned long long *n_hits;
     Pre *ray_pre;                  // (Q,) per-ray constants of the fused losses (fused_preamble)
+    uint32_t *ray_mask;            // (Q, 4): which of the ray's <= 128 listed voxels produced entries (zeroed per call)
 };
 
 __device__ __forceinline__ int ent_kind(int32_t n_ent, int e) { return (n_ent >> (8 + 8 * e)) & 3; }
@@ -225,6 +226,10 @@ wave_eval_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
             }
             it.n_ent = n_ent | packed;
             wv.items[t] = it;
+            if (n_ent > 0) {   // most listed voxels yield no entry: the per-ray stages only visit the flagged ones
+                const int k = (int)(code - ray_id * pre.K);
+                atomicOr(wv.ray_mask + ray_id * 4 + (k >> 5), 1u << (k & 31));
+            }
         }
         // queue the entries that need the wide (SH) stages: warp-aggregated append
         const int mine = __popc((unsigned)n_samp);
@@ -359,7 +364,15 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
         float logT = 0.f, logT_b = 0.f, out0 = 0.f, out1 = 0.f, out2 = 0.f;
         int intersect_i = -1, sample_i = 0;
         bool alive_f = true, alive_b = true;
-        for (int k = 0; k < n && (alive_f || alive_b); ++k) {
+        uint32_t rm[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) rm[w] = wv.ray_mask[ray_id * 4 + w];
+        // voxels without entries change nothing (the early-stop test after them sees the same log-transmittance as after the
+        // previous voxel): visit only the flagged ones, in order
+        for (int w = 0; w < 4; ++w)
+        for (uint32_t mm = rm[w]; mm && (alive_f || alive_b); mm &= mm - 1) {
+            const int k = w * 32 + __ffs(mm) - 1;
+            if (k >= n) break;
             if (k >= n_bwd) alive_b = false;
             const int32_t ne = wv.items[base + k].n_ent;
             const int cnt = ne & 255;
@@ -446,7 +459,10 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
         float accum = fmaf(cc[0], gi[0], fmaf(cc[1], gi[1], cc[2] * gi[2]));
         int sample_b = 0;
         bool live = true;
-        for (int k = 0; k < n_bwd && live; ++k) {
+        for (int w = 0; w < 4; ++w)
+        for (uint32_t mm = rm[w]; mm && live; mm &= mm - 1) {
+            const int k = w * 32 + __ffs(mm) - 1;
+            if (k >= n_bwd) { live = false; break; }
             const int32_t ne = wv.items[base + k].n_ent;
             const int cnt = ne & 255;
             for (int e = 0; e < cnt; ++e) {
