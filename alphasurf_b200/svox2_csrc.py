@@ -342,6 +342,20 @@ def volume_render_cuvol_fused(grid, rays, opt, rgb_gt, beta_loss, sparsity_loss,
                                                 capi.current_stream()), "volume_render_cuvol_fused")
 
 
+# ---- grid maintenance (misc_kernel.cu:1022-1058) ----------------------------------------------------------------------------
+def accel_dist_prop(links):
+    """In place: empty vertices of ``links`` receive the negative skip codes the cuvol marcher reads."""
+    _check_input(links, "grid")
+    if links.is_floating_point() or links.dim() != 3:
+        raise RuntimeError("accel_dist_prop expects the 3-D integer links tensor")
+    if links.dtype != torch.int32:
+        raise RuntimeError("links must be int32")
+    with torch.cuda.device(links.device):
+        capi.check(capi.lib().asurf_accel_dist_prop(capi.ptr(links), capi.size3(links.shape), capi.current_stream()),
+                   "accel_dist_prop")
+    links.add_(0)   # torch bumps tensor._version only for its own ops: force it so that cached pyramids are rebuilt
+
+
 # ---- optimizer steps (optim_kernel.cu:154-267) -------------------------------------------------------------------------
 def _indexer(indexer):
     """-> (kind, pointer, n): 0 all rows (0-dim tensor), bool mask, int64 row list; n == 0 means skip."""
@@ -542,7 +556,7 @@ for _name in ("sample_grid", "sample_grid_backward", "sample_grid_sh_surf", "sam
               "volume_render_expected_term_surf_trav", "volume_render_mode_term_surf_trav",
               "volume_render_sigma_thresh_surf_trav", "volume_render_alpha_surf_trav", "extract_pts_surf_trav",
               "render_normal_surf_trav", "volume_render_expected_term", "volume_render_mode_term", "volume_render_med_term",
-              "volume_render_sigma_thresh", "dilate", "accel_dist_prop", "grid_weight_render", "sparse_grid_weight_render",
+              "volume_render_sigma_thresh", "dilate", "grid_weight_render", "sparse_grid_weight_render",
               "sparse_grid_visbility_render_surf", "sparse_grid_mask_render", "surface_normal_grad",
               "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
               "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",

@@ -203,6 +203,11 @@ int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const 
                       float beta_loss, float sparsity_loss, int64_t norm_rays, float *rgb_out, const asurf_grads_t *grads,
                       void *stream);
 
+/* ---- grid maintenance in front of the render path ----
+ * accel_dist_prop, misc_kernel.cu:1022-1058: rewrites every negative entry of links (in place) with -(1 + number of empty
+ * octree levels above the vertex), the skip codes the cuvol marcher reads. */
+int asurf_accel_dist_prop(int32_t *links, const int32_t size[3], void *stream);
+
 /* ---- optimizer steps, optim_kernel.cu:154-267 ----
  * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */
 int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,

@@ -336,3 +336,34 @@ def cuvol_fused(grid: Grid, opt: dict, origins, dirs, rgb_gt, beta_loss=0.0, spa
                                 _ptr(out), C.c_int(1), C.c_float(norm), _ptr(lt) if beta_loss > 0 else None,
                                 C.c_float(np.float32(beta_loss) / np.float32(qn)), C.c_float(sparsity_loss), C.byref(grads.c))
     return out, grads
+
+
+# ---- accel_dist_prop (misc_kernel.cu:113-182, :1022-1058), numpy restatement --------------------------------------------------
+def accel_dist_prop(links):
+    """Returns a copy of ``links`` (X,Y,Z) int32 with every negative entry replaced by -(1 + number of empty octree levels
+    above the vertex).  Level sizes halve with ceil until an axis reaches 1 (misc_kernel.cu:1035-1041)."""
+    links = np.array(_np(links, np.int32), copy=True)
+    X, Y, Z = links.shape
+    occ = links >= 0
+    levels = []
+    cur, (sx, sy, sz) = occ, (X, Y, Z)
+    while sx > 1 and sy > 1 and sz > 1:
+        nx, ny, nz = (sx + 1) // 2, (sy + 1) // 2, (sz + 1) // 2
+        pad = np.zeros((2 * nx, 2 * ny, 2 * nz), bool)
+        pad[:sx, :sy, :sz] = cur
+        cur = pad.reshape(nx, 2, ny, 2, nz, 2).any(axis=(1, 3, 5))
+        levels.append(cur)
+        sx, sy, sz = nx, ny, nz
+    xs, ys, zs = np.nonzero(~occ)
+    result = np.full(xs.shape, -1, np.int32)
+    alive = np.ones(xs.shape, bool)
+    x, y, z = xs.copy(), ys.copy(), zs.copy()
+    for lv in levels:
+        x >>= 1
+        y >>= 1
+        z >>= 1
+        hit = lv[x, y, z]
+        alive &= ~hit
+        result[alive] -= 1
+    links[xs, ys, zs] = result
+    return links

@@ -104,3 +104,23 @@ def test_sparsify_matches_tensor_restatement():
     assert _rel(ga[:, 0], want_a) < 1e-5
     assert _rel(gs[:, 0], want_s) < 1e-5 or (np.abs(want_s).max() == 0 and np.abs(gs).max() == 0)
     assert np.array_equal(np.nonzero(mask)[0], np.unique(l))
+
+
+def test_accel_dist_prop_oracle_properties():
+    """numpy restatement of accel_dist_prop: stored vertices untouched; an empty vertex next to a stored one gets -1 when
+    they share the 2^3 parent; a vertex whose whole 2^k block is empty gets at most -(k + 1); idempotent."""
+    links = torch.full((16, 16, 16), -1, dtype=torch.int32)
+    links[0, 0, 0] = 0
+    links[9, 9, 9] = 1
+    out = oracle.accel_dist_prop(links)
+    assert out[0, 0, 0] == 0 and out[9, 9, 9] == 1
+    assert out[1, 1, 1] == -1            # shares the 2^3 parent of (0,0,0)
+    assert out[2, 2, 2] == -2            # parent 2^3 empty, 4^3 block holds (0,0,0)
+    assert out[4, 4, 4] == -3            # 2^3 and 4^3 empty, 8^3 block [0,8) holds (0,0,0)
+    assert out[15, 0, 0] == -4           # first occupied ancestor is the 16^3 root
+    assert out[8, 8, 8] == -1 and out[10, 10, 10] == -2
+    assert np.array_equal(oracle.accel_dist_prop(out), out)
+    sg = synth.make_shell_grid(24, basis_dim=1, variant="G")
+    o2 = oracle.accel_dist_prop(sg.links)
+    assert np.array_equal(o2[sg.links.numpy() >= 0], sg.links.numpy()[sg.links.numpy() >= 0])
+    assert o2[sg.links.numpy() < 0].max() == -1
