@@ -15,7 +15,10 @@ def _links(shape, seed, fill=0.1):
     g = torch.Generator().manual_seed(seed)
     occ = torch.rand(shape, generator=g) < fill
     # clustered occupancy: keep only blobs
-    blob = torch.nn.functional.avg_pool3d(occ.float()[None, None], 5, stride=1, padding=2)[0, 0] > 0.16
+    if min(shape) >= 5:
+        blob = torch.nn.functional.avg_pool3d(occ.float()[None, None], 5, stride=1, padding=2)[0, 0] > 0.16
+    else:
+        blob = occ
     links = torch.full(shape, -1, dtype=torch.int32)
     links[blob] = torch.arange(int(blob.sum()), dtype=torch.int32)
     return links
