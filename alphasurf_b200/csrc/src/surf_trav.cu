@@ -1573,6 +1573,7 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
 }
 
 #include "surf_wave.inl"
+#include "surf_scalar.inl"
 
 }  // namespace
 }  // namespace asurf
@@ -1836,6 +1837,51 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     }
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_trav_forward launch");
+}
+
+extern "C" int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,
+                                      float param, float *out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rays(rays, opt);
+    if (rc) return rc;
+    ASURF_REQUIRE(mode >= ASURF_SCALAR_EXPECTED_TERM && mode <= ASURF_SCALAR_NORMAL, ASURF_E_INVALID,
+                  "surf_trav_scalar: unknown mode %d", mode);
+    if (rays->n_rays == 0) return 0;
+    ASURF_REQUIRE(out, ASURF_E_INVALID, "surf_trav_scalar: null output");
+    GridP g;
+    rc = make_grid(grid, opt, false, st, g);
+    if (rc) return rc;
+    // work pyramid of the predicate these renders use: 8 stored corners and a level set within their range -- no density
+    // gate, no fake samples.  Built into its own buffer so that the training renderer's cached pyramid stays valid.
+    {
+        asurf_grid_t tmp = *grid;
+        tmp.accel = g.accel;
+        asurf_opt_t o2 = *opt;
+        o2.sigma_thresh = -INFINITY;
+        o2.surf_fake_sample = 0;
+        AccelLayout lay(grid->size);
+        rc = g_ws_work.reserve((size_t)lay.off[3] * sizeof(uint64_t));
+        if (rc) return rc;
+        rc = asurf_work_build(&tmp, &o2, (uint64_t *)g_ws_work.ptr, st);
+        if (rc) return rc;
+        g.work = (const uint64_t *)g_ws_work.ptr;
+    }
+    const int64_t Q = rays->n_rays;
+    const int blocks = (int)((Q + 127) / 128);
+    switch (mode) {
+#define ASURF_SCALAR_CASE(M)                                                                                         \
+    case M:                                                                                                          \
+        scalar_render_kernel<M><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param, out);           \
+        break;
+        ASURF_SCALAR_CASE(ASURF_SCALAR_EXPECTED_TERM)
+        ASURF_SCALAR_CASE(ASURF_SCALAR_MODE_TERM)
+        ASURF_SCALAR_CASE(ASURF_SCALAR_THRESH_DEPTH)
+        ASURF_SCALAR_CASE(ASURF_SCALAR_THRESH_ALPHA)
+        ASURF_SCALAR_CASE(ASURF_SCALAR_NORMAL)
+#undef ASURF_SCALAR_CASE
+    }
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "surf_trav_scalar launch");
 }
 
 extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,

@@ -250,6 +250,45 @@ def volume_render_surf_trav_backward(grid, rays, opt, grad_out, color_cache, gra
                    "volume_render_surf_trav_backward")
 
 
+# ---- scalar renders for evaluation (render_lerp_kernel_surf_trav.cu:3944-4050+; svox2.py:3690-3830) ------------------
+def _surf_trav_scalar(name, grid, rays, opt, mode, param, width=1):
+    _check_grid(grid)
+    _check_rays(rays)
+    Q = rays.origins.shape[0]
+    out = torch.empty((Q,) if width == 1 else (Q, width), dtype=rays.origins.dtype, device=rays.origins.device)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid)
+        capi.check(capi.lib().asurf_surf_trav_scalar(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                     C.c_int32(mode), C.c_float(param), capi.ptr(out),
+                                                     capi.current_stream()), name)
+    return out
+
+
+def volume_render_expected_term_surf_trav(grid, rays, opt):
+    """expected ray termination depth, (Q,) (:3944-3963)"""
+    return _surf_trav_scalar("volume_render_expected_term_surf_trav", grid, rays, opt, 0, 0.0)
+
+
+def volume_render_mode_term_surf_trav(grid, rays, opt, weight_thresh):
+    """depth of the sample with the largest weight, 0 if the accumulated weight <= weight_thresh, (Q,) (:3965-3985)"""
+    return _surf_trav_scalar("volume_render_mode_term_surf_trav", grid, rays, opt, 1, float(weight_thresh))
+
+
+def volume_render_sigma_thresh_surf_trav(grid, rays, opt, sigma_thresh):
+    """depth of the first sample whose alpha exceeds sigma_thresh, (Q,) (:3987-4007)"""
+    return _surf_trav_scalar("volume_render_sigma_thresh_surf_trav", grid, rays, opt, 2, float(sigma_thresh))
+
+
+def volume_render_alpha_surf_trav(grid, rays, opt, thresh):
+    """alpha of the first sample whose alpha exceeds thresh, (Q,) (:4009-4029)"""
+    return _surf_trav_scalar("volume_render_alpha_surf_trav", grid, rays, opt, 3, float(thresh))
+
+
+def render_normal_surf_trav(grid, rays, opt):
+    """un-normalised surface gradient at the first sample with alpha > 0, (Q, 3) (:4031-4050)"""
+    return _surf_trav_scalar("render_normal_surf_trav", grid, rays, opt, 4, 0.0, width=3)
+
+
 # Global batch size used to normalise the fused losses; None = this call's ray count (the reference behaviour).
 # The ray-sharded data-parallel wrapper (alphasurf_b200.dist) sets it to the global Q.
 _NORM_RAYS = None
@@ -553,9 +592,7 @@ def _not_on_hot_path(name):
 
 
 for _name in ("sample_grid", "sample_grid_backward", "sample_grid_sh_surf", "sample_grid_raw_alpha", "cubic_extract_iso_pts",
-              "volume_render_expected_term_surf_trav", "volume_render_mode_term_surf_trav",
-              "volume_render_sigma_thresh_surf_trav", "volume_render_alpha_surf_trav", "extract_pts_surf_trav",
-              "render_normal_surf_trav", "volume_render_expected_term", "volume_render_mode_term", "volume_render_med_term",
+              "extract_pts_surf_trav", "volume_render_expected_term", "volume_render_mode_term", "volume_render_med_term",
               "volume_render_sigma_thresh", "dilate", "grid_weight_render", "sparse_grid_weight_render",
               "sparse_grid_visbility_render_surf", "sparse_grid_mask_render", "surface_normal_grad",
               "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",

@@ -143,6 +143,20 @@ int asurf_work_build(const asurf_grid_t *grid, const asurf_opt_t *opt, uint64_t 
 /* volume_render_surf_trav, render_lerp_kernel_surf_trav.cu:3596-3654 (forward only; rgb_out (Q,3)) */
 int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
                             float *rgb_out, asurf_stats_t *stats_dev, void *stream);
+/* Scalar renders of the surf_trav backend, one entry for the five reference functions (host side :3944-4050+, kernels
+ * :3458-3560):  volume_render_expected_term_surf_trav (mode EXPECTED_TERM), volume_render_mode_term_surf_trav (MODE_TERM,
+ * param = weight_thresh), volume_render_sigma_thresh_surf_trav (THRESH_DEPTH, param = sigma_thresh),
+ * volume_render_alpha_surf_trav (THRESH_ALPHA, param = thresh), render_normal_surf_trav (NORMAL; out is (Q,3)).
+ * out is (Q,) floats otherwise.  Rays that miss give 0. */
+enum {
+    ASURF_SCALAR_EXPECTED_TERM = 0,
+    ASURF_SCALAR_MODE_TERM = 1,
+    ASURF_SCALAR_THRESH_DEPTH = 2,
+    ASURF_SCALAR_THRESH_ALPHA = 3,
+    ASURF_SCALAR_NORMAL = 4
+};
+int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,
+                           float param, float *out, void *stream);
 /* volume_render_surf_trav_backward, :3708-3800 (grad_out = dL/dRGB (Q,3), color_cache = forward RGB) */
 int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
                              const float *grad_out, const float *color_cache, const asurf_grads_t *grads,

@@ -175,6 +175,21 @@ def surf_trav_forward(grid: Grid, opt: dict, origins, dirs, xf=None, trace: Trac
     return out
 
 
+SCALAR_MODES = dict(expected_term=0, mode_term=1, thresh_depth=2, thresh_alpha=3, normal=4)
+
+
+def surf_trav_scalar(grid: Grid, opt: dict, origins, dirs, mode, param=0.0, xf=None):
+    """depth / alpha / normal renders (render_lerp_kernel_surf_trav.cu:564-1534); mode: key of SCALAR_MODES"""
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    xf = _np(xf, np.float32)
+    Q = o.shape[0]
+    m = SCALAR_MODES[mode]
+    out = np.zeros((Q, 3) if m == 4 else (Q,), np.float32)
+    lib().oracle_surf_trav_scalar(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q),
+                                  C.c_int(m), C.c_float(param), _ptr(out))
+    return out
+
+
 def surf_trav_backward(grid: Grid, opt: dict, origins, dirs, grad_out, color_cache, xf=None, grads: Grads = None):
     o, d = _np(origins, np.float32), _np(dirs, np.float32)
     xf = _np(xf, np.float32)

@@ -898,6 +898,99 @@ void oracle_surf_trav_fused(const OGrid *g, const OOpt *opt, const float *origin
 }
 
 /* test hook: expose the cubic solver and its gradient (analogue of the reference's test_cuda.cu:108-122) */
+/* ===================== scalar renders: trace_ray_expected_term (:564-794), _mode_term_surf_trav (:796-1001),
+ * _sigma_thresh (:1003-1168), _alpha (:1170-1337), _normal (:1339-1534) =====================
+ * Same traversal as the colour renderer but: no density gate, no outward test, no truncated re-weighting, no fake samples,
+ * every in-range root composited.  mode: 0 expected depth, 1 mode depth (param = weight_thresh), 2 depth of the first
+ * sample with alpha > param, 3 alpha of that sample, 4 surface gradient at the first sample with alpha > 0 (3 floats). */
+static void trace_ray_scalar(const OGrid *g, ORay *ray, const OOpt *opt, int mode, float param, float *out) {
+    const int nout = (mode == 4) ? 3 : 1;
+    for (int c = 0; c < nout; ++c) out[c] = 0.f;
+    if (ray->tmin > ray->tmax) return;
+    double const ray_dir_d[3] = {ray->dir[0], ray->dir[1], ray->dir[2]};
+    float t = ray->tmin, outv = 0.f, log_transmit = 0.f, max_weight = 0.f, weight_acc = 0.f;
+    int32_t next_voxel[3];
+    for (int j = 0; j < 3; ++j) {
+        next_voxel[j] = (int32_t)fmaf(t, ray->dir[j], ray->origin[j]);
+        next_voxel[j] = o_mini(o_maxi(next_voxel[j], 0), g->size[j] - 2);
+    }
+    const int offx = g->size[1] * g->size[2], offy = g->size[2];
+    while (t <= ray->tmax) {
+        OStep s;
+        dda_step(g, ray, next_voxel, &t, &s);
+        const int32_t *voxel_l = s.voxel_l;
+        const float t_close = s.t_close;
+        const int32_t *lp = g->links + (offx * voxel_l[0] + offy * voxel_l[1] + voxel_l[2]);
+        if (!voxel_links_ok(g, voxel_l, lp, offx, offy)) continue;
+        double new_origin[3], new_norm_origin[3];
+        for (int k = 0; k < 3; ++k) {
+            new_origin[k] = fmaf(t_close, ray->dir[k], ray->origin[k]);
+            new_norm_origin[k] = new_origin[k] - voxel_l[k];
+        }
+        const int u[8] = {0, 1, offy, offy + 1, offx, offx + 1, offx + offy, offx + offy + 1};
+        double surface[8];
+        for (int k = 0; k < 8; ++k) surface[k] = g->surface[lp[u[k]]];
+        double fs[4];
+        surface_to_cubic_equation_01(surface, new_norm_origin, ray_dir_d, fs);
+        double smin = surface[0], smax = surface[0];
+        for (int k = 1; k < 8; ++k) { if (surface[k] < smin) smin = surface[k]; if (surface[k] > smax) smax = surface[k]; }
+        for (int i = 0; i < g->level_set_num; ++i) {
+            double const lv_set = g->level_set[i];
+            if ((lv_set < smin) || (lv_set > smax)) continue;
+            double st[3] = {-1, -1, -1};
+            cubic_equation_solver_vieta(fs[0] - lv_set, fs[1], fs[2], fs[3], 1e-10, st);
+            for (int j = 0; j < 3; ++j) {
+                if (st[j] <= 0) continue;
+                for (int k = 0; k < 3; ++k) {
+                    ray->pos[k] = fmaf((float)st[j], ray->dir[k], (float)new_origin[k]);
+                    ray->l[k] = o_mini(voxel_l[k], g->size[k] - 2);
+                    ray->pos[k] -= (float)ray->l[k];
+                }
+                if ((ray->pos[0] < 0) | (ray->pos[0] > 1) | (ray->pos[1] < 0) | (ray->pos[1] > 1) | (ray->pos[2] < 0) |
+                    (ray->pos[2] > 1))
+                    continue;
+                const float alpha = surf_alpha_act(o_trilerp_cuvol_one(g->links, g->density, offx, offy, 1, ray->l, ray->pos, 0),
+                                                   opt->alpha_activation_type);
+                const float depth = (float)(((st[j] + (double)t_close) / (double)opt->step_size) * (double)ray->world_step);
+                if (mode <= 1) {
+                    const float pcnt = -1 * logf(1 - alpha);
+                    const float weight = expf(log_transmit) * (1.f - expf(-pcnt));
+                    log_transmit -= pcnt;
+                    if (mode == 0) {
+                        outv = (float)((double)outv + (double)weight * (st[j] + (double)t_close) / (double)opt->step_size *
+                                                          (double)ray->world_step);
+                    } else {
+                        weight_acc += weight;
+                        if (weight > max_weight) { max_weight = weight; outv = depth; }
+                    }
+                } else if (mode == 2 || mode == 3) {
+                    if (alpha > param) { out[0] = (mode == 2) ? depth : alpha; return; }
+                } else {
+                    if (alpha > 0) { compute_field_grad(g->links, g->surface, offx, offy, ray->l, ray->pos, out); return; }
+                }
+            }
+        }
+        if (mode <= 1 && expf(log_transmit) < opt->stop_thresh) {
+            log_transmit = -1e3f;
+            break;
+        }
+    }
+    if (mode == 0) out[0] = outv;
+    else if (mode == 1) out[0] = (weight_acc > param) ? outv : 0.f;
+}
+
+void oracle_surf_trav_scalar(const OGrid *g, const OOpt *opt, const float *origins, const float *dirs, const float *xf,
+                             int64_t Q, int mode, float param, float *out) {
+    const int nout = (mode == 4) ? 3 : 1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t q = 0; q < Q; ++q) {
+        ORay ray;
+        float sphfunc[16];
+        setup_ray(g, opt, origins + q * 3, dirs + q * 3, xf ? xf + q * 9 : NULL, &ray, sphfunc);
+        trace_ray_scalar(g, &ray, opt, mode, param, out + q * nout);
+    }
+}
+
 int oracle_cubic_solve(const double *fs, double *st) {
     st[0] = st[1] = st[2] = -1;
     return cubic_equation_solver_vieta(fs[0], fs[1], fs[2], fs[3], 1e-10, st);
