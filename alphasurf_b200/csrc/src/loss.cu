@@ -329,11 +329,14 @@ surface_normal_kernel(const int32_t *__restrict__ links, const float *__restrict
 // The callers' cell lists are runs of consecutive flat ids (a contiguous window, or every stored cell in z-fastest order),
 // so the 32 cells of a warp are mostly z-neighbours.  A cell and its +x / +y / +z neighbours touch the 20 vertices
 // (x..x+2, y..y+2, z..z+2) \ {i = 2 and j = 2}: 8 vertex columns along z with up to 3 vertices each.  Per column each lane
-// loads only its k = 0 vertex (link + scalar) and takes k = 1, 2 from the next lanes of its run; the <= 48 gradient
+// loads only its k = 0 vertex (link + scalar) and takes k = 1, 2 from the next two lanes; the <= 48 gradient
 // contributions of the reference thread (6 cells x 8 corners, render_util.cuh:1824-1868) are first summed per vertex in
-// registers, then passed down the run (vertex z + 1 of lane L is vertex z of lane L + 1), so that a lane issues ONE
-// red.global.add per column (8 per cell instead of 48) and the run's last lane flushes the two trailing vertices.
+// registers, then passed up the run (vertex z + 1 of lane L is vertex z of lane L + 1), so that a lane issues ONE
+// red.global.add per column (8 per cell instead of 48).  A warp lays its cells out over 32 SLOTS: where a run ends (and after
+// the last cell of a round) two halo slots follow, which only load the vertices z + 1, z + 2 and receive their sums -- so
+// every load, shuffle and atomic of the kernel is executed by full warps, whatever the run structure of the list.
 // Same contributions as the reference; only the fp32 summation order differs (it is unordered atomics there).
+constexpr int NRM_CHUNK = 512;   // consecutive list entries handled by one warp (rounds of 10..30 cells)
 __device__ __forceinline__ void load_vertex(const int32_t *__restrict__ links, const float *__restrict__ surf, const Dims &d,
                                             int x, int y, int z, int32_t &l, float &s) {
     l = -1;
@@ -410,26 +413,60 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
                            int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad,
                            const int *__restrict__ tile_flag) {
     constexpr unsigned FULLM = 0xffffffffu;
+    __shared__ int32_t s_slot[LOSS_THREADS / 32][32];
     if (tile_flag && *tile_flag) return;   // the list is every stored vertex: surface_normal_tile_kernel does the work
     const int lane = threadIdx.x & 31;
+    int32_t *slot = s_slot[threadIdx.x >> 5];
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = warp0 * 32; base < Q; base += n_warps * 32) {
-        const bool act = (base + lane) < Q;
-        const int64_t id = act ? (int64_t)__ldg(cells + base + lane) : -2;
-        int x = 0, y = 0, z = 0;
-        if (act) {   // flat ids are < 2^31: 32-bit divisions
-            const unsigned uid = (unsigned)id;
-            const unsigned xy = uid / (unsigned)d.sz;
-            z = (int)(uid - xy * (unsigned)d.sz);
-            x = (int)(xy / (unsigned)d.sy);
-            y = (int)(xy - (unsigned)x * (unsigned)d.sy);
+    const int64_t n_chunks = (Q + NRM_CHUNK - 1) / NRM_CHUNK;
+    const unsigned usz = (unsigned)d.sz, usy = (unsigned)d.sy;
+    for (int64_t chunk = warp0; chunk < n_chunks; chunk += n_warps) {
+      int64_t pos = chunk * NRM_CHUNK;
+      const int64_t cend = (pos + NRM_CHUNK < Q) ? pos + NRM_CHUNK : Q;
+      while (pos < cend) {
+        // ---- lay the next cells of the list out over the 32 slots: a cell whose z-successor is not the next list entry
+        //      (and the last cell taken this round) is followed by two halo slots for the vertices z + 1 and z + 2 ----
+        const bool cand = (pos + lane) < cend;
+        const int32_t cid = cand ? __ldg(cells + pos + lane) : -2;
+        int32_t cid_next = __shfl_down_sync(FULLM, cid, 1);
+        if (lane == 31) cid_next = (pos + 32 < cend) ? __ldg(cells + pos + 32) : -2;
+        const unsigned cz = cand ? ((unsigned)cid % usz) : 0u;
+        const bool is_end = cand && !((cid_next == cid + 1) && (cz + 1 < usz));
+        const unsigned ends = __ballot_sync(FULLM, is_end);
+        const int sl = lane + 2 * __popc(ends & ((1u << lane) - 1u));
+        const bool take = cand && (sl <= 29);
+        const int n_take = __popc(__ballot_sync(FULLM, take));   // a prefix of the candidates, >= 10
+        const unsigned cellmask = __reduce_or_sync(FULLM, take ? (1u << sl) : 0u);
+        slot[lane] = -1;
+        __syncwarp();
+        if (take) {
+            slot[sl] = cid;
+            if (is_end || lane == n_take - 1) {
+                slot[sl + 1] = (cz + 1 < usz) ? cid + 1 : -1;
+                slot[sl + 2] = (cz + 2 < usz) ? cid + 2 : -1;
+            }
         }
-        const int64_t id_next = __shfl_down_sync(FULLM, id, 1);
-        const bool has_next = act && (lane < 31) && (id_next == id + 1) && (z + 1 < d.sz);
-        const bool has_prev = (__shfl_up_sync(FULLM, (int)has_next, 1) != 0) && (lane > 0);
+        __syncwarp();
+        const int32_t id = slot[lane];
+        __syncwarp();
+        pos += n_take;
+        const bool act = id >= 0;                          // the slot has a vertex column to load
+        const bool is_cell = (cellmask >> lane) & 1u;      // the slot is a list entry (otherwise a halo)
+        int x = 0, y = 0;
+        if (act) {   // flat ids are < 2^31: 32-bit divisions
+            const unsigned xy = (unsigned)id / usz;
+            x = (int)(xy / usy);
+            y = (int)(xy - (unsigned)x * usy);
+        }
+        // slot L + 1 holds the vertices one step up in z
+        const int32_t id_up = __shfl_down_sync(FULLM, id, 1);
+        const bool cont = act && (lane < 31) && (id_up == id + 1);
+        const bool p1 = (__shfl_up_sync(FULLM, (int)cont, 1) != 0) && (lane > 0);          // slot L - 1 continues here
+        const int p1_below = __shfl_up_sync(FULLM, (int)p1, 1);                            // (all lanes take part)
+        const bool p2 = p1 && (p1_below != 0) && (lane > 1);                               // and so does L - 2 -> L - 1
 
-        // ---- vertex columns: k = 0 from memory, k = 1, 2 from the following lanes of the run (or memory at its end) ----
+        // ---- vertex columns: k = 0 from memory, k = 1, 2 from the next two slots ----
         int32_t lk[8][3];
         float sv[8][3];
 #pragma unroll
@@ -441,7 +478,7 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
                 lk[c][0] = -1;
                 sv[c][0] = 0.f;
                 if (act && (x + i < d.sx) && (y + j < d.sy)) {
-                    const int32_t l = __ldg(links + (id + (int64_t)i * d.sy * d.sz + j * d.sz));
+                    const int32_t l = __ldg(links + ((int64_t)id + (int64_t)i * d.sy * d.sz + j * d.sz));
                     lk[c][0] = l;
                     if (l >= 0) sv[c][0] = __ldg(surf + l);
                 }
@@ -452,20 +489,8 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
             for (int c = 0; c < 8; ++c) {
                 const int32_t ln = __shfl_down_sync(FULLM, lk[c][k - 1], 1);
                 const float sn = __shfl_down_sync(FULLM, sv[c][k - 1], 1);
-                lk[c][k] = ln;
-                sv[c][k] = sn;
-            }
-            if (!has_next) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        if (i == 2 && j == 2) continue;
-                        const int c = ncol(i, j);
-                        lk[c][k] = -1;
-                        sv[c][k] = 0.f;
-                        if (act && (k == 1 || (i < 2 && j < 2))) load_vertex(links, surf, d, x + i, y + j, z + k, lk[c][k], sv[c][k]);
-                    }
+                lk[c][k] = cont ? ln : -1;   // a cell slot is always followed by its two upper slots; off-grid ones hold -1
+                sv[c][k] = cont ? sn : 0.f;
             }
         }
 
@@ -477,7 +502,7 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
         Cell8 c0;
         bool ok0;
         cell_from_columns<0, 0, 0>(lk, sv, c0, ok0);
-        if (act && ok0) {
+        if (is_cell && ok0) {
             const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
             float n0[3];
             cell_normal(c0, n0);
@@ -526,38 +551,25 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
 
         // ---- pass the k = 2 and k = 1 sums down the run, then one atomic per column ----
         {
-            const unsigned tw = __shfl_up_sync(FULLM, A.touched, 1);
+            const unsigned tw1 = __shfl_up_sync(FULLM, A.touched, 1);
+            const unsigned tw2 = __shfl_up_sync(FULLM, A.touched, 2);
+            unsigned t0 = A.touched & 0x249249u;                 // bits c * 3 + 0
+            if (p1) t0 |= (tw1 >> 1) & 0x249249u;
+            if (p2) t0 |= (tw2 >> 2) & 0x249249u;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float t = __shfl_up_sync(FULLM, A.a[c][2], 1);
-                if (has_prev) {
-                    A.a[c][1] += t;
-                    A.touched |= ((tw >> (c * 3 + 2)) & 1u) << (c * 3 + 1);
+                const float t1 = __shfl_up_sync(FULLM, A.a[c][1], 1);
+                const float t2 = __shfl_up_sync(FULLM, A.a[c][2], 2);
+                float v = A.a[c][0];
+                if (p1) v += t1;
+                if (p2) v += t2;
+                if ((t0 >> (c * 3)) & 1u) {
+                    atomicAdd(grad + lk[c][0], v);
+                    if (mask) mask[lk[c][0]] = 1;
                 }
             }
         }
-        {
-            const unsigned tw = __shfl_up_sync(FULLM, A.touched, 1);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float t = __shfl_up_sync(FULLM, A.a[c][1], 1);
-                if (has_prev) {
-                    A.a[c][0] += t;
-                    A.touched |= ((tw >> (c * 3 + 1)) & 1u) << (c * 3 + 0);
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k > 0 && has_next) continue;   // handed to the next lane
-                if ((A.touched >> (c * 3 + k)) & 1u) {
-                    atomicAdd(grad + lk[c][k], A.a[c][k]);
-                    if (mask) mask[lk[c][k]] = 1;
-                }
-            }
-        }
+      }
     }
 }
 
