@@ -178,6 +178,91 @@ tv_grad_sparse_kernel(const int32_t *__restrict__ links, const float *__restrict
     }
 }
 
+// Single-channel variant (density / surface TV: one thread per cell).  The callers' lists are runs of consecutive flat
+// ids, so the +z neighbour of lane L is mostly the cell of lane L + 1: its link and value come by shuffle instead of two
+// more gathers, and the gradient for it is handed to that lane, which folds it into its own centre contribution -- three
+// atomics per cell instead of four.  Same contributions as the reference thread; 32-bit index arithmetic.
+template <bool SURF>
+__global__ void __launch_bounds__(LOSS_THREADS)
+tv_grad_sparse_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols,
+                           const float *__restrict__ density, int density_cols, const int32_t *__restrict__ cells, Dims d,
+                           int idx, float scale, int64_t Q, int ignore_edge, float edge_value, int ignore_last_z,
+                           int alpha_dependency, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    float sc[3];
+    ray_scale(d, sc);
+    const int64_t offx = (int64_t)d.sy * d.sz;
+    const int offy = d.sz;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float missing = SURF ? edge_value : 0.f;
+    for (int64_t base = warp0 * 32; base < Q; base += n_warps * 32) {
+        const bool act = (base + lane) < Q;
+        const int32_t xyz = act ? __ldg(cells + base + lane) : -2;
+        int x = 0, y = 0, z = 0;
+        int32_t l000 = -1;
+        float v000 = missing;
+        if (act) {
+            const unsigned xy = (unsigned)xyz / (unsigned)d.sz;
+            z = (int)((unsigned)xyz - xy * (unsigned)d.sz);
+            x = (int)(xy / (unsigned)d.sy);
+            y = (int)(xy - (unsigned)x * (unsigned)d.sy);
+            l000 = __ldg(links + xyz);
+            if (l000 >= 0) v000 = __ldg(data + (int64_t)l000 * n_cols + idx);
+        }
+        const int32_t xyz_up = __shfl_down_sync(FULLM, xyz, 1);
+        const int32_t l_up = __shfl_down_sync(FULLM, l000, 1);
+        const float v_up = __shfl_down_sync(FULLM, v000, 1);
+        const bool has_next = act && (lane < 31) && (xyz_up == xyz + 1) && (z + 1 < d.sz);
+        // the reference thread returns early on these (:758, :766)
+        const bool skip = !act || (ignore_edge && l000 == 0) || (ignore_last_z && z == d.sz - 2);
+        float give = 0.f;
+        bool give_flag = false;
+        float c000 = 0.f;
+        bool own_flag = false;
+        if (!skip) {
+            const int32_t *lp = links + xyz;
+            int32_t l001 = 0;
+            if ((z + 1 < d.sz) && (!ignore_last_z || z != d.sz - 2)) l001 = has_next ? l_up : __ldg(lp + 1);
+            const int32_t l010 = (y + 1 < d.sy) ? __ldg(lp + offy) : 0;
+            const int32_t l100 = (x + 1 < d.sx) ? __ldg(lp + offx) : 0;
+            const float nullv = ignore_edge ? v000 : missing;
+            float v001 = nullv;
+            if (l001 >= 0) v001 = has_next ? v_up : __ldg(data + (int64_t)l001 * n_cols + idx);
+            const float v010 = l010 >= 0 ? __ldg(data + (int64_t)l010 * n_cols + idx) : nullv;
+            const float v100 = l100 >= 0 ? __ldg(data + (int64_t)l100 * n_cols + idx) : nullv;
+            float dx = v100 - v000, dy = v010 - v000, dz = v001 - v000;
+            float idelta = scale * rsqrtf(1e-9f + dx * dx + dy * dy + dz * dz);
+            if (SURF && alpha_dependency) {
+                const float a000 = l000 >= 0 ? __ldg(density + (int64_t)l000 * density_cols + idx) : 0.f;
+                const float a001 = l001 >= 0 ? __ldg(density + (int64_t)l001 * density_cols + idx) : 0.f;
+                const float a010 = l010 >= 0 ? __ldg(density + (int64_t)l010 * density_cols + idx) : 0.f;
+                const float a100 = l100 >= 0 ? __ldg(density + (int64_t)l100 * density_cols + idx) : 0.f;
+                const float max_alpha = fmaxf(a000, fmaxf(a001, fmaxf(a010, a100)));
+                if ((double)max_alpha < 0.1) idelta = (float)((double)idelta / fmax((double)(max_alpha * 10), 1e-1));
+            }
+            dx *= sc[0];
+            dy *= sc[1];
+            dz *= sc[2];
+            const float sm = -(dx + dy + dz);
+            if (l000 >= 0 && sm != 0.f) { c000 = sm * idelta; own_flag = true; }
+            if (l001 >= 0 && dz != 0.f) {
+                if (has_next) { give = dz * idelta; give_flag = true; }
+                else { atomicAdd(grad + (int64_t)l001 * n_cols + idx, dz * idelta); if (mask) mask[l001] = 1; }
+            }
+            if (l010 >= 0 && dy != 0.f) { atomicAdd(grad + (int64_t)l010 * n_cols + idx, dy * idelta); if (mask) mask[l010] = 1; }
+            if (l100 >= 0 && dx != 0.f) { atomicAdd(grad + (int64_t)l100 * n_cols + idx, dx * idelta); if (mask) mask[l100] = 1; }
+        }
+        const float recv = __shfl_up_sync(FULLM, give, 1);
+        const bool recv_flag = (__shfl_up_sync(FULLM, (int)give_flag, 1) != 0) && (lane > 0);
+        if (own_flag || recv_flag) {   // recv_flag: the lane below saw this lane's centre vertex as its stored +z neighbour
+            atomicAdd(grad + (int64_t)l000 * n_cols + idx, recv_flag ? (own_flag ? c000 + recv : recv) : c000);
+            if (mask) mask[l000] = 1;
+        }
+    }
+}
+
 // ---- opacity / surface sparsity (alpha_surf_sparsify_grad_sparse_kernel) -------------------------------------------------
 __global__ void __launch_bounds__(LOSS_THREADS)
 sparsify_kernel(const int32_t *__restrict__ links, const float *__restrict__ alpha, int alpha_cols,
@@ -337,16 +422,6 @@ surface_normal_kernel(const int32_t *__restrict__ links, const float *__restrict
 // every load, shuffle and atomic of the kernel is executed by full warps, whatever the run structure of the list.
 // Same contributions as the reference; only the fp32 summation order differs (it is unordered atomics there).
 constexpr int NRM_CHUNK = 512;   // consecutive list entries handled by one warp (rounds of 10..30 cells)
-__device__ __forceinline__ void load_vertex(const int32_t *__restrict__ links, const float *__restrict__ surf, const Dims &d,
-                                            int x, int y, int z, int32_t &l, float &s) {
-    l = -1;
-    s = 0.f;
-    if (x < d.sx && y < d.sy && z < d.sz) {
-        l = __ldg(links + (((int64_t)x * d.sy + y) * d.sz + z));
-        if (l >= 0) s = __ldg(surf + l);
-    }
-}
-
 // column index of vertex offset (i, j) in {0,1,2}^2 \ {(2,2)}
 __device__ __forceinline__ constexpr int ncol(int i, int j) { return (i == 2) ? 6 + j : ((j == 2) ? 4 + i : 2 * i + j); }
 
@@ -355,17 +430,11 @@ struct NormalAcc {
     unsigned touched;   // bit col * 3 + k
 };
 
-// corner (ci, cj, ck) of the cell at offset (OI, OJ, OK) from the thread's cell
-template <int OI, int OJ, int OK>
-__device__ __forceinline__ void cell_from_columns(const int32_t (&lk)[8][3], const float (&sv)[8][3], Cell8 &c, bool &ok) {
-    ok = true;
+// surface values of the cell at offset (OI, OJ, 0) from the slot's cell, from the columns' k = 0, 1 levels
+template <int OI, int OJ>
+__device__ __forceinline__ void cell_values(const float (&sv)[8][2], Cell8 &c) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int col = ncol(OI + (k >> 2), OJ + ((k >> 1) & 1));
-        c.l[k] = lk[col][OK + (k & 1)];
-        c.s[k] = sv[col][OK + (k & 1)];
-        ok &= (c.l[k] >= 0);
-    }
+    for (int k = 0; k < 8; ++k) c.s[k] = sv[ncol(OI + (k >> 2), OJ + ((k >> 1) & 1))][k & 1];
 }
 
 template <int OI, int OJ, int OK>
@@ -407,7 +476,8 @@ __device__ __forceinline__ void normal_pair_grad(const float *nh0, float rN0, co
     }
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(LOSS_THREADS, MIN_BLOCKS)
 surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf,
                            const int32_t *__restrict__ cells, Dims d, int64_t Q, float lv_set, float scale, int con_check,
                            int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad,
@@ -466,61 +536,68 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
         const int p1_below = __shfl_up_sync(FULLM, (int)p1, 1);                            // (all lanes take part)
         const bool p2 = p1 && (p1_below != 0) && (lane > 1);                               // and so does L - 2 -> L - 1
 
-        // ---- vertex columns: k = 0 from memory, k = 1, 2 from the next two slots ----
-        int32_t lk[8][3];
-        float sv[8][3];
+        // ---- vertex columns: k = 0 from memory, k = 1 from the next slot; links are kept for k = 0 only (the atomics'
+        //      targets), the other levels contribute one validity bit per column ----
+        int32_t lk0[8];
+        float sv[8][2];
+        unsigned v0 = 0u;   // bit c: column c has a stored vertex at k = 0
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 if (i == 2 && j == 2) continue;
                 const int c = ncol(i, j);
-                lk[c][0] = -1;
+                lk0[c] = -1;
                 sv[c][0] = 0.f;
                 if (act && (x + i < d.sx) && (y + j < d.sy)) {
                     const int32_t l = __ldg(links + ((int64_t)id + (int64_t)i * d.sy * d.sz + j * d.sz));
-                    lk[c][0] = l;
-                    if (l >= 0) sv[c][0] = __ldg(surf + l);
+                    lk0[c] = l;
+                    if (l >= 0) {
+                        sv[c][0] = __ldg(surf + l);
+                        v0 |= 1u << c;
+                    }
                 }
             }
+        const unsigned v1_up = __shfl_down_sync(FULLM, v0, 1);
+        const unsigned v01 = cont ? (v0 & v1_up) : 0u;   // bit c: column c is stored at k = 0 and k = 1
 #pragma unroll
-        for (int k = 1; k < 3; ++k) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int32_t ln = __shfl_down_sync(FULLM, lk[c][k - 1], 1);
-                const float sn = __shfl_down_sync(FULLM, sv[c][k - 1], 1);
-                lk[c][k] = cont ? ln : -1;   // a cell slot is always followed by its two upper slots; off-grid ones hold -1
-                sv[c][k] = cont ? sn : 0.f;
-            }
+        for (int c = 0; c < 8; ++c) {
+            const float sn = __shfl_down_sync(FULLM, sv[c][0], 1);
+            sv[c][1] = cont ? sn : 0.f;
         }
+
+        // ---- every slot: normal of its own cell; the +z neighbour's is the next slot's ----
+        Cell8 c0;
+        cell_values<0, 0>(sv, c0);
+        const bool ok0 = (v01 & 0x0Fu) == 0x0Fu;
+        const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
+        float n0[3];
+        cell_normal(c0, n0);
+        const float N0 = NORM3_(n0);
+        const float nh0[3] = {n0[0] / N0, n0[1] / N0, n0[2] / N0};
+        const float rN0 = 1.f / N0;
+        const float nhz[3] = {__shfl_down_sync(FULLM, nh0[0], 1), __shfl_down_sync(FULLM, nh0[1], 1),
+                              __shfl_down_sync(FULLM, nh0[2], 1)};
+        const float rNz = __shfl_down_sync(FULLM, rN0, 1);
+        const int flz = __shfl_down_sync(FULLM, (ok0 ? 1 : 0) | (empty000 ? 2 : 0), 1);
 
         // ---- the reference thread's arithmetic on the four cells ----
         NormalAcc A;
 #pragma unroll
         for (int c = 0; c < 8; ++c) A.a[c][0] = A.a[c][1] = A.a[c][2] = 0.f;
         A.touched = 0u;
-        Cell8 c0;
-        bool ok0;
-        cell_from_columns<0, 0, 0>(lk, sv, c0, ok0);
         if (is_cell && ok0) {
-            const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
-            float n0[3];
-            cell_normal(c0, n0);
-            Cell8 cz, cy, cx;
-            bool uz, uy, ux;
-            cell_from_columns<0, 0, 1>(lk, sv, cz, uz);
-            cell_from_columns<0, 1, 0>(lk, sv, cy, uy);
-            cell_from_columns<1, 0, 0>(lk, sv, cx, ux);
+            Cell8 cy, cx;
+            cell_values<0, 1>(sv, cy);
+            cell_values<1, 0>(sv, cx);
+            bool uz = cont && (flz & 1), uy = (v01 & 0x3Au) == 0x3Au, ux = (v01 & 0xCCu) == 0xCCu;
             uz = uz && (!con_check || face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv_set));
-            uz = uz && (!ignore_empty || (!empty000 || !cell_empty(cz, lv_set)));
+            uz = uz && (!ignore_empty || (!empty000 || !(flz & 2)));
             uy = uy && (!con_check || face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv_set));
             uy = uy && (!ignore_empty || (!empty000 || !cell_empty(cy, lv_set)));
             ux = ux && (!con_check || face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv_set));
             ux = ux && (!ignore_empty || (!empty000 || !cell_empty(cx, lv_set)));
             const int norm_count = (int)ux + (int)uy + (int)uz;
-            const float N0 = NORM3_(n0);
-            const float nh0[3] = {n0[0] / N0, n0[1] / N0, n0[2] / N0};
-            const float rN0 = 1.f / N0;
             const float sc = scale * 1.f / norm_count;
             float n1[3], d0[3], d1[3];
             if (ux) {   // the reference loops i = 0 (x), 1 (y), 2 (z)
@@ -540,16 +617,13 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
                 accumulate_normal_grad<0, 1, 0>(d1, sc, A);
             }
             if (uz) {
-                cell_normal(cz, n1);
-                const float N1 = NORM3_(n1);
-                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
-                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
+                normal_pair_grad(nh0, rN0, nhz, rNz, use_l1, d0, d1);
                 accumulate_normal_grad<0, 0, 0>(d0, sc, A);
                 accumulate_normal_grad<0, 0, 1>(d1, sc, A);
             }
         }
 
-        // ---- pass the k = 2 and k = 1 sums down the run, then one atomic per column ----
+        // ---- pass the k = 2 and k = 1 sums up the run, then one atomic per column ----
         {
             const unsigned tw1 = __shfl_up_sync(FULLM, A.touched, 1);
             const unsigned tw2 = __shfl_up_sync(FULLM, A.touched, 2);
@@ -559,13 +633,15 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float t1 = __shfl_up_sync(FULLM, A.a[c][1], 1);
-                const float t2 = __shfl_up_sync(FULLM, A.a[c][2], 2);
                 float v = A.a[c][0];
                 if (p1) v += t1;
-                if (p2) v += t2;
+                if (c < 4) {   // only the cell's own four columns reach k = 2 (through its +z neighbour)
+                    const float t2 = __shfl_up_sync(FULLM, A.a[c][2], 2);
+                    if (p2) v += t2;
+                }
                 if ((t0 >> (c * 3)) & 1u) {
-                    atomicAdd(grad + lk[c][0], v);
-                    if (mask) mask[lk[c][0]] = 1;
+                    atomicAdd(grad + lk0[c], v);
+                    if (mask) mask[lk0[c]] = 1;
                 }
             }
         }
@@ -794,9 +870,14 @@ extern "C" int asurf_tv_grad_sparse(const int32_t *links, const int32_t size[3],
     ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "tv_grad_sparse: null cell list");
     const int64_t Q = n_cells * (end_dim - start_dim);
     Dims d = {size[0], size[1], size[2]};
-    tv_grad_sparse_kernel<false><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-        links, data, n_cols, nullptr, 0, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q, ignore_edge, 0.f,
-        ignore_last_z, 0, mask_out, grad_data);
+    if (end_dim - start_dim == 1)
+        tv_grad_sparse_runs_kernel<false><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+            links, data, n_cols, nullptr, 0, rand_cells, d, start_dim, scale / (float)(int)n_cells, Q, ignore_edge, 0.f,
+            ignore_last_z, 0, mask_out, grad_data);
+    else
+        tv_grad_sparse_kernel<false><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+            links, data, n_cols, nullptr, 0, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q, ignore_edge, 0.f,
+            ignore_last_z, 0, mask_out, grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "tv_grad_sparse launch");
 }
@@ -815,9 +896,14 @@ extern "C" int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t siz
     ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "surf_tv_grad_sparse: null cell list");
     const int64_t Q = n_cells * (end_dim - start_dim);
     Dims d = {size[0], size[1], size[2]};
-    tv_grad_sparse_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-        links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q,
-        ignore_edge, edge_value, ignore_last_z, alpha_dependency, mask_out, grad_data);
+    if (end_dim - start_dim == 1)
+        tv_grad_sparse_runs_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+            links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, scale / (float)(int)n_cells, Q, ignore_edge,
+            edge_value, ignore_last_z, alpha_dependency, mask_out, grad_data);
+    else
+        tv_grad_sparse_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+            links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q,
+            ignore_edge, edge_value, ignore_last_z, alpha_dependency, mask_out, grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_tv_grad_sparse launch");
 }
@@ -844,8 +930,8 @@ static Workspace g_ws_flag;
 // The dense tiled variant of the normal loss is exact but, as measured on B200 (profiles/r1_ncu_full_normal_tile.txt), not
 // faster than the run-aggregated list kernel (2.2 ms vs 1.3 ms at 512^3): both are instruction-bound on the 48 corner
 // contributions per cell.  It stays behind this switch (tests exercise both) until its per-cell normals are shared.
-static int g_normal_tile = 0;
-extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_normal_tile = enabled ? 1 : 0; }
+static int g_normal_tile = 0;   // bit 0: dense tile kernel for full lists, bit 1: 3 instead of 4 resident CTAs per SM (A/B timing)
+extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_normal_tile = enabled; }
 
 extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                                 const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
@@ -865,7 +951,7 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
         const int *flag = nullptr;
         AccelLayout lay(size);
         // a list that may be "every stored vertex" (at least a tenth of the grid): let the device decide which kernel runs
-        if (g_normal_tile && accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 &&
+        if ((g_normal_tile & 1) && accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 &&
             size[2] >= 16) {
             rc = g_ws_flag.reserve(sizeof(int));
             if (rc) return rc;
@@ -886,9 +972,14 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
             flag = (const int *)g_ws_flag.ptr;
             note_launches(2);
         }
-        surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
-            links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-            grad_data, flag);
+        if (g_normal_tile & 2)
+            surface_normal_runs_kernel<3><<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
+                links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
+                grad_data, flag);
+        else
+            surface_normal_runs_kernel<4><<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
+                links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
+                grad_data, flag);
     } else
         surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
             links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1,
