@@ -40,6 +40,67 @@ __global__ void __launch_bounds__(256) rmsprop_dense_kernel(float *__restrict__ 
     }
 }
 
+// Single-column tensors (density, surface): four rows per thread -- float4 loads / stores of data, rms and grad and one
+// 32-bit load of the four mask bytes.  The alpha-Surf regularisers touch every stored row each step, so nearly all
+// groups take the full-vector path; a partially masked group stores its set rows one by one.
+template <bool MASKED, bool RMS>
+__global__ void __launch_bounds__(256) step_col1_vec4_kernel(float *__restrict__ data, float *__restrict__ rms,
+                                                              float *__restrict__ grad, const uint8_t *__restrict__ mask,
+                                                              int64_t n_rows, float beta, float lr, float eps,
+                                                              float minval) {
+    const int64_t n4 = n_rows >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < n4; i += stride) {
+        unsigned m = 0x01010101u;
+        if (MASKED) {
+            m = reinterpret_cast<const unsigned *>(mask)[i];
+            if (m == 0u) continue;
+        }
+        float4 x = reinterpret_cast<float4 *>(data)[i];
+        float4 g = reinterpret_cast<float4 *>(grad)[i];
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RMS) r = reinterpret_cast<float4 *>(rms)[i];
+        float *xs = &x.x, *gs = &g.x, *rs = &r.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (RMS) rmsprop_once(xs[k], rs[k], gs[k], beta, lr, eps, minval);
+            else { xs[k] = fmaf(-lr, gs[k], xs[k]); gs[k] = 0.f; }
+        }
+        const bool all = !MASKED || ((m & 0xffu) && (m & 0xff00u) && (m & 0xff0000u) && (m & 0xff000000u));
+        if (all) {
+            reinterpret_cast<float4 *>(data)[i] = x;
+            if (RMS) reinterpret_cast<float4 *>(rms)[i] = r;
+            reinterpret_cast<float4 *>(grad)[i] = g;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if ((m >> (8 * k)) & 0xffu) {
+                    data[i * 4 + k] = xs[k];
+                    if (RMS) rms[i * 4 + k] = rs[k];
+                    grad[i * 4 + k] = 0.f;
+                }
+            }
+        }
+    }
+    // tail rows
+    for (int64_t i = n4 * 4 + t0; i < n_rows; i += stride) {
+        if (MASKED && !mask[i]) continue;
+        float x = data[i], g = grad[i];
+        if (RMS) {
+            float r = rms[i];
+            rmsprop_once(x, r, g, beta, lr, eps, minval);
+            rms[i] = r;
+        } else {
+            x = fmaf(-lr, g, x);
+        }
+        data[i] = x;
+        grad[i] = 0.f;
+    }
+}
+
+inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
 // Row-masked steps: training touches a tiny fraction of the rows (the voxels the batch's samples hit), so scanning all
 // N*C elements for their row's mask byte wastes the launch.  Each warp takes 32 rows, reads their 32 mask bytes in one
 // coalesced load, and then walks only the set rows with the lanes striding over the C channels (coalesced rows).
@@ -145,14 +206,22 @@ extern "C" int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t 
     if (lr_last < 0.f) lr_last = lr;  // optim_kernel.cu:171
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_elem = n_rows * n_cols;
+    const bool vec1 = n_cols == 1 && aligned16(data) && aligned16(rms) && aligned16(grad);   // lr of the only column: lr_last
     if (indexer_kind == 0) {
         if (n_elem == 0) return 0;
-        rmsprop_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, nullptr, n_elem, n_cols, beta,
-                                                                         lr, eps, minval, lr_last);
+        if (vec1)
+            step_col1_vec4_kernel<false, true><<<stream_grid(n_elem / 4 + 1), 256, 0, st>>>(data, rms, grad, nullptr, n_rows,
+                                                                                             beta, lr_last, eps, minval);
+        else
+            rmsprop_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, nullptr, n_elem, n_cols, beta,
+                                                                             lr, eps, minval, lr_last);
     } else if (indexer_kind == 1) {
         if (n_index == 0 || n_elem == 0) return 0;  // size(0) == 0 -> skip (:189)
         // narrow tensors (density, surface: C = 1) gain nothing from a warp per row: one thread per element instead
-        if (n_cols < 8)
+        if (vec1 && (((uintptr_t)indexer & 3u) == 0))
+            step_col1_vec4_kernel<true, true><<<stream_grid(n_elem / 4 + 1), 256, 0, st>>>(
+                data, rms, grad, (const uint8_t *)indexer, n_rows, beta, lr_last, eps, minval);
+        else if (n_cols < 8)
             rmsprop_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer, n_elem,
                                                                             n_cols, beta, lr, eps, minval, lr_last);
         else
@@ -177,12 +246,20 @@ extern "C" int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t 
     if (lr_last < 0.f) lr_last = lr;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_elem = n_rows * n_cols;
+    const bool vec1 = n_cols == 1 && aligned16(data) && aligned16(grad);
     if (indexer_kind == 0) {
         if (n_elem == 0) return 0;
-        sgd_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, nullptr, n_elem, n_cols, lr, lr_last);
+        if (vec1)
+            step_col1_vec4_kernel<false, false><<<stream_grid(n_elem / 4 + 1), 256, 0, st>>>(data, nullptr, grad, nullptr, n_rows,
+                                                                                              0.f, lr_last, 0.f, 0.f);
+        else
+            sgd_dense_kernel<false><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, nullptr, n_elem, n_cols, lr, lr_last);
     } else if (indexer_kind == 1) {
         if (n_index == 0 || n_elem == 0) return 0;
-        if (n_cols < 8)
+        if (vec1 && (((uintptr_t)indexer & 3u) == 0))
+            step_col1_vec4_kernel<true, false><<<stream_grid(n_elem / 4 + 1), 256, 0, st>>>(
+                data, nullptr, grad, (const uint8_t *)indexer, n_rows, 0.f, lr_last, 0.f, 0.f);
+        else if (n_cols < 8)
             sgd_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, (const uint8_t *)indexer, n_elem, n_cols,
                                                                         lr, lr_last);
         else

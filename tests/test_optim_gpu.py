@@ -25,7 +25,7 @@ def _indexers(mask, dev):
             "empty": torch.empty((0,), dtype=torch.bool, device=dev)}
 
 
-@pytest.mark.parametrize("N,C", [(1000, 1), (4097, 27), (333, 12)])
+@pytest.mark.parametrize("N,C", [(1000, 1), (1003, 1), (4097, 27), (333, 12)])
 @pytest.mark.parametrize("mode", ["all", "mask", "index", "empty"])
 def test_rmsprop(N, C, mode):
     from oracle import oracle
@@ -48,11 +48,11 @@ def test_rmsprop(N, C, mode):
         assert torch.equal(d, d2) and torch.equal(r, r2) and torch.equal(g, g2), "not bit-exact with the reference kernel"
 
 
+@pytest.mark.parametrize("N,C", [(2049, 27), (1003, 1)])
 @pytest.mark.parametrize("mode", ["all", "mask", "index", "empty"])
-def test_sgd(mode):
+def test_sgd(mode, N, C):
     from oracle import oracle
     dev = "cuda"
-    N, C = 2049, 27
     data, _, grad, mask = _make(N, C, 11)
     d, g = data.to(dev), grad.to(dev)
     ours.sgd_step(d, g, _indexers(mask, dev)[mode], 0.1, 0.02)
