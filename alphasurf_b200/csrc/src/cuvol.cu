@@ -325,6 +325,67 @@ cuvol_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ or
 
 Workspace g_ws_lt;
 
+// ---- depth renders (evaluation): trace_ray_expected_term :127-188, trace_ray_mode_term :190-257, trace_ray_med_term
+//      :259-319, trace_ray_sigma_thresh :322-369; kernels :921-1005.  Thread per ray like the reference: no SH gather, so
+//      a warp per ray would idle; the sample positions are the reference's (same repeated t += step additions).
+template <int MODE>
+__global__ void __launch_bounds__(128)
+cuvol_scalar_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                    const int64_t Q, const float param, const int max_sample, float *__restrict__ out,
+                    float *__restrict__ out2) {
+    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray_id >= Q) return;
+    CvRay r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r.o[i] = origins[ray_id * 3 + i];
+        r.d[i] = dirs[ray_id * 3 + i];
+    }
+    cv_ray_bounds(g, opt, r);
+    float res = 0.f;
+    if (!(r.tmin > r.tmax)) {
+        float t = r.tmin, outv = 0.f, weight_acc = 0.f, max_weight = -1.f, log_transmit = 0.f;
+        int sample_i = 0;
+        while (t <= r.tmax) {
+            CvSample s;
+            s.t = t;
+            cv_density_phase(g, r, s);
+            if (s.skip >= opt.step_size) {
+                t += ceilf(s.skip / opt.step_size) * opt.step_size;
+                continue;
+            }
+            if (MODE == ASURF_CUVOL_SIGMA_THRESH) {
+                if (s.sigma > param) {
+                    res = (t / opt.step_size) * r.world_step;
+                    break;
+                }
+            } else if (s.sigma > opt.sigma_thresh) {
+                const float pcnt = r.world_step * s.sigma;
+                const float weight = __expf(log_transmit) * (1.f - __expf(-pcnt));
+                log_transmit -= pcnt;
+                if (MODE == ASURF_CUVOL_EXPECTED_TERM) {
+                    outv += weight * (t / opt.step_size) * r.world_step;
+                    weight_acc += weight;
+                } else if (MODE == ASURF_CUVOL_MODE_TERM) {
+                    weight_acc += weight;
+                    if (weight > max_weight) {
+                        max_weight = weight;
+                        outv = (t / opt.step_size) * r.world_step;
+                    }
+                } else if (sample_i < max_sample) {
+                    out[ray_id * max_sample + sample_i] = (t / opt.step_size) * r.world_step;
+                    out2[ray_id * max_sample + sample_i] = s.sigma;
+                    sample_i += 1;
+                }
+                if (__expf(log_transmit) < opt.stop_thresh) break;
+            }
+            t += opt.step_size;
+        }
+        if (MODE == ASURF_CUVOL_EXPECTED_TERM || MODE == ASURF_CUVOL_MODE_TERM) res = (weight_acc > param) ? outv : 0.f;
+    }
+    if (MODE != ASURF_CUVOL_MED_TERM) out[ray_id] = res;
+}
+
 int cv_make_grid(const asurf_grid_t *grid, CvGrid &g, const char *who) {
     ASURF_REQUIRE(grid, ASURF_E_INVALID, "%s: null grid", who);
     ASURF_REQUIRE(grid->links && grid->density && grid->sh, ASURF_E_INVALID, "%s: null grid tensor", who);
@@ -367,6 +428,41 @@ extern "C" int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t 
         g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, log_transmit_out, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "cuvol_forward launch");
+}
+
+extern "C" int asurf_cuvol_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,
+                                  float param, int32_t max_sample, float *out, float *out2, void *stream) {
+    ASURF_REQUIRE(rays && opt, ASURF_E_INVALID, "cuvol_scalar: null argument");
+    ASURF_REQUIRE(mode >= ASURF_CUVOL_EXPECTED_TERM && mode <= ASURF_CUVOL_SIGMA_THRESH, ASURF_E_INVALID,
+                  "cuvol_scalar: unknown mode %d", mode);
+    ASURF_REQUIRE(!opt->use_spheric_clip, ASURF_E_UNSUPPORTED, "cuvol_scalar: spheric clip is not on the hot path");
+    const int64_t Q = rays->n_rays;
+    if (Q <= 0) return 0;
+    ASURF_REQUIRE(rays->origins && rays->dirs && out, ASURF_E_INVALID, "cuvol_scalar: null tensor");
+    CvGrid g;
+    int rc = cv_make_grid(grid, g, "cuvol_scalar");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)((Q + 127) / 128);
+    if (mode == ASURF_CUVOL_MED_TERM) {
+        ASURF_REQUIRE(out2 && max_sample >= 0, ASURF_E_INVALID, "cuvol_scalar: med_term needs the sigma output and max_sample >= 0");
+        if (max_sample == 0) return 0;
+        ASURF_CUDA(cudaMemsetAsync(out, 0, (size_t)Q * max_sample * sizeof(float), st));
+        ASURF_CUDA(cudaMemsetAsync(out2, 0, (size_t)Q * max_sample * sizeof(float), st));
+        cuvol_scalar_kernel<ASURF_CUVOL_MED_TERM><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param,
+                                                                          max_sample, out, out2);
+    } else if (mode == ASURF_CUVOL_EXPECTED_TERM) {
+        cuvol_scalar_kernel<ASURF_CUVOL_EXPECTED_TERM><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param, 0,
+                                                                               out, nullptr);
+    } else if (mode == ASURF_CUVOL_MODE_TERM) {
+        cuvol_scalar_kernel<ASURF_CUVOL_MODE_TERM><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param, 0, out,
+                                                                           nullptr);
+    } else {
+        cuvol_scalar_kernel<ASURF_CUVOL_SIGMA_THRESH><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param, 0,
+                                                                              out, nullptr);
+    }
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "cuvol_scalar launch");
 }
 
 extern "C" int asurf_cuvol_image(const asurf_grid_t *grid, const float *c2w_host, float fx, float fy, float cx, float cy,

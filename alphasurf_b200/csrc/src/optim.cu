@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(256) step_col1_vec4_kernel(float *__restrict__
 inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 // Row-masked steps: training touches a tiny fraction of the rows (the voxels the batch's samples hit), so scanning all
-// N*C elements for their row's mask byte wastes the launch.  Each warp takes 32 rows, reads their 32 mask bytes in one
-// coalesced load, and then walks only the set rows with the lanes striding over the C channels (coalesced rows).
+// N*C elements for their row's mask byte wastes the launch.  Each warp takes 128 rows, reads their mask bytes as 32 words
+// in one coalesced load, and then walks only the set rows with the lanes striding over the C channels (coalesced rows).
 template <bool RMS>
 __global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ data, float *__restrict__ rms,
                                                            float *__restrict__ grad, const uint8_t *__restrict__ mask,
@@ -112,12 +112,28 @@ __global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ da
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = warp0 * 32; base < n_rows; base += n_warps * 32) {
-        const int64_t row = base + lane;
-        unsigned m = __ballot_sync(0xffffffffu, row < n_rows && mask[row] != 0);
-        while (m) {
-            const int r = __ffs(m) - 1;
-            m &= m - 1;
+    const bool word_ok = ((uintptr_t)mask & 3u) == 0;
+    for (int64_t base = warp0 * 128; base < n_rows; base += n_warps * 128) {
+        // 128 rows per round: every lane fetches the mask bytes of 4 consecutive rows (one 32-bit load when it can)
+        const int64_t row0 = base + lane * 4;
+        unsigned w = 0u;
+        if (word_ok && row0 + 3 < n_rows) {
+            w = reinterpret_cast<const unsigned *>(mask)[row0 >> 2];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (row0 + k < n_rows && mask[row0 + k]) w |= 1u << (8 * k);
+        }
+        unsigned bits = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) |
+                        ((w & 0xff000000u) ? 8u : 0u);
+        unsigned any = __ballot_sync(0xffffffffu, bits != 0u);
+        while (any) {
+            const int src = __ffs(any) - 1;
+            any &= any - 1;
+            unsigned b = __shfl_sync(0xffffffffu, bits, src);
+          while (b) {
+            const int r = src * 4 + __ffs(b) - 1;
+            b &= b - 1;
             const int64_t off = (base + r) * n_cols;
             for (int c = lane; c < n_cols; c += 32) {
                 const float l = (c == n_cols - 1) ? lr_last : lr;
@@ -131,6 +147,7 @@ __global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ da
                 }
                 grad[off + c] = 0.f;
             }
+          }
         }
     }
 }
@@ -225,7 +242,7 @@ extern "C" int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t 
             rmsprop_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer, n_elem,
                                                                             n_cols, beta, lr, eps, minval, lr_last);
         else
-            masked_rows_kernel<true><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer,
+            masked_rows_kernel<true><<<stream_grid(n_rows / 4 + 1), 256, 0, st>>>(data, rms, grad, (const uint8_t *)indexer,
                                                                               n_rows, n_cols, beta, lr, eps, minval, lr_last);
     } else if (indexer_kind == 2) {
         if (n_index == 0) return 0;
@@ -263,7 +280,7 @@ extern "C" int asurf_sgd_step(float *data, float *grad, int64_t n_rows, int32_t 
             sgd_dense_kernel<true><<<stream_grid(n_elem), 256, 0, st>>>(data, grad, (const uint8_t *)indexer, n_elem, n_cols,
                                                                         lr, lr_last);
         else
-            masked_rows_kernel<false><<<stream_grid(n_rows * 8), 256, 0, st>>>(data, nullptr, grad, (const uint8_t *)indexer,
+            masked_rows_kernel<false><<<stream_grid(n_rows / 4 + 1), 256, 0, st>>>(data, nullptr, grad, (const uint8_t *)indexer,
                                                                                n_rows, n_cols, 0.f, lr, 0.f, 0.f, lr_last);
     } else if (indexer_kind == 2) {
         if (n_index == 0) return 0;

@@ -2,8 +2,8 @@
 // surf_trav.cu inside namespace asurf::{anon}.
 //
 // Reference: trace_ray_expected_term (render_lerp_kernel_surf_trav.cu:564-794), trace_ray_mode_term_surf_trav (:796-1001),
-// trace_ray_sigma_thresh_surf_trav (:1003-1168), trace_ray_alpha_surf_trav (:1170-1337), trace_ray_normal (:1339-1534);
-// kernels :3458-3560, one thread per ray.  They share the DDA of the colour renderer but none of its gates: a voxel counts
+// trace_ray_sigma_thresh_surf_trav (:1003-1168), trace_ray_alpha_surf_trav (:1170-1337), trace_ray_normal (:1339-1534),
+// trace_ray_extract_pt (:1536-1708); kernels :3458-3594, one thread per ray.  They share the DDA of the colour renderer but none of its gates: a voxel counts
 // when its 8 links are stored and a level set lies within the range of its corner values, every root inside the voxel is
 // a sample, alpha = surf_alpha_act(trilerp(density)) with no threshold, no outward test, no truncated re-weighting and no
 // fake samples.
@@ -17,7 +17,8 @@
 template <int MODE>
 __global__ void __launch_bounds__(128)
 scalar_render_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
-                     const int64_t Q, const float param, float *__restrict__ out) {
+                     const int64_t Q, const float param, const int max_sample, float *__restrict__ out,
+                     float *__restrict__ out2) {
     const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ray_id >= Q) return;
     constexpr int NOUT = (MODE == ASURF_SCALAR_NORMAL) ? 3 : 1;
@@ -32,6 +33,7 @@ scalar_render_kernel(const GridP g, const asurf_opt_t opt, const float *__restri
     ray_bounds(g, opt, L, world_step);
     float logT = 0.f, outv = 0.f, max_weight = 0.f, weight_acc = 0.f;
     bool found = false;
+    int sample_id = 0;   // EXTRACT_PTS: samples written so far
     Counters cnt;
     if (!(L.tmin > L.tmax)) {
         dda_init(g, L);
@@ -107,6 +109,14 @@ scalar_render_kernel(const GridP g, const asurf_opt_t opt, const float *__restri
                                          : alpha;
                             found = true;
                         }
+                    } else if (MODE == ASURF_SCALAR_EXTRACT_PTS) {
+                        if (alpha > param) {   // every sample above the threshold, up to max_sample per ray (:1689-1697)
+                            out[ray_id * max_sample + sample_id] =
+                                (float)(((stj + (double)t_close) / (double)opt.step_size) * (double)world_step);
+                            out2[ray_id * max_sample + sample_id] = alpha;
+                            sample_id += 1;
+                            found = sample_id >= max_sample;
+                        }
                     } else {
                         if (alpha > 0) {
                             field_grad8(sf, pos, res);
@@ -122,6 +132,7 @@ scalar_render_kernel(const GridP g, const asurf_opt_t opt, const float *__restri
         if (MODE == ASURF_SCALAR_EXPECTED_TERM) res[0] = outv;
         if (MODE == ASURF_SCALAR_MODE_TERM) res[0] = (weight_acc > param) ? outv : 0.f;
     }
+    if (MODE == ASURF_SCALAR_EXTRACT_PTS) return;   // (Q, max_sample) outputs are zero-filled by the host side
 #pragma unroll
     for (int c = 0; c < NOUT; ++c) out[ray_id * NOUT + c] = res[c];
 }

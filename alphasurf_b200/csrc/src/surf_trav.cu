@@ -1840,14 +1840,20 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
 }
 
 extern "C" int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,
-                                      float param, float *out, void *stream) {
+                                      float param, int32_t max_sample, float *out, float *out2, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_rays(rays, opt);
     if (rc) return rc;
-    ASURF_REQUIRE(mode >= ASURF_SCALAR_EXPECTED_TERM && mode <= ASURF_SCALAR_NORMAL, ASURF_E_INVALID,
+    ASURF_REQUIRE(mode >= ASURF_SCALAR_EXPECTED_TERM && mode <= ASURF_SCALAR_EXTRACT_PTS, ASURF_E_INVALID,
                   "surf_trav_scalar: unknown mode %d", mode);
     if (rays->n_rays == 0) return 0;
     ASURF_REQUIRE(out, ASURF_E_INVALID, "surf_trav_scalar: null output");
+    if (mode == ASURF_SCALAR_EXTRACT_PTS) {
+        ASURF_REQUIRE(out2 && max_sample >= 0, ASURF_E_INVALID, "surf_trav_scalar: extract_pts needs the alpha output and max_sample >= 0");
+        if (max_sample == 0) return 0;
+        ASURF_CUDA(cudaMemsetAsync(out, 0, (size_t)rays->n_rays * max_sample * sizeof(float), st));
+        ASURF_CUDA(cudaMemsetAsync(out2, 0, (size_t)rays->n_rays * max_sample * sizeof(float), st));
+    }
     GridP g;
     rc = make_grid(grid, opt, false, st, g);
     if (rc) return rc;
@@ -1871,13 +1877,15 @@ extern "C" int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays
     switch (mode) {
 #define ASURF_SCALAR_CASE(M)                                                                                         \
     case M:                                                                                                          \
-        scalar_render_kernel<M><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param, out);           \
+        scalar_render_kernel<M><<<blocks, 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, param, max_sample, out, \
+                                                        out2);                                                       \
         break;
         ASURF_SCALAR_CASE(ASURF_SCALAR_EXPECTED_TERM)
         ASURF_SCALAR_CASE(ASURF_SCALAR_MODE_TERM)
         ASURF_SCALAR_CASE(ASURF_SCALAR_THRESH_DEPTH)
         ASURF_SCALAR_CASE(ASURF_SCALAR_THRESH_ALPHA)
         ASURF_SCALAR_CASE(ASURF_SCALAR_NORMAL)
+        ASURF_SCALAR_CASE(ASURF_SCALAR_EXTRACT_PTS)
 #undef ASURF_SCALAR_CASE
     }
     note_launches(1);

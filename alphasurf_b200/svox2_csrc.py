@@ -251,17 +251,19 @@ def volume_render_surf_trav_backward(grid, rays, opt, grad_out, color_cache, gra
 
 
 # ---- scalar renders for evaluation (render_lerp_kernel_surf_trav.cu:3944-4050+; svox2.py:3690-3830) ------------------
-def _surf_trav_scalar(name, grid, rays, opt, mode, param, width=1):
+def _surf_trav_scalar(name, grid, rays, opt, mode, param, width=1, max_sample=0):
     _check_grid(grid)
     _check_rays(rays)
     Q = rays.origins.shape[0]
     out = torch.empty((Q,) if width == 1 else (Q, width), dtype=rays.origins.dtype, device=rays.origins.device)
+    out2 = torch.empty_like(out) if mode == 5 else None
     with torch.cuda.device(grid.sh_data.device):
         g, _keep = _grid_t(grid)
         capi.check(capi.lib().asurf_surf_trav_scalar(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
-                                                     C.c_int32(mode), C.c_float(param), capi.ptr(out),
+                                                     C.c_int32(mode), C.c_float(param), C.c_int32(max_sample), capi.ptr(out),
+                                                     capi.ptr(out2) if out2 is not None else None,
                                                      capi.current_stream()), name)
-    return out
+    return (out, out2) if mode == 5 else out
 
 
 def volume_render_expected_term_surf_trav(grid, rays, opt):
@@ -287,6 +289,16 @@ def volume_render_alpha_surf_trav(grid, rays, opt, thresh):
 def render_normal_surf_trav(grid, rays, opt):
     """un-normalised surface gradient at the first sample with alpha > 0, (Q, 3) (:4031-4050)"""
     return _surf_trav_scalar("render_normal_surf_trav", grid, rays, opt, 4, 0.0, width=3)
+
+
+def extract_pts_surf_trav(grid, rays, opt, max_sample, alpha_thresh):
+    """(depths, alphas) of the first max_sample samples with alpha > alpha_thresh per ray, zero-padded, (Q, max_sample)
+    (:4052-4081; svox2.py:3938)"""
+    if int(max_sample) <= 0:
+        z = torch.zeros((rays.origins.shape[0], 0), dtype=rays.origins.dtype, device=rays.origins.device)
+        return z, z.clone()
+    return _surf_trav_scalar("extract_pts_surf_trav", grid, rays, opt, 5, float(alpha_thresh), width=int(max_sample),
+                             max_sample=int(max_sample))
 
 
 # Global batch size used to normalise the fused losses; None = this call's ray count (the reference behaviour).
@@ -336,6 +348,42 @@ def volume_render_cuvol(grid, rays, opt):
         capi.check(capi.lib().asurf_cuvol_forward(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
                                                   capi.ptr(out), None, capi.current_stream()), "volume_render_cuvol")
     return out
+
+
+# depth renders of the cuvol backend (render_lerp_kernel_cuvol.cu:1356-1442; svox2.py:3732-3775)
+def _cuvol_scalar(name, grid, rays, opt, mode, param, max_sample=0):
+    _check_grid(grid)
+    _check_rays(rays)
+    Q = rays.origins.shape[0]
+    kw = dict(dtype=rays.origins.dtype, device=rays.origins.device)
+    out = torch.empty((Q, max_sample) if mode == 2 else (Q,), **kw)
+    out2 = torch.empty((Q, max_sample), **kw) if mode == 2 else None
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid, need_accel=False)
+        capi.check(capi.lib().asurf_cuvol_scalar(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)),
+                                                 C.c_int32(mode), C.c_float(param), C.c_int32(max_sample), capi.ptr(out),
+                                                 capi.ptr(out2) if out2 is not None else None, capi.current_stream()), name)
+    return (out, out2) if mode == 2 else out
+
+
+def volume_render_expected_term(grid, rays, opt, weight_thresh):
+    """expected termination depth; 0 where the accumulated weight <= weight_thresh, (Q,)"""
+    return _cuvol_scalar("volume_render_expected_term", grid, rays, opt, 0, float(weight_thresh))
+
+
+def volume_render_mode_term(grid, rays, opt, weight_thresh):
+    """depth of the heaviest sample; 0 where the accumulated weight <= weight_thresh, (Q,)"""
+    return _cuvol_scalar("volume_render_mode_term", grid, rays, opt, 1, float(weight_thresh))
+
+
+def volume_render_med_term(grid, rays, opt, max_sample):
+    """(depths, sigmas) of the first max_sample samples per ray, zero-padded, each (Q, max_sample)"""
+    return _cuvol_scalar("volume_render_med_term", grid, rays, opt, 2, 0.0, int(max_sample))
+
+
+def volume_render_sigma_thresh(grid, rays, opt, sigma_thresh):
+    """depth of the first sample whose sigma exceeds sigma_thresh, (Q,)"""
+    return _cuvol_scalar("volume_render_sigma_thresh", grid, rays, opt, 3, float(sigma_thresh))
 
 
 def volume_render_cuvol_image(grid, cam, opt):
@@ -592,8 +640,7 @@ def _not_on_hot_path(name):
 
 
 for _name in ("sample_grid", "sample_grid_backward", "sample_grid_sh_surf", "sample_grid_raw_alpha", "cubic_extract_iso_pts",
-              "extract_pts_surf_trav", "volume_render_expected_term", "volume_render_mode_term", "volume_render_med_term",
-              "volume_render_sigma_thresh", "dilate", "grid_weight_render", "sparse_grid_weight_render",
+              "dilate", "grid_weight_render", "sparse_grid_weight_render",
               "sparse_grid_visbility_render_surf", "sparse_grid_mask_render", "surface_normal_grad",
               "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
               "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",

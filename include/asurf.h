@@ -146,17 +146,20 @@ int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, 
 /* Scalar renders of the surf_trav backend, one entry for the five reference functions (host side :3944-4050+, kernels
  * :3458-3560):  volume_render_expected_term_surf_trav (mode EXPECTED_TERM), volume_render_mode_term_surf_trav (MODE_TERM,
  * param = weight_thresh), volume_render_sigma_thresh_surf_trav (THRESH_DEPTH, param = sigma_thresh),
- * volume_render_alpha_surf_trav (THRESH_ALPHA, param = thresh), render_normal_surf_trav (NORMAL; out is (Q,3)).
- * out is (Q,) floats otherwise.  Rays that miss give 0. */
+ * volume_render_alpha_surf_trav (THRESH_ALPHA, param = thresh), render_normal_surf_trav (NORMAL; out is (Q,3)),
+ * extract_pts_surf_trav (:4052-4081; EXTRACT_PTS, param = alpha_thresh: out = depths and out2 = alphas of the first
+ * max_sample samples with alpha > param, both (Q, max_sample), zero-filled here).
+ * out is (Q,) floats otherwise; out2 / max_sample are ignored unless EXTRACT_PTS.  Rays that miss give 0. */
 enum {
     ASURF_SCALAR_EXPECTED_TERM = 0,
     ASURF_SCALAR_MODE_TERM = 1,
     ASURF_SCALAR_THRESH_DEPTH = 2,
     ASURF_SCALAR_THRESH_ALPHA = 3,
-    ASURF_SCALAR_NORMAL = 4
+    ASURF_SCALAR_NORMAL = 4,
+    ASURF_SCALAR_EXTRACT_PTS = 5
 };
 int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,
-                           float param, float *out, void *stream);
+                           float param, int32_t max_sample, float *out, float *out2, void *stream);
 /* volume_render_surf_trav_backward, :3708-3800 (grad_out = dL/dRGB (Q,3), color_cache = forward RGB) */
 int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
                              const float *grad_out, const float *color_cache, const asurf_grads_t *grads,
@@ -206,6 +209,13 @@ void asurf_debug_set_normal_tile(int32_t enabled);
 /* volume_render_cuvol, :1120-1160 (rgb_out (Q,3); log_transmit_out (Q,) or NULL) */
 int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, float *rgb_out,
                         float *log_transmit_out, void *stream);
+/* Depth renders of the cuvol backend, one entry for four reference functions (render_lerp_kernel_cuvol.cu:1356-1442):
+ * volume_render_expected_term (mode EXPECTED_TERM, param = weight_thresh), volume_render_mode_term (MODE_TERM, param =
+ * weight_thresh), volume_render_med_term (MED_TERM: out = depths, out2 = sigmas, both (Q, max_sample), zero-filled here),
+ * volume_render_sigma_thresh (SIGMA_THRESH, param = sigma_thresh).  out is (Q,) floats unless MED_TERM. */
+enum { ASURF_CUVOL_EXPECTED_TERM = 0, ASURF_CUVOL_MODE_TERM = 1, ASURF_CUVOL_MED_TERM = 2, ASURF_CUVOL_SIGMA_THRESH = 3 };
+int asurf_cuvol_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode, float param,
+                       int32_t max_sample, float *out, float *out2, void *stream);
 /* volume_render_cuvol_image, :1162-1209: rays of a pinhole camera (c2w: 12 host floats, row-major 3x4), rgb_out (H,W,3) */
 int asurf_cuvol_image(const asurf_grid_t *grid, const float *c2w_host, float fx, float fy, float cx, float cy, int32_t width,
                       int32_t height, const asurf_opt_t *opt, float *rgb_out, void *stream);

@@ -175,19 +175,21 @@ def surf_trav_forward(grid: Grid, opt: dict, origins, dirs, xf=None, trace: Trac
     return out
 
 
-SCALAR_MODES = dict(expected_term=0, mode_term=1, thresh_depth=2, thresh_alpha=3, normal=4)
+SCALAR_MODES = dict(expected_term=0, mode_term=1, thresh_depth=2, thresh_alpha=3, normal=4, extract_pts=5)
 
 
-def surf_trav_scalar(grid: Grid, opt: dict, origins, dirs, mode, param=0.0, xf=None):
-    """depth / alpha / normal renders (render_lerp_kernel_surf_trav.cu:564-1534); mode: key of SCALAR_MODES"""
+def surf_trav_scalar(grid: Grid, opt: dict, origins, dirs, mode, param=0.0, xf=None, max_sample=0):
+    """depth / alpha / normal / point renders (render_lerp_kernel_surf_trav.cu:564-1708); mode: key of SCALAR_MODES;
+    extract_pts returns (depths, alphas), each (Q, max_sample)"""
     o, d = _np(origins, np.float32), _np(dirs, np.float32)
     xf = _np(xf, np.float32)
     Q = o.shape[0]
     m = SCALAR_MODES[mode]
-    out = np.zeros((Q, 3) if m == 4 else (Q,), np.float32)
+    out = np.zeros((Q, 3) if m == 4 else ((Q, max_sample) if m == 5 else (Q,)), np.float32)
+    out2 = np.zeros_like(out) if m == 5 else None
     lib().oracle_surf_trav_scalar(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q),
-                                  C.c_int(m), C.c_float(param), _ptr(out))
-    return out
+                                  C.c_int(m), C.c_float(param), C.c_int(max_sample), _ptr(out), _ptr(out2))
+    return (out, out2) if m == 5 else out
 
 
 def surf_trav_backward(grid: Grid, opt: dict, origins, dirs, grad_out, color_cache, xf=None, grads: Grads = None):
@@ -325,6 +327,22 @@ def cuvol_forward(grid: Grid, opt: dict, origins, dirs, xf=None, want_log_transm
     lib().oracle_cuvol_forward(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q), _ptr(out),
                                _ptr(lt))
     return (out, lt) if want_log_transmit else out
+
+
+CUVOL_SCALAR_MODES = dict(expected_term=0, mode_term=1, med_term=2, sigma_thresh=3)
+
+
+def cuvol_scalar(grid: Grid, opt: dict, origins, dirs, mode, param=0.0, max_sample=0, xf=None):
+    """depth renders of the cuvol backend (render_lerp_kernel_cuvol.cu:127-369); med_term returns (depths, sigmas)"""
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    xf = _np(xf, np.float32)
+    Q = o.shape[0]
+    m = CUVOL_SCALAR_MODES[mode]
+    shape = (Q, max_sample) if m == 2 else (Q,)
+    out, out2 = np.zeros(shape, np.float32), np.zeros(shape if m == 2 else (1,), np.float32)
+    lib().oracle_cuvol_scalar(C.byref(grid.c), C.byref(make_opt(opt)), _ptr(o), _ptr(d), _ptr(xf), C.c_int64(Q), C.c_int(m),
+                              C.c_float(param), C.c_int(max_sample), _ptr(out), _ptr(out2))
+    return (out, out2) if m == 2 else out
 
 
 def cuvol_backward(grid: Grid, opt: dict, origins, dirs, grad_out, color_cache, xf=None, grads: Grads = None):

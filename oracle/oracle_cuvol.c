@@ -109,6 +109,61 @@ void oracle_cuvol_forward(const OGrid *g, const OOpt *opt, const float *origins,
     }
 }
 
+/* Depth renders of the cuvol backend: trace_ray_expected_term (render_lerp_kernel_cuvol.cu:127-188), trace_ray_mode_term
+ * (:190-257), trace_ray_med_term (:259-319), trace_ray_sigma_thresh (:322-369).
+ * mode 0 expected depth (param = weight_thresh), 1 depth of the heaviest sample (param = weight_thresh), 2 per-sample
+ * depths and sigmas of the first max_sample samples (out, out2: (Q, max_sample), zero-filled), 3 depth of the first sample
+ * with sigma > param. */
+void oracle_cuvol_scalar(const OGrid *g, const OOpt *opt, const float *origins, const float *dirs, const float *xf, int64_t Q,
+                         int mode, float param, int max_sample, float *out, float *out2) {
+    const int offx = g->size[1] * g->size[2], offy = g->size[2];
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t q = 0; q < Q; ++q) {
+        ORay ray;
+        float sph[9];
+        ray_setup(&ray, g, opt, origins, dirs, xf, q, sph);
+        if (mode == 2) {
+            for (int i = 0; i < max_sample; ++i) out[q * max_sample + i] = out2[q * max_sample + i] = 0.f;
+        } else {
+            out[q] = 0.f;
+        }
+        if (ray.tmin > ray.tmax) continue;
+        float t = ray.tmin, outv = 0.f, weight_acc = 0.f, max_weight = -1.f, log_transmit = 0.f;
+        int sample_i = 0, found = 0;
+        while (t <= ray.tmax) {
+            sample_position(&ray, g, t);
+            const float skip = compute_skip_dist(&ray, g->links, offx, offy);
+            if (skip >= opt->step_size) {
+                t += ceilf(skip / opt->step_size) * opt->step_size;
+                continue;
+            }
+            const float sigma = o_trilerp_cuvol_one(g->links, g->density, offx, offy, 1, ray.l, ray.pos, 0);
+            if (mode == 3) {
+                if (sigma > param) { out[q] = (t / opt->step_size) * ray.world_step; found = 1; break; }
+            } else if (sigma > opt->sigma_thresh) {
+                const float pcnt = ray.world_step * sigma;
+                const float weight = expf(log_transmit) * (1.f - expf(-pcnt));
+                log_transmit -= pcnt;
+                if (mode == 0) {
+                    outv += weight * (t / opt->step_size) * ray.world_step;
+                    weight_acc += weight;
+                } else if (mode == 1) {
+                    weight_acc += weight;
+                    if (weight > max_weight) { max_weight = weight; outv = (t / opt->step_size) * ray.world_step; }
+                } else if (sample_i < max_sample) {
+                    out[q * max_sample + sample_i] = (t / opt->step_size) * ray.world_step;
+                    out2[q * max_sample + sample_i] = sigma;
+                    sample_i += 1;
+                }
+                if (expf(log_transmit) < opt->stop_thresh) break;
+            }
+            t += opt->step_size;
+        }
+        (void)found;
+        if (mode <= 1) out[q] = (weight_acc > param) ? outv : 0.f;
+    }
+}
+
 /* render_ray_backward_kernel :844-919 + trace_ray_cuvol_backward :371-535.
  * grad_is_rgb: grad_in is rgb_gt and dL/dRGB = (colour - gt) * norm_factor (fused, :873-880). */
 void oracle_cuvol_backward(const OGrid *g, const OOpt *opt, const float *origins, const float *dirs, const float *xf, int64_t Q,

@@ -902,10 +902,14 @@ void oracle_surf_trav_fused(const OGrid *g, const OOpt *opt, const float *origin
  * _sigma_thresh (:1003-1168), _alpha (:1170-1337), _normal (:1339-1534) =====================
  * Same traversal as the colour renderer but: no density gate, no outward test, no truncated re-weighting, no fake samples,
  * every in-range root composited.  mode: 0 expected depth, 1 mode depth (param = weight_thresh), 2 depth of the first
- * sample with alpha > param, 3 alpha of that sample, 4 surface gradient at the first sample with alpha > 0 (3 floats). */
-static void trace_ray_scalar(const OGrid *g, ORay *ray, const OOpt *opt, int mode, float param, float *out) {
-    const int nout = (mode == 4) ? 3 : 1;
+ * sample with alpha > param, 3 alpha of that sample, 4 surface gradient at the first sample with alpha > 0 (3 floats),
+ * 5 trace_ray_extract_pt (:1536-1708): depths (out) and alphas (out2) of the first max_sample samples with alpha > param. */
+static void trace_ray_scalar(const OGrid *g, ORay *ray, const OOpt *opt, int mode, float param, int max_sample, float *out,
+                             float *out2) {
+    const int nout = (mode == 4) ? 3 : ((mode == 5) ? max_sample : 1);
+    int sample_id = 0;
     for (int c = 0; c < nout; ++c) out[c] = 0.f;
+    if (mode == 5) for (int c = 0; c < nout; ++c) out2[c] = 0.f;
     if (ray->tmin > ray->tmax) return;
     double const ray_dir_d[3] = {ray->dir[0], ray->dir[1], ray->dir[2]};
     float t = ray->tmin, outv = 0.f, log_transmit = 0.f, max_weight = 0.f, weight_acc = 0.f;
@@ -965,6 +969,13 @@ static void trace_ray_scalar(const OGrid *g, ORay *ray, const OOpt *opt, int mod
                     }
                 } else if (mode == 2 || mode == 3) {
                     if (alpha > param) { out[0] = (mode == 2) ? depth : alpha; return; }
+                } else if (mode == 5) {
+                    if (alpha > param) {
+                        out[sample_id] = depth;
+                        out2[sample_id] = alpha;
+                        sample_id += 1;
+                        if (sample_id >= max_sample) return;
+                    }
                 } else {
                     if (alpha > 0) { compute_field_grad(g->links, g->surface, offx, offy, ray->l, ray->pos, out); return; }
                 }
@@ -980,14 +991,15 @@ static void trace_ray_scalar(const OGrid *g, ORay *ray, const OOpt *opt, int mod
 }
 
 void oracle_surf_trav_scalar(const OGrid *g, const OOpt *opt, const float *origins, const float *dirs, const float *xf,
-                             int64_t Q, int mode, float param, float *out) {
-    const int nout = (mode == 4) ? 3 : 1;
+                             int64_t Q, int mode, float param, int max_sample, float *out, float *out2) {
+    const int nout = (mode == 4) ? 3 : ((mode == 5) ? max_sample : 1);
+    if (mode == 5 && max_sample <= 0) return;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t q = 0; q < Q; ++q) {
         ORay ray;
         float sphfunc[16];
         setup_ray(g, opt, origins + q * 3, dirs + q * 3, xf ? xf + q * 9 : NULL, &ray, sphfunc);
-        trace_ray_scalar(g, &ray, opt, mode, param, out + q * nout);
+        trace_ray_scalar(g, &ray, opt, mode, param, max_sample, out + q * nout, out2 ? out2 + q * nout : NULL);
     }
 }
 

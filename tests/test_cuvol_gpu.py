@@ -194,3 +194,53 @@ def test_cuvol_full_size_properties():
     # gradients only on rows that a hit ray can touch, and the SH DC gradient has the sign of (rgb - gt) on average
     assert int(G.mask.sum()) > 0 and float(G.sh[~G.mask].abs().max()) == 0.0
     assert bool(torch.isfinite(G.sh).all()) and bool(torch.isfinite(G.density).all())
+
+
+@pytest.mark.parametrize("skip_codes", [False, True])
+def test_cuvol_depth_renders(skip_codes):
+    """volume_render_expected_term / _mode_term / _med_term / _sigma_thresh (the depth maps opt.py logs for the cuvol
+    backend): ours vs the CPU oracle on the same grid-space rays and vs the reference kernels.  The sample positions are
+    exact; a ray may flip only where a weight / sigma sits within rounding of the threshold."""
+    from oracle import oracle
+    opts = plenoxels_options()
+    bd, Q = 9, 4096
+    sg = synth.make_shell_grid(64, basis_dim=bd, variant="G", sigma_density=True).to("cuda")
+    o, d, _ = synth.make_camera_rays(Q, device="cuda", seed=synth.SEED + 9)
+    links = _with_skip_codes(sg) if skip_codes else sg.links
+    grid, rays, opt = _grid_spec(ours, sg, links), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts)
+    sg_cpu = sg.to("cpu")
+    og = oracle.Grid(synth.SynthGrid(links.cpu(), sg_cpu.density, None, sg_cpu.sh, None, sg.offset, sg.scaling, bd))
+    xf = _xf(sg, o, d, opts).cpu()
+    ref = H.load_reference_cuda()
+
+    def close(a, b, what, flips=0):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        assert a.shape == b.shape
+        bad = np.abs(a - b) > 1e-5 * np.maximum(1.0, np.abs(b))
+        if bad.ndim == 2:
+            bad = bad.any(1)
+        assert int(bad.sum()) <= flips, (what, int(bad.sum()))
+        assert np.count_nonzero(b) > 0, what
+
+    calls = [("expected_term", "volume_render_expected_term", 0.0), ("expected_term", "volume_render_expected_term", 0.9),
+             ("mode_term", "volume_render_mode_term", 0.5), ("sigma_thresh", "volume_render_sigma_thresh", 18.0)]
+    for mode, fn, param in calls:
+        got = getattr(ours, fn)(grid, rays, opt, param)
+        torch.cuda.synchronize()
+        want = oracle.cuvol_scalar(og, opts, o.cpu(), d.cpu(), mode, param, xf=xf)
+        close(got.cpu().numpy(), want, (fn, param, "oracle"), flips=4)
+        if ref is not None:
+            want_r = getattr(ref, fn)(_grid_spec(ref, sg, links), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), param)
+            close(got.cpu().numpy(), want_r.cpu().numpy(), (fn, param, "reference"), flips=4)
+    dep, sig = ours.volume_render_med_term(grid, rays, opt, 12)
+    torch.cuda.synchronize()
+    dep_o, sig_o = oracle.cuvol_scalar(og, opts, o.cpu(), d.cpu(), "med_term", 0.0, 12, xf=xf)
+    close(dep.cpu().numpy(), dep_o, "med depths vs oracle")
+    close(sig.cpu().numpy(), sig_o, "med sigmas vs oracle")
+    if ref is not None:
+        dep_r, sig_r = ref.volume_render_med_term(_grid_spec(ref, sg, links), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), 12)
+        close(dep.cpu().numpy(), dep_r.cpu().numpy(), "med depths vs reference")
+        close(sig.cpu().numpy(), sig_r.cpu().numpy(), "med sigmas vs reference")
+    # empty batch
+    e = torch.zeros((0, 3), device="cuda")
+    assert ours.volume_render_expected_term(grid, H.fill_rays_spec(ours, e, e), opt, 0.0).shape == (0,)

@@ -74,6 +74,32 @@ def test_scalar_renders_vs_reference_cuda(variant, reso, bd, Q):
         _close(got.cpu().numpy(), want.cpu().numpy(), mode, "reference")
 
 
+@pytest.mark.parametrize("variant,reso", [("G", 64), ("G*", 48)])
+def test_extract_pts(variant, reso):
+    """extract_pts_surf_trav: depth and alpha of every sample above the threshold, up to max_sample per ray."""
+    from oracle import oracle
+    opts = synth.alphasurf_render_options()
+    sg = synth.make_shell_grid(reso, basis_dim=4, variant=variant).to("cuda")
+    o, d, _ = synth.make_camera_rays(2048, device="cuda", seed=14)
+    grid, rays, opt = H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts)
+    xf = ours.debug_ray_bounds(grid, rays, opt).cpu()
+    og = oracle.Grid(sg.to("cpu"))
+    ref = H.load_reference_cuda()
+    for max_sample, thr in ((6, 0.0), (2, 0.39)):
+        dep, alp = ours.extract_pts_surf_trav(grid, rays, opt, max_sample, thr)
+        torch.cuda.synchronize()
+        assert dep.shape == alp.shape == (2048, max_sample)
+        dep_o, alp_o = oracle.surf_trav_scalar(og, opts, o.cpu(), d.cpu(), "extract_pts", thr, xf=xf, max_sample=max_sample)
+        _close(dep.cpu().numpy(), dep_o, "thresh_depth", "depths vs oracle")
+        _close(alp.cpu().numpy(), alp_o, "thresh_alpha", "alphas vs oracle")
+        assert np.count_nonzero(dep_o[:, 1]) > 0      # some rays have a second sample
+        if ref is not None:
+            dep_r, alp_r = ref.extract_pts_surf_trav(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts),
+                                                     max_sample, thr)
+            _close(dep.cpu().numpy(), dep_r.cpu().numpy(), "thresh_depth", "depths vs reference")
+            _close(alp.cpu().numpy(), alp_r.cpu().numpy(), "thresh_alpha", "alphas vs reference")
+
+
 def test_scalar_renders_leave_training_pyramid_alone():
     """An evaluation render between two training renders must not disturb the cached work pyramid of the trainer."""
     from alphasurf_b200 import capi
