@@ -443,6 +443,91 @@ def accel_dist_prop(links):
     links.add_(0)   # torch bumps tensor._version only for its own ops: force it so that cached pyramids are rebuilt
 
 
+def dilate(grid):
+    """3x3x3 OR of a 3-D bool tensor (misc_kernel.cu:1005-1020); returns a new tensor."""
+    _check_input(grid, "grid")
+    if grid.is_floating_point() or grid.dim() != 3:
+        raise RuntimeError("dilate expects a 3-D non-floating tensor")
+    if grid.dtype != torch.bool:
+        raise RuntimeError("dilate expects a bool tensor")     # the reference's accessor is bool as well
+    out = torch.empty_like(grid)
+    with torch.cuda.device(grid.device):
+        capi.check(capi.lib().asurf_dilate(capi.ptr(grid), capi.size3(grid.shape), capi.ptr(out), capi.current_stream()),
+                   "dilate")
+    return out
+
+
+def _f3(t):
+    return (C.c_float * 3)(*[float(v) for v in t.reshape(-1).tolist()[:3]])
+
+
+def _cam_args(cam):
+    _check_input(cam.c2w, "c2w")
+    if cam.ndc_coeffx > 0.0:
+        raise NotImplementedError("NDC cameras are outside the B200 hot path")
+    c2w = (C.c_float * 12)(*[float(v) for v in cam.c2w[:3, :4].reshape(-1).tolist()])
+    return (c2w, C.c_float(cam.fx), C.c_float(cam.fy), C.c_float(cam.cx), C.c_float(cam.cy), C.c_int32(int(cam.width)),
+            C.c_int32(int(cam.height)))
+
+
+def grid_weight_render(data, cam, step_size, stop_thresh, last_sample_opaque, offset, scaling, grid_weight_out):
+    """max rendering weight per vertex of a dense (X,Y,Z) sigma volume over the camera's pixels (misc_kernel.cu:1084-1111)"""
+    _check_input(data, "data")
+    _check_input(offset, "offset")
+    _check_input(scaling, "scaling")
+    _check_input(grid_weight_out, "grid_weight_out")
+    if data.dim() != 3 or tuple(grid_weight_out.shape) != tuple(data.shape):
+        raise RuntimeError("grid_weight_render expects (X,Y,Z) data and an output of the same shape")
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_grid_weight_render(capi.ptr(data), capi.size3(data.shape), _f3(offset), _f3(scaling),
+                                                       *_cam_args(cam), C.c_float(step_size), C.c_float(stop_thresh),
+                                                       C.c_int32(1 if last_sample_opaque else 0), capi.ptr(grid_weight_out),
+                                                       capi.current_stream()), "grid_weight_render")
+
+
+def sparse_grid_weight_render(grid, cam, step_size, stop_thresh, offset, scaling, grid_weight_out):
+    """max transmittance reaching each vertex, marched through the sparse grid (misc_kernel.cu:1113-1138)"""
+    _check_grid(grid)
+    _check_input(offset, "offset")
+    _check_input(scaling, "scaling")
+    _check_input(grid_weight_out, "grid_weight_out")
+    if tuple(grid_weight_out.shape) != tuple(grid.links.shape):
+        raise RuntimeError("sparse_grid_weight_render expects an output shaped like links")
+    with torch.cuda.device(grid.links.device):
+        capi.check(capi.lib().asurf_sparse_grid_weight_render(capi.ptr(grid.links), capi.ptr(grid.density_data),
+                                                              capi.size3(grid.links.shape), _f3(offset), _f3(scaling),
+                                                              *_cam_args(cam), C.c_float(step_size), C.c_float(stop_thresh),
+                                                              capi.ptr(grid_weight_out), capi.current_stream()),
+                   "sparse_grid_weight_render")
+
+
+def sparse_grid_mask_render(grid, rays, near_clip, grid_mask):
+    """rows of the voxels the rays pass through are set to 1 in the float tensor grid_mask (N,) (misc_kernel.cu:1158-1175)"""
+    _check_grid(grid)
+    _check_rays(rays)
+    _check_input(grid_mask, "grid_mask")
+    with torch.cuda.device(grid.links.device):
+        capi.check(capi.lib().asurf_sparse_grid_mask_render(capi.ptr(grid.links), capi.size3(grid.links.shape),
+                                                            _f3(grid._offset), _f3(grid._scaling), capi.ptr(rays.origins),
+                                                            capi.ptr(rays.dirs), C.c_int64(rays.origins.shape[0]),
+                                                            C.c_float(near_clip), capi.ptr(grid_mask), capi.current_stream()),
+                   "sparse_grid_mask_render")
+
+
+def sparse_grid_visbility_render_surf(grid, cam, visibility_out):
+    """visibility_out (N,) += number of pixels whose ray reaches the vertex's voxel before its first surface intersection
+    (misc_kernel.cu:1140-1156; the name is the reference's spelling)"""
+    _check_grid(grid)
+    _check_input(visibility_out, "visibility_out")
+    if not _defined(grid.surface_data) or grid.surface_type == SURFACE_TYPE_NONE:
+        raise RuntimeError("sparse_grid_visbility_render_surf needs a grid with surface data")
+    with torch.cuda.device(grid.links.device):
+        capi.check(capi.lib().asurf_sparse_grid_visibility_render_surf(
+            capi.ptr(grid.links), capi.ptr(grid.surface_data), capi.ptr(grid.level_set_data),
+            C.c_int32(int(grid.level_set_data.shape[0])), capi.size3(grid.links.shape), _f3(grid._offset), _f3(grid._scaling),
+            *_cam_args(cam), capi.ptr(visibility_out), capi.current_stream()), "sparse_grid_visbility_render_surf")
+
+
 # ---- optimizer steps (optim_kernel.cu:154-267) -------------------------------------------------------------------------
 def _indexer(indexer):
     """-> (kind, pointer, n): 0 all rows (0-dim tensor), bool mask, int64 row list; n == 0 means skip."""
@@ -640,8 +725,7 @@ def _not_on_hot_path(name):
 
 
 for _name in ("sample_grid", "sample_grid_backward", "sample_grid_sh_surf", "sample_grid_raw_alpha", "cubic_extract_iso_pts",
-              "dilate", "grid_weight_render", "sparse_grid_weight_render",
-              "sparse_grid_visbility_render_surf", "sparse_grid_mask_render", "surface_normal_grad",
+              "surface_normal_grad",
               "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
               "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
               "volume_render_nvol", "volume_render_nvol_backward", "volume_render_nvol_fused", "volume_render_svox1",

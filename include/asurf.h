@@ -231,6 +231,33 @@ int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const 
  * accel_dist_prop, misc_kernel.cu:1022-1058: rewrites every negative entry of links (in place) with -(1 + number of empty
  * octree levels above the vertex), the skip codes the cuvol marcher reads. */
 int asurf_accel_dist_prop(int32_t *links, const int32_t size[3], void *stream);
+/* dilate, misc_kernel.cu:1005-1020: out = 3x3x3 OR of a bool (one byte per vertex) grid of the given size. */
+int asurf_dilate(const uint8_t *grid, const int32_t size[3], uint8_t *out, void *stream);
+/* Camera passes that decide which voxels to keep.  c2w_host: 12 floats, row-major 3x4, HOST memory (CameraSpec.c2w);
+ * offset / scaling: 3 host floats each (the reference passes them as device tensors).
+ * grid_weight_render, :1084-1111: data is a DENSE (X,Y,Z) sigma volume; grid_weight_out (X,Y,Z) takes, per vertex, the
+ * max over pixels of the rendering weight of a sample in an adjacent voxel (atomic max; the caller zero-fills it). */
+int asurf_grid_weight_render(const float *data, const int32_t size[3], const float offset[3], const float scaling[3],
+                             const float *c2w_host, float fx, float fy, float cx, float cy, int32_t width, int32_t height,
+                             float step_size, float stop_thresh, int32_t last_sample_opaque, float *grid_weight_out,
+                             void *stream);
+/* sparse_grid_weight_render, :1113-1138: same march through links / density (N,1); grid_weight_out (X,Y,Z) takes the max
+ * TRANSMITTANCE in front of the sample. */
+int asurf_sparse_grid_weight_render(const int32_t *links, const float *density, const int32_t size[3], const float offset[3],
+                                    const float scaling[3], const float *c2w_host, float fx, float fy, float cx, float cy,
+                                    int32_t width, int32_t height, float step_size, float stop_thresh, float *grid_weight_out,
+                                    void *stream);
+/* sparse_grid_mask_render, :1158-1175: grid_mask (N,) float rows of every stored vertex of a voxel some ray samples
+ * (step 0.1 voxel from max(t_enter, near_clip)) are set to 1. */
+int asurf_sparse_grid_mask_render(const int32_t *links, const int32_t size[3], const float offset[3], const float scaling[3],
+                                  const float *origins, const float *dirs, int64_t n_rays, float near_clip, float *grid_mask,
+                                  void *stream);
+/* sparse_grid_visbility_render_surf, :1140-1156: visibility_out (N,) += 1 per pixel for the stored vertices of every voxel
+ * the pixel's ray crosses up to and including the voxel of its first level-set intersection. */
+int asurf_sparse_grid_visibility_render_surf(const int32_t *links, const float *surface, const float *level_set,
+                                             int32_t level_set_num, const int32_t size[3], const float offset[3],
+                                             const float scaling[3], const float *c2w_host, float fx, float fy, float cx,
+                                             float cy, int32_t width, int32_t height, float *visibility_out, void *stream);
 
 /* ---- optimizer steps, optim_kernel.cu:154-267 ----
  * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */

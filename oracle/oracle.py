@@ -400,3 +400,48 @@ def accel_dist_prop(links):
         result[alive] -= 1
     links[xs, ys, zs] = result
     return links
+
+
+# ---- grid maintenance renders (oracle_gridtools.c, oracle_surf_trav.c) ---------------------------------------------------
+def cam_rays(c2w, fx, fy, cx, cy, width, height):
+    """cam2world_ray for every pixel in raster order -> (origins, dirs), each (H*W, 3)"""
+    c = np.ascontiguousarray(np.asarray(c2w, np.float32)[:3, :4].reshape(-1))
+    o = np.zeros((height * width, 3), np.float32)
+    d = np.zeros((height * width, 3), np.float32)
+    lib().oracle_cam_rays(_ptr(c), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_int(width), C.c_int(height),
+                          _ptr(o), _ptr(d))
+    return o, d
+
+
+def dilate(grid_bool):
+    g = np.ascontiguousarray(_np(grid_bool, np.uint8))
+    out = np.zeros_like(g)
+    lib().oracle_dilate(_ptr(g), _ptr(np.asarray(g.shape, np.int32)), _ptr(out))
+    return out.astype(bool)
+
+
+def weight_render(data, links, size, offset, scaling, origins, dirs, step_size, stop_thresh, last_sample_opaque, out):
+    """links None: dense (X,Y,Z) volume (grid_weight_render); else sparse (sparse_grid_weight_render).  out (X,Y,Z) max-updated."""
+    dat = _np(data, np.float32)
+    lk = None if links is None else _np(links, np.int32)
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    lib().oracle_weight_render(C.c_int(0 if lk is None else 1), _ptr(dat), _ptr(lk), _ptr(np.asarray(size, np.int32)),
+                               _ptr(_np(offset, np.float32)), _ptr(_np(scaling, np.float32)), _ptr(o), _ptr(d), None,
+                               C.c_int64(o.shape[0]), C.c_float(step_size), C.c_float(stop_thresh),
+                               C.c_int(1 if last_sample_opaque else 0), _ptr(out))
+    return out
+
+
+def mask_render(links, offset, scaling, origins, dirs, near_clip, out):
+    lk = _np(links, np.int32)
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    lib().oracle_mask_render(_ptr(lk), _ptr(np.asarray(lk.shape, np.int32)), _ptr(_np(offset, np.float32)),
+                             _ptr(_np(scaling, np.float32)), _ptr(o), _ptr(d), None, C.c_int64(o.shape[0]), C.c_float(near_clip),
+                             _ptr(out))
+    return out
+
+
+def visibility_surf(grid: Grid, origins, dirs, out):
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    lib().oracle_visibility_surf(C.byref(grid.c), _ptr(o), _ptr(d), None, C.c_int64(o.shape[0]), _ptr(out))
+    return out

@@ -9,6 +9,7 @@
  * and the helpers of include/render_util.cuh cited at each function.
  * One "warp" of the reference is one scalar loop here; per-lane work is a loop over the D SH lanes.
  */
+#include <string.h>
 #include "oracle_common.h"
 
 /* ---- include/render_util.cuh:789-848 surface_to_cubic_equation_01 ---- */
@@ -1000,6 +1001,69 @@ void oracle_surf_trav_scalar(const OGrid *g, const OOpt *opt, const float *origi
         float sphfunc[16];
         setup_ray(g, opt, origins + q * 3, dirs + q * 3, xf ? xf + q * 9 : NULL, &ray, sphfunc);
         trace_ray_scalar(g, &ray, opt, mode, param, max_sample, out + q * nout, out2 ? out2 + q * nout : NULL);
+    }
+}
+
+/* sparse_grid_visbility_trace_ray_surf, misc_kernel.cu:511-719: from t = 0 (no near clip), every voxel the DDA visits adds
+ * 1 to its stored corner rows, until the first in-voxel root of a level set.  xf: (Q,9) origin, dir, t, tmax, - as the GPU
+ * derived them, or NULL.  The reference leaves `ray.tmax` uninitialised where the DDA steps off the grid (:600-609); like
+ * the CUDA side here the march ends there. */
+void oracle_visibility_surf(const OGrid *g, const float *origins, const float *dirs, const float *xf, int64_t Q,
+                            float *visibility) {
+    const int offx = g->size[1] * g->size[2], offy = g->size[2];
+    for (int64_t q = 0; q < Q; ++q) {
+        ORay ray;
+        for (int i = 0; i < 3; ++i) { ray.origin[i] = origins[q * 3 + i]; ray.dir[i] = dirs[q * 3 + i]; }
+        if (xf) {
+            for (int i = 0; i < 3; ++i) { ray.origin[i] = xf[q * 9 + i]; ray.dir[i] = xf[q * 9 + 3 + i]; }
+            ray.tmin = xf[q * 9 + 6]; ray.tmax = xf[q * 9 + 7];
+        } else {
+            OOpt o0;
+            memset(&o0, 0, sizeof(o0));
+            o0.step_size = 1.f;
+            o_ray_find_bounds(&ray, g, &o0);   /* near_clip 0: tmin = max(0, AABB entry) */
+        }
+        if (ray.tmin > ray.tmax) continue;
+        double const ray_dir_d[3] = {ray.dir[0], ray.dir[1], ray.dir[2]};
+        float t = ray.tmin;
+        int32_t next_voxel[3];
+        for (int j = 0; j < 3; ++j) {
+            next_voxel[j] = (int32_t)fmaf(t, ray.dir[j], ray.origin[j]);
+            next_voxel[j] = o_mini(o_maxi(next_voxel[j], 0), g->size[j] - 2);
+        }
+        int hit = 0;
+        while (t <= ray.tmax && !hit) {
+            OStep s;
+            dda_step(g, &ray, next_voxel, &t, &s);
+            const int32_t *voxel_l = s.voxel_l;
+            const int32_t *lp = g->links + (offx * voxel_l[0] + offy * voxel_l[1] + voxel_l[2]);
+            const int u[8] = {0, 1, offy, offy + 1, offx, offx + 1, offx + offy, offx + offy + 1};
+            for (int k = 0; k < 8; ++k) if (lp[u[k]] >= 0) visibility[lp[u[k]]] += 1.f;
+            if (!voxel_links_ok(g, voxel_l, lp, offx, offy)) continue;
+            double new_origin[3], new_norm_origin[3], surface[8];
+            for (int k = 0; k < 3; ++k) {
+                new_origin[k] = fmaf(s.t_close, ray.dir[k], ray.origin[k]);
+                new_norm_origin[k] = new_origin[k] - voxel_l[k];
+            }
+            for (int k = 0; k < 8; ++k) surface[k] = g->surface[lp[u[k]]];
+            double fs[4];
+            surface_to_cubic_equation_01(surface, new_norm_origin, ray_dir_d, fs);
+            double smin = surface[0], smax = surface[0];
+            for (int k = 1; k < 8; ++k) { if (surface[k] < smin) smin = surface[k]; if (surface[k] > smax) smax = surface[k]; }
+            for (int i = 0; i < g->level_set_num && !hit; ++i) {
+                double const lv_set = g->level_set[i];
+                if ((lv_set < smin) || (lv_set > smax)) continue;
+                double st[3] = {-1, -1, -1};
+                cubic_equation_solver_vieta(fs[0] - lv_set, fs[1], fs[2], fs[3], 1e-10, st);
+                for (int j = 0; j < 3 && !hit; ++j) {
+                    if (st[j] <= 0) continue;
+                    float pos[3];
+                    for (int k = 0; k < 3; ++k) pos[k] = fmaf((float)st[j], ray.dir[k], (float)new_origin[k]) - (float)voxel_l[k];
+                    if ((pos[0] < 0) | (pos[0] > 1) | (pos[1] < 0) | (pos[1] > 1) | (pos[2] < 0) | (pos[2] > 1)) continue;
+                    hit = 1;
+                }
+            }
+        }
     }
 }
 
