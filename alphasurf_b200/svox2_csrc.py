@@ -528,6 +528,90 @@ def sparse_grid_visbility_render_surf(grid, cam, visibility_out):
             *_cam_args(cam), capi.ptr(visibility_out), capi.current_stream()), "sparse_grid_visbility_render_surf")
 
 
+# ---- point queries (svox2_kernel.cu:384-582) --------------------------------------------------------------------------------
+def _check_points(points):
+    _check_input(points, "points")
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("points must be (P, 3)")
+
+
+def _sample(grid, data, missing, points, name):
+    out = torch.empty((points.shape[0], data.shape[1]), dtype=points.dtype, device=points.device)
+    capi.check(capi.lib().asurf_sample_grid(capi.ptr(grid.links), capi.size3(grid.links.shape), _f3(grid._offset),
+                                            _f3(grid._scaling), capi.ptr(data), C.c_int32(int(data.shape[1])),
+                                            C.c_float(missing), capi.ptr(points), C.c_int64(points.shape[0]), capi.ptr(out),
+                                            capi.current_stream()), name)
+    return out
+
+
+def sample_grid(grid, points, want_colors):
+    """(density (P,1), sh (P,D) -- (0,D) unless want_colors) at world-space points; empty corners read 0"""
+    _check_grid(grid)
+    _check_points(points)
+    with torch.cuda.device(points.device):
+        dens = _sample(grid, grid.density_data, 0.0, points, "sample_grid")
+        sh = (_sample(grid, grid.sh_data, 0.0, points, "sample_grid") if want_colors
+              else torch.empty((0, grid.sh_data.shape[1]), dtype=points.dtype, device=points.device))
+    return dens, sh
+
+
+def sample_grid_sh_surf(grid, points, want_colors, want_surfaces, default_surf):
+    """(sh (P,D), surface (P,1)); empty corners read 0 for SH and default_surf for the surface"""
+    _check_grid(grid)
+    _check_points(points)
+    empty = lambda t: torch.empty((0, t.shape[1]), dtype=points.dtype, device=points.device)
+    with torch.cuda.device(points.device):
+        sh = _sample(grid, grid.sh_data, 0.0, points, "sample_grid_sh_surf") if want_colors else empty(grid.sh_data)
+        surf = (_sample(grid, grid.surface_data, float(default_surf), points, "sample_grid_sh_surf") if want_surfaces
+                else empty(grid.surface_data))
+    return sh, surf
+
+
+def sample_grid_raw_alpha(grid, points, empty_raw):
+    """raw opacity (P,1); empty corners read empty_raw"""
+    _check_grid(grid)
+    _check_points(points)
+    with torch.cuda.device(points.device):
+        return _sample(grid, grid.density_data, float(empty_raw), points, "sample_grid_raw_alpha")
+
+
+def sample_grid_backward(grid, points, grad_out_density, grad_out_sh, grad_density_out, grad_sh_out, want_colors):
+    _check_grid(grid)
+    _check_points(points)
+    for t, n in ((grad_out_density, "grad_out_density"), (grad_out_sh, "grad_out_sh"), (grad_density_out, "grad_density_out"),
+                 (grad_sh_out, "grad_sh_out")):
+        _check_input(t, n)
+    if grad_out_density.dim() != 2 or grad_out_sh.dim() != 2:
+        raise RuntimeError("sample_grid_backward expects 2-D output gradients")
+    args = (capi.ptr(grid.links), capi.size3(grid.links.shape), _f3(grid._offset), _f3(grid._scaling), capi.ptr(points),
+            C.c_int64(points.shape[0]))
+    with torch.cuda.device(points.device):
+        capi.check(capi.lib().asurf_sample_grid_backward(*args, capi.ptr(grad_out_density),
+                                                         C.c_int32(int(grad_density_out.shape[1])), capi.ptr(grad_density_out),
+                                                         capi.current_stream()), "sample_grid_backward")
+        if want_colors:
+            capi.check(capi.lib().asurf_sample_grid_backward(*args, capi.ptr(grad_out_sh), C.c_int32(int(grad_sh_out.shape[1])),
+                                                             capi.ptr(grad_sh_out), capi.current_stream()),
+                       "sample_grid_backward")
+
+
+def cubic_extract_iso_pts(links, level_data, mask_data, cell_ids, n_sample, density_thresh):
+    """zero crossings of the level function along 3 n_sample^2 lattice lines per cell, (n_cells, 3 n_sample^2, 3) in grid
+    coordinates, zeros where there is none (svox2_kernel.cu:542-582; svox2.py:4537)"""
+    for t, n in ((level_data, "level_data"), (mask_data, "mask_data"), (links, "links"), (cell_ids, "cell_ids")):
+        _check_input(t, n)
+    if links.dtype != torch.int32 or cell_ids.dtype != torch.int32:
+        raise RuntimeError("links and cell_ids must be int32")
+    n_sample = int(n_sample)
+    out = torch.zeros((cell_ids.shape[0], 3 * n_sample * n_sample, 3), dtype=level_data.dtype, device=level_data.device)
+    with torch.cuda.device(level_data.device):
+        capi.check(capi.lib().asurf_cubic_extract_iso_pts(capi.ptr(links), capi.size3(links.shape), capi.ptr(level_data),
+                                                          capi.ptr(mask_data), capi.ptr(cell_ids), C.c_int64(cell_ids.shape[0]),
+                                                          C.c_int32(n_sample), C.c_float(density_thresh), capi.ptr(out),
+                                                          capi.current_stream()), "cubic_extract_iso_pts")
+    return out
+
+
 # ---- optimizer steps (optim_kernel.cu:154-267) -------------------------------------------------------------------------
 def _indexer(indexer):
     """-> (kind, pointer, n): 0 all rows (0-dim tensor), bool mask, int64 row list; n == 0 means skip."""
@@ -724,8 +808,7 @@ def _not_on_hot_path(name):
     return fn
 
 
-for _name in ("sample_grid", "sample_grid_backward", "sample_grid_sh_surf", "sample_grid_raw_alpha", "cubic_extract_iso_pts",
-              "surface_normal_grad",
+for _name in ("surface_normal_grad",
               "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
               "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
               "volume_render_nvol", "volume_render_nvol_backward", "volume_render_nvol_fused", "volume_render_svox1",

@@ -259,6 +259,24 @@ int asurf_sparse_grid_visibility_render_surf(const int32_t *links, const float *
                                              const float scaling[3], const float *c2w_host, float fx, float fy, float cx,
                                              float cy, int32_t width, int32_t height, float *visibility_out, void *stream);
 
+/* ---- point queries, svox2_kernel.cu:384-582 ----
+ * Trilinear gather of one (N, n_cols) tensor at n_points world-space points (P,3); corners without a stored vertex read
+ * `missing`.  Serves sample_grid (density with 0, SH with 0), sample_grid_sh_surf (surface with default_surf) and
+ * sample_grid_raw_alpha (density with empty_raw); out is (P, n_cols). */
+int asurf_sample_grid(const int32_t *links, const int32_t size[3], const float offset[3], const float scaling[3],
+                      const float *data, int32_t n_cols, float missing, const float *points, int64_t n_points, float *out,
+                      void *stream);
+/* sample_grid_backward, :491-539: grad_data (N, n_cols) += transposed gather of grad_out (P, n_cols). */
+int asurf_sample_grid_backward(const int32_t *links, const int32_t size[3], const float offset[3], const float scaling[3],
+                               const float *points, int64_t n_points, const float *grad_out, int32_t n_cols,
+                               float *grad_data, void *stream);
+/* cubic_extract_iso_pts, :542-582: for each listed cell (flat vertex id, all 8 corners stored) and each of the 3 n_sample^2
+ * axis-parallel lattice lines through it, the first zero of the trilinear level function in [0,1] whose interpolated
+ * mask value is >= density_thresh, in grid coordinates; out is (n_cells, 3 n_sample^2, 3), zero where there is none. */
+int asurf_cubic_extract_iso_pts(const int32_t *links, const int32_t size[3], const float *level_data, const float *mask_data,
+                                const int32_t *cell_ids, int64_t n_cells, int32_t n_sample, float density_thresh, float *out,
+                                void *stream);
+
 /* ---- optimizer steps, optim_kernel.cu:154-267 ----
  * indexer_kind: 0 = all rows, 1 = bool mask (n rows), 2 = int64 row indices (n_index entries). */
 int asurf_rmsprop_step(float *data, float *rms, float *grad, int64_t n_rows, int32_t n_cols, int32_t indexer_kind,

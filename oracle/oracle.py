@@ -445,3 +445,29 @@ def visibility_surf(grid: Grid, origins, dirs, out):
     o, d = _np(origins, np.float32), _np(dirs, np.float32)
     lib().oracle_visibility_surf(C.byref(grid.c), _ptr(o), _ptr(d), None, C.c_int64(o.shape[0]), _ptr(out))
     return out
+
+
+# ---- point queries (svox2_kernel.cu:11-376) -------------------------------------------------------------------------------
+def sample_grid(links, offset, scaling, data, missing, points):
+    lk, dat, pts = _np(links, np.int32), _np(data, np.float32), _np(points, np.float32)
+    out = np.zeros((pts.shape[0], dat.shape[1]), np.float32)
+    lib().oracle_sample_grid(_ptr(lk), _ptr(np.asarray(lk.shape, np.int32)), _ptr(_np(offset, np.float32)),
+                             _ptr(_np(scaling, np.float32)), _ptr(dat), C.c_int(dat.shape[1]), C.c_float(missing), _ptr(pts),
+                             C.c_int64(pts.shape[0]), _ptr(out))
+    return out
+
+
+def sample_grid_backward(links, offset, scaling, points, grad_out, grad_data):
+    lk, pts, go = _np(links, np.int32), _np(points, np.float32), _np(grad_out, np.float32)
+    lib().oracle_sample_grid_backward(_ptr(lk), _ptr(np.asarray(lk.shape, np.int32)), _ptr(_np(offset, np.float32)),
+                                      _ptr(_np(scaling, np.float32)), _ptr(pts), C.c_int64(pts.shape[0]), _ptr(go),
+                                      C.c_int(go.shape[1]), _ptr(grad_data))
+    return grad_data
+
+
+def cubic_extract_iso_pts(links, level, maskv, cell_ids, n_sample, density_thresh):
+    lk, lv, mv, ids = _np(links, np.int32), _np(level, np.float32), _np(maskv, np.float32), _np(cell_ids, np.int32)
+    out = np.zeros((ids.shape[0], 3 * n_sample * n_sample, 3), np.float32)
+    lib().oracle_cubic_extract_iso_pts(_ptr(lk), _ptr(np.asarray(lk.shape, np.int32)), _ptr(lv), _ptr(mv), _ptr(ids),
+                                       C.c_int64(ids.shape[0]), C.c_int(n_sample), C.c_float(density_thresh), _ptr(out))
+    return out

@@ -137,3 +137,54 @@ void oracle_mask_render(const int32_t *links, const int32_t *size, const float *
         }
     }
 }
+
+/* ---- point queries, svox2_kernel.cu:11-246 ---- */
+static void sp_locate(const int32_t *size, const float *offset, const float *scaling, const float *pt, int32_t *l, float *w) {
+    for (int i = 0; i < 3; ++i) {
+        float p = fmaf(pt[i], scaling[i], offset[i]);
+        p = fminf(fmaxf(p, 0.f), size[i] - 1.f);
+        l[i] = o_mini((int32_t)p, size[i] - 2);
+        w[i] = p - (float)l[i];
+    }
+}
+
+void oracle_sample_grid(const int32_t *links, const int32_t *size, const float *offset, const float *scaling, const float *data,
+                        int n_cols, float missing, const float *points, int64_t n_points, float *out) {
+    const int offy = size[2], offx = size[1] * size[2];
+    for (int64_t p = 0; p < n_points; ++p) {
+        int32_t l[3];
+        float w[3];
+        sp_locate(size, offset, scaling, points + p * 3, l, w);
+        const int32_t *lp = links + ((int64_t)offx * l[0] + (int64_t)offy * l[1] + l[2]);
+        for (int idx = 0; idx < n_cols; ++idx) {
+#define RD(u) ((lp[u] >= 0) ? data[(int64_t)lp[u] * n_cols + idx] : missing)
+            const float ix0y0 = o_lerp(RD(0), RD(1), w[2]), ix0y1 = o_lerp(RD(offy), RD(offy + 1), w[2]);
+            const float ix0 = o_lerp(ix0y0, ix0y1, w[1]);
+            const float ix1y0 = o_lerp(RD(offx), RD(offx + 1), w[2]), ix1y1 = o_lerp(RD(offy + offx), RD(offy + offx + 1), w[2]);
+            const float ix1 = o_lerp(ix1y0, ix1y1, w[1]);
+#undef RD
+            out[p * n_cols + idx] = o_lerp(ix0, ix1, w[0]);
+        }
+    }
+}
+
+void oracle_sample_grid_backward(const int32_t *links, const int32_t *size, const float *offset, const float *scaling,
+                                 const float *points, int64_t n_points, const float *grad_out, int n_cols, float *grad_data) {
+    const int offy = size[2], offx = size[1] * size[2];
+    for (int64_t p = 0; p < n_points; ++p) {
+        int32_t l[3];
+        float w[3];
+        sp_locate(size, offset, scaling, points + p * 3, l, w);
+        const int32_t *lp = links + ((int64_t)offx * l[0] + (int64_t)offy * l[1] + l[2]);
+        const int u[8] = {0, 1, offy, offy + 1, offx, offx + 1, offx + offy, offx + offy + 1};
+        for (int idx = 0; idx < n_cols; ++idx) {
+            const float go = grad_out[p * n_cols + idx];
+            const float xb = w[0], yb = w[1], zb = w[2], xa = 1.f - w[0], ya = 1.f - w[1], za = 1.f - w[2];
+            const float xago = xa * go, xbgo = xb * go;
+            const float t00 = ya * xago, t01 = yb * xago, t10 = ya * xbgo, t11 = yb * xbgo;
+            const float c[8] = {t00 * za, t00 * zb, t01 * za, t01 * zb, t10 * za, t10 * zb, t11 * za, t11 * zb};
+            for (int q = 0; q < 8; ++q)
+                if (lp[u[q]] >= 0) grad_data[(int64_t)lp[u[q]] * n_cols + idx] += c[q];
+        }
+    }
+}

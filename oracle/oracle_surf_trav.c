@@ -1067,6 +1067,56 @@ void oracle_visibility_surf(const OGrid *g, const float *origins, const float *d
     }
 }
 
+/* cubic_extract_iso_pts_kernel, svox2_kernel.cu:248-376 */
+void oracle_cubic_extract_iso_pts(const int32_t *links, const int32_t *size, const float *level, const float *maskv,
+                                  const int32_t *cell_ids, int64_t n_cells, int n_sample, float density_thresh, float *out) {
+    const int offy = size[2], offx = size[1] * size[2];
+    for (int64_t tid = 0; tid < n_cells; ++tid) {
+        const int xyz = cell_ids[tid];
+        const int z = xyz % size[2], xy = xyz / size[2], y = xy % size[1], x = xy / size[1];
+        if ((x >= size[0] - 1) || (y >= size[1] - 1) || (z >= size[2] - 1)) continue;
+        const int32_t *lp = links + ((int64_t)offx * x + (int64_t)offy * y + z);
+        const int u[8] = {0, 1, offy, offy + 1, offx, offx + 1, offx + offy, offx + offy + 1};
+        int ok = 1;
+        for (int k = 0; k < 8; ++k) ok &= (lp[u[k]] >= 0);
+        if (!ok) continue;
+        double surface[8];
+        float mv[8];
+        for (int k = 0; k < 8; ++k) { surface[k] = level[lp[u[k]]]; mv[k] = maskv[lp[u[k]]]; }
+        const float step_size = 1.f / (n_sample - 1);
+        for (int i = 0; i < n_sample; ++i) {
+            const float pos1 = i * step_size;
+            for (int j = 0; j < n_sample; ++j) {
+                const float pos2 = j * step_size;
+                for (int dir_id = 0; dir_id < 3; ++dir_id) {
+                    double dirs[3] = {0., 0., 0.}, origin[3] = {0., 0., 0.};
+                    if (dir_id == 0) { dirs[0] = 1.; origin[1] = pos1; origin[2] = pos2; }
+                    else if (dir_id == 1) { dirs[1] = 1.; origin[0] = pos1; origin[2] = pos2; }
+                    else { dirs[2] = 1.; origin[0] = pos1; origin[1] = pos2; }
+                    double fs[4], st[3] = {-1, -1, -1};
+                    surface_to_cubic_equation_01(surface, origin, dirs, fs);
+                    cubic_equation_solver_vieta(fs[0], fs[1], fs[2], fs[3], 1e-10, st);
+                    for (int st_i = 0; st_i < 3; ++st_i) {
+                        if ((st[st_i] >= 0.) && (st[st_i] <= 1.)) {
+                            const float pt[3] = {(float)(origin[0] + dirs[0] * st[st_i]), (float)(origin[1] + dirs[1] * st[st_i]),
+                                                 (float)(origin[2] + dirs[2] * st[st_i])};
+                            const float ix0y0 = o_lerp(mv[0], mv[1], pt[2]), ix0y1 = o_lerp(mv[2], mv[3], pt[2]);
+                            const float ix0 = o_lerp(ix0y0, ix0y1, pt[1]);
+                            const float ix1y0 = o_lerp(mv[4], mv[5], pt[2]), ix1y1 = o_lerp(mv[6], mv[7], pt[2]);
+                            const float ix1 = o_lerp(ix1y0, ix1y1, pt[1]);
+                            if (o_lerp(ix0, ix1, pt[0]) >= density_thresh) {
+                                float *o = out + (tid * 3 * n_sample * n_sample + i * n_sample * 3 + j * 3 + dir_id) * 3;
+                                o[0] = pt[0] + x; o[1] = pt[1] + y; o[2] = pt[2] + z;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 int oracle_cubic_solve(const double *fs, double *st) {
     st[0] = st[1] = st[2] = -1;
     return cubic_equation_solver_vieta(fs[0], fs[1], fs[2], fs[3], 1e-10, st);
