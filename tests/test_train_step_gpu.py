@@ -77,7 +77,6 @@ def test_incremental_work_pyramid_equals_full_rebuild():
         ts = S.TrainStep(ours, sg, hyper=hp)
         Q = 8192
         out = torch.zeros((Q, 3), device="cuda")
-        words = (reso // 4 + (1 if (reso - 1) % 4 else 0)) ** 3      # generous: only the first `n3` words are compared
         n3 = L.asurf_accel_words(capi.size3(sg.links.shape))
         cached = torch.zeros((n3,), dtype=torch.int64, device="cuda")
         full = torch.zeros((n3,), dtype=torch.int64, device="cuda")
