@@ -36,6 +36,9 @@ class GradExchange:
         self.last_rows = 0
         self._pending = None
         self._hold = None
+        self._reg = None
+        self._group_b = None
+        self._side = None
 
     def _bucket(self, n, width, like):
         if self.bucket is None or self.bucket.shape[0] < n or self.bucket.shape[1] != width or self.bucket.device != like.device:
@@ -116,6 +119,73 @@ class GradExchange:
         n = self.begin(ts)
         self.end(ts)
         return n
+
+    # ---- the whole multi-GPU iteration ---------------------------------------------------------------------------------
+    def _lane_b(self, ts):
+        """buffers and communicator of the regulariser lane (created on first use; every rank does so at the same point)"""
+        if self._reg is None:
+            N = ts.grad["density"].shape[0]
+            dev = ts.grad["density"].device
+            buf = torch.zeros((2, N, 1), dtype=ts.grad["density"].dtype, device=dev)    # one bucket: density, surface
+            self._reg = dict(buf=buf, grad={"density": buf[0], "surface": buf[1]},
+                             mask=torch.zeros((N,), dtype=torch.bool, device=dev))
+            # a communicator of its own, so that the dense exchange of this lane and the sparse one of the render lane
+            # are not serialised on one NCCL stream
+            self._group_b = dist.new_group(ranks=list(range(self.world))) if self.group is None else self.group
+            self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+            if self._side is not None:
+                # build the cached occupancy pyramid of `links` now, on the main stream: afterwards both lanes only read it
+                from . import svox2_csrc
+                svox2_csrc.accel_for(ts.sg.links)
+                torch.cuda.synchronize(dev)
+        return self._reg
+
+    def step(self, ts, origins, dirs, rgb_gt, rgb_out, events=None):
+        """One training iteration on this rank's rays.  The regularisers depend on the parameters only, not on the render:
+        they run cell-sharded on a side stream into buffers of their own and their dense all-reduce (2 x N floats + N mask
+        bytes) proceeds on a second communicator WHILE the main stream renders, ORs the touched masks and exchanges the
+        touched rows (begin / end above with shard_regularisers off).  Both lanes join before the optimizer.
+        ``events``: optional 4 CUDA events recorded at start / after render + begin / after the join / after the optimizer."""
+        reg = self._lane_b(ts)
+        cuda = self._side is not None
+        if events:
+            events[0].record()
+        if cuda:
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)          # the previous optimizer step has updated the parameters
+            ctx = torch.cuda.stream(self._side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            reg["buf"].zero_()
+            reg["mask"].zero_()
+            if self.shard_regularisers:
+                ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
+                dist.all_reduce(reg["mask"].view(torch.uint8), op=dist.ReduceOp.MAX, group=self._group_b)
+                dist.all_reduce(reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
+            else:
+                ts.regularisers(grad=reg["grad"], mask=reg["mask"])     # every rank the whole lists: nothing to exchange
+        shard = self.shard_regularisers
+        self.shard_regularisers = False           # begin / end: the sparse exchange of the render gradients alone
+        try:
+            ts.render(origins, dirs, rgb_gt, rgb_out)
+            self.begin(ts)
+            if events:
+                events[1].record()
+            self.end(ts)
+        finally:
+            self.shard_regularisers = shard
+        if cuda:
+            torch.cuda.current_stream().wait_stream(self._side)
+        ts.grad["density"].add_(reg["grad"]["density"])
+        ts.grad["surface"].add_(reg["grad"]["surface"])
+        ts.mask.logical_or_(reg["mask"])
+        if events:
+            events[2].record()
+        ts.optimizer()
+        if events:
+            events[3].record()
 
 
 def allreduce_grads(G, group=None):

@@ -190,18 +190,19 @@ def run_ours(args, rank, world, local_rank):
 
     def device_step(o, d, gt, record=False):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if exchange is not None:
+            # render + sparse row exchange on this stream; cell-sharded regularisers + their dense exchange on a side stream
+            # and a second communicator, joined before the optimizer (alphasurf_b200/dist.py::GradExchange.step)
+            exchange.step(ts, o, d, gt, rgb_out, events=evs)
+            if record:
+                phase_ev.append(evs)
+            return
         if record:
             evs[0].record()
         ts.render(o, d, gt, rgb_out)
-        if exchange is not None:
-            exchange.begin(ts)    # mask OR + packed touched rows, all-reduce in flight during the regularisers
         if record:
             evs[1].record()
-        if exchange is not None:
-            ts.regularisers(exchange.rank, exchange.world)   # cell-sharded; end() sums the shards
-            exchange.end(ts)
-        else:
-            ts.regularisers()
+        ts.regularisers()
         if record:
             evs[2].record()
         ts.optimizer()
@@ -230,9 +231,9 @@ def run_ours(args, rank, world, local_rank):
         device_step(*dev_batches[i % NB])
     capi.check(L.asurf_profile_enable(ctypes.c_int32(args.steps)), "profile_enable")
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()      # BEFORE the barrier: its start-up sleep must not delay rank 0 against the other ranks
+    barrier()
     L.asurf_launch_count(ctypes.c_int32(1))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -408,7 +409,18 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries the one JSON line only: NCCL announces its version there when the first communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     try:
         run_ours(args, rank, world, local_rank)
     finally:

@@ -14,19 +14,24 @@ sl = slice(rank * Ql, (rank + 1) * Ql)
 ts = S.TrainStep(C, sg)
 C.set_loss_norm_rays(Qg)
 rgb = torch.zeros((Ql, 3), device=dev)
-ts.render(o[sl].contiguous(), d[sl].contiguous(), gt[sl].contiguous(), rgb)
 ex = adist.GradExchange(ts)
-n = ex.begin(ts)
-ts.regularisers(ex.rank, ex.world)
-ex.end(ts)
+ts.optimizer = lambda: None     # compare the gradients the optimizer would see
+for _ in range(2):              # twice: the second pass exercises the stream hand-over between iterations
+    for k in ts.grad:
+        ts.grad[k].zero_()
+    ex.step(ts, o[sl].contiguous(), d[sl].contiguous(), gt[sl].contiguous(), rgb)
+n = ex.last_rows
 torch.cuda.synchronize()
 res = {}
 if rank == 0:
     C.set_loss_norm_rays(None)
     ts1 = S.TrainStep(C, sg)
     rgb1 = torch.zeros((Qg, 3), device=dev)
-    ts1.render(o, d, gt, rgb1)
-    ts1.regularisers()
+    for _ in range(2):          # same number of passes: the random cell windows of the regularisers advance per pass
+        for k in ts1.grad:
+            ts1.grad[k].zero_()
+        ts1.render(o, d, gt, rgb1)
+        ts1.regularisers()
     torch.cuda.synchronize()
     rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
     res = {"world": world, "rows_exchanged": n, "mask_equal": bool(torch.equal(ts.mask, ts1.mask)),

@@ -131,3 +131,81 @@ def test_sharded_regularisers_sparse_world2():
 
 def test_sharded_regularisers_dense_world2():
     _run_sharded(1500, 27, 0.7)
+
+
+class _FakeStep:
+    """stands in for TrainStep in the protocol test of GradExchange.step: render / regularisers / optimizer are tensor ops"""
+
+    def __init__(self, rank, N, D, frac):
+        self.rank, self.N, self.D, self.frac = rank, N, D, frac
+        self.grad = {"density": torch.zeros((N, 1)), "surface": torch.zeros((N, 1)), "sh": torch.zeros((N, D))}
+        self.mask = torch.zeros((N,), dtype=torch.bool)
+        self.mask_sh = torch.zeros((N,), dtype=torch.bool)
+        self.seen = None
+
+    def render(self, o, d, gt, out):
+        st = _local_state(self.rank, self.N, self.D, self.frac)
+        self.mask.zero_()
+        for k in self.grad:
+            self.grad[k] += st.grad[k]
+        self.mask |= st.mask
+        self.mask_sh.copy_(self.mask)
+
+    @staticmethod
+    def reg_part(r, world, N):
+        g = torch.Generator().manual_seed(900 + r)
+        lo, hi = (N * r) // world, (N * (r + 1)) // world
+        dd, ds = torch.zeros((N, 1)), torch.zeros((N, 1))
+        dd[lo:hi] = torch.randn((hi - lo, 1), generator=g)
+        ds[lo:hi] = torch.randn((hi - lo, 1), generator=g)
+        m = torch.zeros((N,), dtype=torch.bool)
+        m[lo:hi] = True
+        return dd, ds, m
+
+    def regularisers(self, rank, world, grad=None, mask=None):
+        dd, ds, m = self.reg_part(rank, world, self.N)
+        grad["density"] += dd
+        grad["surface"] += ds
+        mask |= m
+
+    def optimizer(self):
+        self.seen = {k: v.clone() for k, v in self.grad.items()}, self.mask.clone(), self.mask_sh.clone()
+        for v in self.grad.values():
+            v.zero_()
+
+
+def _worker_step(rank, world, port, N, D, frac, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ts = _FakeStep(rank, N, D, frac)
+        ex = adist.GradExchange()
+        ok = True
+        for _ in range(2):       # two iterations: buffers of the regulariser lane are reused
+            ex.step(ts, None, None, None, None)
+            grads, mask, mask_sh = ts.seen
+            states = [_local_state(r, N, D, frac) for r in range(world)]
+            regs = [_FakeStep.reg_part(r, world, N) for r in range(world)]
+            ok = ok and torch.equal(mask, torch.ones((N,), dtype=torch.bool))
+            ok = ok and torch.equal(mask_sh, torch.stack([s.mask for s in states]).any(0))
+            ok = ok and torch.allclose(grads["density"], sum(s.grad["density"] for s in states) + sum(x[0] for x in regs), atol=1e-6)
+            ok = ok and torch.allclose(grads["surface"], sum(s.grad["surface"] for s in states) + sum(x[1] for x in regs), atol=1e-6)
+            ok = ok and torch.allclose(grads["sh"], sum(s.grad["sh"] for s in states), atol=1e-6)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_step_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [mp.get_context("spawn").Process(target=_worker_step, args=(r, world, port, 3000, 12, 0.03, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world)), dict(ret)
