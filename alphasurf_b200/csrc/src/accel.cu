@@ -303,7 +303,7 @@ struct WorkCache {
     float sigma_thresh = 0.f;
     unsigned long long accel_gen = 0;
     bool valid = false;
-} g_wc;
+} g_wcs[2];   // [0] the training renderer's options, [1] the gate-free predicate of the evaluation renders
 
 unsigned long long g_accel_gen = 0;          // bumped by every asurf_accel_build
 const void *g_accel_last[16] = {nullptr};    // occupancy buffers built by this library and their generation
@@ -318,7 +318,9 @@ unsigned long long accel_generation(const void *accel) {
 }  // namespace
 
 // Work pyramid for the render call: incremental when the grid is the one of the previous call, full build otherwise.
-int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out) {
+int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out,
+                          int slot) {
+    WorkCache &g_wc = g_wcs[slot ? 1 : 0];
     AccelLayout lay(grid->size);
     const bool every_voxel = opt->surf_fake_sample && !opt->limited_fake_sample;
     const unsigned long long gen = accel_generation(grid->accel);
@@ -372,6 +374,7 @@ int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cuda
 }
 
 int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st) {
+    WorkCache &g_wc = g_wcs[0];
     ASURF_REQUIRE(g_wc.work.ptr && (size_t)words * sizeof(uint64_t) <= g_wc.work.bytes, ASURF_E_INVALID,
                   "work cache: nothing cached / size mismatch");
     return check_cuda(cudaMemcpyAsync(out, g_wc.work.ptr, (size_t)words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st),
@@ -379,8 +382,10 @@ int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st) {
 }
 
 void work_cache_release() {
-    g_wc.work.release(); g_wc.cls.release(); g_wc.inv.release(); g_wc.changed.release(); g_wc.ctr.release();
-    g_wc.valid = false;
+    for (WorkCache &g_wc : g_wcs) {
+        g_wc.work.release(); g_wc.cls.release(); g_wc.inv.release(); g_wc.changed.release(); g_wc.ctr.release();
+        g_wc.valid = false;
+    }
 }
 
 }  // namespace asurf
@@ -442,4 +447,4 @@ extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], ui
 extern "C" int asurf_debug_work_cache_copy(uint64_t *out, int64_t words, void *stream) {
     return work_cache_copy(out, words, (cudaStream_t)stream);
 }
-extern "C" int32_t asurf_debug_work_cache_valid(void) { return g_wc.valid ? 1 : 0; }
+extern "C" int32_t asurf_debug_work_cache_valid(void) { return g_wcs[0].valid ? 1 : 0; }

@@ -41,7 +41,8 @@ void note_launches(int n);
 unsigned long long launches_read(int reset);
 
 // work pyramid of a render call (accel.cu): incremental update of a cached pyramid when the grid is unchanged
-int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out);
+int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out,
+                          int slot = 0);
 void work_cache_release();
 int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st);
 

@@ -476,8 +476,8 @@ __device__ __forceinline__ void normal_pair_grad(const float *nh0, float rN0, co
     }
 }
 
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(LOSS_THREADS, MIN_BLOCKS)
+// 64 registers / 4 resident CTAs per SM measured 9 % faster than 78 registers / 3 CTAs (latency-bound gathers)
+__global__ void __launch_bounds__(LOSS_THREADS, 4)
 surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf,
                            const int32_t *__restrict__ cells, Dims d, int64_t Q, float lv_set, float scale, int con_check,
                            int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad,
@@ -930,8 +930,8 @@ static Workspace g_ws_flag;
 // The dense tiled variant of the normal loss is exact but, as measured on B200 (profiles/r1_ncu_full_normal_tile.txt), not
 // faster than the run-aggregated list kernel (2.2 ms vs 1.3 ms at 512^3): both are instruction-bound on the 48 corner
 // contributions per cell.  It stays behind this switch (tests exercise both) until its per-cell normals are shared.
-static int g_normal_tile = 0;   // bit 0: dense tile kernel for full lists, bit 1: 3 instead of 4 resident CTAs per SM (A/B timing)
-extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_normal_tile = enabled; }
+static int g_normal_tile = 0;   // 1: dense tile kernel for full lists (slower; kept for the comparison in profiles/)
+extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_normal_tile = enabled ? 1 : 0; }
 
 extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                                 const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
@@ -951,7 +951,7 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
         const int *flag = nullptr;
         AccelLayout lay(size);
         // a list that may be "every stored vertex" (at least a tenth of the grid): let the device decide which kernel runs
-        if ((g_normal_tile & 1) && accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 &&
+        if (g_normal_tile && accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 &&
             size[2] >= 16) {
             rc = g_ws_flag.reserve(sizeof(int));
             if (rc) return rc;
@@ -972,14 +972,9 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
             flag = (const int *)g_ws_flag.ptr;
             note_launches(2);
         }
-        if (g_normal_tile & 2)
-            surface_normal_runs_kernel<3><<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
-                links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-                grad_data, flag);
-        else
-            surface_normal_runs_kernel<4><<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
-                links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-                grad_data, flag);
+        surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
+            links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
+            grad_data, flag);
     } else
         surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
             links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1,

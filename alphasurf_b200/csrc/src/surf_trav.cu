@@ -1858,19 +1858,18 @@ extern "C" int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays
     rc = make_grid(grid, opt, false, st, g);
     if (rc) return rc;
     // work pyramid of the predicate these renders use: 8 stored corners and a level set within their range -- no density
-    // gate, no fake samples.  Built into its own buffer so that the training renderer's cached pyramid stays valid.
+    // gate, no fake samples.  Kept in a cache slot of its own (an image is rendered in many 5000-ray calls; each call only
+    // re-validates the pyramid against the data), so the training renderer's cached pyramid stays valid as well.
     {
         asurf_grid_t tmp = *grid;
         tmp.accel = g.accel;
         asurf_opt_t o2 = *opt;
         o2.sigma_thresh = -INFINITY;
         o2.surf_fake_sample = 0;
-        AccelLayout lay(grid->size);
-        rc = g_ws_work.reserve((size_t)lay.off[3] * sizeof(uint64_t));
+        const uint64_t *w = nullptr;
+        rc = work_pyramid_for_call(&tmp, &o2, st, &w, 1);
         if (rc) return rc;
-        rc = asurf_work_build(&tmp, &o2, (uint64_t *)g_ws_work.ptr, st);
-        if (rc) return rc;
-        g.work = (const uint64_t *)g_ws_work.ptr;
+        g.work = w;
     }
     const int64_t Q = rays->n_rays;
     const int blocks = (int)((Q + 127) / 128);

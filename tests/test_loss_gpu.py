@@ -56,14 +56,10 @@ def test_tv_and_tv_grad_dense(reso, ignore_edge):
         g_r = torch.zeros_like(sh)
         ref.tv_grad(links, sh, 1, D, 0.37, False, 2.0, ignore_edge, -1.0, -1.0, g_r)
         _close(grad, g_r.cpu(), "tv_grad vs reference CUDA")
-        if not ignore_edge:
-            # with ignore_edge the reference kernel returns early BEFORE its cub::BlockReduce (loss_kernel.cu:89, :113):
-            # exited threads leave stale partials in the reduction and its value is not reproducible (seen: 2 % off)
-            # and without it the threads past the end of the last block do the same (CUDA_GET_THREAD_ID returns before the
-            # reduction): the reference value wobbles by a few per cent from run to run, so it only bounds ours loosely --
-            # the exact check of the value is the one against the oracle above
-            tv_r = ref.tv(links, sh, 1, D, False, 2.0, ignore_edge, -1.0, -1.0)
-            assert abs(float(tv) - float(tv_r)) < 5e-2 * abs(float(tv_r))
+        # The VALUE of the reference's tv() is not compared: its kernel lets threads return before the cub::BlockReduce
+        # (ignore_edge at loss_kernel.cu:89, and CUDA_GET_THREAD_ID for the tail of the last block), so exited threads leave
+        # stale partials in the reduction -- seen on B200: 2-3 % off from run to run, and NaN.  The value is checked
+        # against the oracle above.
 
 
 @pytest.mark.parametrize("what", ["density", "sh"])
