@@ -443,12 +443,27 @@ __device__ __forceinline__ void accumulate_normal_grad(const float *g, float sca
     const float q = 0.25f * scale;
     const float a0 = q * g[0], a1 = q * g[1], a2 = q * g[2];
     const float u[4] = {-a0 - a1, -a0 + a1, a0 - a1, a0 + a1};   // index (i << 1) | j
+    float v[8];
+    unsigned all = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float val = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
+        v[k] = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
         const int col = ncol(OI + (k >> 2), OJ + ((k >> 1) & 1)), kk = OK + (k & 1);
-        A.a[col][kk] += val;                                       // adding an exact 0 changes nothing
-        A.touched |= (val != 0.f ? 1u : 0u) << (col * 3 + kk);     // but only non-zero contributions mark the row
+        A.a[col][kk] += v[k];                                      // adding an exact 0 changes nothing
+        all |= 1u << (col * 3 + kk);
+    }
+    // ... but only non-zero contributions mark the row (`val != 0` per corner in the reference).  An exact zero is rare:
+    // one min over the magnitudes decides whether all eight bits can be set at once (fminf drops NaNs, NaN != 0 holds).
+    const float m = fminf(fminf(fminf(fabsf(v[0]), fabsf(v[1])), fminf(fabsf(v[2]), fabsf(v[3]))),
+                          fminf(fminf(fabsf(v[4]), fabsf(v[5])), fminf(fabsf(v[6]), fabsf(v[7]))));
+    if (m != 0.f) {
+        A.touched |= all;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int col = ncol(OI + (k >> 2), OJ + ((k >> 1) & 1)), kk = OK + (k & 1);
+            A.touched |= (v[k] != 0.f ? 1u : 0u) << (col * 3 + kk);
+        }
     }
 }
 
@@ -481,7 +496,8 @@ __global__ void __launch_bounds__(LOSS_THREADS, 4)
 surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf,
                            const int32_t *__restrict__ cells, Dims d, int64_t Q, float lv_set, float scale, int con_check,
                            int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad,
-                           const int *__restrict__ tile_flag) {
+                           const int *__restrict__ tile_flag, int shz, int shy) {
+    // shz / shy: log2 of sz / sy when both are powers of two (flat id -> x, y, z by shifts), else -1
     constexpr unsigned FULLM = 0xffffffffu;
     __shared__ int32_t s_slot[LOSS_THREADS / 32][32];
     if (tile_flag && *tile_flag) return;   // the list is every stored vertex: surface_normal_tile_kernel does the work
@@ -501,7 +517,7 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
         const int32_t cid = cand ? __ldg(cells + pos + lane) : -2;
         int32_t cid_next = __shfl_down_sync(FULLM, cid, 1);
         if (lane == 31) cid_next = (pos + 32 < cend) ? __ldg(cells + pos + 32) : -2;
-        const unsigned cz = cand ? ((unsigned)cid % usz) : 0u;
+        const unsigned cz = cand ? (shz >= 0 ? ((unsigned)cid & (usz - 1u)) : ((unsigned)cid % usz)) : 0u;
         const bool is_end = cand && !((cid_next == cid + 1) && (cz + 1 < usz));
         const unsigned ends = __ballot_sync(FULLM, is_end);
         const int sl = lane + 2 * __popc(ends & ((1u << lane) - 1u));
@@ -525,8 +541,8 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
         const bool is_cell = (cellmask >> lane) & 1u;      // the slot is a list entry (otherwise a halo)
         int x = 0, y = 0;
         if (act) {   // flat ids are < 2^31: 32-bit divisions
-            const unsigned xy = (unsigned)id / usz;
-            x = (int)(xy / usy);
+            const unsigned xy = shz >= 0 ? ((unsigned)id >> shz) : ((unsigned)id / usz);
+            x = (int)(shz >= 0 ? (xy >> shy) : (xy / usy));
             y = (int)(xy - (unsigned)x * usy);
         }
         // slot L + 1 holds the vertices one step up in z
@@ -972,9 +988,12 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
             flag = (const int *)g_ws_flag.ptr;
             note_launches(2);
         }
+        auto log2_exact = [](int v) { int k = 0; while ((1 << k) < v) ++k; return (1 << k) == v ? k : -1; };
+        int shz = log2_exact(size[2]), shy = log2_exact(size[1]);
+        if (shz < 0 || shy < 0) shz = shy = -1;
         surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
             links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-            grad_data, flag);
+            grad_data, flag, shz, shy);
     } else
         surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
             links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1,

@@ -180,6 +180,40 @@ def test_surface_normal_grad_sparse(con_check, ignore_empty, use_l1):
         assert torch.equal(mask, m_r)
 
 
+@pytest.mark.parametrize("reso", [32, 28])        # power-of-two sizes decode the flat cell id by shifts
+def test_surface_normal_exact_zero_contributions(reso):
+    """Where neighbouring cells have IDENTICAL normals the loss direction is exactly zero and the reference's
+    `val != 0` test leaves the rows unmarked: a field that is linear in half of the grid and noisy in the other half
+    exercises both the all-non-zero fast path and the exact per-corner path of the mask."""
+    from oracle import oracle
+    sg = _grid(reso, variant="G")
+    lin = torch.nonzero(sg.links.reshape(-1) >= 0).flatten()
+    rows = sg.links.reshape(-1)[lin].long()
+    x, y, z = lin // (reso * reso), (lin // reso) % reso, lin % reso
+    flat = (0.25 * x + 0.5 * y - 0.125 * z).float()          # exactly representable: all cell normals identical
+    surf_c = sg.surface.clone()
+    half = x < reso // 2
+    surf_c[rows[half], 0] = flat[half]
+    cells_c = _cells(sg, 1.0, 2, True)
+    links, surf, cells = sg.links.cuda(), surf_c.cuda(), cells_c.cuda()
+    for use_l1 in (True, False):
+        grad = torch.zeros_like(surf)
+        mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+        ours.surface_normal_grad_sparse(links, surf, cells, mask, 0.0, 0, 1, 1e-2, 0.0, -1.0, -1.0, False, False, use_l1, grad)
+        g_o = np.zeros(tuple(surf_c.shape), np.float32)
+        m_o = np.zeros((sg.capacity,), np.uint8)
+        oracle.surface_normal_grad_sparse(sg.links, surf_c, cells_c, m_o, 0.0, 0, 1, 1e-2, False, False, use_l1, g_o)
+        _close(grad, g_o, "normal loss with exact zeros")
+        assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+        assert 0 < int(m_o.sum()) < int((sg.links >= 0).sum())      # part of the rows stays unmarked
+        ref = H.load_reference_cuda()
+        if ref is not None:
+            g_r, m_r = torch.zeros_like(surf), torch.zeros_like(mask)
+            ref.surface_normal_grad_sparse(links, surf, cells, m_r, 0.0, 0, 1, 1e-2, 0.0, -1.0, -1.0, False, False, use_l1, g_r)
+            _close(grad, g_r.cpu(), "normal loss with exact zeros vs reference CUDA")
+            assert torch.equal(mask, m_r)
+
+
 def test_loss_kernels_at_full_size_properties():
     """512^3-sized property checks: the sparse TV gradient over ALL cells equals the dense TV gradient (same formula,
     scale/nl vs scale/n_cells normalisation accounted for), and gradients of a constant field vanish."""
