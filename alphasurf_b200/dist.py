@@ -195,3 +195,30 @@ def allreduce_grads(G, group=None):
     if G.surface is not None:
         dist.all_reduce(G.surface, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(G.sh, op=dist.ReduceOp.SUM, group=group)
+
+
+def render_sharded(render_fn, origins, dirs, group=None, gather_to=None):
+    """Evaluation render of a ray set split over the ranks (a full image, pixels sharded).
+
+    ``render_fn(origins, dirs) -> (n, C)`` is any per-ray render of the csrc-compatible module bound to its grid and
+    options (``volume_render_surf_trav``, a depth / normal render, ...); every rank passes the SAME full ``origins`` /
+    ``dirs`` (Q, 3), renders the contiguous slice ``[rank * ceil(Q / world), ...)`` and the slices are concatenated in ray
+    order -- on every rank (``gather_to=None``, all-gather) or on rank ``gather_to`` only (the others get ``None``).
+    Rays are independent, so the result equals the single-process render bit for bit."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    Q = origins.shape[0]
+    per = (Q + world - 1) // world
+    lo, hi = min(rank * per, Q), min((rank + 1) * per, Q)
+    part = render_fn(origins[lo:hi].contiguous(), dirs[lo:hi].contiguous())
+    width = tuple(part.shape[1:])
+    if part.shape[0] < per:        # equal-sized slices for the collective; the padding is cut off below
+        pad = torch.zeros((per - part.shape[0],) + width, dtype=part.dtype, device=part.device)
+        part = torch.cat([part, pad])
+    part = part.contiguous()
+    if gather_to is None:
+        out = torch.empty((world * per,) + width, dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(out, part, group=group)
+        return out[:Q]
+    bufs = [torch.empty_like(part) for _ in range(world)] if rank == gather_to else None
+    dist.gather(part, bufs, dst=gather_to, group=group)
+    return torch.cat(bufs)[:Q] if rank == gather_to else None

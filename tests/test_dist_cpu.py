@@ -209,3 +209,37 @@ def test_overlapped_step_world2():
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _worker_render(rank, world, port, Q, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)
+        o, d = torch.randn((Q, 3), generator=g), torch.randn((Q, 3), generator=g)
+        fn = lambda a, b: torch.cat([a * 2.0 + b, (a * b).sum(1, keepdim=True)], dim=1)     # any per-ray function
+        want = fn(o, d)
+        full = adist.render_sharded(fn, o, d)
+        on0 = adist.render_sharded(fn, o, d, gather_to=0)
+        depth = adist.render_sharded(lambda a, b: (a * b).sum(1), o, d)                      # 1-D results (depth maps)
+        ok = torch.equal(full, want) and torch.equal(depth, (o * d).sum(1))
+        ok = ok and ((on0 is None) if rank != 0 else torch.equal(on0, want))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_sharded_world2():
+    for Q in (1001, 4):          # ragged split, and fewer rays than a full slice on the last rank
+        world = 2
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        port = _free_port()
+        procs = [mp.get_context("spawn").Process(target=_worker_render, args=(r, world, port, Q, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert all(ret.get(r) for r in range(world)), (Q, dict(ret))
