@@ -39,6 +39,8 @@ class GradExchange:
         self._reg = None
         self._group_b = None
         self._side = None
+        if ts is not None and hasattr(ts, "sg"):
+            self._lane_b(ts)     # buffers, side stream and second communicator up front (collective: every rank is here)
 
     def _bucket(self, n, width, like):
         if self.bucket is None or self.bucket.shape[0] < n or self.bucket.shape[1] != width or self.bucket.device != like.device:
