@@ -40,3 +40,27 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.GradsT) == 40
     assert ctypes.sizeof(capi.GridT) == 8 + 12 + 4 + 8 * 4 + 4 * 3 + 4 + 8 + 12 + 12 + 4 + 4 + 8 + 8
     assert ctypes.sizeof(capi.FusedT) == 18 * 4 + 8
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/asurf.h is the drop-in boundary: it must compile as C99 (no C++ or torch types) and link against the
+    library from a C translation unit."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text('#include "asurf.h"\n#include <stdio.h>\n'
+                   'int main(void) { int32_t sz[3] = {512, 512, 512};\n'
+                   '  printf("%d %lld\\n", (int)asurf_abi_version(), (long long)asurf_accel_words(sz)); return 0; }\n')
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                           "-I", os.path.join(root, "include"), str(src)])
+    lib = os.path.join(root, "alphasurf_b200", "csrc", "libasurf.so")
+    exe = tmp_path / "t"
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), lib, "-o", str(exe),
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) >= 1 and int(out[1]) == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2 + 1
