@@ -11,6 +11,8 @@ Deliberately absent (part of the contract): ``volume_render_surf_t
 """
 import ctypes as C
 
+import weakref
+
 import torch
 
 from . import capi
@@ -165,12 +167,14 @@ _ACCEL = {}
 
 
 def accel_for(links: torch.Tensor) -> torch.Tensor:
-    """Bitmap pyramid of ``links`` (built by asurf_accel_build); rebuilt when links is modified in place."""
+    """Bitmap pyramid of ``links`` (built by asurf_accel_build); rebuilt when links is modified in place or when another
+    tensor object turns up at the same address (the caching allocator hands freed blocks out again: a pruned grid's new
+    ``links`` may well land where the old one was, with the same shape and a fresh version counter)."""
     key = (links.data_ptr(), tuple(links.shape), links.device.index)
     ver = links._version
     hit = _ACCEL.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    if hit is not None and hit[0]() is links and hit[1] == ver:
+        return hit[2]
     L = capi.lib()
     words = L.asurf_accel_words(capi.size3(links.shape))
     acc = torch.empty((words,), dtype=torch.int64, device=links.device)
@@ -178,7 +182,7 @@ def accel_for(links: torch.Tensor) -> torch.Tensor:
                                    capi.current_stream(links.device)), "asurf_accel_build")
     if len(_ACCEL) > 8:
         _ACCEL.clear()
-    _ACCEL[key] = (ver, acc)
+    _ACCEL[key] = (weakref.ref(links), ver, acc)
     return acc
 
 

@@ -55,3 +55,25 @@ def test_render_options_round_trip_into_the_abi_struct():
     assert o.only_outward_intersect == 1 and o.truncated_vol_render == 1 and abs(o.trunc_vol_weight_min - 1e-10) < 1e-16
     f = capi.make_fused(synth.alphasurf_fused_args(), norm_rays=123)
     assert f.l_dist_max_sample == 64 and f.norm_rays == 123 and abs(f.lambda_conv_mode_samp - 1e-6) < 1e-12
+
+
+def test_accel_cache_is_keyed_by_tensor_identity(monkeypatch):
+    """The cached occupancy pyramid of `links` must not survive a NEW tensor at the same address (caching allocator reuse
+    after pruning), nor an in-place edit; it must survive repeated calls with the same tensor."""
+    import types
+    builds = []
+    fake = types.SimpleNamespace(asurf_accel_words=lambda sz: 8,
+                                 asurf_accel_build=lambda *a: builds.append(1) or 0)
+    monkeypatch.setattr(C.capi, "lib", lambda: fake)
+    monkeypatch.setattr(C.capi, "current_stream", lambda dev=None: None)
+    monkeypatch.setattr(C, "_ACCEL", {})
+    storage = torch.zeros((4, 4, 4), dtype=torch.int32)
+    a = C.accel_for(storage)
+    assert C.accel_for(storage) is a and len(builds) == 1          # same tensor, same version: cached
+    storage.add_(1)
+    b = C.accel_for(storage)
+    assert b is not a and len(builds) == 2                         # in-place edit: rebuilt
+    alias = storage.view(4, 4, 4)                                  # another tensor object on the same memory, same version
+    assert alias.data_ptr() == storage.data_ptr() and alias._version == storage._version
+    C.accel_for(alias)
+    assert len(builds) == 3                                        # not trusted: rebuilt
