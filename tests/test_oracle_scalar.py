@@ -69,3 +69,45 @@ def test_miss_and_thresholds():
     # thresholds above every alpha: nothing is reported
     assert oracle.surf_trav_scalar(og, opts, o, d, "thresh_depth", 1.5).max() == 0.0
     assert oracle.surf_trav_scalar(og, opts, o, d, "mode_term", 1.5).max() == 0.0
+
+
+def test_cuvol_depth_oracle_homogeneous_box():
+    """oracle_cuvol_scalar on a fully stored grid of constant sigma (a homogeneous box): the thresholded depth is the
+    distance to the box (to one step), the expected termination depth
+    lies about one mean free path behind the entry and equals the re-compositing of the med-term samples, which are equally
+    spaced by the world step."""
+    R = 24
+    links = torch.arange(R ** 3, dtype=torch.int32).reshape(R, R, R)
+    sigma = 3.0
+    dens = torch.full((R ** 3, 1), sigma)
+    sh = torch.zeros((R ** 3, 3))
+    gsz = torch.tensor([R, R, R], dtype=torch.float32)
+    sg = synth.SynthGrid(links, dens, None, sh, None, 0.5 * gsz, 0.5 * gsz, 1)
+    opts = synth.alphasurf_render_options()
+    opts.update(backend="cuvol", sigma_thresh=1e-8, stop_thresh=1e-7, step_size=0.5)
+    og = oracle.Grid(sg)
+    # rays along -z from above the box, spread over its top face
+    g = torch.Generator().manual_seed(5)
+    xy = (torch.rand((32, 2), generator=g) - 0.5) * 1.2
+    o = torch.cat([xy, torch.full((32, 1), 3.0)], dim=1)
+    d = torch.tensor([[0.0, 0.0, -1.0]]).repeat(32, 1)
+    # world <-> grid: p_grid = p * R/2 + R/2, the sampled volume spans grid [-0.5, R-0.5] -> world z in [-1 - 1/R, 1 - 1/R]
+    top = 1.0 - 1.0 / R
+    bottom = -1.0 - 1.0 / R
+    d0 = 3.0 - top
+    step_w = 0.5 / (R / 2.0)                      # step_size voxels in world units
+    depth = oracle.cuvol_scalar(og, opts, o, d, "sigma_thresh", 1.0)
+    assert np.abs(depth - d0).max() <= step_w * 1.01
+    dep, sig = oracle.cuvol_scalar(og, opts, o, d, "med_term", 0.0, 6)
+    np.testing.assert_allclose(np.diff(dep, axis=1), step_w, rtol=1e-4)
+    assert np.abs(sig[:, 1:] - sigma).max() < 1e-5          # interior samples see the constant density
+    e = oracle.cuvol_scalar(og, opts, o, d, "expected_term", 0.0)
+    # the expected depth re-composited from the per-sample depths / sigmas of med_term: weight_k = T_k (1 - exp(-ws sigma_k))
+    dep_all, sig_all = oracle.cuvol_scalar(og, opts, o, d, "med_term", 0.0, 80)
+    att = np.exp(-step_w * sig_all.astype(np.float64))
+    trans = np.cumprod(np.concatenate([np.ones((32, 1)), att[:, :-1]], axis=1), axis=1)
+    want = (trans * (1.0 - att) * dep_all).sum(1)
+    np.testing.assert_allclose(e, want, rtol=2e-5)
+    assert ((e > d0) & (e < d0 + 3.0 / sigma)).all()           # about one mean free path (1/sigma) behind the entry
+    m = oracle.cuvol_scalar(og, opts, o, d, "mode_term", 0.0)
+    assert np.abs(m - dep[:, 1]).max() <= step_w * 1.01     # heaviest sample: the first interior one
