@@ -314,6 +314,10 @@ def run_ours(args, rank, world, local_rank):
                                  if fwd_ms + bwd_ms > 0 else 0.0},
                      "counters_per_ray": {k: st[k] / Q for k in ("n_steps", "n_linked", "n_active", "n_samples")}},
         "step_phases": phases,
+        "step_phases_note": ("sequential: fused render | regularisers | optimizer" if world == 1 else
+                             "two lanes (dist.GradExchange.step): render_ms = render + mask OR + row pack on the main stream while the "
+                             "cell-sharded regularisers and their dense all-reduce run on a side stream; regularisers_ms = sparse row "
+                             "all-reduce wait + join of the lanes; optimizer_ms = RMSprop steps"),
         "render_only_rays_per_s": Q * world / ((fwd_ms + bwd_ms) * 1e-3) if fwd_ms + bwd_ms > 0 else None,
     }
     if world == 1 and not args.no_extras:
