@@ -64,3 +64,32 @@ def test_header_is_plain_c(tmp_path):
                            "-Wl,-rpath," + os.path.dirname(lib)])
     out = subprocess.check_output([str(exe)]).decode().split()
     assert int(out[0]) >= 1 and int(out[1]) == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2 + 1
+
+
+def test_ctypes_call_sites_pass_the_declared_number_of_arguments():
+    """ctypes does not check arity: every `...asurf_xxx(...)` call in the package, the tests and bench.py must pass exactly
+    as many arguments as include/asurf.h declares for that entry (the compiled shim gets this check from the C++ compiler)."""
+    import ast
+    src = open(os.path.join(ROOT, "include", "asurf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = {}
+    for m in re.finditer(r"\b(asurf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = m.group(2).strip()
+        declared[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    assert len(declared) > 40
+    files = [os.path.join(ROOT, "bench.py")]
+    for d in ("alphasurf_b200", "tests", "scratch"):
+        files += [os.path.join(ROOT, d, f) for f in os.listdir(os.path.join(ROOT, d)) if f.endswith(".py")]
+    checked, bad = 0, []
+    for path in files:
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in declared:
+                starred = sum(isinstance(a, ast.Starred) for a in node.args)
+                if starred:
+                    continue          # argument packs (camera tuples) are expanded at run time
+                checked += 1
+                if len(node.args) != declared[node.func.attr]:
+                    bad.append("%s:%d %s passes %d of %d" % (os.path.basename(path), node.lineno, node.func.attr, len(node.args),
+                                                            declared[node.func.attr]))
+    assert checked > 50, checked
+    assert not bad, bad
