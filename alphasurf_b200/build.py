@@ -31,7 +31,7 @@ def sources():
 
 
 def _deps():
-    hdrs = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cuh", ".h"))]
+    hdrs = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cuh", ".h", ".inl"))]
     hdrs += [os.path.join(INC, f) for f in os.listdir(INC)]
     return hdrs
 

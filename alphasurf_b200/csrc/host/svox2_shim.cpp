@@ -726,11 +726,12 @@ void surf_tv_grad_sparse(Tensor links, Tensor data, Tensor density_data, Tensor 
     const c10::cuda::CUDAGuard guard(data.device());
     int32_t sz[3];
     size3(links, sz);
+    Tensor acc = accel_for(links);
     check_rc(asurf_surf_tv_grad_sparse(links.data_ptr<int32_t>(), sz, data.data_ptr<float>(), (int32_t)data.size(1),
                                        density_data.data_ptr<float>(), (int32_t)density_data.size(1),
                                        rand_cells.data_ptr<int32_t>(), rand_cells.size(0), mask_ptr(mask_out), start_dim, end_dim,
                                        scale, ignore_edge, edge_value, ignore_last_z, alpha_dependency,
-                                       grad_data.data_ptr<float>(), stream_of(data)),
+                                       grad_data.data_ptr<float>(), (const uint64_t *)acc.data_ptr<int64_t>(), stream_of(data)),
              "surf_tv_grad_sparse");
 }
 void alpha_surf_sparsify_grad_sparse(Tensor links, Tensor alpha_data, Tensor surf_data, Tensor rand_cells, Tensor mask_out,

@@ -209,6 +209,71 @@ __global__ void __launch_bounds__(256) accel_list1_kernel(AccelLayout lay, uint6
     if (on) ((uint32_t *)(buf + lay.off[3] + 1))[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)w;
 }
 
+
+// List of the 16^3 VERTEX blocks (vertices [16b, 16b + 16) per axis) that hold a stored vertex, kept behind the stored-vertex
+// count: word = their number, then their indices as uint32 (2 per word).  The tiled regularisers (loss.cu) walk it: the
+// non-empty level-1 list above only names blocks with a COMPLETE cell, which a TV term does not need.
+__global__ void __launch_bounds__(256) vblock_list_kernel(const int32_t *__restrict__ links, int sx, int sy, int sz, int nby,
+                                                           int nbz, uint64_t *__restrict__ out) {
+    const int w = blockIdx.x;
+    const int bz = w % nbz, by = (w / nbz) % nby, bx = w / (nbz * nby);
+    const int x = bx * 16 + (threadIdx.x >> 4), y = by * 16 + (threadIdx.x & 15), z0 = bz * 16;
+    int any = 0;
+    if (x < sx && y < sy) {
+        const int32_t *p = links + ((int64_t)x * sy + y) * sz;
+        const int ze = (z0 + 16 < sz) ? z0 + 16 : sz;
+        for (int z = z0; z < ze; ++z) any |= (__ldg(p + z) >= 0) ? 1 : 0;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0 && any) {
+        const unsigned long long at = atomicAdd((unsigned long long *)out, 1ull);
+        ((uint32_t *)(out + 1))[at] = (uint32_t)w;
+    }
+}
+
+// Stored vertices per (x, y) column (warp per column), then their exclusive prefix sum in place (one CTA: the table has
+// X * Y + 1 entries and is rebuilt only when `links` changes).
+__global__ void __launch_bounds__(256) column_count_kernel(const int32_t *__restrict__ links, int64_t n_cols, int sz,
+                                                            uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; col < n_cols;
+         col += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int32_t *p = links + col * sz;
+        unsigned c = 0;
+        for (int z = lane; z < sz; z += 32) c += (__ldg(p + z) >= 0) ? 1u : 0u;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (lane == 0) out[col] = c;
+    }
+}
+__global__ void __launch_bounds__(1024) column_prefix_kernel(uint32_t *__restrict__ tab, int64_t n_cols) {
+    // in: tab[i] = count of column i (i < n_cols); out: tab[i] = sum of the counts of the columns below i, tab[n_cols] = total
+    __shared__ unsigned s_part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n_cols + 1023) / 1024;
+    const int64_t b = (int64_t)t * per, e = (b + per < n_cols) ? b + per : n_cols;
+    unsigned sum = 0;
+    for (int64_t i = b; i < e; ++i) sum += tab[i];
+    s_part[t] = sum;
+    __syncthreads();
+    if (t == 0) {
+        unsigned run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const unsigned v = s_part[i];
+            s_part[i] = run;
+            run += v;
+        }
+        tab[n_cols] = run;
+    }
+    __syncthreads();
+    unsigned run = s_part[t];
+    for (int64_t i = b; i < e; ++i) {
+        const unsigned v = tab[i];
+        tab[i] = run;
+        run += v;
+    }
+}
+
 // ---- incremental maintenance of the work pyramid across calls -------------------------------------------------------------
 // A voxel's work bit is a function of its 8 corner vertices through three per-vertex predicates only:
 // (surface < lv), (surface > lv) [smin <= lv <= smax  <=>  not all corners > lv and not all < lv] and (density >= sigma_thresh).
@@ -416,7 +481,9 @@ extern "C" int asurf_work_build(const asurf_grid_t *grid, const asurf_opt_t *opt
 
 extern "C" int64_t asurf_accel_words(const int32_t size[3]) {
     AccelLayout lay(size);
-    return lay.off[3] + 1 + (lay.count(1) + 1) / 2 + 1;   // pyramid + list of non-empty level-1 blocks + stored-vertex count
+    // pyramid + list of non-empty level-1 blocks + stored-vertex count + list of the vertex blocks with a stored vertex
+    // + per-column prefix counts of the stored vertices
+    return accel_total_words(size);
 }
 
 extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], uint64_t *accel_out, void *stream) {
@@ -440,7 +507,15 @@ extern "C" int asurf_accel_build(const int32_t *links, const int32_t size[3], ui
     uint64_t *n_stored = accel_out + lay.off[3] + 1 + (lay.count(1) + 1) / 2;
     ASURF_CUDA(cudaMemsetAsync(n_stored, 0, sizeof(uint64_t), st));
     count_stored_kernel<<<148 * 8, 256, 0, st>>>(links, (int64_t)size[0] * size[1] * size[2], (unsigned long long *)n_stored);
-    note_launches(5);
+    uint64_t *vbl = accel_out + accel_vblock_offset(size);
+    ASURF_CUDA(cudaMemsetAsync(vbl, 0, sizeof(uint64_t), st));
+    const int nby = (size[1] + 15) / 16, nbz = (size[2] + 15) / 16;
+    vblock_list_kernel<<<(unsigned)accel_vblock_count(size), 256, 0, st>>>(links, size[0], size[1], size[2], nby, nbz, vbl);
+    uint32_t *colp = (uint32_t *)(accel_out + accel_colprefix_offset(size));
+    const int64_t n_columns = (int64_t)size[0] * size[1];
+    column_count_kernel<<<148 * 8, 256, 0, st>>>(links, n_columns, size[2], colp);
+    column_prefix_kernel<<<1, 1024, 0, st>>>(colp, n_columns);
+    note_launches(8);
     return check_cuda(cudaGetLastError(), "accel_build launch");
 }
 

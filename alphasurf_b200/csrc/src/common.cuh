@@ -44,6 +44,9 @@ unsigned long long launches_read(int reset);
 int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out,
                           int slot = 0);
 void work_cache_release();
+void loss_release();    // per-file workspaces, freed by asurf_release
+void cuvol_release();
+void misc_release();
 int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st);
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -70,5 +73,24 @@ struct AccelLayout {
     }
     __host__ __device__ int64_t count(int l) const { return off[l + 1] - off[l]; }
 };
+
+// Tail of the occupancy buffer (asurf_accel_build): [pyramid | n level-1 blocks, their list | n stored vertices |
+// n vertex blocks with a stored vertex, their list].  Word offsets of the last two parts:
+static inline int64_t accel_stored_offset(const int32_t size[3]) {
+    AccelLayout lay(size);
+    return lay.off[3] + 1 + (lay.count(1) + 1) / 2;
+}
+static inline int64_t accel_vblock_offset(const int32_t size[3]) { return accel_stored_offset(size) + 1; }
+static inline int64_t accel_vblock_count(const int32_t size[3]) {
+    return (int64_t)((size[0] + 15) / 16) * ((size[1] + 15) / 16) * ((size[2] + 15) / 16);
+}
+// ... followed by the exclusive prefix count of stored vertices per (x, y) column: X * Y + 1 uint32 (the number of stored
+// vertices with a flat id below any bound is then one table read plus a partial column)
+static inline int64_t accel_colprefix_offset(const int32_t size[3]) {
+    return accel_vblock_offset(size) + 1 + (accel_vblock_count(size) + 1) / 2;
+}
+static inline int64_t accel_total_words(const int32_t size[3]) {
+    return accel_colprefix_offset(size) + ((int64_t)size[0] * size[1] + 2) / 2;
+}
 
 }  // namespace asurf

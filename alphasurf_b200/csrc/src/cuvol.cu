@@ -409,6 +409,7 @@ int cv_make_grid(const asurf_grid_t *grid, CvGrid &g, const char *who) {
 inline int cv_blocks(int64_t Q) { return (int)((Q * 32 + CV_THREADS - 1) / CV_THREADS); }
 
 }  // namespace
+void cuvol_release() { g_ws_lt.release(); }
 }  // namespace asurf
 
 using namespace asurf;

@@ -187,8 +187,10 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 tv_grad_sparse_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols,
                            const float *__restrict__ density, int density_cols, const int32_t *__restrict__ cells, Dims d,
                            int idx, float scale, int64_t Q, int ignore_edge, float edge_value, int ignore_last_z,
-                           int alpha_dependency, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+                           int alpha_dependency, uint8_t *__restrict__ mask, float *__restrict__ grad,
+                           const int *__restrict__ verdict_bad) {
     constexpr unsigned FULLM = 0xffffffffu;
+    if (verdict_bad && *verdict_bad == 0) return;   // the list is a window of the stored vertices: tv_tile_kernel does the work
     float sc[3];
     ray_scale(d, sc);
     const int64_t offx = (int64_t)d.sy * d.sz;
@@ -496,11 +498,11 @@ __global__ void __launch_bounds__(LOSS_THREADS, 4)
 surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf,
                            const int32_t *__restrict__ cells, Dims d, int64_t Q, float lv_set, float scale, int con_check,
                            int ignore_empty, int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad,
-                           const int *__restrict__ tile_flag, int shz, int shy) {
+                           const int *__restrict__ verdict_bad, int shz, int shy) {
     // shz / shy: log2 of sz / sy when both are powers of two (flat id -> x, y, z by shifts), else -1
     constexpr unsigned FULLM = 0xffffffffu;
     __shared__ int32_t s_slot[LOSS_THREADS / 32][32];
-    if (tile_flag && *tile_flag) return;   // the list is every stored vertex: surface_normal_tile_kernel does the work
+    if (verdict_bad && *verdict_bad == 0) return;   // the list is a window of the stored vertices: normal_tile_kernel does the work
     const int lane = threadIdx.x & 31;
     int32_t *slot = s_slot[threadIdx.x >> 5];
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -665,165 +667,396 @@ surface_normal_runs_kernel(const int32_t *__restrict__ links, const float *__res
     }
 }
 
-// ---- the same loss when the list is "every stored vertex" (norm_surface_sparsity = 1, the alpha-Surf training config) ------
-// Then the work is dense over the occupied part of the grid: one CTA per non-empty 16^3-cell block (the block list behind
-// the occupancy pyramid), the block's 18^3 vertices (link + scalar) staged once in shared memory, each thread handling 16
-// cells, the <= 48 contributions per cell accumulated in shared memory (27 conflict-free colour rounds, no atomics), and ONE red.global.add per touched
-// vertex of the tile at the end (~1.4 per cell instead of 48).  cells_cover_check_kernel proves on the device that the
-// list really is the ascending enumeration of all stored vertices; each of the two kernels (tile / list) returns at once
-// when the flag says the other one applies, so no host synchronisation is needed.
-constexpr int NT_V = 18;
-constexpr int NT_NV = NT_V * NT_V * NT_V;
-constexpr int NT_THREADS = 256;
-constexpr size_t NT_SMEM = (size_t)NT_NV * (4 + 4 + 4 + 1);
+// ---- surface TV / surface-normal loss when the list is a window of "every stored vertex" -------------------------------------
+// norm_surface_sparsity = tv_surface_sparsity = 1 (the alpha-Surf training configuration) hands both regularisers the
+// ascending list of ALL stored vertices (svox2/svox2.py:6354-6361); a sparse fraction hands them a contiguous window of
+// that list (:6369-6372), and so does the cell-sharded multi-GPU step.  list_window_check_kernel proves on the device that
+// the list is exactly { stored vertices with lo <= flat id <= hi }; then the work is dense over the occupied part of the
+// grid and is done tile by tile (8 x 16 x 16 cells, half of a 16^3 vertex block of the list behind the occupancy pyramid,
+// persistent CTAs fetching tiles from a counter):
+//   * the tile's vertices (link + scalar, one halo layer below, one or two above) are staged once in shared memory by
+//     batches of independent loads -- every vertex is used by up to 32 cell terms of the tile;
+//   * every per-cell quantity is computed once per tile and shared through shared memory (the unit normal and 1/|n| of a
+//     cell serve its own 3 pairs and the pairs of its -x/-y/-z neighbours);
+//   * gradients are GATHERED per vertex from the cells around it, so a vertex receives ONE red.global.add per tile
+//     (1.0 per cell for the TV, 1.27 for the normal loss; the reference thread issues 4 / up to 48).
+// Each of the two kernels of a call (tile / list) returns at once when the verdict says the other one applies: no host
+// synchronisation.  Same contributions as the reference kernels; only the fp32 summation order differs.
+constexpr int TS_X = 8, TS_Y = 16, TS_Z = 16;   // own cells of a tile
+constexpr int TILE_THREADS = 512;
+constexpr int32_t L_OUT = INT32_MIN;            // staged "link" of a vertex outside the grid
+
+struct TileVerdict {
+    int bad;        // 0: the list is the window [lo, hi] of the stored vertices -> tile kernel; else the list kernels run
+    int lo, hi;     // flat vertex ids
+    unsigned ctr;   // tile fetch counter
+};
+
+// stored vertices with a flat id < bound (bound in [0, X*Y*Z]); whole warp, result on every lane
+__device__ __forceinline__ unsigned stored_below(const int32_t *__restrict__ links, const uint32_t *__restrict__ colp,
+                                                 int64_t bound, int sz, int lane) {
+    const int64_t col = bound / sz;
+    const int zr = (int)(bound - col * sz);
+    unsigned c = 0;
+    for (int z = lane; z < zr; z += 32) c += (__ldg(links + col * sz + z) >= 0) ? 1u : 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    return c + colp[col];
+}
 
 __global__ void __launch_bounds__(256)
-cells_cover_check_kernel(const int32_t *__restrict__ links, const int32_t *__restrict__ cells, int64_t n_cells,
-                         const uint64_t *__restrict__ accel, AccelLayout lay, int *__restrict__ flag) {
-    // flag starts at 1; cleared when the list is not exactly the ascending list of all vertices with link >= 0
-    const int64_t n_stored = (int64_t)accel[lay.off[3] + 1 + (lay.count(1) + 1) / 2];
-    if (n_cells != n_stored) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
-        return;
+list_window_check_kernel(const int32_t *__restrict__ links, const int32_t *__restrict__ cells, int64_t n_cells, int64_t n_vertices,
+                         int sz, const uint32_t *__restrict__ colp, TileVerdict *__restrict__ v) {
+    // v->bad starts at 0; set when the list is not the strictly ascending list of all stored vertices between its ends
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const int32_t lo = __ldg(cells), hi = __ldg(cells + n_cells - 1);
+        bool ok = (lo >= 0) && (hi >= lo) && ((int64_t)hi < n_vertices);
+        if (ok) {
+            const unsigned a = stored_below(links, colp, lo, sz, threadIdx.x);
+            const unsigned b = stored_below(links, colp, (int64_t)hi + 1, sz, threadIdx.x);
+            ok = (int64_t)(b - a) == n_cells;
+        }
+        if (threadIdx.x == 0) {
+            v->lo = lo;
+            v->hi = hi;
+            if (!ok) v->bad = 1;
+        }
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t c = __ldg(cells + i);
-        const bool ok = (c >= 0) && (__ldg(links + c) >= 0) && (i == 0 || __ldg(cells + i - 1) < c);
-        if (!ok) *flag = 0;
+        const bool ok = (c >= 0) && ((int64_t)c < n_vertices) && (i == 0 || __ldg(cells + i - 1) < c) && (__ldg(links + c) >= 0);
+        if (!ok) v->bad = 1;
     }
 }
 
-__device__ __forceinline__ void tile_cell(const int32_t *s_link, const float *s_surf, int cx, int cy, int cz, Cell8 &c, bool &ok) {
-    ok = true;
+// stage the vertices [x0 - 1, x0 - 1 + NX) x ... of a tile: link (L_OUT outside the grid) and value (0 where not stored)
+template <int NX, int NY, int NZ>
+__device__ __forceinline__ void stage_tile(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols,
+                                           int idx, const Dims &d, int x0, int y0, int z0, int32_t *s_link, float *s_val,
+                                           int tid) {
+    constexpr int NV = NX * NY * NZ;
+    for (int vb = tid; vb < NV; vb += 4 * TILE_THREADS) {
+        int32_t l[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int v = ((cx + (k >> 2)) * NT_V + (cy + ((k >> 1) & 1))) * NT_V + (cz + (k & 1));
-        c.l[k] = s_link[v];
-        c.s[k] = s_surf[v];
-        ok &= (c.l[k] >= 0);
-    }
-}
-
-__device__ __forceinline__ void tile_scatter(float *s_grad, uint8_t *s_touch, int cx, int cy, int cz, const float *g, float scale) {
-    const float q = 0.25f * scale;
-    const float a0 = q * g[0], a1 = q * g[1], a2 = q * g[2];
-    const float u[4] = {-a0 - a1, -a0 + a1, a0 - a1, a0 + a1};
+        for (int r = 0; r < 4; ++r) {
+            const int v = vb + r * TILE_THREADS;
+            l[r] = L_OUT;
+            if (v < NV) {
+                const int i = v / (NY * NZ), rem = v - i * (NY * NZ), j = rem / NZ, k = rem - j * NZ;
+                const int x = x0 - 1 + i, y = y0 - 1 + j, z = z0 - 1 + k;
+                if (x >= 0 && y >= 0 && z >= 0 && x < d.sx && y < d.sy && z < d.sz)
+                    l[r] = __ldg(links + (((int64_t)x * d.sy + y) * d.sz + z));
+            }
+        }
+        float s[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float val = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
-        if (val != 0.f) {   // plain read-modify-write: cells processed together are >= 3 apart on every axis
-            const int v = ((cx + (k >> 2)) * NT_V + (cy + ((k >> 1) & 1))) * NT_V + (cz + (k & 1));
-            s_grad[v] += val;
-            s_touch[v] = 1;
+        for (int r = 0; r < 4; ++r) s[r] = (l[r] >= 0) ? __ldg(data + (int64_t)l[r] * n_cols + idx) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int v = vb + r * TILE_THREADS;
+            if (v < NV) {
+                s_link[v] = l[r];
+                s_val[v] = s[r];
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(NT_THREADS)
-surface_normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, Dims d,
-                           const uint64_t *__restrict__ accel, AccelLayout lay, const int *__restrict__ flag, float lv_set,
-                           float scale, int con_check, int ignore_empty, int use_l1, uint8_t *__restrict__ mask,
-                           float *__restrict__ grad) {
-    if (*flag == 0) return;   // not the full enumeration: the list kernel does the work
-    extern __shared__ unsigned char nt_smem[];
-    int32_t *s_link = (int32_t *)nt_smem;
-    float *s_surf = (float *)(nt_smem + (size_t)NT_NV * 4);
-    float *s_grad = (float *)(nt_smem + (size_t)NT_NV * 8);
-    uint8_t *s_touch = (uint8_t *)(nt_smem + (size_t)NT_NV * 12);
+// next tile of the walk: (block of the vertex-block list, half); false when the list is exhausted
+__device__ __forceinline__ bool next_tile(TileVerdict *v, const uint64_t *__restrict__ vbl, const Dims &d, int *s_tile,
+                                          int &x0, int &y0, int &z0) {
+    __syncthreads();   // the shared buffers of the previous tile are free
+    if (threadIdx.x == 0) *s_tile = (int)atomicAdd(&v->ctr, 1u);
+    __syncthreads();
+    const int t = *s_tile;
+    const int n_blocks = (int)vbl[0];
+    if (t >= 2 * n_blocks) return false;
+    const int w = (int)((const uint32_t *)(vbl + 1))[t >> 1];
+    const int nby = (d.sy + 15) >> 4, nbz = (d.sz + 15) >> 4;
+    z0 = (w % nbz) * 16;
+    y0 = ((w / nbz) % nby) * 16;
+    x0 = (w / (nbz * nby)) * 16 + (t & 1) * TS_X;
+    return true;
+}
+
+// -- surface TV (tv_grad_sparse_kernel / surf_tv_grad_sparse_kernel semantics of one channel, no alpha dependency) --
+constexpr int TV_VX = TS_X + 2, TV_VY = TS_Y + 2, TV_VZ = TS_Z + 2;   // vertices -1 .. T
+constexpr int TV_CX = TS_X + 1, TV_CY = TS_Y + 1, TV_CZ = TS_Z + 1;   // cells    -1 .. T-1
+constexpr int TV_NV = TV_VX * TV_VY * TV_VZ, TV_NC = TV_CX * TV_CY * TV_CZ;
+constexpr size_t TV_SMEM = (size_t)TV_NV * 8 + (size_t)TV_NC * 16 + (size_t)TV_NC;
+
+template <bool SURF>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols, int idx, Dims d,
+               const uint64_t *__restrict__ vbl, TileVerdict *__restrict__ verdict, float scale, int ignore_edge,
+               float edge_value, int ignore_last_z, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    if (verdict->bad) return;   // not a window of the stored vertices: the list kernel does the work
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    int32_t *s_link = (int32_t *)tile_smem;
+    float *s_val = (float *)(tile_smem + (size_t)TV_NV * 4);
+    float4 *s_g = (float4 *)(tile_smem + (size_t)TV_NV * 8);          // per cell: to +x, +y, +z neighbour, to itself
+    uint8_t *s_f = (uint8_t *)(tile_smem + (size_t)TV_NV * 8 + (size_t)TV_NC * 16);
+    __shared__ int s_tile;
     const int tid = threadIdx.x;
-    const int64_t n_active = (int64_t)accel[lay.off[3]];
-    const uint32_t *active = (const uint32_t *)(accel + lay.off[3] + 1);
-    for (int64_t it = blockIdx.x; it < n_active; it += gridDim.x) {
+    const int lo = verdict->lo, hi = verdict->hi;
+    float sc[3];
+    ray_scale(d, sc);
+    const float missing = SURF ? edge_value : 0.f;
+    int x0, y0, z0;
+    while (next_tile(verdict, vbl, d, &s_tile, x0, y0, z0)) {
+        if (x0 >= d.sx) continue;
+        {   // flat ids of the tile's own vertices lie in [x0 * Y * Z, (x0 + TS_X) * Y * Z): skip tiles outside the window
+            const int64_t a = (int64_t)x0 * d.sy * d.sz, b = (int64_t)(x0 + TS_X) * d.sy * d.sz;
+            if (b <= (int64_t)lo || a - (int64_t)d.sy * d.sz > (int64_t)hi) continue;   // (cells of the x layer below may own terms)
+        }
+        stage_tile<TV_VX, TV_VY, TV_VZ>(links, data, n_cols, idx, d, x0, y0, z0, s_link, s_val, tid);
         __syncthreads();
-        const int64_t w1 = active[it];
-        const int bz = (int)(w1 % lay.b[1][2]);
-        const int by = (int)((w1 / lay.b[1][2]) % lay.b[1][1]);
-        const int bx = (int)(w1 / ((int64_t)lay.b[1][2] * lay.b[1][1]));
-        const int x0 = bx * 16, y0 = by * 16, z0 = bz * 16;
-        for (int vb = tid; vb < NT_NV; vb += 4 * NT_THREADS) {
-            int32_t l[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int v = vb + r * NT_THREADS;
-                l[r] = -1;
-                if (v < NT_NV) {
-                    const int x = x0 + v / (NT_V * NT_V), y = y0 + (v / NT_V) % NT_V, z = z0 + v % NT_V;
-                    if (x < d.sx && y < d.sy && z < d.sz) l[r] = __ldg(links + (((int64_t)x * d.sy + y) * d.sz + z));
+        // phase 1: the TV term of every listed cell in [-1, T)^3
+        for (int c = tid; c < TV_NC; c += TILE_THREADS) {
+            const int i = c / (TV_CY * TV_CZ), rem = c - i * (TV_CY * TV_CZ), j = rem / TV_CZ, k = rem - j * TV_CZ;
+            const int vb = (i * TV_VY + j) * TV_VZ + k;
+            const int32_t l000 = s_link[vb];
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned fl = 0u;
+            const int x = x0 - 1 + i, y = y0 - 1 + j, z = z0 - 1 + k;
+            bool valid = l000 >= 0;
+            if (valid) {
+                const int64_t id = ((int64_t)x * d.sy + y) * d.sz + z;
+                valid = (id >= lo) && (id <= hi) && !(ignore_edge && l000 == 0) && !(ignore_last_z && z == d.sz - 2);
+            }
+            if (valid) {
+                const bool own = (i >= 1) && (j >= 1) && (k >= 1);
+                const float v000 = s_val[vb];
+                const float nullv = ignore_edge ? v000 : missing;
+                // a neighbour outside the grid reads link 0 in the reference (sic, :761-763): row 0's value and gradient
+                int32_t l001 = s_link[vb + 1], l010 = s_link[vb + TV_VZ], l100 = s_link[vb + TV_VY * TV_VZ];
+                const bool oz = (l001 == L_OUT), oy = (l010 == L_OUT), ox = (l100 == L_OUT);
+                const float row0 = (ox || oy || oz) ? __ldg(data + idx) : 0.f;
+                const float v001 = oz ? row0 : (l001 >= 0 ? s_val[vb + 1] : nullv);
+                const float v010 = oy ? row0 : (l010 >= 0 ? s_val[vb + TV_VZ] : nullv);
+                const float v100 = ox ? row0 : (l100 >= 0 ? s_val[vb + TV_VY * TV_VZ] : nullv);
+                float dx = v100 - v000, dy = v010 - v000, dz = v001 - v000;
+                const float idelta = scale * rsqrtf(1e-9f + dx * dx + dy * dy + dz * dz);
+                dx *= sc[0];
+                dy *= sc[1];
+                dz *= sc[2];
+                const float sm = -(dx + dy + dz);
+                if (sm != 0.f) { g.w = sm * idelta; fl |= 8u; }
+                if ((oz || l001 >= 0) && dz != 0.f) {
+                    if (!oz) { g.z = dz * idelta; fl |= 4u; }
+                    else if (own) { atomicAdd(grad + idx, dz * idelta); if (mask) mask[0] = 1; }
+                }
+                if ((oy || l010 >= 0) && dy != 0.f) {
+                    if (!oy) { g.y = dy * idelta; fl |= 2u; }
+                    else if (own) { atomicAdd(grad + idx, dy * idelta); if (mask) mask[0] = 1; }
+                }
+                if ((ox || l100 >= 0) && dx != 0.f) {
+                    if (!ox) { g.x = dx * idelta; fl |= 1u; }
+                    else if (own) { atomicAdd(grad + idx, dx * idelta); if (mask) mask[0] = 1; }
                 }
             }
+            s_g[c] = g;
+            s_f[c] = (uint8_t)fl;
+        }
+        __syncthreads();
+        // phase 2: every own vertex gathers its own term and those of the cells below it: one atomic per vertex
+        for (int o = tid; o < TS_X * TS_Y * TS_Z; o += TILE_THREADS) {
+            const int i = o / (TS_Y * TS_Z), j = (o / TS_Z) % TS_Y, k = o % TS_Z;
+            const int c = ((i + 1) * TV_CY + (j + 1)) * TV_CZ + (k + 1);
+            const unsigned f = (s_f[c] & 8u) | (s_f[c - TV_CY * TV_CZ] & 1u) | (s_f[c - TV_CZ] & 2u) | (s_f[c - 1] & 4u);
+            if (f) {
+                const float sum = ((s_g[c].w + s_g[c - TV_CY * TV_CZ].x) + s_g[c - TV_CZ].y) + s_g[c - 1].z;
+                const int32_t l = s_link[((i + 1) * TV_VY + (j + 1)) * TV_VZ + (k + 1)];
+                atomicAdd(grad + (int64_t)l * n_cols + idx, sum);
+                if (mask) mask[l] = 1;
+            }
+        }
+    }
+}
+
+// -- surface-normal consistency (add_surface_normal_grad, render_util.cuh:1870-2133) --
+constexpr int NT_VX = TS_X + 3, NT_VY = TS_Y + 3, NT_VZ = TS_Z + 3;   // vertices -1 .. T+1
+constexpr int NT_CX = TS_X + 2, NT_CY = TS_Y + 2, NT_CZ = TS_Z + 2;   // cells    -1 .. T
+constexpr int NT_NV = NT_VX * NT_VY * NT_VZ, NT_NC = NT_CX * NT_CY * NT_CZ;
+constexpr int NT_OWN = TS_X * TS_Y * TS_Z;
+constexpr int NT_PER = NT_OWN / TILE_THREADS;                          // own cells per thread
+constexpr size_t NT_OFF_NRM = (((size_t)NT_NV * 8 + 15) / 16) * 16;
+constexpr size_t NT_SMEM = NT_OFF_NRM + (size_t)NT_NC * 16 + (size_t)NT_NC;
+static_assert(((size_t)TV_NV * 8) % 16 == 0, "float4 alignment of the TV tile");
+static_assert(NT_OWN % TILE_THREADS == 0, "own cells must divide over the threads");
+static_assert(NT_OWN <= NT_NC, "the per-cell gradients reuse the normals' buffer");
+
+// Contribution of the pair (own cell, other cell) to d(loss)/d(normal of the own cell), times q.  For the lower cell a of a
+// pair (a, b) the reference forms d0 = (s - nh_a (s.nh_a)) / N_a with s = sign(nh_a - nh_b) [L1] or 2 (nh_a - nh_b) [L2];
+// for the upper cell d1 = -(s - nh_b (s.nh_b)) / N_b, which is the SAME expression with the roles swapped (every step is
+// odd in s), so one routine serves both sides.  nh = n / N keeps the reference's true divisions (normals phase).
+__device__ __forceinline__ void normal_side(const float4 &nc, const float4 &no, float q, int use_l1, float &A0, float &A1,
+                                            float &A2, unsigned &touched) {
+    const float L0 = nc.x - no.x, L1 = nc.y - no.y, L2 = nc.z - no.z;
+    float s0, s1, s2;
+    if (use_l1) {
+        s0 = (L0 > 0.f) ? 1.f : (L0 == 0.f ? 0.f : -1.f);
+        s1 = (L1 > 0.f) ? 1.f : (L1 == 0.f ? 0.f : -1.f);
+        s2 = (L2 > 0.f) ? 1.f : (L2 == 0.f ? 0.f : -1.f);
+    } else {
+        s0 = 2.f * L0;
+        s1 = 2.f * L1;
+        s2 = 2.f * L2;
+    }
+    const float dot = s0 * nc.x + s1 * nc.y + s2 * nc.z;
+    const float a0 = q * ((s0 - nc.x * dot) * nc.w), a1 = q * ((s1 - nc.y * dot) * nc.w), a2 = q * ((s2 - nc.z * dot) * nc.w);
+    A0 += a0;
+    A1 += a1;
+    A2 += a2;
+    // corner values are (+-a0 +- a1) +- a2: one of them is an exact zero iff |a0 + a1| or |a0 - a1| equals |a2|; only
+    // non-zero contributions mark a row (`val != 0` per corner in the reference).  NaNs compare unequal: all marked.
+    const float p = a0 + a1, m = a0 - a1;
+    if (fabsf(p) != fabsf(a2) && fabsf(m) != fabsf(a2)) {
+        touched |= 0xFFu;
+    } else {
+        const float u[4] = {-p, -m, m, p};   // index (dx << 1) | dy
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int v = vb + r * NT_THREADS;
-                if (v < NT_NV) {
-                    s_link[v] = l[r];
-                    s_surf[v] = (l[r] >= 0) ? __ldg(surf + l[r]) : 0.f;
-                    s_grad[v] = 0.f;
-                    s_touch[v] = 0;
+        for (int k = 0; k < 8; ++k) {
+            const float v = (k & 1) ? (u[k >> 1] + a2) : (u[k >> 1] - a2);
+            touched |= (v != 0.f ? 1u : 0u) << k;
+        }
+    }
+}
+
+// per-cell flag byte: 1 all 8 corners stored, 2 "empty" (level set outside the corner range), 4 / 8 / 16 the +x / +y / +z
+// face is crossed by the level set
+template <bool CHECKS>
+__device__ __forceinline__ bool pair_used(unsigned f_lower, unsigned f_upper, int axis, int con_check, int ignore_empty) {
+    if (!(f_upper & 1u)) return false;
+    if (!CHECKS) return true;
+    if (con_check && !((f_lower >> (2 + axis)) & 1u)) return false;
+    if (ignore_empty && (f_lower & 2u) && (f_upper & 2u)) return false;
+    return true;
+}
+
+template <bool CHECKS>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, Dims d, const uint64_t *__restrict__ vbl,
+                   TileVerdict *__restrict__ verdict, float lv_set, float scale, int con_check, int ignore_empty, int use_l1,
+                   uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    if (verdict->bad) return;
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    int32_t *s_link = (int32_t *)tile_smem;
+    float *s_val = (float *)(tile_smem + (size_t)NT_NV * 4);
+    float4 *s_nrm = (float4 *)(tile_smem + NT_OFF_NRM);   // per cell: unit normal, 1 / |n|; later d(loss)/d(normal) of the own cells
+    uint8_t *s_cf = (uint8_t *)(tile_smem + NT_OFF_NRM + (size_t)NT_NC * 16);
+    __shared__ int s_tile;
+    const int tid = threadIdx.x;
+    const int lo = verdict->lo, hi = verdict->hi;
+    const int64_t gstride[3] = {(int64_t)d.sy * d.sz, (int64_t)d.sz, 1};
+    constexpr int cstride[3] = {NT_CY * NT_CZ, NT_CZ, 1};
+    int x0, y0, z0;
+    while (next_tile(verdict, vbl, d, &s_tile, x0, y0, z0)) {
+        if (x0 >= d.sx) continue;
+        {
+            const int64_t a = (int64_t)x0 * d.sy * d.sz, b = (int64_t)(x0 + TS_X) * d.sy * d.sz;
+            if (b <= (int64_t)lo || a - (int64_t)d.sy * d.sz > (int64_t)hi) continue;
+        }
+        stage_tile<NT_VX, NT_VY, NT_VZ>(links, surf, 1, 0, d, x0, y0, z0, s_link, s_val, tid);
+        __syncthreads();
+        // phase 1: unit normal of every complete cell in [-1, T]^3
+        int any = 0;
+        for (int c = tid; c < NT_NC; c += TILE_THREADS) {
+            const int i = c / (NT_CY * NT_CZ), rem = c - i * (NT_CY * NT_CZ), j = rem / NT_CZ, k = rem - j * NT_CZ;
+            const int vb = (i * NT_VY + j) * NT_VZ + k;
+            Cell8 cc;
+            bool ok = true;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int v = vb + (q >> 2) * (NT_VY * NT_VZ) + ((q >> 1) & 1) * NT_VZ + (q & 1);
+                ok &= (s_link[v] >= 0);
+                cc.s[q] = s_val[v];
+            }
+            unsigned f = 0u;
+            if (ok) {
+                float n[3];
+                cell_normal(cc, n);
+                const float N = NORM3_(n);
+                s_nrm[c] = make_float4(n[0] / N, n[1] / N, n[2] / N, 1.f / N);
+                f = 1u;
+                if (CHECKS) {
+                    f |= cell_empty(cc, lv_set) ? 2u : 0u;
+                    f |= face_connected(cc.s[4], cc.s[5], cc.s[6], cc.s[7], lv_set) ? 4u : 0u;
+                    f |= face_connected(cc.s[2], cc.s[3], cc.s[6], cc.s[7], lv_set) ? 8u : 0u;
+                    f |= face_connected(cc.s[1], cc.s[3], cc.s[5], cc.s[7], lv_set) ? 16u : 0u;
+                }
+                any |= (i >= 1 && i <= TS_X && j >= 1 && j <= TS_Y && k >= 1 && k <= TS_Z) ? 1 : 0;
+            }
+            s_cf[c] = (uint8_t)f;
+        }
+        if (!__syncthreads_or(any)) continue;   // no complete own cell: nothing to do (next_tile synchronises)
+        // phase 2: d(loss)/d(normal) of every own cell, summed over the <= 6 pairs it takes part in (kept in registers: the
+        // result overwrites the normals once every thread is done reading them)
+        float4 G[NT_PER];
+#pragma unroll
+        for (int r = 0; r < NT_PER; ++r) {
+            const int o = tid + r * TILE_THREADS;
+            const int i = o / (TS_Y * TS_Z), j = (o / TS_Z) % TS_Y, k = o % TS_Z;
+            const int ci = ((i + 1) * NT_CY + (j + 1)) * NT_CZ + (k + 1);
+            float A0 = 0.f, A1 = 0.f, A2 = 0.f;
+            unsigned touched = 0u;
+            const unsigned f = s_cf[ci];
+            if (f & 1u) {
+                const int64_t id = ((int64_t)(x0 + i) * d.sy + (y0 + j)) * d.sz + (z0 + k);
+                const float4 nc = s_nrm[ci];
+                // pairs this cell owns (itself and its +x / +y / +z neighbour), if it is on the list
+                if (id >= lo && id <= hi) {
+                    bool u[3];
+                    int cnt = 0;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        u[e] = pair_used<CHECKS>(f, s_cf[ci + cstride[e]], e, con_check, ignore_empty);
+                        cnt += u[e] ? 1 : 0;
+                    }
+                    const float q = 0.25f * (scale * 1.f / cnt);
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                        if (u[e]) normal_side(nc, s_nrm[ci + cstride[e]], q, use_l1, A0, A1, A2, touched);
+                }
+                // pairs owned by the -x / -y / -z neighbour
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const int cl = ci - cstride[e];
+                    const unsigned fl = s_cf[cl];
+                    const int64_t idl = id - gstride[e];
+                    if (!(fl & 1u) || idl < lo || idl > hi || !pair_used<CHECKS>(fl, f, e, con_check, ignore_empty)) continue;
+                    int cnt = 1;
+#pragma unroll
+                    for (int e2 = 0; e2 < 3; ++e2)
+                        if (e2 != e) cnt += pair_used<CHECKS>(fl, s_cf[cl + cstride[e2]], e2, con_check, ignore_empty) ? 1 : 0;
+                    const float q = 0.25f * (scale * 1.f / cnt);
+                    normal_side(nc, s_nrm[cl], q, use_l1, A0, A1, A2, touched);
                 }
             }
+            G[r] = make_float4(A0, A1, A2, __uint_as_float(touched));
         }
         __syncthreads();
-        // 27 colours: cells with the same (cx, cy, cz) mod 3 touch disjoint vertex sets (a cell writes vertices
-        // [c, c + 2]^3), so each colour round needs no atomics; 6^3 = 216 cells per round on 256 threads
-        for (int colour = 0; colour < 27; ++colour) {
-            if (colour) __syncthreads();
-            const int cx = 3 * (tid / 36) + colour / 9, cy = 3 * ((tid / 6) % 6) + (colour / 3) % 3, cz = 3 * (tid % 6) + colour % 3;
-            if (tid >= 216 || cx >= 16 || cy >= 16 || cz >= 16) continue;
-            Cell8 c0;
-            bool ok0;
-            tile_cell(s_link, s_surf, cx, cy, cz, c0, ok0);
-            if (!ok0) continue;
-            const bool empty000 = ignore_empty ? cell_empty(c0, lv_set) : false;
-            float n0[3];
-            cell_normal(c0, n0);
-            Cell8 cz1, cy1, cx1;
-            bool uz, uy, ux;
-            tile_cell(s_link, s_surf, cx, cy, cz + 1, cz1, uz);
-            tile_cell(s_link, s_surf, cx, cy + 1, cz, cy1, uy);
-            tile_cell(s_link, s_surf, cx + 1, cy, cz, cx1, ux);
-            uz = uz && (!con_check || face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv_set));
-            uz = uz && (!ignore_empty || (!empty000 || !cell_empty(cz1, lv_set)));
-            uy = uy && (!con_check || face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv_set));
-            uy = uy && (!ignore_empty || (!empty000 || !cell_empty(cy1, lv_set)));
-            ux = ux && (!con_check || face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv_set));
-            ux = ux && (!ignore_empty || (!empty000 || !cell_empty(cx1, lv_set)));
-            const int norm_count = (int)ux + (int)uy + (int)uz;
-            if (norm_count == 0) continue;
-            const float N0 = NORM3_(n0);
-            const float nh0[3] = {n0[0] / N0, n0[1] / N0, n0[2] / N0};
-            const float rN0 = 1.f / N0;
-            const float sc = scale * 1.f / norm_count;
-            float n1[3], d0[3], d1[3];
-            if (ux) {
-                cell_normal(cx1, n1);
-                const float N1 = NORM3_(n1);
-                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
-                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
-                tile_scatter(s_grad, s_touch, cx, cy, cz, d0, sc);
-                tile_scatter(s_grad, s_touch, cx + 1, cy, cz, d1, sc);
-            }
-            if (uy) {
-                cell_normal(cy1, n1);
-                const float N1 = NORM3_(n1);
-                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
-                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
-                tile_scatter(s_grad, s_touch, cx, cy, cz, d0, sc);
-                tile_scatter(s_grad, s_touch, cx, cy + 1, cz, d1, sc);
-            }
-            if (uz) {
-                cell_normal(cz1, n1);
-                const float N1 = NORM3_(n1);
-                const float nh1[3] = {n1[0] / N1, n1[1] / N1, n1[2] / N1};
-                normal_pair_grad(nh0, rN0, nh1, 1.f / N1, use_l1, d0, d1);
-                tile_scatter(s_grad, s_touch, cx, cy, cz, d0, sc);
-                tile_scatter(s_grad, s_touch, cx, cy, cz + 1, d1, sc);
-            }
-        }
+#pragma unroll
+        for (int r = 0; r < NT_PER; ++r) s_nrm[tid + r * TILE_THREADS] = G[r];
         __syncthreads();
-        for (int v = tid; v < NT_NV; v += NT_THREADS) {
-            if (s_touch[v]) {
-                const int32_t l = s_link[v];
-                atomicAdd(grad + l, s_grad[v]);
+        // phase 3: every vertex of [0, T]^3 gathers from the own cells around it: one atomic per vertex
+        for (int v = tid; v < (TS_X + 1) * (TS_Y + 1) * (TS_Z + 1); v += TILE_THREADS) {
+            const int i = v / ((TS_Y + 1) * (TS_Z + 1)), rem = v - i * ((TS_Y + 1) * (TS_Z + 1)), j = rem / (TS_Z + 1),
+                      k = rem - j * (TS_Z + 1);
+            float val = 0.f;
+            unsigned tch = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {   // the vertex is corner q of the cell at (i, j, k) - (q >> 2, (q >> 1) & 1, q & 1)
+                const int ci = i - (q >> 2), cj = j - ((q >> 1) & 1), ck = k - (q & 1);
+                if (ci < 0 || cj < 0 || ck < 0 || ci >= TS_X || cj >= TS_Y || ck >= TS_Z) continue;
+                const float4 g = s_nrm[(ci * TS_Y + cj) * TS_Z + ck];
+                const float u = ((q & 4) ? g.x : -g.x) + ((q & 2) ? g.y : -g.y);
+                val += (q & 1) ? (u + g.z) : (u - g.z);
+                tch |= (__float_as_uint(g.w) >> q) & 1u;
+            }
+            if (tch) {
+                const int32_t l = s_link[((i + 1) * NT_VY + (j + 1)) * NT_VZ + (k + 1)];
+                atomicAdd(grad + l, val);
                 if (mask) mask[l] = 1;
             }
         }
@@ -874,6 +1107,39 @@ extern "C" int asurf_tv_grad(const int32_t *links, const int32_t size[3], const 
     return check_cuda(cudaGetLastError(), "tv_grad launch");
 }
 
+static Workspace g_ws_verdict;
+namespace asurf {
+void loss_release() { g_ws_verdict.release(); }
+}  // namespace asurf
+// 1 (default): lists that are a window of the stored vertices take the tiled kernels; 0: always the list kernels (tests
+// compare the two; see asurf_debug_set_normal_tile)
+static int g_tile_path = 1;
+
+// Start the tile path of a regulariser call: verdict block cleared, list check enqueued.  *verdict stays NULL when the
+// call cannot take it (no occupancy buffer, tiny list, grid of 2^31 vertices or more).
+static int tile_path_begin(const int32_t *links, const int32_t size[3], const int32_t *cells, int64_t n_cells,
+                           const uint64_t *accel, cudaStream_t st, TileVerdict **verdict) {
+    *verdict = nullptr;
+    const int64_t nv = (int64_t)size[0] * size[1] * size[2];
+    if (!g_tile_path || !accel || n_cells < 256 || nv >= ((int64_t)1 << 31)) return 0;
+    int rc = g_ws_verdict.reserve(sizeof(TileVerdict));
+    if (rc) return rc;
+    TileVerdict *v = (TileVerdict *)g_ws_verdict.ptr;
+    ASURF_CUDA(cudaMemsetAsync(v, 0, sizeof(TileVerdict), st));
+    const uint32_t *colp = (const uint32_t *)(accel + accel_colprefix_offset(size));
+    list_window_check_kernel<<<loss_grid(n_cells), 256, 0, st>>>(links, cells, n_cells, nv, size[2], colp, v);
+    note_launches(1);
+    *verdict = v;
+    return check_cuda(cudaGetLastError(), "list check launch");
+}
+
+static int tile_ctas() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * 2;
+}
+
 extern "C" int asurf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
                                     const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, int32_t start_dim,
                                     int32_t end_dim, float scale, int32_t ignore_edge, int32_t ignore_last_z,
@@ -889,7 +1155,7 @@ extern "C" int asurf_tv_grad_sparse(const int32_t *links, const int32_t size[3],
     if (end_dim - start_dim == 1)
         tv_grad_sparse_runs_kernel<false><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
             links, data, n_cols, nullptr, 0, rand_cells, d, start_dim, scale / (float)(int)n_cells, Q, ignore_edge, 0.f,
-            ignore_last_z, 0, mask_out, grad_data);
+            ignore_last_z, 0, mask_out, grad_data, nullptr);
     else
         tv_grad_sparse_kernel<false><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
             links, data, n_cols, nullptr, 0, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q, ignore_edge, 0.f,
@@ -902,7 +1168,7 @@ extern "C" int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t siz
                                          const float *density, int32_t density_cols, const int32_t *rand_cells,
                                          int64_t n_cells, uint8_t *mask_out, int32_t start_dim, int32_t end_dim, float scale,
                                          int32_t ignore_edge, float edge_value, int32_t ignore_last_z,
-                                         int32_t alpha_dependency, float *grad_data, void *stream) {
+                                         int32_t alpha_dependency, float *grad_data, const uint64_t *accel, void *stream) {
     int rc = check_common(links, size, surf, grad_data, "surf_tv_grad_sparse");
     if (rc) return rc;
     ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID,
@@ -912,14 +1178,33 @@ extern "C" int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t siz
     ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "surf_tv_grad_sparse: null cell list");
     const int64_t Q = n_cells * (end_dim - start_dim);
     Dims d = {size[0], size[1], size[2]};
-    if (end_dim - start_dim == 1)
-        tv_grad_sparse_runs_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-            links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, scale / (float)(int)n_cells, Q, ignore_edge,
-            edge_value, ignore_last_z, alpha_dependency, mask_out, grad_data);
-    else
-        tv_grad_sparse_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-            links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, end_dim, scale / (float)(int)n_cells, Q,
-            ignore_edge, edge_value, ignore_last_z, alpha_dependency, mask_out, grad_data);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float cell_scale = scale / (float)(int)n_cells;
+    if (end_dim - start_dim == 1) {
+        TileVerdict *verdict = nullptr;
+        if (!alpha_dependency) {
+            rc = tile_path_begin(links, size, rand_cells, n_cells, accel, st, &verdict);
+            if (rc) return rc;
+        }
+        if (verdict) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                ASURF_CUDA(cudaFuncSetAttribute(tv_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM));
+                attr_set = true;
+            }
+            tv_tile_kernel<true><<<tile_ctas(), TILE_THREADS, TV_SMEM, st>>>(links, surf, n_cols, start_dim, d,
+                                                                            accel + accel_vblock_offset(size), verdict, cell_scale,
+                                                                            ignore_edge, edge_value, ignore_last_z, mask_out,
+                                                                            grad_data);
+            note_launches(1);
+        }
+        tv_grad_sparse_runs_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
+            links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, cell_scale, Q, ignore_edge, edge_value,
+            ignore_last_z, alpha_dependency, mask_out, grad_data, verdict ? &verdict->bad : nullptr);
+    } else
+        tv_grad_sparse_kernel<true><<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
+            links, surf, n_cols, density, density_cols, rand_cells, d, start_dim, end_dim, cell_scale, Q, ignore_edge, edge_value,
+            ignore_last_z, alpha_dependency, mask_out, grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_tv_grad_sparse launch");
 }
@@ -942,12 +1227,7 @@ extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const
     return check_cuda(cudaGetLastError(), "alpha_surf_sparsify_grad_sparse launch");
 }
 
-static Workspace g_ws_flag;
-// The dense tiled variant of the normal loss is exact but, as measured on B200 (profiles/r1_ncu_full_normal_tile.txt), not
-// faster than the run-aggregated list kernel (2.2 ms vs 1.3 ms at 512^3): both are instruction-bound on the 48 corner
-// contributions per cell.  It stays behind this switch (tests exercise both) until its per-cell normals are shared.
-static int g_normal_tile = 0;   // 1: dense tile kernel for full lists (slower; kept for the comparison in profiles/)
-extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_normal_tile = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_tile_path = enabled ? 1 : 0; }
 
 extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                                 const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
@@ -962,42 +1242,37 @@ extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int3
     const int n_rep = end_dim - start_dim;   // the reference launches one thread per (cell, channel) and ignores the channel
     const int64_t Q = n_cells * n_rep;
     Dims d = {size[0], size[1], size[2]};
+    cudaStream_t st = (cudaStream_t)stream;
+    const float cell_scale = scale / (float)(int)n_cells;
     if (n_rep == 1) {
-        cudaStream_t st = (cudaStream_t)stream;
-        const int *flag = nullptr;
-        AccelLayout lay(size);
-        // a list that may be "every stored vertex" (at least a tenth of the grid): let the device decide which kernel runs
-        if (g_normal_tile && accel && n_cells * 10 >= (int64_t)size[0] * size[1] * size[2] / 10 && size[0] >= 16 && size[1] >= 16 &&
-            size[2] >= 16) {
-            rc = g_ws_flag.reserve(sizeof(int));
-            if (rc) return rc;
+        TileVerdict *verdict = nullptr;
+        rc = tile_path_begin(links, size, rand_cells, n_cells, accel, st, &verdict);
+        if (rc) return rc;
+        if (verdict) {
             static bool attr_set = false;
             if (!attr_set) {
-                ASURF_CUDA(cudaFuncSetAttribute(surface_normal_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
+                ASURF_CUDA(cudaFuncSetAttribute(normal_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
+                ASURF_CUDA(cudaFuncSetAttribute(normal_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
                 attr_set = true;
             }
-            int one = 1;
-            ASURF_CUDA(cudaMemcpyAsync(g_ws_flag.ptr, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-            cells_cover_check_kernel<<<loss_grid(n_cells), 256, 0, st>>>(links, rand_cells, n_cells, accel, lay, (int *)g_ws_flag.ptr);
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            surface_normal_tile_kernel<<<sms * 2, NT_THREADS, NT_SMEM, st>>>(links, surf, d, accel, lay, (const int *)g_ws_flag.ptr,
-                                                                            lv_set, scale / (float)(int)n_cells, con_check,
-                                                                            ignore_empty, use_l1, mask_out, grad_data);
-            flag = (const int *)g_ws_flag.ptr;
-            note_launches(2);
+            const uint64_t *vbl = accel + accel_vblock_offset(size);
+            if (con_check || ignore_empty)
+                normal_tile_kernel<true><<<tile_ctas(), TILE_THREADS, NT_SMEM, st>>>(links, surf, d, vbl, verdict, lv_set, cell_scale,
+                                                                                    con_check, ignore_empty, use_l1, mask_out, grad_data);
+            else
+                normal_tile_kernel<false><<<tile_ctas(), TILE_THREADS, NT_SMEM, st>>>(links, surf, d, vbl, verdict, lv_set, cell_scale,
+                                                                                     0, 0, use_l1, mask_out, grad_data);
+            note_launches(1);
         }
         auto log2_exact = [](int v) { int k = 0; while ((1 << k) < v) ++k; return (1 << k) == v ? k : -1; };
         int shz = log2_exact(size[2]), shy = log2_exact(size[1]);
         if (shz < 0 || shy < 0) shz = shy = -1;
         surface_normal_runs_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
-            links, surf, rand_cells, d, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1, mask_out,
-            grad_data, flag, shz, shy);
+            links, surf, rand_cells, d, Q, lv_set, cell_scale, con_check, ignore_empty, use_l1, mask_out, grad_data,
+            verdict ? &verdict->bad : nullptr, shz, shy);
     } else
-        surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-            links, surf, rand_cells, d, n_rep, Q, lv_set, scale / (float)(int)n_cells, con_check, ignore_empty, use_l1,
-            mask_out, grad_data);
+        surface_normal_kernel<<<loss_grid(Q), LOSS_THREADS, 0, st>>>(
+            links, surf, rand_cells, d, n_rep, Q, lv_set, cell_scale, con_check, ignore_empty, use_l1, mask_out, grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surface_normal_grad_sparse launch");
 }

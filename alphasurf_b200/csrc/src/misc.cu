@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) dist_code_kernel(int32_t *__restrict__ li
 Workspace g_ws_pyr;
 
 }  // namespace
+void misc_release() { g_ws_pyr.release(); }
 }  // namespace asurf
 
 using namespace asurf;

@@ -2129,4 +2129,7 @@ extern "C" void asurf_release(void) {
     g_ws_pre.release();
     g_ws_wave.release();
     g_ws_seg.release();
+    loss_release();
+    cuvol_release();
+    misc_release();
 }

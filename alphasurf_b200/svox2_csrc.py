@@ -726,8 +726,8 @@ def surf_tv_grad_sparse(links, data, density_data, rand_cells, mask_out, start_d
             capi.ptr(links), capi.size3(links.shape), capi.ptr(data), C.c_int32(data.shape[1]), capi.ptr(density_data),
             C.c_int32(density_data.shape[1]), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]), _mask_ptr(mask_out),
             C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale), C.c_int32(bool(ignore_edge)), C.c_float(edge_value),
-            C.c_int32(bool(ignore_last_z)), C.c_int32(bool(alpha_dependency)), capi.ptr(grad_data), capi.current_stream()),
-            "surf_tv_grad_sparse")
+            C.c_int32(bool(ignore_last_z)), C.c_int32(bool(alpha_dependency)), capi.ptr(grad_data),
+            capi.ptr(accel_for(links)), capi.current_stream()), "surf_tv_grad_sparse")
 
 
 def alpha_surf_sparsify_grad_sparse(links, alpha_data, surf_data, rand_cells, mask_out, scale_alpha, scale_surf,

@@ -357,7 +357,7 @@ def reference_cuda_same_gpu(args, sg, dev_batches):
     from alphasurf_b200 import step as S
     from tests import helpers as H
     try:
-        ref = H.load_reference_cuda()
+        ref = H.load_reference_cuda(required=False)
     except Exception as e:  # noqa
         return {"unavailable": repr(e)[:200]}
     if ref is None:

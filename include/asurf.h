@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ASURF_ABI_VERSION 1
+#define ASURF_ABI_VERSION 2
 
 enum {
     ASURF_OK = 0,
@@ -200,8 +200,8 @@ int asurf_debug_counters(uint64_t *out8);
 int asurf_debug_work_cache_copy(uint64_t *out, int64_t words, void *stream);
 int32_t asurf_debug_work_cache_valid(void);
 
-/* test hook: let surface_normal_grad_sparse take its dense tiled kernel when the list enumerates every stored vertex
- * (0, default: always the run-aggregated list kernel).  Same result either way up to summation order. */
+/* test hook: tiled kernels of surf_tv_grad_sparse / surface_normal_grad_sparse for lists that are a window of the stored
+ * vertices on (non-zero, default) / off (0: always the list kernels).  Same result either way up to summation order. */
 void asurf_debug_set_normal_tile(int32_t enabled);
 
 /* ---- Plenoxels "cuvol" renderer, render_lerp_kernel_cuvol.cu:1120-1354 (grid->surface / level_set / accel / work unused;
@@ -298,12 +298,14 @@ int asurf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const floa
                          const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, int32_t start_dim,
                          int32_t end_dim, float scale, int32_t ignore_edge, int32_t ignore_last_z, float *grad_data,
                          void *stream);
-/* surf_tv_grad_sparse, :1375-1427 */
+/* surf_tv_grad_sparse, :1375-1427.  accel: optional occupancy buffer of `links` (asurf_accel_build); with it, a list that is
+ * a contiguous window of the ascending list of all stored vertices (what svox2.py:6354-6372 produces) is recognised on the
+ * device and processed tile by tile instead of cell by cell (same result up to summation order). */
 int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf, int32_t n_cols,
                               const float *density, int32_t density_cols, const int32_t *rand_cells, int64_t n_cells,
                               uint8_t *mask_out, int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
                               float edge_value, int32_t ignore_last_z, int32_t alpha_dependency, float *grad_data,
-                              void *stream);
+                              const uint64_t *accel, void *stream);
 /* alpha_surf_sparsify_grad_sparse, :1512-1570 */
 int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,
                                           int32_t alpha_cols, const float *surf, int32_t surf_cols,
@@ -311,8 +313,7 @@ int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t si
                                           float scale_surf, int32_t surf_decrease, float surf_thresh, float alpha_bound,
                                           float surf_bound, float *grad_alpha, float *grad_surf, void *stream);
 /* surface_normal_grad_sparse, :1572-1622 (eikonal_scale and the ndc coefficients of the reference are unused there).
- * accel: optional occupancy buffer of `links` (asurf_accel_build); with it, a list that enumerates every stored vertex is
- * processed by a dense tiled kernel instead of cell by cell (same result up to summation order). */
+ * accel: as for asurf_surf_tv_grad_sparse. */
 int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                      const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,
                                      int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,

@@ -78,10 +78,17 @@ def fused_positional(fd):
     return [fd[k] for k in FUSED_ORDER]
 
 
-def load_reference_cuda():
-    """The UNMODIFIED reference extension compiled by oracle/build_ref_cuda.sh (None if not built)."""
+def load_reference_cuda(required=None):
+    """The UNMODIFIED reference extension compiled by oracle/build_ref_cuda.sh.  On a machine with a GPU the comparator is
+    REQUIRED: a missing build fails the calling test instead of silently reducing it to the oracle comparison
+    (``required=False``: return None instead, for bench.py's optional extra)."""
     cands = glob.glob(os.path.join(ROOT, "oracle", "_ref", "svox2_ref_csrc*.so"))
     if not cands:
+        if required is None:
+            required = torch.cuda.is_available()
+        if required:
+            raise RuntimeError("oracle/_ref/svox2_ref_csrc*.so is missing: run __graft_entry__.build() where /root/reference "
+                               "exists (oracle/build_ref_cuda.sh); the GPU parity tests compare against it")
         return None
     name = "svox2_ref_csrc"
     if name in sys.modules:

@@ -22,7 +22,7 @@ def test_library_exports_every_symbol():
     lib = capi.lib()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.asurf_abi_version() == 1
+    assert lib.asurf_abi_version() == 2
     assert isinstance(lib.asurf_last_error(), bytes)
 
 
@@ -30,7 +30,8 @@ def test_accel_words_is_host_only():
     lib = capi.lib()
     n = lib.asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
     # three pyramid levels + the list of non-empty 16^3 blocks (count word + uint32 ids, 2 per word) + stored-vertex count
-    assert n == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2 + 1
+    # + the list of the 16^3 vertex blocks with a stored vertex (same form) + X*Y + 1 per-column prefix counts (uint32)
+    assert n == (128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2 + 1) + (1 + (32 ** 3 + 1) // 2) + (512 * 512 + 2) // 2
 
 
 def test_struct_layouts_match_header():
@@ -63,7 +64,7 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), lib, "-o", str(exe),
                            "-Wl,-rpath," + os.path.dirname(lib)])
     out = subprocess.check_output([str(exe)]).decode().split()
-    assert int(out[0]) >= 1 and int(out[1]) == 128 ** 3 + 32 ** 3 + 8 ** 3 + 1 + (32 ** 3 + 1) // 2 + 1
+    assert int(out[0]) >= 2 and int(out[1]) == capi.lib().asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
 
 
 def test_ctypes_call_sites_pass_the_declared_number_of_arguments():

@@ -1,0 +1,179 @@
+"""Parity on the configurations BASELINE.json quotes the numbers on (not scaled-down stand-ins): our kernels through the
+svox2.csrc-compatible API against the UNMODIFIED reference CUDA kernels (oracle/_ref) on the same seeded grid and rays.
+
+  C2  Plenoxels cuvol fused, 256^3, SH deg 2, 5000 rays
+  C3  alpha-Surf fused surf_trav render + TV / normal / sparsity regularisers + RMSprop, 512^3, SH deg 2, 65 536 rays
+  C5  full-image evaluation renders (colour, depth, normal), 800 x 800, 640^3
+
+Bar (north_star): hit selection / touched masks bit-exact, colours, depths and gradients <= 1e-4 relative of the tensor max
+plus the reference's own atomic-order noise where it was measured.
+"""
+import pytest
+import torch
+
+from alphasurf_b200 import step as S
+from alphasurf_b200 import svox2_csrc as ours
+from alphasurf_b200 import synth
+from tests import helpers as H
+from tests.test_cuvol_gpu import Grads as CuvolGrads, _grid_spec as cuvol_grid_spec, plenoxels_options
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _clone_grid(sg):
+    return synth.SynthGrid(sg.links, sg.density.clone(), sg.surface.clone(), sg.sh.clone(), sg.level_set, sg.offset,
+                           sg.scaling, sg.basis_dim, sg.fake_sample_std, sg.truncated_vol_render_a, dict(sg.meta))
+
+
+@pytest.fixture(scope="module")
+def grid512():
+    return synth.make_shell_grid(512, basis_dim=9, variant="G").to("cuda")
+
+
+def test_c3_fused_render_512_65536_vs_reference_cuda(grid512):
+    """The call the headline rays/s is quoted on (render_lerp_kernel_surf_trav.cu:3802-3942)."""
+    ref = H.load_reference_cuda()
+    sg = grid512
+    opts, fused = synth.alphasurf_render_options(), synth.alphasurf_fused_args()
+    o, d, gt = synth.make_camera_rays(65536, device="cuda")
+    G, Gr = H.GradSet(sg, "cuda", with_std=False), H.GradSet(sg, "cuda", with_std=False)
+    rgb, rgb_r = torch.zeros_like(o), torch.zeros_like(o)
+    ours.volume_render_surf_trav_fused(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts), gt,
+                                       *H.fused_positional(fused), rgb, G.spec(ours))
+    ref.volume_render_surf_trav_fused(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), gt,
+                                      *H.fused_positional(fused), rgb_r, Gr.spec(ref))
+    # atomic-order noise of the reference itself
+    Gr2 = H.GradSet(sg, "cuda", with_std=False)
+    rgb_r2 = torch.zeros_like(o)
+    ref.volume_render_surf_trav_fused(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), gt,
+                                      *H.fused_positional(fused), rgb_r2, Gr2.spec(ref))
+    torch.cuda.synchronize()
+    assert torch.equal(G.mask, Gr.mask) and int(G.mask.sum()) > 10000, "touched-voxel masks differ (hit selection)"
+    assert H.rel_err(rgb, rgb_r) < TOL
+    assert float((rgb - 1.0).abs().max()) > 1e-2
+    for k in ("sh", "density", "surface"):
+        noise = H.rel_err(getattr(Gr2, k), getattr(Gr, k))
+        assert H.rel_err(getattr(G, k), getattr(Gr, k)) < TOL + 3 * noise, k
+
+
+def test_c3_train_step_512_65536_vs_reference_cuda(grid512):
+    """Two whole C3 iterations (fused render, density TV, surface TV + normal loss over all 15.2 M stored cells, sparsity,
+    RMSprop on density / surface / SH) on both modules."""
+    ref = H.load_reference_cuda()
+    a, b = S.TrainStep(ours, _clone_grid(grid512), seed=5), S.TrainStep(ref, _clone_grid(grid512), seed=5)
+    Q = 65536
+    out_a, out_b = torch.zeros((Q, 3), device="cuda"), torch.zeros((Q, 3), device="cuda")
+    for it in range(2):
+        o, d, gt = synth.make_camera_rays(Q, device="cuda", seed=77 + it)
+        for ts, out in ((a, out_a), (b, out_b)):
+            ts.render(o, d, gt, out)
+            ts.regularisers()
+        torch.cuda.synchronize()
+        assert H.rel_err(out_a, out_b) < TOL
+        assert torch.equal(a.mask, b.mask) and torch.equal(a.mask_sh, b.mask_sh)
+        assert int(a.mask.sum()) > grid512.capacity // 2
+        for k in ("density", "surface", "sh"):
+            assert H.rel_err(a.grad[k], b.grad[k]) < 2e-4, (it, k)
+        for k in ("density", "surface", "sh"):      # one gradient into both optimizers (see test_train_step_gpu.py)
+            b.grad[k].copy_(a.grad[k])
+        a.optimizer()
+        b.optimizer()
+        torch.cuda.synchronize()
+        for k in ("density", "surface", "sh"):
+            assert torch.equal(getattr(a.sg, k), getattr(b.sg, k)), (it, k)
+
+
+def test_c2_cuvol_fused_256_5000_vs_reference_cuda():
+    ref = H.load_reference_cuda()
+    opts = plenoxels_options()
+    sg = synth.make_shell_grid(256, basis_dim=9, variant="G", sigma_density=True).to("cuda")
+    links = sg.links.clone()
+    ref.accel_dist_prop(links)             # the skip codes the cuvol marcher reads (svox2.py accelerate())
+    links_o = sg.links.clone()
+    ours.accel_dist_prop(links_o)
+    assert torch.equal(links, links_o)
+    o, d, gt = synth.make_camera_rays(5000, device="cuda", seed=synth.SEED + 9)
+    G, Gr = CuvolGrads(sg), CuvolGrads(sg)
+    rgb, rgb_r = torch.zeros_like(o), torch.zeros_like(o)
+    ours.volume_render_cuvol_fused(cuvol_grid_spec(ours, sg, links), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts), gt,
+                                   0.0, 0.0, rgb, G.spec(ours))
+    ref.volume_render_cuvol_fused(cuvol_grid_spec(ref, sg, links), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), gt,
+                                  0.0, 0.0, rgb_r, Gr.spec(ref))
+    Gr2 = CuvolGrads(sg)
+    ref.volume_render_cuvol_fused(cuvol_grid_spec(ref, sg, links), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), gt,
+                                  0.0, 0.0, torch.zeros_like(o), Gr2.spec(ref))
+    torch.cuda.synchronize()
+    assert torch.equal(G.mask, Gr.mask) and int(G.mask.sum()) > 1000
+    assert H.rel_err(rgb, rgb_r) < TOL
+    for k in ("sh", "density"):
+        noise = H.rel_err(getattr(Gr2, k), getattr(Gr, k))
+        assert H.rel_err(getattr(G, k), getattr(Gr, k)) < TOL + 3 * noise, k
+
+
+def test_c5_eval_image_640_800x800_vs_reference_cuda():
+    """Colour, expected / mode depth and normal images of one 800 x 800 camera on a 640^3 grid: one call per image on our
+    side, and the reference's 5000-ray chunks (svox2.py:3671-3683) on both sides for the colour image."""
+    ref = H.load_reference_cuda()
+    opts = synth.alphasurf_render_options()
+    sg = synth.make_shell_grid(640, basis_dim=9, variant="G").to("cuda")
+    o, d = synth.make_image_rays(device="cuda")[:2]
+    Q = o.shape[0]
+    assert Q == 640000
+    res = {}
+    for name, mod in (("ours", ours), ("ref", ref)):
+        grid, opt, rays = H.fill_grid_spec(mod, sg), H.fill_opt(mod, opts), H.fill_rays_spec(mod, o, d)
+        res[name] = dict(
+            colour=mod.volume_render_surf_trav(grid, rays, opt),
+            depth_expected=mod.volume_render_expected_term_surf_trav(grid, rays, opt),
+            depth_mode=mod.volume_render_mode_term_surf_trav(grid, rays, opt, 0.1),
+            normal=mod.render_normal_surf_trav(grid, rays, opt))
+    grid, opt = H.fill_grid_spec(ours, sg), H.fill_opt(ours, opts)
+    chunks = torch.cat([ours.volume_render_surf_trav(grid, H.fill_rays_spec(ours, o[i:i + 5000].contiguous(),
+                                                                           d[i:i + 5000].contiguous()), opt)
+                        for i in range(0, Q, 5000)])
+    torch.cuda.synchronize()
+    assert torch.equal(chunks, res["ours"]["colour"])
+    assert float((res["ours"]["colour"] - 1.0).abs().max()) > 1e-2
+    for k in ("colour", "depth_expected", "depth_mode", "normal"):
+        a, b = res["ours"][k], res["ref"][k]
+        assert a.shape == b.shape
+        assert H.rel_err(a, b) < TOL, k
+    hit = res["ref"]["depth_expected"] > 0
+    assert torch.equal(res["ours"]["depth_expected"] > 0, hit) and int(hit.sum()) > Q // 10
+
+
+def test_rows_pack_unpack_round_trip():
+    """asurf_rows_pack / asurf_rows_unpack_add (the sparse gradient exchange of alphasurf_b200.dist) on one GPU: packing the
+    touched rows, clearing them and adding the bucket back restores the gradients bit for bit; a doubled bucket doubles
+    exactly those rows."""
+    import ctypes as C
+    from alphasurf_b200 import capi
+    L = capi.lib()
+    N, D = 50000, 27
+    g = torch.Generator(device="cuda").manual_seed(3)
+    gd, gs, gsh = (torch.randn((N, 1), device="cuda", generator=g), torch.randn((N, 1), device="cuda", generator=g),
+                   torch.randn((N, D), device="cuda", generator=g))
+    rows = torch.nonzero(torch.rand((N,), device="cuda", generator=g) < 0.07).flatten().contiguous()
+    n = rows.shape[0]
+    assert n > 100
+    ref_d, ref_s, ref_sh = gd.clone(), gs.clone(), gsh.clone()
+    bucket = torch.empty((n, 2 + D), device="cuda")
+    st = capi.current_stream()
+    capi.check(L.asurf_rows_pack(capi.ptr(rows), C.c_int64(n), capi.ptr(gd), capi.ptr(gs), capi.ptr(gsh), C.c_int32(D),
+                                 capi.ptr(bucket), C.c_int32(1), st), "rows_pack")
+    torch.cuda.synchronize()
+    assert torch.equal(bucket[:, 0], ref_d[rows, 0]) and torch.equal(bucket[:, 1], ref_s[rows, 0])
+    assert torch.equal(bucket[:, 2:], ref_sh[rows])
+    assert float(gd[rows].abs().max()) == 0.0 and float(gsh[rows].abs().max()) == 0.0 and float(gs[rows].abs().max()) == 0.0
+    keep = torch.ones((N,), dtype=torch.bool, device="cuda")
+    keep[rows] = False
+    assert torch.equal(gd[keep], ref_d[keep]) and torch.equal(gsh[keep], ref_sh[keep])
+    capi.check(L.asurf_rows_unpack_add(capi.ptr(rows), C.c_int64(n), capi.ptr(gd), capi.ptr(gs), capi.ptr(gsh), C.c_int32(D),
+                                       capi.ptr(bucket), st), "rows_unpack_add")
+    torch.cuda.synchronize()
+    assert torch.equal(gd, ref_d) and torch.equal(gs, ref_s) and torch.equal(gsh, ref_sh)
+    capi.check(L.asurf_rows_unpack_add(capi.ptr(rows), C.c_int64(n), capi.ptr(gd), capi.ptr(gs), capi.ptr(gsh), C.c_int32(D),
+                                       capi.ptr(bucket), st), "rows_unpack_add")
+    torch.cuda.synchronize()
+    assert torch.equal(gsh[rows], 2 * ref_sh[rows]) and torch.equal(gsh[keep], ref_sh[keep])

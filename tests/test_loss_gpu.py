@@ -237,34 +237,54 @@ def test_loss_kernels_at_full_size_properties():
     assert n == R ** 3
 
 
-@pytest.mark.parametrize("reso,variant,z_order", [(40, "G*", None), (64, "G", None), (33, "G*", False)])
+def _tile_path(enabled):
+    from alphasurf_b200 import capi
+    capi.lib().asurf_debug_set_normal_tile(1 if enabled else 0)
+
+
+def _window(sg, frac, seed):
+    """the list svox2.py:6354-6372 builds: all stored vertices in ascending order, or a contiguous window of that list"""
+    ne = torch.where(sg.links.view(-1) >= 0)[0].int()
+    if frac >= 1.0:
+        return ne
+    n = int(ne.shape[0] * frac)
+    start = int(torch.randint(0, ne.shape[0] - n + 1, (1,), generator=torch.Generator().manual_seed(seed)))
+    return ne[start:start + n].contiguous()
+
+
+# shell_half = 1.0: every vertex stored (the far faces of the grid are reached: the reference's link-0 reads, :761-763);
+# shell_half = 0.25: the shell touches the faces but not the corners
+TILE_GRIDS = [(40, "G*", None, 0.05), (64, "G", None, 0.05), (33, "G*", False, 0.05), (24, "G*", False, 1.0), (36, "G", False, 0.25)]
+
+
+@pytest.mark.parametrize("reso,variant,z_order,shell_half", TILE_GRIDS)
 @pytest.mark.parametrize("con_check,ignore_empty,use_l1", [(False, False, True), (True, True, False)])
-def test_surface_normal_all_stored_cells_tile_path(reso, variant, z_order, con_check, ignore_empty, use_l1):
-    """norm_surface_sparsity = 1: the list is every stored vertex in ascending order (svox2.py:6354-6361); the library
-    recognises it on the device and runs the dense tiled kernel.  Same result as the oracle / the reference kernel, and as
-    our list kernel on a permuted copy of the list (which cannot take the tile path)."""
+@pytest.mark.parametrize("frac", [1.0, 0.37])
+def test_surface_normal_window_lists_take_the_tile_path(reso, variant, z_order, shell_half, con_check, ignore_empty, use_l1,
+                                                        frac):
+    """norm_surface_sparsity = 1 hands the kernel every stored vertex in ascending order, a smaller fraction a contiguous
+    window of that list (svox2.py:6354-6372); the library recognises both on the device and runs the tiled kernel.  Same
+    result as the oracle / the reference kernel, and as our list kernel (tile path switched off)."""
     from oracle import oracle
-    sg = _grid(reso, variant=variant, z_order=z_order)
-    cells_c = torch.where(sg.links.view(-1) >= 0)[0].int()
+    sg = synth.make_shell_grid(reso, basis_dim=4, variant=variant, z_order=z_order, shell_half=shell_half)
+    cells_c = _window(sg, frac, 11)
     links, surf, cells = sg.links.cuda(), sg.surface.cuda(), cells_c.cuda()
     lv = float(sg.level_set[0])
     args = (lv, 0, 1, 1e-2, 0.0, -1.0, -1.0, con_check, ignore_empty, use_l1)
     grad = torch.zeros_like(surf)
     mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
-    from alphasurf_b200 import capi
-    capi.lib().asurf_debug_set_normal_tile(1)
-    try:
-        ours.surface_normal_grad_sparse(links, surf, cells, mask, *args, grad)
-    finally:
-        capi.lib().asurf_debug_set_normal_tile(0)
+    ours.surface_normal_grad_sparse(links, surf, cells, mask, *args, grad)
     g_o = np.zeros(tuple(sg.surface.shape), np.float32)
     m_o = np.zeros((sg.capacity,), np.uint8)
     oracle.surface_normal_grad_sparse(sg.links, sg.surface, cells_c, m_o, lv, 0, 1, 1e-2, con_check, ignore_empty, use_l1, g_o)
     _close(grad, g_o, "normal loss, tile path vs oracle")
     assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
-    perm = cells[torch.randperm(cells.shape[0], device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))]
     g_p, m_p = torch.zeros_like(surf), torch.zeros_like(mask)
-    ours.surface_normal_grad_sparse(links, surf, perm.contiguous(), m_p, *args, g_p)
+    _tile_path(False)
+    try:
+        ours.surface_normal_grad_sparse(links, surf, cells, m_p, *args, g_p)
+    finally:
+        _tile_path(True)
     assert H.rel_err(grad, g_p) < TOL and torch.equal(mask, m_p)
     ref = H.load_reference_cuda()
     if ref is not None:
@@ -272,3 +292,72 @@ def test_surface_normal_all_stored_cells_tile_path(reso, variant, z_order, con_c
         ref.surface_normal_grad_sparse(links, surf, cells, m_r, *args, g_r)
         _close(grad, g_r.cpu(), "normal loss, tile path vs reference CUDA")
         assert torch.equal(mask, m_r)
+
+
+@pytest.mark.parametrize("reso,variant,z_order,shell_half", TILE_GRIDS)
+@pytest.mark.parametrize("ignore_edge,edge_value,ignore_last_z", [(True, -1.0, False), (False, -1.0, False), (False, 0.5, True)])
+@pytest.mark.parametrize("frac", [1.0, 0.37])
+def test_surf_tv_window_lists_take_the_tile_path(reso, variant, z_order, shell_half, ignore_edge, edge_value, ignore_last_z, frac):
+    """tv_surface_sparsity = 1 / a window of the stored vertices: tiled surface TV vs the oracle, the reference kernel and
+    our list kernel; includes grids whose stored vertices reach the far faces (out-of-range neighbours read link 0 there)."""
+    from oracle import oracle
+    sg = synth.make_shell_grid(reso, basis_dim=4, variant=variant, z_order=z_order, shell_half=shell_half)
+    cells_c = _window(sg, frac, 12)
+    links, surf, dens, cells = sg.links.cuda(), sg.surface.cuda(), sg.density.cuda(), cells_c.cuda()
+    args = (0, 1, 1e-3, ignore_edge, edge_value, ignore_last_z, -1.0, -1.0, False)
+    grad = torch.zeros_like(surf)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.surf_tv_grad_sparse(links, surf, dens, cells, mask, *args, grad)
+    g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.tv_grad_sparse(sg.links, sg.surface, sg.density, cells_c, m_o, 0, 1, 1e-3, ignore_edge, edge_value, ignore_last_z,
+                          False, True, g_o)
+    _close(grad, g_o, "surface TV, tile path vs oracle")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o)
+    g_p, m_p = torch.zeros_like(surf), torch.zeros_like(mask)
+    _tile_path(False)
+    try:
+        ours.surf_tv_grad_sparse(links, surf, dens, cells, m_p, *args, g_p)
+    finally:
+        _tile_path(True)
+    assert H.rel_err(grad, g_p) < TOL and torch.equal(mask, m_p)
+    ref = H.load_reference_cuda()
+    if ref is not None:
+        g_r, m_r = torch.zeros_like(surf), torch.zeros_like(mask)
+        ref.surf_tv_grad_sparse(links, surf, dens, cells, m_r, *args, g_r)
+        _close(grad, g_r.cpu(), "surface TV, tile path vs reference CUDA")
+        assert torch.equal(mask, m_r)
+
+
+def test_lists_that_are_not_windows_fall_back_to_the_list_kernels():
+    """A window with one entry removed / duplicated / unordered is not the set of stored vertices between its ends: the
+    device-side check must send it to the list kernels (same result as the oracle)."""
+    from oracle import oracle
+    sg = synth.make_shell_grid(40, basis_dim=4, variant="G*")
+    ne = _window(sg, 1.0, 0)
+    n = ne.shape[0]
+    variants = {
+        "hole": torch.cat([ne[:n // 2], ne[n // 2 + 1:]]),
+        "duplicate": torch.cat([ne[:n // 2], ne[n // 2 - 1:]]),
+        "swapped": torch.cat([ne[:7], ne[8:9], ne[7:8], ne[9:]]),
+    }
+    links, surf = sg.links.cuda(), sg.surface.cuda()
+    for name, cells_c in variants.items():
+        cells_c = cells_c.contiguous()
+        grad = torch.zeros_like(surf)
+        mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+        ours.surface_normal_grad_sparse(links, surf, cells_c.cuda(), mask, 0.0, 0, 1, 1e-2, 0.0, -1.0, -1.0, False, False, True, grad)
+        g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+        m_o = np.zeros((sg.capacity,), np.uint8)
+        oracle.surface_normal_grad_sparse(sg.links, sg.surface, cells_c, m_o, 0.0, 0, 1, 1e-2, False, False, True, g_o)
+        _close(grad, g_o, "normal loss, %s list" % name)
+        assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o), name
+        grad = torch.zeros_like(surf)
+        mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+        ours.surf_tv_grad_sparse(links, surf, sg.density.cuda(), cells_c.cuda(), mask, 0, 1, 1e-3, True, -1.0, False, -1.0, -1.0,
+                                 False, grad)
+        g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+        m_o = np.zeros((sg.capacity,), np.uint8)
+        oracle.tv_grad_sparse(sg.links, sg.surface, sg.density, cells_c, m_o, 0, 1, 1e-3, True, -1.0, False, False, True, g_o)
+        _close(grad, g_o, "surface TV, %s list" % name)
+        assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o), name

@@ -89,7 +89,9 @@ def test_incremental_work_pyramid_equals_full_rebuild():
             # size of the three pyramid levels
             from alphasurf_b200.svox2_csrc import accel_for, _grid_t
             g, keep = _grid_t(ts.grid_spec)
-            lay_words = n3 - 2 - (((reso + 14) // 16) ** 3 + 1) // 2      # accel_words = levels + 1 + ids/2 + 1
+            b0 = (max(reso - 1, 1) + 3) // 4                              # AccelLayout (common.cuh): 4^3, 16^3, 64^3 cells
+            b1 = (b0 + 3) // 4
+            lay_words = b0 ** 3 + b1 ** 3 + ((b1 + 3) // 4) ** 3
             capi.check(L.asurf_debug_work_cache_copy(capi.ptr(cached), C.c_int64(lay_words), capi.current_stream()), "copy")
             capi.check(L.asurf_work_build(C.byref(g), C.byref(capi.make_opt(ts.opt_spec)), capi.ptr(full),
                                           capi.current_stream()), "work_build")
