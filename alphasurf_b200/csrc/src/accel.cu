@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) accel_list1_kernel(AccelLayout lay, uint6
 
 
 // List of the 16^3 VERTEX blocks (vertices [16b, 16b + 16) per axis) that hold a stored vertex, kept behind the stored-vertex
-// count: word = their number, then their indices as uint32 (2 per word).  The tiled regularisers (loss.cu) walk it: the
+// count: word = their number, then their block coordinates packed as bx | by << 10 | bz << 20 (uint32, 2 per word).  The tiled regularisers (loss.cu) walk it: the
 // non-empty level-1 list above only names blocks with a COMPLETE cell, which a TV term does not need.
 __global__ void __launch_bounds__(256) vblock_list_kernel(const int32_t *__restrict__ links, int sx, int sy, int sz, int nby,
                                                            int nbz, uint64_t *__restrict__ out) {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) vblock_list_kernel(const int32_t *__restr
     any = __syncthreads_or(any);
     if (threadIdx.x == 0 && any) {
         const unsigned long long at = atomicAdd((unsigned long long *)out, 1ull);
-        ((uint32_t *)(out + 1))[at] = (uint32_t)w;
+        ((uint32_t *)(out + 1))[at] = (uint32_t)bx | ((uint32_t)by << 10) | ((uint32_t)bz << 20);
     }
 }
 

@@ -689,7 +689,7 @@ constexpr int32_t L_OUT = INT32_MIN;            // staged "link" of a vertex out
 struct TileVerdict {
     int bad;        // 0: the list is the window [lo, hi] of the stored vertices -> tile kernel; else the list kernels run
     int lo, hi;     // flat vertex ids
-    unsigned ctr;   // tile fetch counter
+    unsigned ctr;   // reserved
 };
 
 // stored vertices with a flat id < bound (bound in [0, X*Y*Z]); whole warp, result on every lane
@@ -722,114 +722,188 @@ list_window_check_kernel(const int32_t *__restrict__ links, const int32_t *__res
             if (!ok) v->bad = 1;
         }
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t c = __ldg(cells + i);
-        const bool ok = (c >= 0) && ((int64_t)c < n_vertices) && (i == 0 || __ldg(cells + i - 1) < c) && (__ldg(links + c) >= 0);
+    // four entries per thread and round: 8 independent loads, then 4 independent gathers of the links
+    for (int64_t base = (int64_t)blockIdx.x * (blockDim.x * 4) + threadIdx.x; base < n_cells; base += (int64_t)gridDim.x * (blockDim.x * 4)) {
+        int32_t c[4], pr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + (int64_t)k * blockDim.x;
+            c[k] = (i < n_cells) ? __ldg(cells + i) : -2;
+            pr[k] = (i < n_cells && i > 0) ? __ldg(cells + i - 1) : -1;
+        }
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] == -2) continue;
+            const bool in = (c[k] >= 0) && ((int64_t)c[k] < n_vertices) && (pr[k] < c[k]);
+            ok &= in && (__ldg(links + (in ? c[k] : 0)) >= 0);
+        }
         if (!ok) v->bad = 1;
     }
 }
 
-// stage the vertices [x0 - 1, x0 - 1 + NX) x ... of a tile: link (L_OUT outside the grid) and value (0 where not stored)
+// ---- tile staging, software-pipelined: the links of the NEXT tile are loaded into registers before the first compute
+//      phase of the current one; after that phase (which is the last reader of the current scalars) they go to the other
+//      link buffer and the scalars behind them are fetched by cp.async (4 bytes each, no register round trip) while the
+//      remaining phases run.  Every global access of a tile is therefore issued one or two phases before it is needed. ----
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// (i, j, k) of the flat index tid + r * TILE_THREADS in an (.., NY, NZ) box, advanced without divisions
+template <int NY, int NZ>
+struct BoxIter {
+    static constexpr int DI = TILE_THREADS / (NY * NZ), REM = TILE_THREADS % (NY * NZ), DJ = REM / NZ, DK = REM % NZ;
+    int i, j, k;
+    __device__ __forceinline__ explicit BoxIter(int v) {
+        i = v / (NY * NZ);
+        const int rem = v - i * (NY * NZ);
+        j = rem / NZ;
+        k = rem - j * NZ;
+    }
+    __device__ __forceinline__ void next() {
+        k += DK;
+        if (k >= NZ) { k -= NZ; ++j; }
+        j += DJ;
+        if (j >= NY) { j -= NY; ++i; }
+        i += DI;
+    }
+};
+
 template <int NX, int NY, int NZ>
-__device__ __forceinline__ void stage_tile(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols,
-                                           int idx, const Dims &d, int x0, int y0, int z0, int32_t *s_link, float *s_val,
-                                           int tid) {
-    constexpr int NV = NX * NY * NZ;
-    for (int vb = tid; vb < NV; vb += 4 * TILE_THREADS) {
-        int32_t l[4];
+struct TileBox {   // staged vertices: [x0 - 1, x0 - 1 + NX) x [y0 - 1, ...) x [z0 - 1, ...)
+    static constexpr int NV = NX * NY * NZ;
+    static constexpr int PER = (NV + TILE_THREADS - 1) / TILE_THREADS;
+
+    // flat ids fit 32 bits on this path (the host checks the grid size)
+    static __device__ __forceinline__ void load_links(const int32_t *__restrict__ links, const Dims &d, int x0, int y0, int z0,
+                                                      int tid, int32_t (&l)[PER]) {
+        const bool inside = (x0 >= 1) && (y0 >= 1) && (z0 >= 1) && (x0 - 1 + NX <= d.sx) && (y0 - 1 + NY <= d.sy) &&
+                            (z0 - 1 + NZ <= d.sz);
+        const int slab = d.sy * d.sz;
+        const int base = ((x0 - 1) * d.sy + (y0 - 1)) * d.sz + (z0 - 1);
+        BoxIter<NY, NZ> it(tid);
+        if (inside) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int v = vb + r * TILE_THREADS;
-            l[r] = L_OUT;
-            if (v < NV) {
-                const int i = v / (NY * NZ), rem = v - i * (NY * NZ), j = rem / NZ, k = rem - j * NZ;
-                const int x = x0 - 1 + i, y = y0 - 1 + j, z = z0 - 1 + k;
-                if (x >= 0 && y >= 0 && z >= 0 && x < d.sx && y < d.sy && z < d.sz)
-                    l[r] = __ldg(links + (((int64_t)x * d.sy + y) * d.sz + z));
+            for (int r = 0; r < PER; ++r) {
+                l[r] = L_OUT;
+                if (r < PER - 1 || tid + r * TILE_THREADS < NV) l[r] = __ldg(links + (base + it.i * slab + it.j * d.sz + it.k));
+                it.next();
             }
-        }
-        float s[4];
+        } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) s[r] = (l[r] >= 0) ? __ldg(data + (int64_t)l[r] * n_cols + idx) : 0.f;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int v = vb + r * TILE_THREADS;
-            if (v < NV) {
-                s_link[v] = l[r];
-                s_val[v] = s[r];
+            for (int r = 0; r < PER; ++r) {
+                l[r] = L_OUT;
+                if (r < PER - 1 || tid + r * TILE_THREADS < NV) {
+                    const int x = x0 - 1 + it.i, y = y0 - 1 + it.j, z = z0 - 1 + it.k;
+                    if (x >= 0 && y >= 0 && z >= 0 && x < d.sx && y < d.sy && z < d.sz)
+                        l[r] = __ldg(links + (base + it.i * slab + it.j * d.sz + it.k));
+                }
+                it.next();
             }
         }
     }
-}
+    // links -> shared, their scalars -> shared through cp.async (0 where not stored); one commit group
+    static __device__ __forceinline__ void store_and_gather(const int32_t (&l)[PER], const float *__restrict__ data, int n_cols,
+                                                            int idx, int32_t *s_link, float *s_val, int tid) {
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int v = tid + r * TILE_THREADS;
+            if (r < PER - 1 || v < NV) {
+                s_link[v] = l[r];
+                if (l[r] >= 0) cp_async4(s_val + v, data + (int64_t)l[r] * n_cols + idx);
+                else s_val[v] = 0.f;
+            }
+        }
+        cp_async_commit();
+    }
+};
 
-// next tile of the walk: (block of the vertex-block list, half); false when the list is exhausted
-__device__ __forceinline__ bool next_tile(TileVerdict *v, const uint64_t *__restrict__ vbl, const Dims &d, int *s_tile,
-                                          int &x0, int &y0, int &z0) {
-    __syncthreads();   // the shared buffers of the previous tile are free
-    if (threadIdx.x == 0) *s_tile = (int)atomicAdd(&v->ctr, 1u);
-    __syncthreads();
-    const int t = *s_tile;
-    const int n_blocks = (int)vbl[0];
-    if (t >= 2 * n_blocks) return false;
-    const int w = (int)((const uint32_t *)(vbl + 1))[t >> 1];
-    const int nby = (d.sy + 15) >> 4, nbz = (d.sz + 15) >> 4;
-    z0 = (w % nbz) * 16;
-    y0 = ((w / nbz) % nby) * 16;
-    x0 = (w / (nbz * nby)) * 16 + (t & 1) * TS_X;
-    return true;
+// tiles of this CTA: t, t + gridDim.x, ... over (vertex block of the list behind the occupancy pyramid, half); skips tiles
+// outside the grid or the window.  The ids of a tile's own vertices lie in [x0 Y Z, (x0 + TS_X) Y Z); cells of the x layer
+// below may own terms that land on them.  all_in: every cell the tile looks at is inside the window (no per-cell test).
+__device__ __forceinline__ bool tile_seek(int &t, int n_tiles, const uint64_t *__restrict__ vbl, const Dims &d, int lo, int hi,
+                                          int &x0, int &y0, int &z0, bool &all_in) {
+    const int64_t slab = (int64_t)d.sy * d.sz;
+    for (; t < n_tiles; t += gridDim.x) {
+        const unsigned w = __ldg((const uint32_t *)(vbl + 1) + (t >> 1));   // block coordinates, 10 bits each (accel.cu)
+        x0 = (int)(w & 1023u) * 16 + (t & 1) * TS_X;
+        if (x0 >= d.sx) continue;
+        const int64_t a = (int64_t)x0 * slab, b = (int64_t)(x0 + TS_X) * slab;
+        if (b <= (int64_t)lo || a - slab > (int64_t)hi) continue;
+        y0 = (int)((w >> 10) & 1023u) * 16;
+        z0 = (int)((w >> 20) & 1023u) * 16;
+        all_in = (a - slab >= (int64_t)lo) && (b + slab - 1 <= (int64_t)hi);
+        return true;
+    }
+    return false;
 }
 
 // -- surface TV (tv_grad_sparse_kernel / surf_tv_grad_sparse_kernel semantics of one channel, no alpha dependency) --
 constexpr int TV_VX = TS_X + 2, TV_VY = TS_Y + 2, TV_VZ = TS_Z + 2;   // vertices -1 .. T
 constexpr int TV_CX = TS_X + 1, TV_CY = TS_Y + 1, TV_CZ = TS_Z + 1;   // cells    -1 .. T-1
 constexpr int TV_NV = TV_VX * TV_VY * TV_VZ, TV_NC = TV_CX * TV_CY * TV_CZ;
-constexpr size_t TV_SMEM = (size_t)TV_NV * 8 + (size_t)TV_NC * 16 + (size_t)TV_NC;
+constexpr size_t TV_OFF_VAL = (size_t)TV_NV * 8, TV_OFF_G = (size_t)TV_NV * 12, TV_OFF_F = TV_OFF_G + (size_t)TV_NC * 16;
+constexpr size_t TV_SMEM = TV_OFF_F + (size_t)TV_NC;
+static_assert(TV_OFF_G % 16 == 0, "float4 alignment of the TV tile");
 
 template <bool SURF>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols, int idx, Dims d,
-               const uint64_t *__restrict__ vbl, TileVerdict *__restrict__ verdict, float scale, int ignore_edge,
+               const uint64_t *__restrict__ vbl, const TileVerdict *__restrict__ verdict, float scale, int ignore_edge,
                float edge_value, int ignore_last_z, uint8_t *__restrict__ mask, float *__restrict__ grad) {
     if (verdict->bad) return;   // not a window of the stored vertices: the list kernel does the work
+    using Box = TileBox<TV_VX, TV_VY, TV_VZ>;
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    int32_t *s_link = (int32_t *)tile_smem;
-    float *s_val = (float *)(tile_smem + (size_t)TV_NV * 4);
-    float4 *s_g = (float4 *)(tile_smem + (size_t)TV_NV * 8);          // per cell: to +x, +y, +z neighbour, to itself
-    uint8_t *s_f = (uint8_t *)(tile_smem + (size_t)TV_NV * 8 + (size_t)TV_NC * 16);
-    __shared__ int s_tile;
+    int32_t *s_link2 = (int32_t *)tile_smem;                               // two link buffers
+    float *s_val = (float *)(tile_smem + TV_OFF_VAL);
+    float4 *s_g = (float4 *)(tile_smem + TV_OFF_G);                        // per cell: to +x, +y, +z neighbour, to itself
+    uint8_t *s_f = (uint8_t *)(tile_smem + TV_OFF_F);
     const int tid = threadIdx.x;
     const int lo = verdict->lo, hi = verdict->hi;
+    const int n_tiles = 2 * (int)vbl[0];
     float sc[3];
     ray_scale(d, sc);
     const float missing = SURF ? edge_value : 0.f;
-    int x0, y0, z0;
-    while (next_tile(verdict, vbl, d, &s_tile, x0, y0, z0)) {
-        if (x0 >= d.sx) continue;
-        {   // flat ids of the tile's own vertices lie in [x0 * Y * Z, (x0 + TS_X) * Y * Z): skip tiles outside the window
-            const int64_t a = (int64_t)x0 * d.sy * d.sz, b = (int64_t)(x0 + TS_X) * d.sy * d.sz;
-            if (b <= (int64_t)lo || a - (int64_t)d.sy * d.sz > (int64_t)hi) continue;   // (cells of the x layer below may own terms)
-        }
-        stage_tile<TV_VX, TV_VY, TV_VZ>(links, data, n_cols, idx, d, x0, y0, z0, s_link, s_val, tid);
+    int t = blockIdx.x, x0, y0, z0, buf = 0;
+    bool all_in = false, n_all_in = false;
+    if (!tile_seek(t, n_tiles, vbl, d, lo, hi, x0, y0, z0, all_in)) return;
+    {
+        int32_t l[Box::PER];
+        Box::load_links(links, d, x0, y0, z0, tid, l);
+        Box::store_and_gather(l, data, n_cols, idx, s_link2, s_val, tid);
+    }
+    for (;;) {
+        cp_async_wait_all();
         __syncthreads();
+        const int32_t *s_link = s_link2 + buf * TV_NV;
+        int tn = t + gridDim.x, nx0 = 0, ny0 = 0, nz0 = 0;
+        const bool has_next = tile_seek(tn, n_tiles, vbl, d, lo, hi, nx0, ny0, nz0, n_all_in);
+        int32_t ln[Box::PER];
+        if (has_next) Box::load_links(links, d, nx0, ny0, nz0, tid, ln);
         // phase 1: the TV term of every listed cell in [-1, T)^3
-        for (int c = tid; c < TV_NC; c += TILE_THREADS) {
-            const int i = c / (TV_CY * TV_CZ), rem = c - i * (TV_CY * TV_CZ), j = rem / TV_CZ, k = rem - j * TV_CZ;
+        BoxIter<TV_CY, TV_CZ> it(tid);
+        for (int c = tid; c < TV_NC; c += TILE_THREADS, it.next()) {
+            const int i = it.i, j = it.j, k = it.k;
             const int vb = (i * TV_VY + j) * TV_VZ + k;
             const int32_t l000 = s_link[vb];
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             unsigned fl = 0u;
-            const int x = x0 - 1 + i, y = y0 - 1 + j, z = z0 - 1 + k;
-            bool valid = l000 >= 0;
-            if (valid) {
-                const int64_t id = ((int64_t)x * d.sy + y) * d.sz + z;
-                valid = (id >= lo) && (id <= hi) && !(ignore_edge && l000 == 0) && !(ignore_last_z && z == d.sz - 2);
+            const int z = z0 - 1 + k;
+            bool valid = (l000 >= 0) && !(ignore_edge && l000 == 0) && !(ignore_last_z && z == d.sz - 2);
+            if (valid && !all_in) {
+                const int id = ((x0 - 1 + i) * d.sy + (y0 - 1 + j)) * d.sz + z;
+                valid = (id >= lo) && (id <= hi);
             }
             if (valid) {
                 const bool own = (i >= 1) && (j >= 1) && (k >= 1);
                 const float v000 = s_val[vb];
                 const float nullv = ignore_edge ? v000 : missing;
                 // a neighbour outside the grid reads link 0 in the reference (sic, :761-763): row 0's value and gradient
-                int32_t l001 = s_link[vb + 1], l010 = s_link[vb + TV_VZ], l100 = s_link[vb + TV_VY * TV_VZ];
+                const int32_t l001 = s_link[vb + 1], l010 = s_link[vb + TV_VZ], l100 = s_link[vb + TV_VY * TV_VZ];
                 const bool oz = (l001 == L_OUT), oy = (l010 == L_OUT), ox = (l100 == L_OUT);
                 const float row0 = (ox || oy || oz) ? __ldg(data + idx) : 0.f;
                 const float v001 = oz ? row0 : (l001 >= 0 ? s_val[vb + 1] : nullv);
@@ -858,7 +932,8 @@ tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data
             s_g[c] = g;
             s_f[c] = (uint8_t)fl;
         }
-        __syncthreads();
+        __syncthreads();   // the scalars of this tile are consumed: the next tile's may land
+        if (has_next) Box::store_and_gather(ln, data, n_cols, idx, s_link2 + (buf ^ 1) * TV_NV, s_val, tid);
         // phase 2: every own vertex gathers its own term and those of the cells below it: one atomic per vertex
         for (int o = tid; o < TS_X * TS_Y * TS_Z; o += TILE_THREADS) {
             const int i = o / (TS_Y * TS_Z), j = (o / TS_Z) % TS_Y, k = o % TS_Z;
@@ -871,6 +946,10 @@ tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data
                 if (mask) mask[l] = 1;
             }
         }
+        if (!has_next) break;
+        t = tn; x0 = nx0; y0 = ny0; z0 = nz0;
+        all_in = n_all_in;
+        buf ^= 1;
     }
 }
 
@@ -880,9 +959,10 @@ constexpr int NT_CX = TS_X + 2, NT_CY = TS_Y + 2, NT_CZ = TS_Z + 2;   // cells  
 constexpr int NT_NV = NT_VX * NT_VY * NT_VZ, NT_NC = NT_CX * NT_CY * NT_CZ;
 constexpr int NT_OWN = TS_X * TS_Y * TS_Z;
 constexpr int NT_PER = NT_OWN / TILE_THREADS;                          // own cells per thread
-constexpr size_t NT_OFF_NRM = (((size_t)NT_NV * 8 + 15) / 16) * 16;
-constexpr size_t NT_SMEM = NT_OFF_NRM + (size_t)NT_NC * 16 + (size_t)NT_NC;
-static_assert(((size_t)TV_NV * 8) % 16 == 0, "float4 alignment of the TV tile");
+constexpr size_t NT_OFF_VAL = (size_t)NT_NV * 8;                       // after the two link buffers
+constexpr size_t NT_OFF_NRM = (((size_t)NT_NV * 12 + 15) / 16) * 16;
+constexpr size_t NT_OFF_CF = NT_OFF_NRM + (size_t)NT_NC * 16;
+constexpr size_t NT_SMEM = NT_OFF_CF + (size_t)NT_NC;
 static_assert(NT_OWN % TILE_THREADS == 0, "own cells must divide over the threads");
 static_assert(NT_OWN <= NT_NC, "the per-cell gradients reuse the normals' buffer");
 
@@ -937,32 +1017,43 @@ __device__ __forceinline__ bool pair_used(unsigned f_lower, unsigned f_upper, in
 template <bool CHECKS>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, Dims d, const uint64_t *__restrict__ vbl,
-                   TileVerdict *__restrict__ verdict, float lv_set, float scale, int con_check, int ignore_empty, int use_l1,
-                   uint8_t *__restrict__ mask, float *__restrict__ grad) {
+                   const TileVerdict *__restrict__ verdict, float lv_set, float scale, int con_check, int ignore_empty,
+                   int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad) {
     if (verdict->bad) return;
+    using Box = TileBox<NT_VX, NT_VY, NT_VZ>;
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    int32_t *s_link = (int32_t *)tile_smem;
-    float *s_val = (float *)(tile_smem + (size_t)NT_NV * 4);
-    float4 *s_nrm = (float4 *)(tile_smem + NT_OFF_NRM);   // per cell: unit normal, 1 / |n|; later d(loss)/d(normal) of the own cells
-    uint8_t *s_cf = (uint8_t *)(tile_smem + NT_OFF_NRM + (size_t)NT_NC * 16);
-    __shared__ int s_tile;
+    int32_t *s_link2 = (int32_t *)tile_smem;                 // two link buffers
+    float *s_val = (float *)(tile_smem + NT_OFF_VAL);
+    float4 *s_nrm = (float4 *)(tile_smem + NT_OFF_NRM);     // per cell: unit normal, 1 / |n|; later d(loss)/d(normal) of the own cells
+    uint8_t *s_cf = (uint8_t *)(tile_smem + NT_OFF_CF);
     const int tid = threadIdx.x;
     const int lo = verdict->lo, hi = verdict->hi;
-    const int64_t gstride[3] = {(int64_t)d.sy * d.sz, (int64_t)d.sz, 1};
+    const int n_tiles = 2 * (int)vbl[0];
+    const int gstride[3] = {d.sy * d.sz, d.sz, 1};
     constexpr int cstride[3] = {NT_CY * NT_CZ, NT_CZ, 1};
-    int x0, y0, z0;
-    while (next_tile(verdict, vbl, d, &s_tile, x0, y0, z0)) {
-        if (x0 >= d.sx) continue;
-        {
-            const int64_t a = (int64_t)x0 * d.sy * d.sz, b = (int64_t)(x0 + TS_X) * d.sy * d.sz;
-            if (b <= (int64_t)lo || a - (int64_t)d.sy * d.sz > (int64_t)hi) continue;
-        }
-        stage_tile<NT_VX, NT_VY, NT_VZ>(links, surf, 1, 0, d, x0, y0, z0, s_link, s_val, tid);
+    // 0.25 scale / (number of pairs the owner cell forms), as the reference computes it
+    const float q1 = 0.25f * (scale * 1.f / 1), q2 = 0.25f * (scale * 1.f / 2), q3 = 0.25f * (scale * 1.f / 3);
+    int t = blockIdx.x, x0, y0, z0, buf = 0;
+    bool all_in = false, n_all_in = false;
+    if (!tile_seek(t, n_tiles, vbl, d, lo, hi, x0, y0, z0, all_in)) return;
+    {
+        int32_t l[Box::PER];
+        Box::load_links(links, d, x0, y0, z0, tid, l);
+        Box::store_and_gather(l, surf, 1, 0, s_link2, s_val, tid);
+    }
+    for (;;) {
+        cp_async_wait_all();
         __syncthreads();
+        const int32_t *s_link = s_link2 + buf * NT_NV;
+        int tn = t + gridDim.x, nx0 = 0, ny0 = 0, nz0 = 0;
+        const bool has_next = tile_seek(tn, n_tiles, vbl, d, lo, hi, nx0, ny0, nz0, n_all_in);
+        int32_t ln[Box::PER];
+        if (has_next) Box::load_links(links, d, nx0, ny0, nz0, tid, ln);
         // phase 1: unit normal of every complete cell in [-1, T]^3
         int any = 0;
-        for (int c = tid; c < NT_NC; c += TILE_THREADS) {
-            const int i = c / (NT_CY * NT_CZ), rem = c - i * (NT_CY * NT_CZ), j = rem / NT_CZ, k = rem - j * NT_CZ;
+        BoxIter<NT_CY, NT_CZ> it(tid);
+        for (int c = tid; c < NT_NC; c += TILE_THREADS, it.next()) {
+            const int i = it.i, j = it.j, k = it.k;
             const int vb = (i * NT_VY + j) * NT_VZ + k;
             Cell8 cc;
             bool ok = true;
@@ -985,81 +1076,89 @@ normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ 
                     f |= face_connected(cc.s[2], cc.s[3], cc.s[6], cc.s[7], lv_set) ? 8u : 0u;
                     f |= face_connected(cc.s[1], cc.s[3], cc.s[5], cc.s[7], lv_set) ? 16u : 0u;
                 }
-                any |= (i >= 1 && i <= TS_X && j >= 1 && j <= TS_Y && k >= 1 && k <= TS_Z) ? 1 : 0;
+                any |= ((unsigned)(i - 1) < (unsigned)TS_X && (unsigned)(j - 1) < (unsigned)TS_Y && (unsigned)(k - 1) < (unsigned)TS_Z) ? 1 : 0;
             }
             s_cf[c] = (uint8_t)f;
         }
-        if (!__syncthreads_or(any)) continue;   // no complete own cell: nothing to do (next_tile synchronises)
-        // phase 2: d(loss)/d(normal) of every own cell, summed over the <= 6 pairs it takes part in (kept in registers: the
-        // result overwrites the normals once every thread is done reading them)
-        float4 G[NT_PER];
+        any = __syncthreads_or(any);   // also: the scalars of this tile are consumed, the next tile's may land
+        if (has_next) Box::store_and_gather(ln, surf, 1, 0, s_link2 + (buf ^ 1) * NT_NV, s_val, tid);
+        if (any) {   // some own cell is complete
+            // phase 2: d(loss)/d(normal) of every own cell, summed over the <= 6 pairs it takes part in (kept in registers:
+            // the result overwrites the normals once every thread is done reading them)
+            float4 G[NT_PER];
 #pragma unroll
-        for (int r = 0; r < NT_PER; ++r) {
-            const int o = tid + r * TILE_THREADS;
-            const int i = o / (TS_Y * TS_Z), j = (o / TS_Z) % TS_Y, k = o % TS_Z;
-            const int ci = ((i + 1) * NT_CY + (j + 1)) * NT_CZ + (k + 1);
-            float A0 = 0.f, A1 = 0.f, A2 = 0.f;
-            unsigned touched = 0u;
-            const unsigned f = s_cf[ci];
-            if (f & 1u) {
-                const int64_t id = ((int64_t)(x0 + i) * d.sy + (y0 + j)) * d.sz + (z0 + k);
-                const float4 nc = s_nrm[ci];
-                // pairs this cell owns (itself and its +x / +y / +z neighbour), if it is on the list
-                if (id >= lo && id <= hi) {
-                    bool u[3];
-                    int cnt = 0;
+            for (int r = 0; r < NT_PER; ++r) {
+                const int o = tid + r * TILE_THREADS;
+                const int i = o / (TS_Y * TS_Z), j = (o / TS_Z) % TS_Y, k = o % TS_Z;
+                const int ci = ((i + 1) * NT_CY + (j + 1)) * NT_CZ + (k + 1);
+                float A0 = 0.f, A1 = 0.f, A2 = 0.f;
+                unsigned touched = 0u;
+                const unsigned f = s_cf[ci];
+                if (f & 1u) {
+                    const int id = all_in ? 0 : ((x0 + i) * d.sy + (y0 + j)) * d.sz + (z0 + k);
+                    const float4 nc = s_nrm[ci];
+                    // pairs this cell owns (itself and its +x / +y / +z neighbour), if it is on the list
+                    if (all_in || (id >= lo && id <= hi)) {
+                        bool u[3];
+                        int cnt = 0;
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) {
+                            u[e] = pair_used<CHECKS>(f, s_cf[ci + cstride[e]], e, con_check, ignore_empty);
+                            cnt += u[e] ? 1 : 0;
+                        }
+                        const float q = (cnt == 1) ? q1 : ((cnt == 2) ? q2 : q3);
+#pragma unroll
+                        for (int e = 0; e < 3; ++e)
+                            if (u[e]) normal_side(nc, s_nrm[ci + cstride[e]], q, use_l1, A0, A1, A2, touched);
+                    }
+                    // pairs owned by the -x / -y / -z neighbour
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
-                        u[e] = pair_used<CHECKS>(f, s_cf[ci + cstride[e]], e, con_check, ignore_empty);
-                        cnt += u[e] ? 1 : 0;
+                        const int cl = ci - cstride[e];
+                        const unsigned fl = s_cf[cl];
+                        const int idl = id - gstride[e];
+                        if (!(fl & 1u) || (!all_in && (idl < lo || idl > hi)) ||
+                            !pair_used<CHECKS>(fl, f, e, con_check, ignore_empty))
+                            continue;
+                        int cnt = 1;
+#pragma unroll
+                        for (int e2 = 0; e2 < 3; ++e2)
+                            if (e2 != e) cnt += pair_used<CHECKS>(fl, s_cf[cl + cstride[e2]], e2, con_check, ignore_empty) ? 1 : 0;
+                        normal_side(nc, s_nrm[cl], (cnt == 1) ? q1 : ((cnt == 2) ? q2 : q3), use_l1, A0, A1, A2, touched);
                     }
-                    const float q = 0.25f * (scale * 1.f / cnt);
-#pragma unroll
-                    for (int e = 0; e < 3; ++e)
-                        if (u[e]) normal_side(nc, s_nrm[ci + cstride[e]], q, use_l1, A0, A1, A2, touched);
                 }
-                // pairs owned by the -x / -y / -z neighbour
+                G[r] = make_float4(A0, A1, A2, __uint_as_float(touched));
+            }
+            __syncthreads();
 #pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    const int cl = ci - cstride[e];
-                    const unsigned fl = s_cf[cl];
-                    const int64_t idl = id - gstride[e];
-                    if (!(fl & 1u) || idl < lo || idl > hi || !pair_used<CHECKS>(fl, f, e, con_check, ignore_empty)) continue;
-                    int cnt = 1;
+            for (int r = 0; r < NT_PER; ++r) s_nrm[tid + r * TILE_THREADS] = G[r];
+            __syncthreads();
+            // phase 3: every vertex of [0, T]^3 gathers from the own cells around it: one atomic per vertex
+            BoxIter<TS_Y + 1, TS_Z + 1> iv(tid);
+            for (int v = tid; v < (TS_X + 1) * (TS_Y + 1) * (TS_Z + 1); v += TILE_THREADS, iv.next()) {
+                const int i = iv.i, j = iv.j, k = iv.k;
+                float val = 0.f;
+                unsigned tch = 0u;
 #pragma unroll
-                    for (int e2 = 0; e2 < 3; ++e2)
-                        if (e2 != e) cnt += pair_used<CHECKS>(fl, s_cf[cl + cstride[e2]], e2, con_check, ignore_empty) ? 1 : 0;
-                    const float q = 0.25f * (scale * 1.f / cnt);
-                    normal_side(nc, s_nrm[cl], q, use_l1, A0, A1, A2, touched);
+                for (int q = 0; q < 8; ++q) {   // the vertex is corner q of the cell at (i, j, k) - (q >> 2, (q >> 1) & 1, q & 1)
+                    const int ci = i - (q >> 2), cj = j - ((q >> 1) & 1), ck = k - (q & 1);
+                    if (ci < 0 || cj < 0 || ck < 0 || ci >= TS_X || cj >= TS_Y || ck >= TS_Z) continue;
+                    const float4 g = s_nrm[(ci * TS_Y + cj) * TS_Z + ck];
+                    const float u = ((q & 4) ? g.x : -g.x) + ((q & 2) ? g.y : -g.y);
+                    val += (q & 1) ? (u + g.z) : (u - g.z);
+                    tch |= (__float_as_uint(g.w) >> q) & 1u;
                 }
-            }
-            G[r] = make_float4(A0, A1, A2, __uint_as_float(touched));
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < NT_PER; ++r) s_nrm[tid + r * TILE_THREADS] = G[r];
-        __syncthreads();
-        // phase 3: every vertex of [0, T]^3 gathers from the own cells around it: one atomic per vertex
-        for (int v = tid; v < (TS_X + 1) * (TS_Y + 1) * (TS_Z + 1); v += TILE_THREADS) {
-            const int i = v / ((TS_Y + 1) * (TS_Z + 1)), rem = v - i * ((TS_Y + 1) * (TS_Z + 1)), j = rem / (TS_Z + 1),
-                      k = rem - j * (TS_Z + 1);
-            float val = 0.f;
-            unsigned tch = 0u;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {   // the vertex is corner q of the cell at (i, j, k) - (q >> 2, (q >> 1) & 1, q & 1)
-                const int ci = i - (q >> 2), cj = j - ((q >> 1) & 1), ck = k - (q & 1);
-                if (ci < 0 || cj < 0 || ck < 0 || ci >= TS_X || cj >= TS_Y || ck >= TS_Z) continue;
-                const float4 g = s_nrm[(ci * TS_Y + cj) * TS_Z + ck];
-                const float u = ((q & 4) ? g.x : -g.x) + ((q & 2) ? g.y : -g.y);
-                val += (q & 1) ? (u + g.z) : (u - g.z);
-                tch |= (__float_as_uint(g.w) >> q) & 1u;
-            }
-            if (tch) {
-                const int32_t l = s_link[((i + 1) * NT_VY + (j + 1)) * NT_VZ + (k + 1)];
-                atomicAdd(grad + l, val);
-                if (mask) mask[l] = 1;
+                if (tch) {
+                    const int32_t l = s_link[((i + 1) * NT_VY + (j + 1)) * NT_VZ + (k + 1)];
+                    atomicAdd(grad + l, val);
+                    if (mask) mask[l] = 1;
+                }
             }
         }
+        if (!has_next) break;
+        t = tn; x0 = nx0; y0 = ny0; z0 = nz0;
+        all_in = n_all_in;
+        buf ^= 1;
     }
 }
 
@@ -1228,6 +1327,10 @@ extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const
 }
 
 extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_tile_path = enabled ? 1 : 0; }
+extern "C" int asurf_debug_last_verdict(int32_t *out4) {   // synchronises: {bad, lo, hi, tiles fetched} of the last list check
+    ASURF_REQUIRE(out4 && g_ws_verdict.ptr, ASURF_E_INVALID, "debug_last_verdict: no list check has run");
+    return check_cuda(cudaMemcpy(out4, g_ws_verdict.ptr, sizeof(TileVerdict), cudaMemcpyDeviceToHost), "debug_last_verdict");
+}
 
 extern "C" int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3], const float *surf,
                                                 const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float lv_set,

@@ -203,6 +203,9 @@ int32_t asurf_debug_work_cache_valid(void);
 /* test hook: tiled kernels of surf_tv_grad_sparse / surface_normal_grad_sparse for lists that are a window of the stored
  * vertices on (non-zero, default) / off (0: always the list kernels).  Same result either way up to summation order. */
 void asurf_debug_set_normal_tile(int32_t enabled);
+/* test hook (synchronises): verdict of the last device-side list check, 4 ints = {bad (0: the tiled kernel ran), lo, hi
+ * (flat ids of the window), tiles fetched by the persistent CTAs} */
+int asurf_debug_last_verdict(int32_t *out4);
 
 /* ---- Plenoxels "cuvol" renderer, render_lerp_kernel_cuvol.cu:1120-1354 (grid->surface / level_set / accel / work unused;
  *      links may hold the negative skip codes written by accel_dist_prop) ---- */

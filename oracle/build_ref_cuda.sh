@@ -39,3 +39,9 @@ OBJS=""; for s in $SRCS svox2; do OBJS="$OBJS $OBJ/$s.o"; done
 g++ -shared -o "$OUT/$NAME$SUFFIX" $OBJS -L"$TORCH_LIB" -lc10 -lc10_cuda -ltorch_cpu -ltorch_cuda -ltorch -ltorch_python \
    -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,"$TORCH_LIB"
 echo "built $OUT/$NAME$SUFFIX"
+# The reference's own Python package, staged UNMODIFIED beside the comparator (git-ignored like the .so, travels to the GPU
+# box): tests/test_dropin_gpu.py imports it twice -- with `svox2.csrc` = our compiled shim and = the reference extension --
+# and bench.py's cpu_baseline times its pure-PyTorch gradcheck renderer (config C1) on the box's host cores.
+mkdir -p "$OUT/pyref/svox2"
+cp -f "$REF"/svox2/*.py "$OUT/pyref/svox2/"
+echo "staged $OUT/pyref/svox2 ($(ls "$OUT/pyref/svox2" | wc -l) files)"

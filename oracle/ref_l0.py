@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- runs the reference's own pure-PyTorch "gradcheck" renderer (L0) on CPU.
 
-Imports /root/reference/svox2 UNMODIFIED (nothing is copied).  Works only in the development container
-(the GPU box has no /root/reference); used by oracle/gen_golden.py to write tests/golden/*.npz and by the
-CPU tests that are skipped when the reference tree is absent.
+Imports /root/reference/svox2 UNMODIFIED (nothing is copied into the repository's history).  On the GPU box, which has no
+/root/reference, the package is found where oracle/build_ref_cuda.sh staged it (oracle/_ref/pyref, git-ignored, travels with
+the snapshot like the compiled comparator).  Used by oracle/gen_golden.py to write tests/golden/*.npz, by the CPU tests
+that are skipped when the package is absent, and by bench.py's cpu_baseline (config C1, kind "reference").
 
 Shims needed to import and run it on CPU:
   * ``mcubes`` is not installed -> stub module (module-level import at svox2/svox2.py:16);
@@ -18,7 +19,8 @@ import warnings
 
 import torch
 
-REF_ROOT = os.environ.get("ASURF_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")   # oracle/build_ref_cuda.sh
+REF_ROOT = os.environ.get("ASURF_REFERENCE", "/root/reference" if os.path.isdir("/root/reference/svox2") else _STAGED)
 
 
 def available() -> bool:

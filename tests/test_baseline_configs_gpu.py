@@ -31,57 +31,73 @@ def grid512():
     return synth.make_shell_grid(512, basis_dim=9, variant="G").to("cuda")
 
 
+def _perturbed(sg, seed=0):
+    """the same grid with every surface scalar moved by one ulp (tests/helpers.py::assert_close_conditioned)"""
+    return synth.SynthGrid(sg.links, sg.density, H.ulp_perturbed(sg.surface, seed), sg.sh, sg.level_set, sg.offset, sg.scaling,
+                           sg.basis_dim, sg.fake_sample_std, sg.truncated_vol_render_a, dict(sg.meta))
+
+
+def _fused(mod, sg, o, d, gt, opts, fused):
+    G = H.GradSet(sg, "cuda", with_std=False)
+    rgb = torch.zeros_like(o)
+    mod.volume_render_surf_trav_fused(H.fill_grid_spec(mod, sg), H.fill_rays_spec(mod, o, d), H.fill_opt(mod, opts), gt,
+                                      *H.fused_positional(fused), rgb, G.spec(mod))
+    return rgb, G
+
+
 def test_c3_fused_render_512_65536_vs_reference_cuda(grid512):
-    """The call the headline rays/s is quoted on (render_lerp_kernel_surf_trav.cu:3802-3942)."""
+    """The call the headline rays/s is quoted on (render_lerp_kernel_surf_trav.cu:3802-3942).  Measured on B200
+    (profiles/r2_c3_parity_diag.log): colours bit-identical, SH / density gradients 5e-8 / 3e-7, surface gradients 1e-6 except
+    the 8 corners of ONE voxel holding a near-double root, where the reference moves by 4.4e-4 under a one-ulp change of its
+    own input and we differ from it by 4.2e-4."""
     ref = H.load_reference_cuda()
     sg = grid512
     opts, fused = synth.alphasurf_render_options(), synth.alphasurf_fused_args()
     o, d, gt = synth.make_camera_rays(65536, device="cuda")
-    G, Gr = H.GradSet(sg, "cuda", with_std=False), H.GradSet(sg, "cuda", with_std=False)
-    rgb, rgb_r = torch.zeros_like(o), torch.zeros_like(o)
-    ours.volume_render_surf_trav_fused(H.fill_grid_spec(ours, sg), H.fill_rays_spec(ours, o, d), H.fill_opt(ours, opts), gt,
-                                       *H.fused_positional(fused), rgb, G.spec(ours))
-    ref.volume_render_surf_trav_fused(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), gt,
-                                      *H.fused_positional(fused), rgb_r, Gr.spec(ref))
-    # atomic-order noise of the reference itself
-    Gr2 = H.GradSet(sg, "cuda", with_std=False)
-    rgb_r2 = torch.zeros_like(o)
-    ref.volume_render_surf_trav_fused(H.fill_grid_spec(ref, sg), H.fill_rays_spec(ref, o, d), H.fill_opt(ref, opts), gt,
-                                      *H.fused_positional(fused), rgb_r2, Gr2.spec(ref))
+    rgb, G = _fused(ours, sg, o, d, gt, opts, fused)
+    rgb_r, Gr = _fused(ref, sg, o, d, gt, opts, fused)
+    rgb_p, Gp = _fused(ref, _perturbed(sg), o, d, gt, opts, fused)
     torch.cuda.synchronize()
     assert torch.equal(G.mask, Gr.mask) and int(G.mask.sum()) > 10000, "touched-voxel masks differ (hit selection)"
     assert H.rel_err(rgb, rgb_r) < TOL
     assert float((rgb - 1.0).abs().max()) > 1e-2
     for k in ("sh", "density", "surface"):
-        noise = H.rel_err(getattr(Gr2, k), getattr(Gr, k))
-        assert H.rel_err(getattr(G, k), getattr(Gr, k)) < TOL + 3 * noise, k
+        n = H.assert_close_conditioned(getattr(G, k), getattr(Gr, k), getattr(Gp, k), TOL, k)
+        assert n <= (64 if k != "sh" else 64 * 27), (k, n)
 
 
 def test_c3_train_step_512_65536_vs_reference_cuda(grid512):
     """Two whole C3 iterations (fused render, density TV, surface TV + normal loss over all 15.2 M stored cells, sparsity,
-    RMSprop on density / surface / SH) on both modules."""
+    RMSprop on density / surface / SH) on both modules; the third TrainStep runs the reference on a grid whose surface
+    scalars are one ulp off (the conditioning yardstick of assert_close_conditioned)."""
     ref = H.load_reference_cuda()
     a, b = S.TrainStep(ours, _clone_grid(grid512), seed=5), S.TrainStep(ref, _clone_grid(grid512), seed=5)
+    p = S.TrainStep(ref, _clone_grid(grid512), seed=5)
     Q = 65536
-    out_a, out_b = torch.zeros((Q, 3), device="cuda"), torch.zeros((Q, 3), device="cuda")
+    outs = [torch.zeros((Q, 3), device="cuda") for _ in range(3)]
     for it in range(2):
+        p.sg.surface.copy_(H.ulp_perturbed(b.sg.surface, seed=it))
         o, d, gt = synth.make_camera_rays(Q, device="cuda", seed=77 + it)
-        for ts, out in ((a, out_a), (b, out_b)):
+        for ts, out in zip((a, b, p), outs):
             ts.render(o, d, gt, out)
             ts.regularisers()
         torch.cuda.synchronize()
-        assert H.rel_err(out_a, out_b) < TOL
+        assert H.rel_err(outs[0], outs[1]) < TOL
         assert torch.equal(a.mask, b.mask) and torch.equal(a.mask_sh, b.mask_sh)
         assert int(a.mask.sum()) > grid512.capacity // 2
         for k in ("density", "surface", "sh"):
-            assert H.rel_err(a.grad[k], b.grad[k]) < 2e-4, (it, k)
-        for k in ("density", "surface", "sh"):      # one gradient into both optimizers (see test_train_step_gpu.py)
+            H.assert_close_conditioned(a.grad[k], b.grad[k], p.grad[k], TOL, "%s, iteration %d" % (k, it))
+        for k in ("density", "surface", "sh"):      # one gradient into all optimizers (see test_train_step_gpu.py)
             b.grad[k].copy_(a.grad[k])
+            p.grad[k].copy_(a.grad[k])
         a.optimizer()
         b.optimizer()
+        p.optimizer()
         torch.cuda.synchronize()
         for k in ("density", "surface", "sh"):
             assert torch.equal(getattr(a.sg, k), getattr(b.sg, k)), (it, k)
+        for k in ("density", "sh"):
+            getattr(p.sg, k).copy_(getattr(b.sg, k))
 
 
 def test_c2_cuvol_fused_256_5000_vs_reference_cuda():
