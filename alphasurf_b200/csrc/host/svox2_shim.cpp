@@ -262,6 +262,43 @@ Tensor volume_render_surf_trav(SparseGridSpec &grid, RaysSpec &rays, RenderOptio
     return out;
 }
 
+// march counters of SURVEY.md 8(d) for one forward march (bench.py's algorithmic bytes): surf_trav / cuvol flavour
+py::dict stats_dict(const Tensor &st) {
+    const Tensor h = st.cpu();
+    const int64_t *v = h.data_ptr<int64_t>();
+    py::dict d;
+    d["n_steps"] = v[0];
+    d["n_skips"] = v[1];
+    d["n_linked"] = v[2];
+    d["n_active"] = v[3];
+    d["n_samples"] = v[4];
+    return d;
+}
+py::dict render_stats(SparseGridSpec &grid, RaysSpec &rays, RenderOptions &opt) {
+    check_grid(grid);
+    check_rays(rays);
+    const c10::cuda::CUDAGuard guard(grid.sh_data.device());
+    Tensor out = torch::empty_like(rays.origins);
+    Tensor st = torch::zeros({6}, rays.origins.options().dtype(torch::kInt64));
+    GridArg g = grid_t(grid, true);
+    asurf_rays_t r = rays_t(rays);
+    asurf_opt_t o = opt_t(opt);
+    check_rc(asurf_surf_trav_forward(&g.g, &r, &o, out.data_ptr<float>(), (asurf_stats_t *)st.data_ptr<int64_t>(), stream_of(out)),
+             "render_stats");
+    return stats_dict(st);
+}
+py::dict cuvol_render_stats(SparseGridSpec &grid, RaysSpec &rays, RenderOptions &opt) {
+    check_grid(grid);
+    check_rays(rays);
+    const c10::cuda::CUDAGuard guard(grid.sh_data.device());
+    Tensor st = torch::zeros({6}, rays.origins.options().dtype(torch::kInt64));
+    GridArg g = grid_t(grid, false);
+    asurf_rays_t r = rays_t(rays);
+    asurf_opt_t o = opt_t(opt);
+    check_rc(asurf_cuvol_stats(&g.g, &r, &o, (asurf_stats_t *)st.data_ptr<int64_t>(), stream_of(st)), "cuvol_render_stats");
+    return stats_dict(st);
+}
+
 void volume_render_surf_trav_backward(SparseGridSpec &grid, RaysSpec &rays, RenderOptions &opt, Tensor grad_out,
                                       Tensor color_cache, GridOutputGrads &grads) {
     check_grid(grid);
@@ -828,6 +865,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("set_loss_norm_rays", [](py::object n) { g_norm_rays = n.is_none() ? 0 : n.cast<int64_t>(); },
           "global ray count used to normalise the fused losses in a ray-sharded run (None: per call)");
     m.def("abi_version", []() { return asurf_abi_version(); });
+    m.def("render_stats", &render_stats, "march counters of one surf_trav forward pass (SURVEY.md 8d)");
+    m.def("cuvol_render_stats", &cuvol_render_stats, "march counters of one cuvol forward pass (SURVEY.md 8d)");
+    m.def("accel_for", &accel_for, "occupancy pyramid of a links tensor (built on the current stream and cached)");
 
     py::class_<SparseGridSpec>(m, "SparseGridSpec")
         .def(py::init<>())

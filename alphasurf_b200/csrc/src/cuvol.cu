@@ -386,6 +386,61 @@ cuvol_scalar_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restri
     if (MODE != ASURF_CUVOL_MED_TERM) out[ray_id] = res;
 }
 
+// march counters of SURVEY.md 8(d) for the cuvol flavour (bench.py's algorithmic bytes): thread per ray, the sample
+// positions and the early stop of trace_ray_cuvol (:30-125)
+__global__ void __launch_bounds__(128)
+cuvol_count_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
+                   const int64_t Q, unsigned long long *__restrict__ stats) {
+    const int64_t ray_id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n_pos = 0, n_skip = 0, n_samp = 0, n_contrib = 0;
+    if (ray_id < Q) {
+        CvRay r;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            r.o[i] = origins[ray_id * 3 + i];
+            r.d[i] = dirs[ray_id * 3 + i];
+        }
+        cv_ray_bounds(g, opt, r);
+        if (!(r.tmin > r.tmax)) {
+            float t = r.tmin, log_transmit = 0.f;
+            while (t <= r.tmax) {
+                CvSample s;
+                s.t = t;
+                cv_density_phase(g, r, s);
+                ++n_pos;
+                if (s.skip >= opt.step_size) {
+                    ++n_skip;
+                    t += ceilf(s.skip / opt.step_size) * opt.step_size;
+                    continue;
+                }
+                ++n_samp;
+                float world_step = r.world_step;
+                if (opt.last_sample_opaque && t + opt.step_size > r.tmax) world_step = r.world_step = 1e9f;
+                if (s.sigma > opt.sigma_thresh) {
+                    ++n_contrib;
+                    log_transmit -= world_step * s.sigma;
+                    if (__expf(log_transmit) < opt.stop_thresh) break;
+                }
+                t += opt.step_size;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_pos += __shfl_xor_sync(FULL, n_pos, off);
+        n_skip += __shfl_xor_sync(FULL, n_skip, off);
+        n_samp += __shfl_xor_sync(FULL, n_samp, off);
+        n_contrib += __shfl_xor_sync(FULL, n_contrib, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + 0, n_pos);       // asurf_stats_t.n_steps: sample positions (one skip-link read each)
+        atomicAdd(stats + 1, n_skip);      // n_skips: positions that jump over an empty block
+        atomicAdd(stats + 2, n_samp);      // n_linked: samples whose 8 links + 8 densities are gathered
+        atomicAdd(stats + 3, n_samp);      // n_active
+        atomicAdd(stats + 4, n_contrib);   // n_samples: samples with sigma > sigma_thresh (SH gather, gradients)
+    }
+}
+
 int cv_make_grid(const asurf_grid_t *grid, CvGrid &g, const char *who) {
     ASURF_REQUIRE(grid, ASURF_E_INVALID, "%s: null grid", who);
     ASURF_REQUIRE(grid->links && grid->density && grid->sh, ASURF_E_INVALID, "%s: null grid tensor", who);
@@ -429,6 +484,20 @@ extern "C" int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t 
         g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, log_transmit_out, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "cuvol_forward launch");
+}
+
+extern "C" int asurf_cuvol_stats(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
+                                 asurf_stats_t *stats_dev, void *stream) {
+    ASURF_REQUIRE(rays && opt && stats_dev, ASURF_E_INVALID, "cuvol_stats: null argument");
+    const int64_t Q = rays->n_rays;
+    if (Q <= 0) return 0;
+    CvGrid g;
+    int rc = cv_make_grid(grid, g, "cuvol_stats");
+    if (rc) return rc;
+    cuvol_count_kernel<<<(int)((Q + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, *opt, rays->origins, rays->dirs, Q,
+                                                                                 (unsigned long long *)stats_dev);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "cuvol_stats launch");
 }
 
 extern "C" int asurf_cuvol_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,

@@ -19,6 +19,11 @@ __global__ void __launch_bounds__(256) rows_kernel(const int64_t *__restrict__ r
     const int W = 2 + D;
     for (int64_t i = warp0; i < n; i += n_warps) {
         const int64_t r = rows[i];
+        if (r < 0) {   // padding of a fixed-capacity row list (torch.nonzero_static): zeros travel, nothing is added back
+            if (PACK)
+                for (int c = lane; c < W; c += 32) bucket[i * W + c] = 0.f;
+            continue;
+        }
         for (int c = lane; c < W; c += 32) {
             float *src = (c == 0) ? (density + r) : ((c == 1) ? (surface + r) : (sh + r * D + (c - 2)));
             if (PACK) {

@@ -689,7 +689,7 @@ constexpr int32_t L_OUT = INT32_MIN;            // staged "link" of a vertex out
 struct TileVerdict {
     int bad;        // 0: the list is the window [lo, hi] of the stored vertices -> tile kernel; else the list kernels run
     int lo, hi;     // flat vertex ids
-    unsigned ctr;   // reserved
+    unsigned ctr;   // tile fetch counter
 };
 
 // stored vertices with a flat id < bound (bound in [0, X*Y*Z]); whole warp, result on every lane
@@ -722,22 +722,29 @@ list_window_check_kernel(const int32_t *__restrict__ links, const int32_t *__res
             if (!ok) v->bad = 1;
         }
     }
-    // four entries per thread and round: 8 independent loads, then 4 independent gathers of the links
-    for (int64_t base = (int64_t)blockIdx.x * (blockDim.x * 4) + threadIdx.x; base < n_cells; base += (int64_t)gridDim.x * (blockDim.x * 4)) {
-        int32_t c[4], pr[4];
+    // eight entries per thread and round, branch-free: 16 independent loads of the list, then 8 independent gathers of links
+    constexpr int CHK = 8;
+    for (int64_t base = (int64_t)blockIdx.x * (blockDim.x * CHK) + threadIdx.x; base < n_cells;
+         base += (int64_t)gridDim.x * (blockDim.x * CHK)) {
+        int32_t c[CHK], pr[CHK];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CHK; ++k) {
             const int64_t i = base + (int64_t)k * blockDim.x;
-            c[k] = (i < n_cells) ? __ldg(cells + i) : -2;
-            pr[k] = (i < n_cells && i > 0) ? __ldg(cells + i - 1) : -1;
+            const int64_t ic = (i < n_cells) ? i : (n_cells - 1);       // tail: re-check the last entry
+            c[k] = __ldg(cells + ic);
+            pr[k] = __ldg(cells + (ic > 0 ? ic - 1 : 0));
+            if (ic == 0) pr[k] = -1;
         }
+        int32_t lk[CHK];
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (c[k] == -2) continue;
-            const bool in = (c[k] >= 0) && ((int64_t)c[k] < n_vertices) && (pr[k] < c[k]);
-            ok &= in && (__ldg(links + (in ? c[k] : 0)) >= 0);
+        for (int k = 0; k < CHK; ++k) {
+            const bool in = (c[k] >= 0) && ((int64_t)c[k] < n_vertices);
+            ok &= in && (pr[k] < c[k]);
+            lk[k] = __ldg(links + (in ? c[k] : 0));
         }
+#pragma unroll
+        for (int k = 0; k < CHK; ++k) ok &= (lk[k] >= 0);
         if (!ok) v->bad = 1;
     }
 }
@@ -822,24 +829,34 @@ struct TileBox {   // staged vertices: [x0 - 1, x0 - 1 + NX) x [y0 - 1, ...) x [
     }
 };
 
-// tiles of this CTA: t, t + gridDim.x, ... over (vertex block of the list behind the occupancy pyramid, half); skips tiles
-// outside the grid or the window.  The ids of a tile's own vertices lie in [x0 Y Z, (x0 + TS_X) Y Z); cells of the x layer
-// below may own terms that land on them.  all_in: every cell the tile looks at is inside the window (no per-cell test).
-__device__ __forceinline__ bool tile_seek(int &t, int n_tiles, const uint64_t *__restrict__ vbl, const Dims &d, int lo, int hi,
-                                          int &x0, int &y0, int &z0, bool &all_in) {
+// Tiles are handed out dynamically (their costs differ with the fill of the block): (vertex block of the list behind the
+// occupancy pyramid, half), index from a global counter.  Tiles outside the grid or the window are skipped by the fetching
+// thread.  The ids of a tile's own vertices lie in [x0 Y Z, (x0 + TS_X) Y Z); cells of the x layer below may own terms that
+// land on them.  all_in: every cell the tile looks at is inside the window (no per-cell test).
+struct TileRef {
+    int x0, y0, z0;
+    int flags;   // 1 valid, 2 all_in
+};
+
+__device__ __forceinline__ bool tile_decode(int t, int n_tiles, const uint64_t *__restrict__ vbl, const Dims &d, int lo, int hi,
+                                            TileRef &r) {
+    if (t >= n_tiles) { r.flags = 0; return true; }   // the list is exhausted: "no tile"
     const int64_t slab = (int64_t)d.sy * d.sz;
-    for (; t < n_tiles; t += gridDim.x) {
-        const unsigned w = __ldg((const uint32_t *)(vbl + 1) + (t >> 1));   // block coordinates, 10 bits each (accel.cu)
-        x0 = (int)(w & 1023u) * 16 + (t & 1) * TS_X;
-        if (x0 >= d.sx) continue;
-        const int64_t a = (int64_t)x0 * slab, b = (int64_t)(x0 + TS_X) * slab;
-        if (b <= (int64_t)lo || a - slab > (int64_t)hi) continue;
-        y0 = (int)((w >> 10) & 1023u) * 16;
-        z0 = (int)((w >> 20) & 1023u) * 16;
-        all_in = (a - slab >= (int64_t)lo) && (b + slab - 1 <= (int64_t)hi);
-        return true;
-    }
-    return false;
+    const unsigned w = __ldg((const uint32_t *)(vbl + 1) + (t >> 1));   // block coordinates, 10 bits each (accel.cu)
+    r.x0 = (int)(w & 1023u) * 16 + (t & 1) * TS_X;
+    if (r.x0 >= d.sx) return false;
+    const int64_t a = (int64_t)r.x0 * slab, b = (int64_t)(r.x0 + TS_X) * slab;
+    if (b <= (int64_t)lo || a - slab > (int64_t)hi) return false;
+    r.y0 = (int)((w >> 10) & 1023u) * 16;
+    r.z0 = (int)((w >> 20) & 1023u) * 16;
+    r.flags = 1 | (((a - slab >= (int64_t)lo) && (b + slab - 1 <= (int64_t)hi)) ? 2 : 0);
+    return true;
+}
+// one thread: next tile of the walk (flags == 0 when there is none); `first` is an index already drawn from the counter
+__device__ __forceinline__ void tile_fetch(unsigned first, TileVerdict *v, int n_tiles, const uint64_t *__restrict__ vbl,
+                                           const Dims &d, int lo, int hi, TileRef &r) {
+    unsigned t = first;
+    while (!tile_decode((int)(t < 0x7fffffffu ? t : 0x7fffffffu), n_tiles, vbl, d, lo, hi, r)) t = atomicAdd(&v->ctr, 1u);
 }
 
 // -- surface TV (tv_grad_sparse_kernel / surf_tv_grad_sparse_kernel semantics of one channel, no alpha dependency) --
@@ -853,7 +870,7 @@ static_assert(TV_OFF_G % 16 == 0, "float4 alignment of the TV tile");
 template <bool SURF>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols, int idx, Dims d,
-               const uint64_t *__restrict__ vbl, const TileVerdict *__restrict__ verdict, float scale, int ignore_edge,
+               const uint64_t *__restrict__ vbl, TileVerdict *__restrict__ verdict, float scale, int ignore_edge,
                float edge_value, int ignore_last_z, uint8_t *__restrict__ mask, float *__restrict__ grad) {
     if (verdict->bad) return;   // not a window of the stored vertices: the list kernel does the work
     using Box = TileBox<TV_VX, TV_VY, TV_VZ>;
@@ -868,22 +885,32 @@ tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data
     float sc[3];
     ray_scale(d, sc);
     const float missing = SURF ? edge_value : 0.f;
-    int t = blockIdx.x, x0, y0, z0, buf = 0;
-    bool all_in = false, n_all_in = false;
-    if (!tile_seek(t, n_tiles, vbl, d, lo, hi, x0, y0, z0, all_in)) return;
+    __shared__ TileRef s_ref[2];   // [0] the first tile, then alternately "the tile after this one"
+    int buf = 0;
+    if (tid == 0) {
+        tile_fetch(atomicAdd(&verdict->ctr, 1u), verdict, n_tiles, vbl, d, lo, hi, s_ref[0]);
+        tile_fetch(atomicAdd(&verdict->ctr, 1u), verdict, n_tiles, vbl, d, lo, hi, s_ref[1]);
+    }
+    __syncthreads();
+    TileRef cur = s_ref[0];
+    if (!cur.flags) return;
     {
         int32_t l[Box::PER];
-        Box::load_links(links, d, x0, y0, z0, tid, l);
+        Box::load_links(links, d, cur.x0, cur.y0, cur.z0, tid, l);
         Box::store_and_gather(l, data, n_cols, idx, s_link2, s_val, tid);
     }
-    for (;;) {
+    for (int it_no = 1;; ++it_no) {
         cp_async_wait_all();
         __syncthreads();
         const int32_t *s_link = s_link2 + buf * TV_NV;
-        int tn = t + gridDim.x, nx0 = 0, ny0 = 0, nz0 = 0;
-        const bool has_next = tile_seek(tn, n_tiles, vbl, d, lo, hi, nx0, ny0, nz0, n_all_in);
+        const TileRef nxt = s_ref[it_no & 1];
+        const bool has_next = nxt.flags != 0;
+        unsigned drawn = 0u;
+        if (tid == 0 && has_next) drawn = atomicAdd(&verdict->ctr, 1u);   // consumed after phase 1: its latency is hidden
+        const int x0 = cur.x0, y0 = cur.y0, z0 = cur.z0;
+        const bool all_in = (cur.flags & 2) != 0;
         int32_t ln[Box::PER];
-        if (has_next) Box::load_links(links, d, nx0, ny0, nz0, tid, ln);
+        if (has_next) Box::load_links(links, d, nxt.x0, nxt.y0, nxt.z0, tid, ln);
         // phase 1: the TV term of every listed cell in [-1, T)^3
         BoxIter<TV_CY, TV_CZ> it(tid);
         for (int c = tid; c < TV_NC; c += TILE_THREADS, it.next()) {
@@ -933,6 +960,10 @@ tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data
             s_f[c] = (uint8_t)fl;
         }
         __syncthreads();   // the scalars of this tile are consumed: the next tile's may land
+        if (tid == 0) {       // everybody has read s_ref[it_no & 1]; the other slot receives the tile after the next one
+            if (has_next) tile_fetch(drawn, verdict, n_tiles, vbl, d, lo, hi, s_ref[(it_no & 1) ^ 1]);
+            else s_ref[(it_no & 1) ^ 1].flags = 0;
+        }
         if (has_next) Box::store_and_gather(ln, data, n_cols, idx, s_link2 + (buf ^ 1) * TV_NV, s_val, tid);
         // phase 2: every own vertex gathers its own term and those of the cells below it: one atomic per vertex
         for (int o = tid; o < TS_X * TS_Y * TS_Z; o += TILE_THREADS) {
@@ -947,8 +978,7 @@ tv_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ data
             }
         }
         if (!has_next) break;
-        t = tn; x0 = nx0; y0 = ny0; z0 = nz0;
-        all_in = n_all_in;
+        cur = nxt;
         buf ^= 1;
     }
 }
@@ -1017,7 +1047,7 @@ __device__ __forceinline__ bool pair_used(unsigned f_lower, unsigned f_upper, in
 template <bool CHECKS>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, Dims d, const uint64_t *__restrict__ vbl,
-                   const TileVerdict *__restrict__ verdict, float lv_set, float scale, int con_check, int ignore_empty,
+                   TileVerdict *__restrict__ verdict, float lv_set, float scale, int con_check, int ignore_empty,
                    int use_l1, uint8_t *__restrict__ mask, float *__restrict__ grad) {
     if (verdict->bad) return;
     using Box = TileBox<NT_VX, NT_VY, NT_VZ>;
@@ -1033,22 +1063,32 @@ normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ 
     constexpr int cstride[3] = {NT_CY * NT_CZ, NT_CZ, 1};
     // 0.25 scale / (number of pairs the owner cell forms), as the reference computes it
     const float q1 = 0.25f * (scale * 1.f / 1), q2 = 0.25f * (scale * 1.f / 2), q3 = 0.25f * (scale * 1.f / 3);
-    int t = blockIdx.x, x0, y0, z0, buf = 0;
-    bool all_in = false, n_all_in = false;
-    if (!tile_seek(t, n_tiles, vbl, d, lo, hi, x0, y0, z0, all_in)) return;
+    __shared__ TileRef s_ref[2];   // [0] the first tile, then alternately "the tile after this one"
+    int buf = 0;
+    if (tid == 0) {
+        tile_fetch(atomicAdd(&verdict->ctr, 1u), verdict, n_tiles, vbl, d, lo, hi, s_ref[0]);
+        tile_fetch(atomicAdd(&verdict->ctr, 1u), verdict, n_tiles, vbl, d, lo, hi, s_ref[1]);
+    }
+    __syncthreads();
+    TileRef cur = s_ref[0];
+    if (!cur.flags) return;
     {
         int32_t l[Box::PER];
-        Box::load_links(links, d, x0, y0, z0, tid, l);
+        Box::load_links(links, d, cur.x0, cur.y0, cur.z0, tid, l);
         Box::store_and_gather(l, surf, 1, 0, s_link2, s_val, tid);
     }
-    for (;;) {
+    for (int it_no = 1;; ++it_no) {
         cp_async_wait_all();
         __syncthreads();
         const int32_t *s_link = s_link2 + buf * NT_NV;
-        int tn = t + gridDim.x, nx0 = 0, ny0 = 0, nz0 = 0;
-        const bool has_next = tile_seek(tn, n_tiles, vbl, d, lo, hi, nx0, ny0, nz0, n_all_in);
+        const TileRef nxt = s_ref[it_no & 1];
+        const bool has_next = nxt.flags != 0;
+        unsigned drawn = 0u;
+        if (tid == 0 && has_next) drawn = atomicAdd(&verdict->ctr, 1u);   // consumed after phase 1: its latency is hidden
+        const int x0 = cur.x0, y0 = cur.y0, z0 = cur.z0;
+        const bool all_in = (cur.flags & 2) != 0;
         int32_t ln[Box::PER];
-        if (has_next) Box::load_links(links, d, nx0, ny0, nz0, tid, ln);
+        if (has_next) Box::load_links(links, d, nxt.x0, nxt.y0, nxt.z0, tid, ln);
         // phase 1: unit normal of every complete cell in [-1, T]^3
         int any = 0;
         BoxIter<NT_CY, NT_CZ> it(tid);
@@ -1081,6 +1121,10 @@ normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ 
             s_cf[c] = (uint8_t)f;
         }
         any = __syncthreads_or(any);   // also: the scalars of this tile are consumed, the next tile's may land
+        if (tid == 0) {       // everybody has read s_ref[it_no & 1]; the other slot receives the tile after the next one
+            if (has_next) tile_fetch(drawn, verdict, n_tiles, vbl, d, lo, hi, s_ref[(it_no & 1) ^ 1]);
+            else s_ref[(it_no & 1) ^ 1].flags = 0;
+        }
         if (has_next) Box::store_and_gather(ln, surf, 1, 0, s_link2 + (buf ^ 1) * NT_NV, s_val, tid);
         if (any) {   // some own cell is complete
             // phase 2: d(loss)/d(normal) of every own cell, summed over the <= 6 pairs it takes part in (kept in registers:
@@ -1156,8 +1200,7 @@ normal_tile_kernel(const int32_t *__restrict__ links, const float *__restrict__ 
             }
         }
         if (!has_next) break;
-        t = tn; x0 = nx0; y0 = ny0; z0 = nz0;
-        all_in = n_all_in;
+        cur = nxt;
         buf ^= 1;
     }
 }

@@ -26,8 +26,14 @@ class GradExchange:
     the regulariser kernels.  ``run`` does both phases back to back.
     """
 
-    def __init__(self, ts=None, group=None, dense_threshold=0.25, shard_regularisers=True):
+    def __init__(self, ts=None, group=None, dense_threshold=0.25, shard_regularisers=True, sync_free=True):
         self.group = group
+        # sync_free: after the first step the list of touched rows is taken with a fixed capacity (1.5 x the largest count
+        # seen so far) instead of a data-dependent size, so the host never waits for the device inside the step; the true
+        # count is read back one step later and an overflow raises (it cannot be repaired after the optimizer has run).
+        self.sync_free = sync_free
+        self.cap = None
+        self._count_probe = None     # (pinned host count, event, capacity it was taken with)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.shard_regularisers = shard_regularisers   # end() also sums the cell-sharded regulariser gradients
@@ -55,8 +61,7 @@ class GradExchange:
         dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group)
         ts.mask_sh.copy_(ts.mask)
         N = ts.mask.shape[0]
-        rows = torch.nonzero(ts.mask).flatten()          # identical on every rank (host sync: the count)
-        n = int(rows.shape[0])
+        rows, n = self._touched_rows(ts.mask)             # identical on every rank
         self.last_rows = n
         if n == 0:
             self._pending = None
@@ -88,6 +93,63 @@ class GradExchange:
         work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._pending = (work, rows, buf)
         return n
+
+    def _touched_rows(self, mask):
+        """-> (rows int64 (n,), n).  First call (and host tensors): torch.nonzero, which waits for the count.  Afterwards, on
+        CUDA with sync_free: a list of fixed capacity padded with -1 (the pack / unpack kernels skip negative rows)."""
+        if not (self.sync_free and mask.is_cuda) or self.cap is None:
+            rows = torch.nonzero(mask).flatten()
+            n = int(rows.shape[0])
+            if self.sync_free and mask.is_cuda:
+                self.cap = min(int(mask.shape[0]), int(1.5 * n) + 1024)
+            return rows, n
+        if self._count_probe is not None:                 # the count of the PREVIOUS step: long since on the host
+            host, ev, cap_used = self._count_probe
+            ev.synchronize()
+            cnt = int(host.item())
+            if cnt > cap_used:
+                raise RuntimeError("GradExchange: %d touched rows exceeded the list capacity %d of the previous step; "
+                                   "its gradient exchange was incomplete (use sync_free=False)" % (cnt, cap_used))
+            if cnt > 0.8 * self.cap:
+                self.cap = min(int(mask.shape[0]), int(1.5 * cnt) + 1024)
+        cap = self.cap
+        rows = torch.nonzero_static(mask, size=cap, fill_value=-1).flatten()
+        host = torch.empty((), dtype=torch.int64).pin_memory()
+        host.copy_(mask.sum(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._count_probe = (host, ev, cap)
+        return rows, cap
+
+    def collective_breakdown(self, ts, iters=5):
+        """Each collective / kernel of one exchange timed ALONE (CUDA events on this stream, synchronous NCCL calls), outside
+        any timed region: names the limiter of the multi-GPU step.  Sizes are those of the last step."""
+        g, dev = ts.grad, ts.mask.device
+        N, D = ts.mask.shape[0], g["sh"].shape[1]
+        n = max(int(self.last_rows), 1)
+        out = {"rows_in_bucket": n, "world": self.world}
+        mask_u8 = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        bucket = torch.zeros((n, 2 + D), dtype=g["sh"].dtype, device=dev)
+        dense = torch.zeros((2, N, 1), dtype=g["sh"].dtype, device=dev)
+
+        def t(fn):
+            fn()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / iters
+        out["mask_or_allreduce_ms"] = t(lambda: dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group))
+        out["mask_or_bytes"] = N
+        out["sparse_bucket_allreduce_ms"] = t(lambda: dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group))
+        out["sparse_bucket_bytes"] = n * (2 + D) * 4
+        out["dense_regulariser_allreduce_ms"] = t(lambda: dist.all_reduce(dense, op=dist.ReduceOp.SUM, group=self.group))
+        out["dense_regulariser_bytes"] = 2 * N * 4
+        out["nonzero_static_ms"] = t(lambda: torch.nonzero_static(ts.mask, size=n, fill_value=-1))
+        return out
 
     def end(self, ts):
         g = ts.grad
@@ -137,12 +199,11 @@ class GradExchange:
             self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
             if self._side is not None:
                 # build the cached occupancy pyramid of `links` now, on the main stream: afterwards both lanes only read it
-                from . import svox2_csrc
-                svox2_csrc.accel_for(ts.sg.links)
+                ts.C.accel_for(ts.sg.links)
                 torch.cuda.synchronize(dev)
         return self._reg
 
-    def step(self, ts, origins, dirs, rgb_gt, rgb_out, events=None):
+    def step(self, ts, origins, dirs, rgb_gt, rgb_out, events=None, skip_optimizer=False):
         """One training iteration on this rank's rays.  The regularisers depend on the parameters only, not on the render:
         they run cell-sharded on a side stream into buffers of their own and their dense all-reduce (2 x N floats + N mask
         bytes) proceeds on a second communicator WHILE the main stream renders, ORs the touched masks and exchanges the
@@ -185,7 +246,8 @@ class GradExchange:
         ts.mask.logical_or_(reg["mask"])
         if events:
             events[2].record()
-        ts.optimizer()
+        if not skip_optimizer:
+            ts.optimizer()
         if events:
             events[3].record()
 

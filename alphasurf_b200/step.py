@@ -186,3 +186,71 @@ class TrainStep:
                        -1e9, hp["lr_surface"])
         C.rmsprop_step(sg.sh, self.rms["sh"], self.grad["sh"], self.mask_sh, RMS_BETA, hp["lr_sh"], RMS_EPS, -1e9,
                        hp["lr_sh"])
+
+
+SURFACE_TYPE_NONE = 100
+
+
+def plenoxels_render_options():
+    """RenderOptions of the cuvol backend: opt/util/config_util.py:81-92 defaults as configs/syn.yaml leaves them."""
+    o = synth.alphasurf_render_options()
+    o.update(backend="cuvol", sigma_thresh=1e-8, stop_thresh=1e-7, step_size=0.5)
+    return o
+
+
+def c2_hyper():
+    """Plenoxels regulariser / optimizer settings (config_util.py:564-640 defaults + configs/syn.yaml)."""
+    return dict(lr_sigma=3e1, lr_sh=1e-2, lambda_tv=1e-5, tv_sparsity=0.01, lambda_tv_sh=1e-3, tv_sh_sparsity=0.01)
+
+
+class CuvolStep:
+    """One Plenoxels iteration (config C2) as opt/opt.py drives it for a grid without a surface: volume_render_fused with the
+    cuvol backend (svox2.py:3477-3638), inplace_tv_grad on sigma and inplace_tv_color_grad on the SH coefficients over a
+    contiguous 1 % window of cells (:4947-4985, :5768-5812), RMSprop on sigma and SH (:5972-6009, :6110-6150)."""
+
+    def __init__(self, C, sg, render_opts=None, hyper=None, seed=synth.SEED):
+        self.C, self.sg = C, sg
+        dev = sg.density.device
+        self.dev = dev
+        self.opts = render_opts or plenoxels_render_options()
+        self.hp = hyper or c2_hyper()
+        self.grad = {k: torch.zeros_like(getattr(sg, k)) for k in ("density", "sh")}
+        self.rms = {k: torch.zeros_like(getattr(sg, k)) for k in ("density", "sh")}
+        self.mask = torch.zeros((sg.capacity,), dtype=torch.bool, device=dev)
+        self.mask_sh = torch.zeros((sg.capacity,), dtype=torch.bool, device=dev)
+        self.rng = np.random.RandomState(seed & 0x7fffffff)
+        self.grid_size = sg.links.numel()
+        g = C.SparseGridSpec()
+        g.density_data, g.sh_data, g.links = sg.density, sg.sh, sg.links
+        g._offset, g._scaling = sg.offset, sg.scaling
+        g.basis_dim, g.basis_type, g.surface_type = sg.basis_dim, BASIS_TYPE_SH, SURFACE_TYPE_NONE
+        self.grid_spec, self.opt_spec = g, opt_to_cpp(C, self.opts)
+        gs = C.GridOutputGrads()
+        gs.grad_density_out, gs.grad_sh_out, gs.mask_out = self.grad["density"], self.grad["sh"], self.mask
+        self.grad_spec = gs
+
+    rand_cells = TrainStep.rand_cells
+
+    def render(self, origins, dirs, rgb_gt, rgb_out):
+        self.mask.zero_()
+        self.C.volume_render_cuvol_fused(self.grid_spec, rays_to_cpp(self.C, origins, dirs), self.opt_spec, rgb_gt, 0.0, 0.0,
+                                         rgb_out, self.grad_spec)
+        self.mask_sh.copy_(self.mask)
+
+    def regularisers(self):
+        C, sg, hp = self.C, self.sg, self.hp
+        C.tv_grad_sparse(sg.links, sg.density, self.rand_cells(hp["tv_sparsity"]), self.mask, 0, 1, hp["lambda_tv"], False, 2.0,
+                         False, bool(self.opts["last_sample_opaque"]), -1.0, -1.0, self.grad["density"])
+        C.tv_grad_sparse(sg.links, sg.sh, self.rand_cells(hp["tv_sh_sparsity"]), self.mask_sh, 0, sg.sh.shape[1],
+                         hp["lambda_tv_sh"], False, 2.0, True, False, -1.0, -1.0, self.grad["sh"])
+
+    def optimizer(self):
+        C, sg, hp = self.C, self.sg, self.hp
+        C.rmsprop_step(sg.density, self.rms["density"], self.grad["density"], self.mask, RMS_BETA, hp["lr_sigma"], RMS_EPS, -1e9,
+                       hp["lr_sigma"])
+        C.rmsprop_step(sg.sh, self.rms["sh"], self.grad["sh"], self.mask_sh, RMS_BETA, hp["lr_sh"], RMS_EPS, -1e9, hp["lr_sh"])
+
+    def step(self, origins, dirs, rgb_gt, rgb_out):
+        self.render(origins, dirs, rgb_gt, rgb_out)
+        self.regularisers()
+        self.optimizer()

@@ -802,6 +802,20 @@ def render_stats(grid, rays, opt):
     return dict(n_steps=v[0], n_skips=v[1], n_linked=v[2], n_active=v[3], n_samples=v[4])
 
 
+def cuvol_render_stats(grid, rays, opt):
+    """Counters of SURVEY.md 8(d) for one cuvol forward march: dict(n_steps = sample positions, n_skips, n_linked = gathered
+    samples, n_samples = samples with sigma > sigma_thresh)."""
+    _check_grid(grid)
+    _check_rays(rays)
+    st = torch.zeros((6,), dtype=torch.int64, device=rays.origins.device)
+    with torch.cuda.device(grid.sh_data.device):
+        g, _keep = _grid_t(grid, need_accel=False)
+        capi.check(capi.lib().asurf_cuvol_stats(C.byref(g), C.byref(_rays_t(rays)), C.byref(capi.make_opt(opt)), capi.ptr(st),
+                                                capi.current_stream()), "cuvol_render_stats")
+    v = st.tolist()
+    return dict(n_steps=v[0], n_skips=v[1], n_linked=v[2], n_active=v[3], n_samples=v[4])
+
+
 # ---- entry points of svox2.cpp that are outside the hot path (SURVEY.md 8f / Appendix D) ----------------------------------
 # They exist so that `hasattr(_C, name)` probes of the reference behave (svox2/utils.py:36 requires `sample_grid`), and
 # raise instead of silently doing nothing: there is no fallback implementation in this package.

@@ -219,6 +219,11 @@ int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, cons
 enum { ASURF_CUVOL_EXPECTED_TERM = 0, ASURF_CUVOL_MODE_TERM = 1, ASURF_CUVOL_MED_TERM = 2, ASURF_CUVOL_SIGMA_THRESH = 3 };
 int asurf_cuvol_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode, float param,
                        int32_t max_sample, float *out, float *out2, void *stream);
+/* march counters of one forward pass (the caller zero-fills stats_dev): n_steps = sample positions, n_skips =
+ * positions that jump over an empty block, n_linked = n_active = samples whose 8 links + 8 densities are gathered,
+ * n_samples = samples with sigma > sigma_thresh (SH gather and gradients) */
+int asurf_cuvol_stats(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, asurf_stats_t *stats_dev,
+                      void *stream);
 /* volume_render_cuvol_image, :1162-1209: rays of a pinhole camera (c2w: 12 host floats, row-major 3x4), rgb_out (H,W,3) */
 int asurf_cuvol_image(const asurf_grid_t *grid, const float *c2w_host, float fx, float fy, float cx, float cy, int32_t width,
                       int32_t height, const asurf_opt_t *opt, float *rgb_out, void *stream);
@@ -324,7 +329,8 @@ int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3]
                                      void *stream);
 
 /* ---- multi-GPU gradient exchange helpers (ours; alphasurf_b200/dist.py) ----
- * rows: device int64 (n_rows,), ascending row indices touched on some rank; bucket: device (n_rows, 2 + sh_dim) floats,
+ * rows: device int64 (n_rows,), ascending row indices touched on some rank, optionally padded with negative entries (a list
+ * of fixed capacity: their bucket rows are zero-filled and ignored); bucket: device (n_rows, 2 + sh_dim) floats,
  * row = [density.grad, surface.grad, sh.grad...].  pack copies the rows into the bucket (and clears them in the gradient
  * tensors when clear_rows != 0); unpack_add adds the (all-reduced) bucket back. */
 int asurf_rows_pack(const int64_t *rows, int64_t n_rows, float *grad_density, float *grad_surface, float *grad_sh,

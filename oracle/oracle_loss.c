@@ -8,6 +8,9 @@
  */
 #include "oracle_common.h"
 
+#define OMP_MIN_CELLS 200000
+#define ATOMIC_ADD(dst, val) do { const float _v = (val); _Pragma("omp atomic") (dst) += _v; } while (0)
+
 static void ray_scale(const int32_t *size, float *s) { /* :22-62 */
     s[0] = size[0] * (1.f / 256.f);
     s[1] = size[1] * (1.f / 256.f);
@@ -76,6 +79,9 @@ void oracle_tv_grad_sparse(const int32_t *links, const int32_t *size, const floa
     scale = scale / (float)(int)n_cells;
     const int64_t offx = (int64_t)size[1] * size[2];
     const int offy = size[2];
+    /* lists above OMP_MIN_CELLS entries (bench.py's CPU arm) run on all host threads, like the CUDA grid; the accumulations
+     * are atomic then and their order is unspecified, as on the GPU.  The parity tests stay below it: serial, one order. */
+#pragma omp parallel for schedule(static) if (n_cells > OMP_MIN_CELLS)
     for (int64_t i = 0; i < n_cells; ++i)
         for (int idx = start_dim; idx < end_dim; ++idx) {
             const int64_t xyz = cells[i];
@@ -111,7 +117,7 @@ void oracle_tv_grad_sparse(const int32_t *links, const int32_t *size, const floa
             }
             dx *= sc[0]; dy *= sc[1]; dz *= sc[2];
             const float sm = -(dx + dy + dz);
-#define MAYBE(l, v) if ((l) >= 0 && (v) != 0.f) { grad[(int64_t)(l) * n_cols + idx] += (v) * idelta; if (mask) mask[l] = 1; }
+#define MAYBE(l, v) if ((l) >= 0 && (v) != 0.f) { ATOMIC_ADD(grad[(int64_t)(l) * n_cols + idx], (v) * idelta); if (mask) mask[l] = 1; }
             MAYBE(l000, sm);
             MAYBE(l001, dz);
             MAYBE(l010, dy);
@@ -125,16 +131,17 @@ void oracle_alpha_surf_sparsify(const int32_t *links, const float *alpha, int al
                                 int surf_cols, const int32_t *cells, int64_t n_cells, uint8_t *mask, float scale_alpha,
                                 float scale_surf, int surf_decrease, float surf_thresh, float alpha_bound,
                                 float surf_bound, float *grad_alpha, float *grad_surf) {
+#pragma omp parallel for schedule(static) if (n_cells > OMP_MIN_CELLS)
     for (int64_t i = 0; i < n_cells; ++i) {
         const int32_t l = links[cells[i]];
         if (l < 0) continue;
         if (mask) mask[l] = 1;
         const float a = alpha[(int64_t)l * alpha_cols];
         const float safe_grad = 1.f / o_maxf(a, 1e-8f);
-        if (a > alpha_bound) grad_alpha[(int64_t)l * alpha_cols] += scale_alpha * safe_grad;
+        if (a > alpha_bound) ATOMIC_ADD(grad_alpha[(int64_t)l * alpha_cols], scale_alpha * safe_grad);
         const float s = surf[(int64_t)l * surf_cols];
         const int reg = surf_decrease ? (s > surf_bound) : (s < surf_bound);
-        if (reg && (a < surf_thresh)) grad_surf[(int64_t)l * alpha_cols] += surf_decrease ? (scale_surf * safe_grad) : (-scale_surf * safe_grad);
+        if (reg && (a < surf_thresh)) ATOMIC_ADD(grad_surf[(int64_t)l * alpha_cols], surf_decrease ? (scale_surf * safe_grad) : (-scale_surf * safe_grad));
     }
 }
 
@@ -167,7 +174,7 @@ static void scatter_normal(const Cell8 *c, const float *g, float scale, uint8_t 
     for (int k = 0; k < 8; ++k) {
         const float sx = (k & 4) ? 0.25f : -0.25f, sy = (k & 2) ? 0.25f : -0.25f, sz = (k & 1) ? 0.25f : -0.25f;
         const float val = scale * (sx * g[0] + sy * g[1] + sz * g[2]);
-        if (val != 0.f) { grad[c->l[k]] += val; if (mask) mask[c->l[k]] = 1; }
+        if (val != 0.f) { ATOMIC_ADD(grad[c->l[k]], val); if (mask) mask[c->l[k]] = 1; }
     }
 }
 #define NORM3(v) sqrtf(1e-9f + (v)[0] * (v)[0] + (v)[1] * (v)[1] + (v)[2] * (v)[2])
@@ -179,6 +186,7 @@ void oracle_surface_normal_grad_sparse(const int32_t *links, const int32_t *size
                                        int64_t n_cells, uint8_t *mask, float lv, int start_dim, int end_dim, float scale,
                                        int con_check, int ignore_empty, int use_l1, float *grad) {
     scale = scale / (float)(int)n_cells;
+#pragma omp parallel for schedule(static) if (n_cells > OMP_MIN_CELLS)
     for (int64_t i = 0; i < n_cells; ++i)
         for (int rep = start_dim; rep < end_dim; ++rep) {
             const int64_t xyz = cells[i];
