@@ -360,6 +360,62 @@ work_patch_kernel(const int32_t *__restrict__ links, const float *__restrict__ d
     }
 }
 
+// The update scan, four rows per thread (128-bit loads of surface / density, one 32-bit load of the class bytes); changed
+// rows are rare (a few thousand per step), so they are appended one by one.
+__global__ void __launch_bounds__(256)
+class_scan4_kernel(const float *__restrict__ surface, const float *__restrict__ density, int64_t n_rows,
+                   const float *__restrict__ level_set, float sigma_thresh, uint8_t *__restrict__ cls,
+                   int32_t *__restrict__ changed, unsigned long long *__restrict__ n_changed) {
+    const float lv = __ldg(level_set);
+    const int64_t n4 = n_rows >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 s = __ldg((const float4 *)surface + q), dn = __ldg((const float4 *)density + q);
+        const uint32_t old = ((const uint32_t *)cls)[q];
+        const uint32_t now = (uint32_t)vertex_class(s.x, dn.x, lv, sigma_thresh) | ((uint32_t)vertex_class(s.y, dn.y, lv, sigma_thresh) << 8) |
+                             ((uint32_t)vertex_class(s.z, dn.z, lv, sigma_thresh) << 16) |
+                             ((uint32_t)vertex_class(s.w, dn.w, lv, sigma_thresh) << 24);
+        if (now != old) {
+            ((uint32_t *)cls)[q] = now;
+            const uint32_t diff = now ^ old;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((diff >> (8 * k)) & 0xffu) changed[atomicAdd(n_changed, 1ull)] = (int32_t)(q * 4 + k);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n_rows & 3)) {   // tail rows
+        const int64_t r = (n4 << 2) + threadIdx.x;
+        const uint8_t c = vertex_class(surface[r], density[r], lv, sigma_thresh);
+        if (c != cls[r]) {
+            cls[r] = c;
+            changed[atomicAdd(n_changed, 1ull)] = (int32_t)r;
+        }
+    }
+}
+
+// After work_patch_kernel: the level-1 / level-2 bits above the voxels that were re-derived, recomputed from the (now final)
+// words of the level below.  Replaces two full coarsening passes by two passes over the changed list.
+__global__ void __launch_bounds__(256)
+work_fix_level_kernel(int level, int sx, int sy, int sz, AccelLayout lay, const int32_t *__restrict__ inv,
+                      const int32_t *__restrict__ changed, const unsigned long long *__restrict__ n_changed,
+                      uint64_t *__restrict__ work) {
+    const int64_t n = (int64_t)*n_changed * 8;
+    const int sh = 2 * level;   // voxel coordinate -> word coordinate of level-1 below: >> sh
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t flat = inv[changed[i >> 3]];
+        const int k = (int)(i & 7);
+        const int vz = flat % sz, vy = (flat / sz) % sy, vx = flat / (sz * sy);
+        const int x = vx - (k >> 2), y = vy - ((k >> 1) & 1), z = vz - (k & 1);
+        if (x < 0 || y < 0 || z < 0 || x >= sx - 1 || y >= sy - 1 || z >= sz - 1) continue;
+        // word of the level below that holds the voxel, and its bit in the word of this level
+        const int cx = x >> sh, cy = y >> sh, cz = z >> sh;
+        const uint64_t below = work[lay.off[level - 1] + ((int64_t)cx * lay.b[level - 1][1] + cy) * lay.b[level - 1][2] + cz];
+        const int64_t kw = lay.off[level] + ((int64_t)(cx >> 2) * lay.b[level][1] + (cy >> 2)) * lay.b[level][2] + (cz >> 2);
+        const int bit = ((cx & 3) << 4) | ((cy & 3) << 2) | (cz & 3);
+        if (below != 0) atomicOr((unsigned long long *)(work + kw), 1ull << bit);
+        else atomicAnd((unsigned long long *)(work + kw), ~(1ull << bit));
+    }
+}
+
 struct WorkCache {
     Workspace work, cls, inv, changed, ctr;
     const void *links = nullptr, *surface = nullptr, *density = nullptr, *accel = nullptr;
@@ -407,13 +463,22 @@ int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cuda
     if (hit) {
         unsigned long long *ctr = (unsigned long long *)g_wc.ctr.ptr;
         ASURF_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
-        class_scan_kernel<false><<<scan_blocks, 256, 0, st>>>(grid->surface, grid->density, N, grid->level_set, opt->sigma_thresh,
-                                                              (uint8_t *)g_wc.cls.ptr, (int32_t *)g_wc.changed.ptr, ctr);
+        const bool vec4 = ((((uintptr_t)grid->surface) | ((uintptr_t)grid->density)) & 15) == 0;
+        if (vec4)
+            class_scan4_kernel<<<sms * 8, 256, 0, st>>>(grid->surface, grid->density, N, grid->level_set, opt->sigma_thresh,
+                                                        (uint8_t *)g_wc.cls.ptr, (int32_t *)g_wc.changed.ptr, ctr);
+        else
+            class_scan_kernel<false><<<scan_blocks, 256, 0, st>>>(grid->surface, grid->density, N, grid->level_set,
+                                                                  opt->sigma_thresh, (uint8_t *)g_wc.cls.ptr,
+                                                                  (int32_t *)g_wc.changed.ptr, ctr);
         work_patch_kernel<<<sms * 4, 256, 0, st>>>(grid->links, grid->density, grid->surface, grid->level_set, opt->sigma_thresh,
                                                    grid->size[0], grid->size[1], grid->size[2], lay, grid->accel,
                                                    (const int32_t *)g_wc.inv.ptr, (const int32_t *)g_wc.changed.ptr, ctr, work);
-        accel_coarsen_kernel<<<div_up(lay.count(1), 128), 128, 0, st>>>(lay, 1, work);
-        accel_coarsen_kernel<<<div_up(lay.count(2), 128), 128, 0, st>>>(lay, 2, work);
+        // levels 1 and 2: only the bits above the re-derived voxels can have changed
+        for (int level = 1; level <= 2; ++level)
+            work_fix_level_kernel<<<sms * 2, 256, 0, st>>>(level, grid->size[0], grid->size[1], grid->size[2], lay,
+                                                          (const int32_t *)g_wc.inv.ptr, (const int32_t *)g_wc.changed.ptr, ctr,
+                                                          work);
         note_launches(4);
         return check_cuda(cudaGetLastError(), "work pyramid update");
     }

@@ -67,12 +67,19 @@ struct DebugP {
 // lane state: what the lane needs next; phase: where it is inside a work voxel
 // Output of the pre-march (premarch_kernel): per ray the first PRE_K voxels whose work bit is set, in march order,
 // and where to resume the march if there are more.
-constexpr int PRE_K_MAX = 128;   // list capacity per ray (PreP::K <= PRE_K_MAX; the count is stored in 8 bits)
+constexpr int PRE_K_MAX = 512;   // list capacity per ray (PreP::K <= PRE_K_MAX; the counts are stored in 10 bits)
+constexpr int PRE_K_DEFAULT = 128;   // ... used unless the previous call listed many voxels per ray (see premarch())
+// words of the per-ray "voxel produced entries" mask of the wavefront path
+__host__ __device__ __forceinline__ int mask_words(int K) { return (K + 31) >> 5; }
+// PreP::code layout
+constexpr int CODE_CNT_BITS = 10, CODE_CNT_MASK = (1 << CODE_CNT_BITS) - 1;
+constexpr int CODE_CONT = 2 * CODE_CNT_BITS, CODE_BWD_ALIVE = CODE_CONT + 1, CODE_FORCE_FINE = CODE_CONT + 2;
+static_assert(PRE_K_MAX <= CODE_CNT_MASK, "list counts must fit their bit field");
 struct PreP {
     int32_t *cells;        // (Q, K) linear voxel index x*Y*Z + y*Z + z
     int K;                 // list capacity per ray
-    int32_t *code;         // (Q,)  bits 0-7 count, 8-15 count visible to the backward loop, 16 continuation,
-                           //       17 backward loop still alive at the continuation, 18 force_fine at the continuation
+    int32_t *code;         // (Q,)  bits 0-9 count, 10-19 count visible to the backward loop, 20 continuation,
+                           //       21 backward loop still alive at the continuation, 22 force_fine at the continuation
     float *cont_t;         // (Q,)  t at the continuation
     int32_t *cont_vox;     // (Q,)  next voxel at the continuation, 10 bits per axis
     int32_t *rays;         // compact list of the rays the persistent shading kernels serve
@@ -417,14 +424,14 @@ __device__ __forceinline__ void next_from_list(const GridP &g, const PreP &pre, 
         L.phase = PH_ENTER;
         return;
     }
-    const bool cont = ((L.list_code >> 16) & 1) && (!BWD || ((L.list_code >> 17) & 1));
+    const bool cont = ((L.list_code >> CODE_CONT) & 1) && (!BWD || ((L.list_code >> CODE_BWD_ALIVE) & 1));
     if (cont) {
         const int32_t pv = __ldg(pre.cont_vox + L.ray_id);
         L.nx = pv & 1023;
         L.ny = (pv >> 10) & 1023;
         L.nz = (pv >> 20) & 1023;
         L.t = __ldg(pre.cont_t + L.ray_id);
-        L.force_fine = (L.list_code >> 18) & 1;
+        L.force_fine = (L.list_code >> CODE_FORCE_FINE) & 1;
         L.bwd_alive = true;
         dda_restart(L);   // -> ST_MARCH, in_list = false
         return;
@@ -820,9 +827,9 @@ __device__ __forceinline__ void premarch_finish(const GridP &g, const asurf_opt_
     const int lane = threadIdx.x & 31;
     bool has_work = false;
     if (valid) {
-        int code = n | (n_bwd << 8);
+        int code = n | (n_bwd << CODE_CNT_BITS);
         if (cont) {
-            code |= (1 << 16) | ((L.bwd_alive ? 1 : 0) << 17) | ((L.force_fine ? 1 : 0) << 18);
+            code |= (1 << CODE_CONT) | ((L.bwd_alive ? 1 : 0) << CODE_BWD_ALIVE) | ((L.force_fine ? 1 : 0) << CODE_FORCE_FINE);
             pre.cont_t[ray_id] = L.t;
             pre.cont_vox[ray_id] = L.nx | (L.ny << 10) | (L.nz << 20);
         }
@@ -909,7 +916,7 @@ premarch_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__ 
 // fine:   thread per item, voxel-by-voxel steps inside that one block, listing its work voxels.  Items are homogeneous
 //         (<= 46 steps), so warps stay full -- the long fine stretches of grazing rays no longer hold 31 other rays up.
 // merge:  thread per ray, concatenates its items' lists in order and runs the per-ray epilogue.
-constexpr int CI_MAX = 40;       // items per ray (non-empty 16^3 blocks it crosses); more -> the ray goes to the persistent kernels
+constexpr int CI_MAX = 96;       // items per ray (non-empty 16^3 blocks it crosses); more -> the ray goes to the persistent kernels
 constexpr int FI_K = 48;         // work voxels listed per item (a ray crosses at most 46 voxels of a 16^3 block)
 struct TwoP {
     int32_t *ray_items;          // (Q, CI_MAX, 2): packed voxel (10 bits per axis), t bits
@@ -1456,7 +1463,7 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
                     L.ray_done = true;   // misses the grid: background colour / no gradient (:59-65, :1811-1816)
                 } else if (pre.enabled) {
                     L.list_code = __ldg(pre.code + ray_id);
-                    L.list_cnt = BWD ? ((L.list_code >> 8) & 255) : (L.list_code & 255);
+                    L.list_cnt = BWD ? ((L.list_code >> CODE_CNT_BITS) & CODE_CNT_MASK) : (L.list_code & CODE_CNT_MASK);
                     L.list_pos = 0;
                     L.in_list = true;
                     next_from_list<BWD>(g, pre, L);
@@ -1681,6 +1688,36 @@ int ray_counters(cudaStream_t st, unsigned long long **ctr) {
     return 0;
 }
 
+// asynchronous read-back of the item count of a call (see the capacity rule in premarch())
+struct ItemProbe {
+    unsigned long long *host = nullptr;   // pinned copy of the 8 call counters (ray_counters)
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+    int64_t q = 0;
+    double per_ray = 0.0;        // listed voxels (items of the wavefront queue) per ray of the batch
+    double fine_per_ray = 0.0;   // (ray, non-empty 16^3 block) items of the two-level pre-march per ray
+    double long_frac = 0.0;      // share of the rays with work that went to the persistent kernels
+} g_item_probe;
+
+void item_probe_record(unsigned long long *ctr, int64_t Q, cudaStream_t st) {
+    if (!g_item_probe.host) {
+        if (cudaMallocHost((void **)&g_item_probe.host, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_item_probe.ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            g_item_probe.host = nullptr;
+            return;
+        }
+    }
+    if (g_item_probe.pending) return;   // the previous probe has not been consumed yet: its buffer is still in flight
+    if (cudaMemcpyAsync(g_item_probe.host, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaEventRecord(g_item_probe.ev, st);
+    g_item_probe.pending = true;
+    g_item_probe.q = Q;
+}
+
 // Runs the pre-march for this call (forward output / cache counts optional) and returns its record.
 int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, unsigned long long *ctr, float *rgb_out,
              int *cache_n, cudaStream_t st, PreP &pre) {
@@ -1688,9 +1725,31 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
     if (!g_skip_enabled || g.size[0] > 1024 || g.size[1] > 1024 || g.size[2] > 1024) return 0;   // shading kernels march
     const int64_t Q = rays->n_rays;
     // list capacity per ray: as long as the buffers stay moderate (a grazing ray through a thin sheet lists ~100 voxels)
-    int K = PRE_K_MAX;
+    if (g_item_probe.host && g_item_probe.pending && cudaEventQuery(g_item_probe.ev) == cudaSuccess) {
+        g_item_probe.pending = false;
+        const double q = (double)(g_item_probe.q > 0 ? g_item_probe.q : 1);
+        g_item_probe.per_ray = (double)g_item_probe.host[4] / q;
+        g_item_probe.fine_per_ray = (double)g_item_probe.host[6] / q;
+        const double with_work = (double)(g_item_probe.host[2] + g_item_probe.host[3]);
+        g_item_probe.long_frac = with_work > 0 ? (double)g_item_probe.host[2] / with_work : 0.0;
+    }
+    // a grid with a crossing in most voxels (G*: ~90 listed voxels per ray against 3 on the training grids, or most rays
+    // overflowing the short lists): long lists
+    const bool dense_crossings = g_item_probe.per_ray > 4.5 || g_item_probe.long_frac > 0.1;
+    int K = dense_crossings ? PRE_K_MAX : PRE_K_DEFAULT;
     while (K > 16 && (int64_t)Q * K > ((int64_t)1 << 27)) K >>= 1;
-    const int64_t item_cap = Q * 6 + 4096;
+    // Item queue capacity: 6 listed voxels per ray serve a thin level-set sheet (1.3 per ray on the training grids); a grid
+    // with a crossing in most voxels (G*) lists ~100 per ray.  The library learns it from the previous call: the item
+    // count is read back asynchronously (pinned host word + event, never waited for) and the next call on a batch of
+    // similar size reserves 1.25 x that, up to the lists' own capacity.  A call that overflows is still correct -- the rays
+    // that do not fit are rendered by the persistent kernels -- only slower.
+    int64_t item_cap = Q * 6 + 4096;
+    if (dense_crossings) {
+        int64_t want = (int64_t)(1.25 * g_item_probe.per_ray * (double)Q) + 4096;
+        const int64_t hard = (int64_t)Q * K < ((int64_t)24 << 20) ? (int64_t)Q * K : ((int64_t)24 << 20);
+        if (want > hard) want = hard;
+        if (want > item_cap) item_cap = want;
+    }
     const size_t per = (size_t)Q * sizeof(int32_t);
     int rc = g_ws_pre.reserve(per * (K + 6) + (size_t)item_cap * sizeof(int32_t));
     if (rc) return rc;
@@ -1714,6 +1773,11 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
         // large batch: coarse (block jumps, thread per ray) -> fine (thread per non-empty 16^3 block crossed) -> merge
         TwoP tw;
         tw.fq_cap = Q * 8 + 4096;
+        if (g_item_probe.fine_per_ray > 6.0) {   // same feedback for the fine-item queue
+            int64_t want = (int64_t)(1.25 * g_item_probe.fine_per_ray * (double)Q) + 4096;
+            if (want > Q * CI_MAX) want = Q * CI_MAX;
+            if (want > tw.fq_cap) tw.fq_cap = want;
+        }
         const size_t b_items = (size_t)Q * CI_MAX * 2 * sizeof(int32_t), b_q = (size_t)Q * sizeof(int32_t),
                      b_fq = (size_t)tw.fq_cap * sizeof(int32_t), b_cells = (size_t)tw.fq_cap * FI_K * sizeof(int32_t);
         rc = g_ws_seg.reserve(b_items + 2 * b_q + 2 * b_fq + b_cells);
@@ -1726,15 +1790,17 @@ int premarch(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *rays, u
         tw.fi_meta = (int32_t *)(sb + b_items + 2 * b_q + b_fq);
         tw.fi_cells = (int32_t *)(sb + b_items + 2 * b_q + 2 * b_fq);
         tw.n_fq = ctr + 6;
-        premarch_coarse_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, tw);
+        premarch_coarse_kernel<<<(int)((Q + 63) / 64), 64, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, tw);
         premarch_fine_kernel<<<(int)((tw.fq_cap + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, tw);
         premarch_merge_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, tw, rgb_out,
                                                                       cache_n);
         note_launches(3);
+        item_probe_record(ctr, Q, st);
         return check_cuda(cudaGetLastError(), "two-level premarch launch");
     }
     premarch_kernel<<<(int)((Q + 255) / 256), 256, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, pre, rgb_out, cache_n);
     note_launches(1);
+    item_probe_record(ctr, Q, st);
     return check_cuda(cudaGetLastError(), "premarch launch");
 }
 
@@ -1758,7 +1824,7 @@ inline int wave_grid(int64_t want_threads, int threads, int ctas_per_sm) {
 int wave_buffers(const PreP &pre, int64_t Q, unsigned long long *ctr, WaveP &wv) {
     const size_t n = (size_t)pre.item_cap;
     const size_t b_items = n * sizeof(ItemRec), b_hits = n * WAVE_ENT * sizeof(HitRec), b_q = n * WAVE_ENT * sizeof(int32_t);
-    const size_t b_pre = (size_t)Q * sizeof(Pre), b_mask = (size_t)Q * 4 * sizeof(uint32_t);
+    const size_t b_pre = (size_t)Q * sizeof(Pre), b_mask = (size_t)Q * mask_words(pre.K) * sizeof(uint32_t);
     int rc = g_ws_wave.reserve(b_items + b_hits + b_q + b_pre + b_mask);
     if (rc) return rc;
     char *base = (char *)g_ws_wave.ptr;
@@ -1778,7 +1844,7 @@ int wave_forward(const GridP &g, const asurf_opt_t *opt, const asurf_rays_t *ray
     const int64_t Q = rays->n_rays;
     FusedP nof = {};
     asurf_grads_t nog = {};
-    ASURF_CUDA(cudaMemsetAsync(wv.ray_mask, 0, (size_t)Q * 4 * sizeof(uint32_t), st));
+    ASURF_CUDA(cudaMemsetAsync(wv.ray_mask, 0, (size_t)Q * mask_words(pre.K) * sizeof(uint32_t), st));
     wave_eval_kernel<<<wave_grid(Q * 2, 128, 16), 128, 0, st>>>(g, *opt, rays->origins, rays->dirs, pre, wv);
     wave_wide_kernel<false><<<wave_grid(Q * 32, 128, 16), 128, 0, st>>>(g, *opt, rays->dirs, pre, wv, nullptr, nullptr, nof, nog);
     wave_composite_kernel<<<wave_grid(Q, 128, 8), 128, 0, st>>>(g, *opt, pre, wv, cache, M, rgb_out, grad_in, color_cache, f);

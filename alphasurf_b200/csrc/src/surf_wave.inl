@@ -45,7 +45,7 @@ struct WaveP {
     int32_t *hitq;                 // compact queue of sample entries: item index * 4 + entry
     unsigned long long *n_hits;
     Pre *ray_pre;                  // (Q,) per-ray constants of the fused losses (fused_preamble)
-    uint32_t *ray_mask;            // (Q, 4): which of the ray's <= 128 listed voxels produced entries (zeroed per call)
+    uint32_t *ray_mask;            // (Q, mask_words(K)): which of the ray's listed voxels produced entries (zeroed per call)
 };
 
 __device__ __forceinline__ int ent_kind(int32_t n_ent, int e) { return (n_ent >> (8 + 8 * e)) & 3; }
@@ -228,7 +228,7 @@ wave_eval_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
             wv.items[t] = it;
             if (n_ent > 0) {   // most listed voxels yield no entry: the per-ray stages only visit the flagged ones
                 const int k = (int)(code - ray_id * pre.K);
-                atomicOr(wv.ray_mask + ray_id * 4 + (k >> 5), 1u << (k & 31));
+                atomicOr(wv.ray_mask + ray_id * mask_words(pre.K) + (k >> 5), 1u << (k & 31));
             }
         }
         // queue the entries that need the wide (SH) stages: warp-aggregated append
@@ -359,17 +359,16 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_short; s += (int64_t)gridDim.x * blockDim.x) {
         const int64_t ray_id = __ldg(pre.rays_short + s);
         const int32_t code = __ldg(pre.code + ray_id);
-        const int n = code & 255, n_bwd = (code >> 8) & 255;
+        const int n = code & CODE_CNT_MASK, n_bwd = (code >> CODE_CNT_BITS) & CODE_CNT_MASK;
         const int64_t base = __ldg(pre.item_base + ray_id);
         float logT = 0.f, logT_b = 0.f, out0 = 0.f, out1 = 0.f, out2 = 0.f;
         int intersect_i = -1, sample_i = 0;
         bool alive_f = true, alive_b = true;
-        uint32_t rm[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) rm[w] = wv.ray_mask[ray_id * 4 + w];
+        const uint32_t *rm = wv.ray_mask + ray_id * mask_words(pre.K);
+        const int n_words = (n + 31) >> 5;
         // voxels without entries change nothing (the early-stop test after them sees the same log-transmittance as after the
         // previous voxel): visit only the flagged ones, in order
-        for (int w = 0; w < 4; ++w)
+        for (int w = 0; w < n_words; ++w)
         for (uint32_t mm = rm[w]; mm && (alive_f || alive_b); mm &= mm - 1) {
             const int k = w * 32 + __ffs(mm) - 1;
             if (k >= n) break;
@@ -459,7 +458,7 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
         float accum = fmaf(cc[0], gi[0], fmaf(cc[1], gi[1], cc[2] * gi[2]));
         int sample_b = 0;
         bool live = true;
-        for (int w = 0; w < 4; ++w)
+        for (int w = 0; w < n_words; ++w)
         for (uint32_t mm = rm[w]; mm && live; mm &= mm - 1) {
             const int k = w * 32 + __ffs(mm) - 1;
             if (k >= n_bwd) { live = false; break; }
