@@ -101,8 +101,15 @@ void check_grid(const SparseGridSpec &g) {
     TORCH_CHECK(g.links.scalar_type() == torch::kInt32, "links must be int32");
     check_f32(g.density_data, "density_data");
     check_f32(g.sh_data, "sh_data");
-    if (g.background_links.defined() && g.background_links.numel() > 0)
-        not_on_path("MSI background layers are outside the B200 hot path (SURVEY.md 8f #4)");
+    if (g.background_links.defined() && g.background_links.numel() > 0) {   // MSI background (data_spec.hpp:47-48)
+        check_input(g.background_links, "background_links");
+        check_input(g.background_data, "background_data");
+        TORCH_CHECK(g.background_links.dim() == 2 && g.background_links.scalar_type() == torch::kInt32,
+                    "background_links must be a 2-D int32 tensor");
+        TORCH_CHECK(g.background_data.dim() == 3 && g.background_data.size(2) == 4 &&
+                        g.background_data.scalar_type() == torch::kFloat32,
+                    "background_data must be a float32 (n, nlayers, 4) tensor");
+    }
     if (g.basis_type != BASIS_TYPE_SH) not_on_path("only the SH basis is on the B200 hot path");
 }
 void check_rays(const RaysSpec &r) {
@@ -186,6 +193,12 @@ GridArg grid_t(const SparseGridSpec &s, bool need_accel) {
     host3(s._scaling, g.scaling);
     g.fake_sample_std = s.fake_sample_std;
     g.truncated_vol_render_a = s.truncated_vol_render_a;
+    if (s.background_links.defined() && s.background_links.numel() > 0) {
+        g.background_links = s.background_links.data_ptr<int32_t>();
+        g.background_data = s.background_data.data_ptr<float>();
+        g.background_reso = (int32_t)s.background_links.size(1);
+        g.background_nlayers = (int32_t)s.background_data.size(1);
+    }
     if (need_accel) {
         a.keep = accel_for(s.links);
         g.accel = (const uint64_t *)a.keep.data_ptr<int64_t>();
@@ -228,6 +241,10 @@ asurf_grads_t grads_t(const GridOutputGrads &g) {
     if (g.grad_fake_sample_std_out.defined() && g.grad_fake_sample_std_out.numel() > 0)
         o.grad_fake_sample_std = g.grad_fake_sample_std_out.data_ptr<float>();
     if (g.mask_out.defined() && g.mask_out.numel() > 0) o.mask = (uint8_t *)g.mask_out.data_ptr();
+    if (g.grad_background_out.defined() && g.grad_background_out.numel() > 0)
+        o.grad_background = g.grad_background_out.data_ptr<float>();
+    if (g.mask_background_out.defined() && g.mask_background_out.numel() > 0)
+        o.mask_background = (uint8_t *)g.mask_background_out.data_ptr();
     return o;
 }
 struct CamArg {
@@ -804,6 +821,25 @@ void surface_normal_grad_sparse(Tensor links, Tensor data, Tensor rand_cells, Te
              "surface_normal_grad_sparse");
 }
 
+// msi_tv_grad_sparse, loss_kernel.cu:1624-1659
+void msi_tv_grad_sparse(Tensor links, Tensor msi, Tensor rand_cells, Tensor mask_out, float scale, float scale_last,
+                        Tensor grad_msi) {
+    check_input(links, "links");
+    check_input(msi, "msi");
+    check_input(grad_msi, "grad_msi");
+    check_cells(rand_cells);
+    check_input(mask_out, "mask_out");
+    TORCH_CHECK(msi.is_floating_point() && grad_msi.is_floating_point() && msi.dim() == 3 && links.dim() == 2,
+                "msi must be a (n, nlayers, channels) floating point tensor and links 2-D");
+    const c10::cuda::CUDAGuard guard(msi.device());
+    uint8_t *mp = (mask_out.numel() > 0) ? (uint8_t *)mask_out.data_ptr() : nullptr;
+    check_rc(asurf_msi_tv_grad_sparse(links.data_ptr<int32_t>(), (int32_t)links.size(0), (int32_t)links.size(1),
+                                      msi.data_ptr<float>(), (int32_t)msi.size(1), (int32_t)msi.size(2),
+                                      rand_cells.data_ptr<int32_t>(), rand_cells.size(0), mp, scale, scale_last,
+                                      grad_msi.data_ptr<float>(), stream_of(msi)),
+             "msi_tv_grad_sparse");
+}
+
 // ---- names of svox2.cpp that are outside the hot path: present (the reference's Python probes by name), never silent ----------
 py::object off_path(const std::string &name) {
     return py::cpp_function(
@@ -846,6 +882,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     REG(alpha_surf_sparsify_grad_sparse);
     REG(tv_grad_sparse);
     REG(surf_tv_grad_sparse);
+    REG(msi_tv_grad_sparse);
     REG(dilate);
     REG(accel_dist_prop);
     REG(grid_weight_render);
@@ -860,7 +897,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                              "volume_render_surface_fused", "volume_render_nvol", "volume_render_nvol_backward",
                              "volume_render_nvol_fused", "volume_render_svox1", "volume_render_svox1_backward",
                              "volume_render_svox1_fused", "surface_normal_grad", "surf_sign_change_grad_sparse",
-                             "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse"})
+                             "lumisphere_tv_grad_sparse"})
         m.attr(name) = off_path(name);
     m.def("set_loss_norm_rays", [](py::object n) { g_norm_rays = n.is_none() ? 0 : n.cast<int64_t>(); },
           "global ray count used to normalise the fused losses in a ray-sharded run (None: per call)");

@@ -44,6 +44,12 @@ unsigned long long launches_read(int reset);
 int work_pyramid_for_call(const asurf_grid_t *grid, const asurf_opt_t *opt, cudaStream_t st, const uint64_t **work_out,
                           int slot = 0);
 void work_cache_release();
+void msi_release();
+// per-ray state a foreground pass leaves for the MSI background pass (msi.cu): two (Q,) float arrays in a library workspace
+int bg_state_reserve(int64_t Q, float **log_transmit, float **accum);
+static inline bool grid_has_background(const asurf_grid_t *g) {
+    return g->background_links != nullptr && g->background_data != nullptr && g->background_nlayers > 0;
+}
 void loss_release();    // per-file workspaces, freed by asurf_release
 void cuvol_release();
 void misc_release();

@@ -153,7 +153,11 @@ __global__ void __launch_bounds__(CV_THREADS)
 cuvol_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ origins, const float *__restrict__ dirs,
              const CvCam cam, const int64_t Q, float *__restrict__ rgb_out, float *__restrict__ log_transmit_out,
              const float *__restrict__ grad_in, const float *__restrict__ color_cache, int grad_is_rgb, float norm_factor,
-             const float *__restrict__ log_transmit_in, float beta_loss, float sparsity_loss, const asurf_grads_t grads) {
+             const float *__restrict__ log_transmit_in, float beta_loss, float sparsity_loss, const asurf_grads_t grads,
+             const int has_bg, float *__restrict__ accum_out) {
+    // has_bg: an MSI background follows (msi.cu): no background_brightness term here (:113-115); the backward leaves what
+    // remains of `accum` (minus the beta term, :524-529) in accum_out and, when log_transmit_out is given, its own final
+    // log-transmittance
     __shared__ float s_sph[CV_WARPS][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t ray_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -196,10 +200,15 @@ cuvol_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ or
     float out0 = 0.f, out1 = 0.f, out2 = 0.f;
     float log_transmit = 0.f;
     if (r.tmin > r.tmax) {
-        if (!BWD && lane == 0) {
-            rgb_out[ray_id * 3 + 0] = opt.background_brightness;
-            rgb_out[ray_id * 3 + 1] = opt.background_brightness;
-            rgb_out[ray_id * 3 + 2] = opt.background_brightness;
+        if (lane == 0) {
+            if (!BWD) {
+                const float bg = has_bg ? 0.f : opt.background_brightness;
+                rgb_out[ray_id * 3 + 0] = bg;
+                rgb_out[ray_id * 3 + 1] = bg;
+                rgb_out[ray_id * 3 + 2] = bg;
+            } else if (accum_out) {
+                accum_out[ray_id] = accum;     // (:405-409: before the beta term is cancelled)
+            }
             if (log_transmit_out) log_transmit_out[ray_id] = 0.f;
         }
         return;
@@ -314,11 +323,15 @@ cuvol_kernel(const CvGrid g, const asurf_opt_t opt, const float *__restrict__ or
             break;
         }
     }
-    if (!BWD && lane == 0) {
-        const float bg = __expf(log_transmit) * opt.background_brightness;
-        rgb_out[ray_id * 3 + 0] = out0 + bg;
-        rgb_out[ray_id * 3 + 1] = out1 + bg;
-        rgb_out[ray_id * 3 + 2] = out2 + bg;
+    if (lane == 0) {
+        if (!BWD) {
+            const float bg = has_bg ? 0.f : __expf(log_transmit) * opt.background_brightness;
+            rgb_out[ray_id * 3 + 0] = out0 + bg;
+            rgb_out[ray_id * 3 + 1] = out1 + bg;
+            rgb_out[ray_id * 3 + 2] = out2 + bg;
+        } else if (accum_out) {
+            accum_out[ray_id] = accum - beta_loss;
+        }
         if (log_transmit_out) log_transmit_out[ray_id] = log_transmit;
     }
 }
@@ -480,10 +493,24 @@ extern "C" int asurf_cuvol_forward(const asurf_grid_t *grid, const asurf_rays_t 
     if (rc) return rc;
     asurf_grads_t nog = {};
     CvCam cam = {};
+    const int has_bg = grid_has_background(grid) ? 1 : 0;
+    float *lt = log_transmit_out;
+    if (has_bg) {
+        float *acc = nullptr;
+        rc = bg_state_reserve(Q, &lt, &acc);
+        if (rc) return rc;
+    }
     cuvol_kernel<false, false><<<cv_blocks(Q), CV_THREADS, 0, (cudaStream_t)stream>>>(
-        g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, log_transmit_out, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
+        g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, lt, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog, has_bg, nullptr);
     note_launches(1);
-    return check_cuda(cudaGetLastError(), "cuvol_forward launch");
+    rc = check_cuda(cudaGetLastError(), "cuvol_forward launch");
+    if (rc) return rc;
+    if (has_bg) {
+        rc = asurf_msi_forward(grid, rays, opt, lt, rgb_out, stream);
+        if (rc) return rc;
+        if (log_transmit_out) ASURF_CUDA(cudaMemcpyAsync(log_transmit_out, lt, (size_t)Q * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return 0;
 }
 
 extern "C" int asurf_cuvol_stats(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
@@ -549,10 +576,20 @@ extern "C" int asurf_cuvol_image(const asurf_grid_t *grid, const float *c2w_host
     for (int i = 0; i < 12; ++i) cam.c2w[i] = c2w_host[i];
     cam.fx = fx; cam.fy = fy; cam.cx = cx; cam.cy = cy;
     cam.width = width; cam.height = height;
+    const int has_bg = grid_has_background(grid) ? 1 : 0;
+    float *lt = nullptr;
+    if (has_bg) {
+        float *acc = nullptr;
+        rc = bg_state_reserve(Q, &lt, &acc);
+        if (rc) return rc;
+    }
     cuvol_kernel<false, true><<<cv_blocks(Q), CV_THREADS, 0, (cudaStream_t)stream>>>(
-        g, *opt, nullptr, nullptr, cam, Q, rgb_out, nullptr, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
+        g, *opt, nullptr, nullptr, cam, Q, rgb_out, lt, nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog, has_bg, nullptr);
     note_launches(1);
-    return check_cuda(cudaGetLastError(), "cuvol_image launch");
+    rc = check_cuda(cudaGetLastError(), "cuvol_image launch");
+    if (rc) return rc;
+    if (has_bg) return asurf_msi_forward_image(grid, c2w_host, fx, fy, cx, cy, width, height, opt, lt, rgb_out, stream);
+    return 0;
 }
 
 extern "C" int asurf_cuvol_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
@@ -567,10 +604,21 @@ extern "C" int asurf_cuvol_backward(const asurf_grid_t *grid, const asurf_rays_t
     int rc = cv_make_grid(grid, g, "cuvol_backward");
     if (rc) return rc;
     CvCam cam = {};
+    const int has_bg = grid_has_background(grid) ? 1 : 0;
+    float *lt = nullptr, *acc = nullptr;
+    if (has_bg) {   // the stand-alone backward hands its own log-transmittance and accum to the background (:1226-1262)
+        ASURF_REQUIRE(grads->grad_background, ASURF_E_INVALID, "cuvol_backward: the grid has a background but no gradient buffer for it");
+        rc = bg_state_reserve(Q, &lt, &acc);
+        if (rc) return rc;
+    }
     cuvol_kernel<true, false><<<cv_blocks(Q), CV_THREADS, 0, (cudaStream_t)stream>>>(
-        g, *opt, rays->origins, rays->dirs, cam, Q, nullptr, nullptr, grad_out, color_cache, 0, 0.f, nullptr, 0.f, 0.f, *grads);
+        g, *opt, rays->origins, rays->dirs, cam, Q, nullptr, lt, grad_out, color_cache, 0, 0.f, nullptr, 0.f, 0.f, *grads, has_bg,
+        acc);
     note_launches(1);
-    return check_cuda(cudaGetLastError(), "cuvol_backward launch");
+    rc = check_cuda(cudaGetLastError(), "cuvol_backward launch");
+    if (rc) return rc;
+    if (has_bg) return asurf_msi_backward(grid, rays, opt, grad_out, color_cache, 0, 0, lt, acc, 0.f, 0.f, grads, stream);
+    return 0;
 }
 
 extern "C" int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
@@ -585,8 +633,13 @@ extern "C" int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *r
     int rc = cv_make_grid(grid, g, "cuvol_fused");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    float *lt = nullptr;
-    if (beta_loss > 0.f) {   // the backward needs the forward's final log-transmittance (:1291-1296)
+    float *lt = nullptr, *acc = nullptr;
+    const int has_bg = grid_has_background(grid) ? 1 : 0;
+    if (has_bg) {            // forward log-transmittance + the backward's leftover accum for the background pass (:1289-1350)
+        ASURF_REQUIRE(grads->grad_background, ASURF_E_INVALID, "cuvol_fused: the grid has a background but no gradient buffer for it");
+        rc = bg_state_reserve(Q, &lt, &acc);
+        if (rc) return rc;
+    } else if (beta_loss > 0.f) {   // the backward needs the forward's final log-transmittance (:1291-1296)
         rc = g_ws_lt.reserve((size_t)Q * sizeof(float));
         if (rc) return rc;
         lt = (float *)g_ws_lt.ptr;
@@ -595,10 +648,21 @@ extern "C" int asurf_cuvol_fused(const asurf_grid_t *grid, const asurf_rays_t *r
     asurf_grads_t nog = {};
     CvCam cam = {};
     cuvol_kernel<false, false><<<cv_blocks(Q), CV_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, cam, Q, rgb_out, lt,
-                                                                    nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog);
+                                                                    nullptr, nullptr, 0, 0.f, nullptr, 0.f, 0.f, nog, has_bg, nullptr);
+    note_launches(1);
+    if (has_bg) {
+        rc = check_cuda(cudaGetLastError(), "cuvol_fused forward launch");
+        if (rc) return rc;
+        rc = asurf_msi_forward(grid, rays, opt, lt, rgb_out, stream);
+        if (rc) return rc;
+    }
     cuvol_kernel<true, false><<<cv_blocks(Q), CV_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, cam, Q, nullptr, nullptr,
-                                                                   rgb_gt, rgb_out, 1, 2.f / (float)(3 * (int)qn), lt,
-                                                                   beta_loss / (float)qn, sparsity_loss, *grads);
-    note_launches(2);
-    return check_cuda(cudaGetLastError(), "cuvol_fused launch");
+                                                                   rgb_gt, rgb_out, 1, 2.f / (float)(3 * (int)qn),
+                                                                   beta_loss > 0.f ? lt : nullptr, beta_loss / (float)qn,
+                                                                   sparsity_loss, *grads, has_bg, acc);
+    note_launches(1);
+    rc = check_cuda(cudaGetLastError(), "cuvol_fused launch");
+    if (rc) return rc;
+    if (has_bg) return asurf_msi_backward(grid, rays, opt, rgb_gt, rgb_out, 1, qn, lt, acc, 0.f, sparsity_loss, grads, stream);
+    return 0;
 }

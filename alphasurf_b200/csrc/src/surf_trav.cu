@@ -38,6 +38,13 @@ struct GridP {
     int use_skip;   // hierarchical empty-block skipping (off for the counting kernel)
     float offset[3], scaling[3];
     float fake_sample_std, trunc_a;
+    // MSI background behind the grid (msi.cu): the pass then ends WITHOUT the background_brightness term (:550-552) and leaves
+    // its per-ray state for the background pass -- bg_lt: final log-transmittance (written by the forward pass, or by a
+    // backward pass that is not part of a fused call, :3776-3781 vs :3905); bg_accum: what the backward loop left of
+    // `accum`, minus the beta term (:2901-2905).  Either pointer may be NULL.
+    int has_bg;
+    float *bg_lt, *bg_accum;
+    float bg_beta;
 };
 
 // fused-loss scalars after the launch-time scaling of render_lerp_kernel_surf_trav.cu:3896-3914
@@ -837,9 +844,13 @@ __device__ __forceinline__ void premarch_finish(const GridP &g, const asurf_opt_
         has_work = (n > 0) || cont;
         if (!has_work) {
             if (rgb_out) {   // forward: the ray composites nothing -> background (:59-65, :553-555)
-                const float bg = opt.background_brightness;
+                const float bg = g.has_bg ? 0.f : opt.background_brightness;
                 rgb_out[ray_id * 3 + 0] = bg; rgb_out[ray_id * 3 + 1] = bg; rgb_out[ray_id * 3 + 2] = bg;
             }
+            if (g.bg_lt) g.bg_lt[ray_id] = 0.f;
+            // bg_accum keeps its NaN = "never visited by the backward loop" (msi_backward_kernel starts such a ray from the
+            // initial accum minus the beta term, :2901-2905); a ray that misses the grid returns before that (:1810-1815): +Inf
+            if (g.bg_accum && (L.tmin > L.tmax)) g.bg_accum[ray_id] = INFINITY;
             if (cache_n) cache_n[ray_id] = 0;
         }
     }
@@ -1561,12 +1572,16 @@ surf_trav_kernel(const GridP g, const asurf_opt_t opt, const float *__restrict__
             L.state = ST_IDLE;
             const int64_t ray_id = L.ray_id;
             if (!BWD) {
-                const float bg = __expf(L.logT) * opt.background_brightness;  // a miss keeps logT == 0: pure background
+                // a miss keeps logT == 0: pure background
+                const float bg = g.has_bg ? 0.f : __expf(L.logT) * opt.background_brightness;
                 rgb_out[ray_id * 3 + 0] = out0 + bg;
                 rgb_out[ray_id * 3 + 1] = out1 + bg;
                 rgb_out[ray_id * 3 + 2] = out2 + bg;
                 if (M > 0) cache.n[ray_id] = L.sample_i;
+            } else if (g.bg_accum) {
+                g.bg_accum[ray_id] = accum - g.bg_beta;
             }
+            if (g.bg_lt) g.bg_lt[ray_id] = L.logT;
             if (DEBUG && dbg.hit_count) dbg.hit_count[ray_id] = L.n_hits;
         }
     }
@@ -1629,6 +1644,9 @@ int make_grid(const asurf_grid_t *grid, const asurf_opt_t *opt, bool need_work, 
     g.sh_dim = grid->sh_dim;
     g.fake_sample_std = grid->fake_sample_std;
     g.trunc_a = grid->truncated_vol_render_a;
+    g.has_bg = grid_has_background(grid) ? 1 : 0;
+    g.bg_lt = g.bg_accum = nullptr;
+    g.bg_beta = 0.f;
     AccelLayout lay(grid->size);
     g.ab1 = lay.b[0][1];
     g.ab2 = lay.b[0][2];
@@ -1883,6 +1901,11 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
     rc = ray_counters(st, &ctr);
     if (rc) return rc;
     PreP pre = PreP();
+    if (g.has_bg && !stats_dev) {
+        float *acc = nullptr;
+        rc = bg_state_reserve(rays->n_rays, &g.bg_lt, &acc);
+        if (rc) return rc;
+    }
     if (stats_dev) {
         dbg.stats = (unsigned long long *)stats_dev;
         g.use_skip = 0;   // count every voxel of the reference DDA
@@ -1902,7 +1925,10 @@ extern "C" int asurf_surf_trav_forward(const asurf_grid_t *grid, const asurf_ray
             g, *opt, rays->origins, rays->dirs, rays->n_rays, rgb_out, nullptr, nullptr, f, cache, grads, dbg, ctr, pre);
     }
     note_launches(1);
-    return check_cuda(cudaGetLastError(), "surf_trav_forward launch");
+    rc = check_cuda(cudaGetLastError(), "surf_trav_forward launch");
+    if (rc) return rc;
+    if (g.has_bg && !stats_dev) return asurf_msi_forward(grid, rays, opt, g.bg_lt, rgb_out, stream);   // :3639-3648
+    return 0;
 }
 
 extern "C" int asurf_surf_trav_scalar(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, int32_t mode,
@@ -1975,6 +2001,12 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
     unsigned long long *ctr = nullptr;
     rc = ray_counters(st, &ctr);
     if (rc) return rc;
+    if (g.has_bg) {   // the stand-alone backward leaves its own log-transmittance and accum for the background (:3776-3796)
+        ASURF_REQUIRE(grads->grad_background, ASURF_E_INVALID, "surf_trav_backward: the grid has a background but no gradient buffer for it");
+        rc = bg_state_reserve(rays->n_rays, &g.bg_lt, &g.bg_accum);
+        if (rc) return rc;
+        ASURF_CUDA(cudaMemsetAsync(g.bg_accum, 0xFF, (size_t)rays->n_rays * sizeof(float), st));   // NaN: ray not visited
+    }
     PreP pre;
     rc = premarch(g, opt, rays, ctr, nullptr, nullptr, st, pre);
     if (rc) return rc;
@@ -1991,7 +2023,11 @@ extern "C" int asurf_surf_trav_backward(const asurf_grid_t *grid, const asurf_ra
         g, *opt, rays->origins, rays->dirs, rays->n_rays, nullptr, grad_out, color_cache, f, cache, *grads, dbg, ctr + 1,
         pre);
     note_launches(1);
-    return check_cuda(cudaGetLastError(), "surf_trav_backward launch");
+    rc = check_cuda(cudaGetLastError(), "surf_trav_backward launch");
+    if (rc) return rc;
+    if (g.has_bg)
+        return asurf_msi_backward(grid, rays, opt, grad_out, color_cache, 0, 0, g.bg_lt, g.bg_accum, 0.f, 0.f, grads, stream);
+    return 0;
 }
 
 extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt,
@@ -2058,6 +2094,15 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
     if (rc) return rc;
     PreP pre = PreP(), nopre = PreP();
     WaveP wv = WaveP();
+    float *bg_accum = nullptr;
+    if (g.has_bg && !stats_dev) {   // forward state for the background pass; the backward adds its leftover accum (:3862-3940)
+        ASURF_REQUIRE(grads->grad_background, ASURF_E_INVALID, "surf_trav_fused: the grid has a background but no gradient buffer for it");
+        rc = bg_state_reserve(Q, &g.bg_lt, &bg_accum);
+        if (rc) return rc;
+        ASURF_CUDA(cudaMemsetAsync(bg_accum, 0xFF, (size_t)Q * sizeof(float), st));   // NaN: ray not visited by the backward
+        g.bg_accum = bg_accum;       // (only backward code paths write it)
+        g.bg_beta = fu->beta_loss / Qf;
+    }
     if (!stats_dev) {
         rc = premarch(g, opt, rays, ctr, rgb_out, cache.n, st, pre);
         if (rc) return rc;
@@ -2073,13 +2118,28 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
         if (pre.wave) {
             rc = wave_buffers(pre, rays->n_rays, ctr, wv);
             if (rc) return rc;
-            rc = wave_forward(g, opt, rays, pre, wv, cache, M, rgb_out, rgb_gt, nullptr, f, st);
+            // with a background the loss gradient needs the FINAL colours (foreground + background, :3877-3890): the
+            // backward recurrences of the composite stage are then walked in a second pass behind the background forward
+            rc = wave_forward(g, opt, rays, pre, wv, cache, M, rgb_out, g.has_bg ? nullptr : rgb_gt, nullptr, f, st);
             if (rc) return rc;
         }
         surf_trav_kernel<false, false><<<n_ctas(Q), CTA_THREADS, 0, st>>>(g, *opt, rays->origins, rays->dirs, Q, rgb_out,
                                                                            nullptr, nullptr, ff, cache, nog, dbg, ctr, pre);
     }
     DebugP nodbg = {};
+    float *bg_lt = g.bg_lt;
+    if (g.has_bg && !stats_dev) {
+        rc = check_cuda(cudaGetLastError(), "surf_trav_fused forward launch");
+        if (rc) return rc;
+        rc = asurf_msi_forward(grid, rays, opt, bg_lt, rgb_out, stream);
+        if (rc) return rc;
+        g.bg_lt = nullptr;           // the fused backward keeps the FORWARD's log-transmittance (:3934)
+        if (pre.wave) {              // second pass of the wavefront stages: same entries, recurrences from the final colours
+            ASURF_CUDA(cudaMemsetAsync(ctr + 5, 0, sizeof(unsigned long long), st));
+            rc = wave_forward(g, opt, rays, pre, wv, cache, M, nullptr, rgb_gt, rgb_out, f, st);
+            if (rc) return rc;
+        }
+    }
     if (prof) cudaEventRecord(pe[3], st);
     if (pre.wave) {
         rc = wave_backward(g, opt, rays, pre, wv, rgb_gt, rgb_out, f, cache, *grads, st);
@@ -2092,7 +2152,12 @@ extern "C" int asurf_surf_trav_fused(const asurf_grid_t *grid, const asurf_rays_
         ++g_prof.n;
     }
     note_launches(2);
-    return check_cuda(cudaGetLastError(), "surf_trav_fused launch");
+    rc = check_cuda(cudaGetLastError(), "surf_trav_fused launch");
+    if (rc) return rc;
+    if (g.has_bg && !stats_dev)
+        return asurf_msi_backward(grid, rays, opt, rgb_gt, rgb_out, 1, qn, bg_lt, bg_accum, fu->beta_loss / Qf,
+                                  fu->sparsity_loss, grads, stream);
+    return 0;
 }
 
 static int debug_launch(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, DebugP dbg,
@@ -2196,6 +2261,7 @@ extern "C" void asurf_release(void) {
     g_ws_wave.release();
     g_ws_seg.release();
     loss_release();
+    msi_release();
     cuvol_release();
     misc_release();
 }

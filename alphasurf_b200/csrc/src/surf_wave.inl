@@ -421,8 +421,9 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
             }
             if (alive_b && (__expf(logT_b) < opt.stop_thresh)) alive_b = false;
         }
-        const float bg = __expf(logT) * opt.background_brightness;
+        const float bg = g.has_bg ? 0.f : __expf(logT) * opt.background_brightness;
         float cc[3] = {out0 + bg, out1 + bg, out2 + bg};
+        if (g.bg_lt) g.bg_lt[ray_id] = rgb_out ? logT : logT_b;   // forward state, or a stand-alone backward's own (msi.cu)
         if (rgb_out) {
             rgb_out[ray_id * 3 + 0] = cc[0];
             rgb_out[ray_id * 3 + 1] = cc[1];
@@ -479,6 +480,7 @@ wave_composite_kernel(const GridP g, const asurf_opt_t opt, const PreP pre, cons
                 if ((kind == ENT_SAMPLE || opt.fake_sample_l_dist) && (sample_b < M - 1)) sample_b += 1;
             }
         }
+        if (g.bg_accum) g.bg_accum[ray_id] = accum - g.bg_beta;
     }
 }
 

@@ -137,8 +137,13 @@ def _check_grid(grid: SparseGridSpec):
         raise RuntimeError("links must be int32")
     _check_f32(grid.density_data, "density_data")
     _check_f32(grid.sh_data, "sh_data")
-    if _defined(grid.background_links) and grid.background_links.numel() > 0:
-        raise NotImplementedError("MSI background layers are outside the B200 hot path (SURVEY.md 8f #4)")
+    if _defined(grid.background_links) and grid.background_links.numel() > 0:     # MSI background (data_spec.hpp:47-48)
+        _check_input(grid.background_links, "background_links")
+        _check_input(grid.background_data, "background_data")
+        if grid.background_links.dim() != 2 or grid.background_links.dtype != torch.int32:
+            raise RuntimeError("background_links must be a 2-D int32 tensor")
+        if grid.background_data.dim() != 3 or grid.background_data.shape[2] != 4 or grid.background_data.dtype != torch.float32:
+            raise RuntimeError("background_data must be a float32 (n, nlayers, 4) tensor")
     if grid.basis_type != BASIS_TYPE_SH:
         raise NotImplementedError("only the SH basis is on the B200 hot path")
 
@@ -203,6 +208,11 @@ def _grid_t(grid: SparseGridSpec, need_surface=True, need_accel=True):
     g.scaling[:] = [float(v) for v in grid._scaling.tolist()]
     g.fake_sample_std = float(grid.fake_sample_std)
     g.truncated_vol_render_a = float(grid.truncated_vol_render_a)
+    if _defined(grid.background_links) and grid.background_links.numel() > 0:
+        g.background_links = grid.background_links.data_ptr()
+        g.background_data = grid.background_data.data_ptr()
+        g.background_reso = int(grid.background_links.shape[1])
+        g.background_nlayers = int(grid.background_data.shape[1])
     acc = accel_for(grid.links) if need_accel else None
     g.accel = acc.data_ptr() if need_accel else None
     return g, acc
@@ -224,6 +234,10 @@ def _grads_t(g: GridOutputGrads):
     o.grad_fake_sample_std = (g.grad_fake_sample_std_out.data_ptr()
                               if _defined(g.grad_fake_sample_std_out) and g.grad_fake_sample_std_out.numel() > 0 else None)
     o.mask = g.mask_out.data_ptr() if _defined(g.mask_out) and g.mask_out.numel() > 0 else None
+    o.grad_background = (g.grad_background_out.data_ptr()
+                         if _defined(g.grad_background_out) and g.grad_background_out.numel() > 0 else None)
+    o.mask_background = (g.mask_background_out.data_ptr()
+                         if _defined(g.mask_background_out) and g.mask_background_out.numel() > 0 else None)
     return o
 
 
@@ -757,6 +771,29 @@ def surface_normal_grad_sparse(links, data, rand_cells, mask_out, lv_set, start_
             capi.ptr(accel_for(links)), capi.current_stream()), "surface_normal_grad_sparse")
 
 
+def msi_tv_grad_sparse(links, msi, rand_cells, mask_out, scale, scale_last, grad_msi):
+    """TV over (texel, layer) cells of the MSI background (loss_kernel.cu:979-1064, :1624-1659)"""
+    for t, n in ((links, "links"), (msi, "msi"), (grad_msi, "grad_msi"), (mask_out, "mask_out")):
+        _check_input(t, n)
+    _check_cells(rand_cells)
+    if msi.dim() != 3 or links.dim() != 2 or not msi.is_floating_point():
+        raise RuntimeError("msi must be a (n, nlayers, channels) floating point tensor and links 2-D")
+    with torch.cuda.device(msi.device):
+        capi.check(capi.lib().asurf_msi_tv_grad_sparse(
+            capi.ptr(links), C.c_int32(links.shape[0]), C.c_int32(links.shape[1]), capi.ptr(msi), C.c_int32(msi.shape[1]),
+            C.c_int32(msi.shape[2]), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]),
+            capi.ptr(mask_out) if mask_out.numel() > 0 else None, C.c_float(scale), C.c_float(scale_last), capi.ptr(grad_msi),
+            capi.current_stream()), "msi_tv_grad_sparse")
+
+
+def debug_bg_state(n_rays, device="cuda"):
+    """(log_transmit (Q,), accum (Q,)) the last foreground pass over a grid with a background left for the MSI pass"""
+    lt = torch.empty((n_rays,), dtype=torch.float32, device=device)
+    acc = torch.empty((n_rays,), dtype=torch.float32, device=device)
+    capi.check(capi.lib().asurf_debug_bg_state(capi.ptr(lt), capi.ptr(acc), C.c_int64(n_rays)), "debug_bg_state")
+    return lt, acc
+
+
 # ---- test hooks -----------------------------------------------------------------------------------------------------------
 def debug_ray_bounds(grid, rays, opt):
     """(Q,9) grid-space rays as the kernels see them: origin3, dir3, tmin, tmax, world_step."""
@@ -827,7 +864,7 @@ def _not_on_hot_path(name):
 
 
 for _name in ("surface_normal_grad",
-              "surf_sign_change_grad_sparse", "msi_tv_grad_sparse", "lumisphere_tv_grad_sparse",
+              "surf_sign_change_grad_sparse", "lumisphere_tv_grad_sparse",
               "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
               "volume_render_nvol", "volume_render_nvol_backward", "volume_render_nvol_fused", "volume_render_svox1",
               "volume_render_svox1_backward", "volume_render_svox1_fused", "test_cubic_root_grad"):

@@ -155,7 +155,8 @@ def workload_config(args, world, sample_note=None):
          "rays_per_step_global": rays_rank * world, "sh_dim": 27, "scaling": args.scaling,
          "l2_policy": "inputs larger than L2 (grid data %s); a different ray batch every step" %
                       ("2.3 GB" if args.reso >= 512 else "0.3 GB"),
-         "parallelism": "ray-sharded dp%d, grid replicated" % world}
+         "parallelism": "ray-sharded dp%d, grid replicated%s" % (
+             world, "" if world == 1 else (", regularisers cell-sharded" if args.shard_regularisers else ", regularisers redundant"))}
     if sample_note:
         c["note"] = sample_note
     return c
@@ -361,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
         assert w["kind"] == "surf_trav", "the multi-GPU step is implemented for the alpha-Surf workloads"
         from alphasurf_b200 import dist as adist
         C.set_loss_norm_rays(Q * world)
-        exchange = adist.GradExchange(ts)
+        exchange = adist.GradExchange(ts, shard_regularisers=(args.shard_regularisers != 0))
     L = capi.lib()
     phase_ev = []   # per step: 4 events (start, after render [+ exchange], after regularisers, after optimizer)
 
@@ -725,6 +726,9 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=8192)
     ap.add_argument("--l0-rays", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--shard-regularisers", type=int, default=1,
+                    help="multi-GPU: 1 = every rank takes 1/N of the regulariser cell lists and the shards are all-reduced (dense), "
+                         "0 = every rank runs the whole lists redundantly (no regulariser exchange)")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline, the L0 baseline, the reference-CUDA comparison and "
                                                              "the N-rank parity block (profiling runs)")
     args = ap.parse_args()

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ASURF_ABI_VERSION 2
+#define ASURF_ABI_VERSION 3
 
 enum {
     ASURF_OK = 0,
@@ -51,6 +51,13 @@ typedef struct {
     /* Optional work pyramid built by asurf_work_build() for exactly this grid content (links, density, surface,
      * level sets) and the render options of the call (NULL: the library builds a transient one per call). */
     const uint64_t *work;
+    /* Multi-sphere-image background (SparseGridSpec.background_links / background_data, data_spec.hpp:47-48): links int32
+     * (2 reso, reso), value = row of background_data or < 0; data float32 (n, nlayers, 4) = r, g, b, sigma per layer.
+     * NULL / 0 layers: no background (the renders then end on opt.background_brightness). */
+    const int32_t *background_links;
+    const float *background_data;
+    int32_t background_reso;
+    int32_t background_nlayers;
 } asurf_grid_t;
 
 /* include/data_spec.hpp:168-201 (RenderOptions); bools widened to int32 */
@@ -88,6 +95,8 @@ typedef struct {
     float *grad_sh;              /* (N,D) */
     float *grad_fake_sample_std; /* (1,) or NULL */
     uint8_t *mask;               /* (N,) bool or NULL */
+    float *grad_background;      /* (n, nlayers, 4) or NULL: GridOutputGrads.grad_background_out */
+    uint8_t *mask_background;    /* (n, nlayers) bool or NULL: GridOutputGrads.mask_background_out */
 } asurf_grads_t;
 
 /* scalar arguments of volume_render_surf_trav_fused, render_lerp_kernel_surf_trav.cu:3802-3828 */
@@ -327,6 +336,35 @@ int asurf_surface_normal_grad_sparse(const int32_t *links, const int32_t size[3]
                                      int32_t start_dim, int32_t end_dim, float scale, int32_t con_check,
                                      int32_t ignore_empty, int32_t use_l1, float *grad_data, const uint64_t *accel,
                                      void *stream);
+
+/* ---- multi-sphere-image background, render_lerp_kernel_surf_trav.cu:2914-3137, :3370-3455 (the same code serves the cuvol
+ *      renderer, render_lerp_kernel_cuvol.cu:540-760) ----
+ * The render entries above run these passes themselves when the grid carries a background (forward: after the foreground
+ * pass, onto its colours; backward / fused: after the foreground backward).  They are exported for callers that hold the
+ * per-ray state of a foreground pass: log_transmit (Q,) = log-transmittance behind the grid, accum (Q,) = what the foreground
+ * backward left of its running sum (NaN: the foreground never visited the ray; the pass then starts from
+ * sum_c colour_c * dL/dcolour_c - beta_loss; +Inf: the ray missed the grid: the same without the beta term). */
+/* render_background_kernel, :3370-3387: rgb_out (Q,3) += background colours + exp(log_transmit_final) * background_brightness */
+int asurf_msi_forward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, const float *log_transmit,
+                      float *rgb_out, void *stream);
+/* render_background_image_kernel, :3389-3411: the same for the pixels of a pinhole camera (c2w: 12 host floats) */
+int asurf_msi_forward_image(const asurf_grid_t *grid, const float *c2w_host, float fx, float fy, float cx, float cy,
+                            int32_t width, int32_t height, const asurf_opt_t *opt, const float *log_transmit, float *rgb_out,
+                            void *stream);
+/* render_background_backward_kernel, :3413-3455: grad_is_rgb != 0: grad_in is rgb_gt, dL/dRGB = (color_cache - rgb_gt) * 2 /
+ * (3 norm_rays) (norm_rays = 0: this call's Q); grads->grad_background (+ mask_background) receive the gradients */
+int asurf_msi_backward(const asurf_grid_t *grid, const asurf_rays_t *rays, const asurf_opt_t *opt, const float *grad_in,
+                       const float *color_cache, int32_t grad_is_rgb, int64_t norm_rays, const float *log_transmit,
+                       const float *accum, float beta_loss, float sparsity_loss, const asurf_grads_t *grads, void *stream);
+/* msi_tv_grad_sparse, loss_kernel.cu:979-1064, :1624-1659: TV over (texel, layer) cells of the background; links is
+ * (links_x, links_y), msi (n, nlayers, n_channels); the last channel (sigma) uses scale_last; rand_cells holds
+ * (x * links_y + y) * nlayers + z; mask_out (n, nlayers) bool or NULL */
+int asurf_msi_tv_grad_sparse(const int32_t *links, int32_t links_x, int32_t links_y, const float *msi, int32_t nlayers,
+                             int32_t n_channels, const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, float scale,
+                             float scale_last, float *grad_msi, void *stream);
+/* test hook (synchronises): per-ray state the last foreground pass with a background left behind: log_transmit (Q,) and
+ * accum (Q,) (either may be NULL) */
+int asurf_debug_bg_state(float *log_transmit_out, float *accum_out, int64_t n_rays);
 
 /* ---- multi-GPU gradient exchange helpers (ours; alphasurf_b200/dist.py) ----
  * rows: device int64 (n_rows,), ascending row indices touched on some rank, optionally padded with negative entries (a list

@@ -471,3 +471,41 @@ def cubic_extract_iso_pts(links, level, maskv, cell_ids, n_sample, density_thres
     lib().oracle_cubic_extract_iso_pts(_ptr(lk), _ptr(np.asarray(lk.shape, np.int32)), _ptr(lv), _ptr(mv), _ptr(ids),
                                        C.c_int64(ids.shape[0]), C.c_int(n_sample), C.c_float(density_thresh), _ptr(out))
     return out
+
+
+# ---- MSI background (oracle_msi.c) ---------------------------------------------------------------------------------------------
+def _f3(t):
+    a = np.ascontiguousarray(np.asarray(t, dtype=np.float32).reshape(-1)[:3])
+    return a
+
+
+def msi_forward(bg_links, bg_data, size, offset, scaling, opt: dict, origins, dirs, log_transmit, rgb):
+    """rgb (Q,3) float32 numpy, updated in place: += background colours (render_background_kernel)"""
+    links, data = _np(bg_links, np.int32), _np(bg_data, np.float32)
+    o, d, lt = _np(origins, np.float32), _np(dirs, np.float32), _np(log_transmit, np.float32)
+    sz = (C.c_int32 * 3)(*[int(v) for v in size])
+    off, sc = _f3(offset), _f3(scaling)
+    oo = make_opt(opt)
+    lib().oracle_msi_forward(_ptr(links), _ptr(data), C.c_int(links.shape[1]), C.c_int(data.shape[1]), sz, _ptr(off), _ptr(sc),
+                             C.byref(oo), _ptr(o), _ptr(d), C.c_int64(o.shape[0]), _ptr(lt), _ptr(rgb))
+
+
+def msi_backward(bg_links, bg_data, size, offset, scaling, opt: dict, origins, dirs, grad_in, color_cache, grad_is_rgb,
+                 log_transmit, accum, sparsity_loss, grad_bg, mask_bg):
+    links, data = _np(bg_links, np.int32), _np(bg_data, np.float32)
+    o, d = _np(origins, np.float32), _np(dirs, np.float32)
+    gi, cc = _np(grad_in, np.float32), _np(color_cache, np.float32)
+    lt, acc = _np(log_transmit, np.float32), _np(accum, np.float32)
+    sz = (C.c_int32 * 3)(*[int(v) for v in size])
+    off, sc = _f3(offset), _f3(scaling)
+    oo = make_opt(opt)
+    lib().oracle_msi_backward(_ptr(links), _ptr(data), C.c_int(links.shape[1]), C.c_int(data.shape[1]), sz, _ptr(off), _ptr(sc),
+                              C.byref(oo), _ptr(o), _ptr(d), C.c_int64(o.shape[0]), _ptr(gi), _ptr(cc), C.c_int(int(grad_is_rgb)),
+                              _ptr(lt), _ptr(acc), C.c_float(sparsity_loss), _ptr(grad_bg), _ptr(mask_bg))
+
+
+def msi_tv_grad_sparse(bg_links, msi, cells, mask, scale, scale_last, grad):
+    links, data, cells = _np(bg_links, np.int32), _np(msi, np.float32), _np(cells, np.int32)
+    lib().oracle_msi_tv_grad_sparse(_ptr(links), C.c_int(links.shape[0]), C.c_int(links.shape[1]), _ptr(data),
+                                    C.c_int(data.shape[1]), C.c_int(data.shape[2]), _ptr(cells), C.c_int64(cells.shape[0]),
+                                    _ptr(mask), C.c_float(scale), C.c_float(scale_last), _ptr(grad))

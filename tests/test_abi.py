@@ -22,7 +22,7 @@ def test_library_exports_every_symbol():
     lib = capi.lib()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.asurf_abi_version() == 2
+    assert lib.asurf_abi_version() == 3
     assert isinstance(lib.asurf_last_error(), bytes)
 
 
@@ -38,8 +38,8 @@ def test_struct_layouts_match_header():
     # sizes follow from the field lists in include/asurf.h (natural alignment)
     assert ctypes.sizeof(capi.OptT) == 17 * 4
     assert ctypes.sizeof(capi.RaysT) == 24
-    assert ctypes.sizeof(capi.GradsT) == 40
-    assert ctypes.sizeof(capi.GridT) == 8 + 12 + 4 + 8 * 4 + 4 * 3 + 4 + 8 + 12 + 12 + 4 + 4 + 8 + 8
+    assert ctypes.sizeof(capi.GradsT) == 56
+    assert ctypes.sizeof(capi.GridT) == 8 + 12 + 4 + 8 * 4 + 4 * 3 + 4 + 8 + 12 + 12 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4
     assert ctypes.sizeof(capi.FusedT) == 18 * 4 + 8
 
 
@@ -64,7 +64,7 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), lib, "-o", str(exe),
                            "-Wl,-rpath," + os.path.dirname(lib)])
     out = subprocess.check_output([str(exe)]).decode().split()
-    assert int(out[0]) >= 2 and int(out[1]) == capi.lib().asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
+    assert int(out[0]) >= 3 and int(out[1]) == capi.lib().asurf_accel_words((ctypes.c_int32 * 3)(512, 512, 512))
 
 
 def test_ctypes_call_sites_pass_the_declared_number_of_arguments():
