@@ -34,6 +34,7 @@ class GradExchange:
         self.sync_free = sync_free
         self.cap = None
         self._count_probe = None     # (pinned host count, event, capacity it was taken with)
+        self._mask_bufs = {}
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.shard_regularisers = shard_regularisers   # end() also sums the cell-sharded regulariser gradients
@@ -54,11 +55,34 @@ class GradExchange:
             self.bucket = torch.empty((cap, width), dtype=like.dtype, device=like.device)
         return self.bucket[:n]
 
+    def mask_or(self, mask, group=None):
+        """mask (N,) bool <- OR over the ranks.  On CUDA the mask travels bit-packed (asurf_mask_pack -> all-gather of N / 8
+        bytes per rank -> asurf_mask_unpack_or) instead of an N-byte MAX all-reduce; host tensors (gloo tests) take the latter."""
+        group = self.group if group is None else group
+        if not mask.is_cuda:
+            dist.all_reduce(mask.view(torch.uint8), op=dist.ReduceOp.MAX, group=group)
+            return
+        from . import capi
+        import ctypes as C
+        N = mask.shape[0]
+        nw = (N + 31) // 32
+        key = (N, mask.device, torch.cuda.current_stream(mask.device).cuda_stream)
+        buf = self._mask_bufs.get(key)
+        if buf is None:
+            buf = (torch.empty((nw,), dtype=torch.int32, device=mask.device),
+                   torch.empty((self.world * nw,), dtype=torch.int32, device=mask.device))
+            self._mask_bufs[key] = buf
+        words, gathered = buf
+        st = capi.current_stream(mask.device)
+        capi.check(capi.lib().asurf_mask_pack(capi.ptr(mask), C.c_int64(N), capi.ptr(words), st), "mask_pack")
+        dist.all_gather_into_tensor(gathered, words, group=group)
+        capi.check(capi.lib().asurf_mask_unpack_or(capi.ptr(gathered), C.c_int32(self.world), C.c_int64(N), capi.ptr(mask), st),
+                   "mask_unpack_or")
+
     def begin(self, ts):
         """``ts``: object with ``grad`` = {density (N,1), surface (N,1), sh (N,D)}, ``mask`` and ``mask_sh`` (N,) bool."""
         g = ts.grad
-        mask_u8 = ts.mask.view(torch.uint8)
-        dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group)
+        self.mask_or(ts.mask)
         ts.mask_sh.copy_(ts.mask)
         N = ts.mask.shape[0]
         rows, n = self._touched_rows(ts.mask)             # identical on every rank
@@ -142,8 +166,10 @@ class GradExchange:
             b.record()
             torch.cuda.synchronize(dev)
             return a.elapsed_time(b) / iters
-        out["mask_or_allreduce_ms"] = t(lambda: dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group))
-        out["mask_or_bytes"] = N
+        out["mask_or_allreduce_bytewise_ms"] = t(lambda: dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group))
+        mb = torch.zeros((N,), dtype=torch.bool, device=dev)
+        out["mask_or_bitpacked_allgather_ms"] = t(lambda: self.mask_or(mb))
+        out["mask_or_bytes_per_rank"] = (N + 31) // 32 * 4
         out["sparse_bucket_allreduce_ms"] = t(lambda: dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group))
         out["sparse_bucket_bytes"] = n * (2 + D) * 4
         out["dense_regulariser_allreduce_ms"] = t(lambda: dist.all_reduce(dense, op=dist.ReduceOp.SUM, group=self.group))
@@ -156,7 +182,7 @@ class GradExchange:
         if self.shard_regularisers and self.world > 1:
             # the regularisers ran on this rank's share of the cells: sum the shards (they touch every stored row, so
             # this exchange is dense) and OR the masks they set
-            dist.all_reduce(ts.mask.view(torch.uint8), op=dist.ReduceOp.MAX, group=self.group)
+            self.mask_or(ts.mask)
             dist.all_reduce(g["density"], op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(g["surface"], op=dist.ReduceOp.SUM, group=self.group)
             if self._hold is not None:
@@ -225,7 +251,7 @@ class GradExchange:
             reg["mask"].zero_()
             if self.shard_regularisers:
                 ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
-                dist.all_reduce(reg["mask"].view(torch.uint8), op=dist.ReduceOp.MAX, group=self._group_b)
+                self.mask_or(reg["mask"], group=self._group_b)
                 dist.all_reduce(reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
             else:
                 ts.regularisers(grad=reg["grad"], mask=reg["mask"])     # every rank the whole lists: nothing to exchange

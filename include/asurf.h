@@ -376,6 +376,11 @@ int asurf_rows_pack(const int64_t *rows, int64_t n_rows, float *grad_density, fl
 int asurf_rows_unpack_add(const int64_t *rows, int64_t n_rows, float *grad_density, float *grad_surface, float *grad_sh,
                           int32_t sh_dim, const float *bucket, void *stream);
 
+/* Touched-row masks for the same exchange, bit-packed (NCCL has no bitwise OR): pack a (n,) bool mask into (n + 31) / 32
+ * words; unpack_or writes mask[i] = OR over the `world` word arrays laid end to end in words_all (an all-gather's output). */
+int asurf_mask_pack(const uint8_t *mask, int64_t n, uint32_t *words, void *stream);
+int asurf_mask_unpack_or(const uint32_t *words_all, int32_t world, int64_t n, uint8_t *mask, void *stream);
+
 /* ---- per-kernel timing (ours; feeds bench.py's roofline) ----
  * After asurf_profile_enable(capacity > 0) every asurf_surf_trav_fused call records CUDA events around its forward
  * (work pyramid build, pre-march, shading) and its backward pass on the launching stream (up to `capacity` calls are kept).  asurf_profile_read waits for

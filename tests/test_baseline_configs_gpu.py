@@ -193,3 +193,27 @@ def test_rows_pack_unpack_round_trip():
                                        capi.ptr(bucket), st), "rows_unpack_add")
     torch.cuda.synchronize()
     assert torch.equal(gsh[rows], 2 * ref_sh[rows]) and torch.equal(gsh[keep], ref_sh[keep])
+
+
+def test_mask_pack_unpack_or():
+    """asurf_mask_pack / asurf_mask_unpack_or (bit-packed OR of the touched-row masks): two masks packed, laid end to end as an
+    all-gather would leave them, unpacked to their OR."""
+    import ctypes as C
+    from alphasurf_b200 import capi
+    L = capi.lib()
+    N = 100003                                    # not a multiple of 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    m0 = torch.rand((N,), device="cuda", generator=g) < 0.03
+    m1 = torch.rand((N,), device="cuda", generator=g) < 0.5
+    nw = (N + 31) // 32
+    gathered = torch.zeros((2 * nw,), dtype=torch.int32, device="cuda")
+    st = capi.current_stream()
+    for r, m in enumerate((m0, m1)):
+        capi.check(L.asurf_mask_pack(capi.ptr(m), C.c_int64(N), capi.ptr(gathered[r * nw:(r + 1) * nw]), st), "mask_pack")
+    out = torch.zeros((N,), dtype=torch.bool, device="cuda")
+    capi.check(L.asurf_mask_unpack_or(capi.ptr(gathered), C.c_int32(2), C.c_int64(N), capi.ptr(out), st), "mask_unpack_or")
+    torch.cuda.synchronize()
+    assert torch.equal(out, m0 | m1)
+    capi.check(L.asurf_mask_unpack_or(capi.ptr(gathered), C.c_int32(1), C.c_int64(N), capi.ptr(out), st), "mask_unpack_or")
+    torch.cuda.synchronize()
+    assert torch.equal(out, m0)
