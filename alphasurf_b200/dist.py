@@ -35,6 +35,7 @@ class GradExchange:
         self.cap = None
         self._count_probe = None     # (pinned host count, event, capacity it was taken with)
         self._mask_bufs = {}
+        self.bitpack_masks = False
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.shard_regularisers = shard_regularisers   # end() also sums the cell-sharded regulariser gradients
@@ -55,11 +56,14 @@ class GradExchange:
             self.bucket = torch.empty((cap, width), dtype=like.dtype, device=like.device)
         return self.bucket[:n]
 
-    def mask_or(self, mask, group=None):
-        """mask (N,) bool <- OR over the ranks.  On CUDA the mask travels bit-packed (asurf_mask_pack -> all-gather of N / 8
-        bytes per rank -> asurf_mask_unpack_or) instead of an N-byte MAX all-reduce; host tensors (gloo tests) take the latter."""
+    def mask_or(self, mask, group=None, bitpack=None):
+        """mask (N,) bool <- OR over the ranks: a MAX all-reduce of the N bytes, or (bitpack) asurf_mask_pack -> all-gather
+        of N / 8 bytes per rank -> asurf_mask_unpack_or.  Measured on B200 / NVSwitch (profiles/r2_scale_*): the 15 MB
+        byte-wise all-reduce takes 0.064 ms at 2 ranks and 0.090 ms at 8, the bit-packed form 0.086 ms at 2 ranks (two extra
+        launches and the all-gather's latency outweigh the 8x smaller message), so the byte-wise form is the default."""
         group = self.group if group is None else group
-        if not mask.is_cuda:
+        bitpack = self.bitpack_masks if bitpack is None else bitpack
+        if not mask.is_cuda or not bitpack:
             dist.all_reduce(mask.view(torch.uint8), op=dist.ReduceOp.MAX, group=group)
             return
         from . import capi
@@ -168,7 +172,7 @@ class GradExchange:
             return a.elapsed_time(b) / iters
         out["mask_or_allreduce_bytewise_ms"] = t(lambda: dist.all_reduce(mask_u8, op=dist.ReduceOp.MAX, group=self.group))
         mb = torch.zeros((N,), dtype=torch.bool, device=dev)
-        out["mask_or_bitpacked_allgather_ms"] = t(lambda: self.mask_or(mb))
+        out["mask_or_bitpacked_allgather_ms"] = t(lambda: self.mask_or(mb, bitpack=True))
         out["mask_or_bytes_per_rank"] = (N + 31) // 32 * 4
         out["sparse_bucket_allreduce_ms"] = t(lambda: dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group))
         out["sparse_bucket_bytes"] = n * (2 + D) * 4
