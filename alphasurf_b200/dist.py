@@ -36,6 +36,7 @@ class GradExchange:
         self._count_probe = None     # (pinned host count, event, capacity it was taken with)
         self._mask_bufs = {}
         self.bitpack_masks = False
+        self.render_first = True
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.shard_regularisers = shard_regularisers   # end() also sums the cell-sharded regulariser gradients
@@ -243,22 +244,32 @@ class GradExchange:
         cuda = self._side is not None
         if events:
             events[0].record()
+        import contextlib
+        ev_start = None
         if cuda:
-            main = torch.cuda.current_stream()
-            self._side.wait_stream(main)          # the previous optimizer step has updated the parameters
-            ctx = torch.cuda.stream(self._side)
-        else:
-            import contextlib
-            ctx = contextlib.nullcontext()
-        with ctx:
-            reg["buf"].zero_()
-            reg["mask"].zero_()
-            if self.shard_regularisers:
-                ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
-                self.mask_or(reg["mask"], group=self._group_b)
-                dist.all_reduce(reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
+            ev_start = torch.cuda.Event()
+            ev_start.record()                     # the previous optimizer step has updated the parameters
+
+        def side_lane():
+            if cuda:
+                self._side.wait_event(ev_start)
+                ctx = torch.cuda.stream(self._side)
             else:
-                ts.regularisers(grad=reg["grad"], mask=reg["mask"])     # every rank the whole lists: nothing to exchange
+                ctx = contextlib.nullcontext()
+            with ctx:
+                reg["buf"].zero_()
+                reg["mask"].zero_()
+                if self.shard_regularisers:
+                    ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
+                    self.mask_or(reg["mask"], group=self._group_b)
+                    dist.all_reduce(reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
+                else:
+                    ts.regularisers(grad=reg["grad"], mask=reg["mask"])     # every rank the whole lists: nothing to exchange
+
+        # Enqueue order: the render lane first (it then has the GPU to itself, as on one GPU, and its exchange -- mostly waiting
+        # for the wire -- overlaps the regulariser kernels), or the regulariser lane first.  Same order on every rank either way.
+        if not self.render_first:
+            side_lane()
         shard = self.shard_regularisers
         self.shard_regularisers = False           # begin / end: the sparse exchange of the render gradients alone
         try:
@@ -266,6 +277,10 @@ class GradExchange:
             self.begin(ts)
             if events:
                 events[1].record()
+            if self.render_first:
+                self.shard_regularisers = shard
+                side_lane()
+                self.shard_regularisers = False
             self.end(ts)
         finally:
             self.shard_regularisers = shard
