@@ -422,9 +422,11 @@ def run_ours(args, rank, world, local_rank):
     L.asurf_launch_count(ctypes.c_int32(1))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         device_step(*dev_batches[(args.warmup + i) % NB], record=True)
     ev1.record()
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps   # CPU time to ENQUEUE a step (no synchronisation inside)
     barrier()
     n_launch = int(L.asurf_launch_count(ctypes.c_int32(0)))
     clocks = sampler.stop() if rank == 0 else None
@@ -514,6 +516,9 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "alphasurf_b200/csrc/svox2_csrc_shim*.so (compiled pybind11/torch module replacing svox2.csrc)"},
         "gpu_launches": n_launch,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
+        "host_enqueue_note": "CPU time the Python host needs to enqueue one step (rank 0); a value close to ms_per_step means the "
+                             "step is bound by the host's launch rate, not by the GPU",
         "roofline": roof,
         "step_phases": phases,
         "step_phases_note": ("sequential: fused render | regularisers | optimizer" if world == 1 else
