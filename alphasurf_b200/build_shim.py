@@ -39,7 +39,7 @@ def build_shim(name="svox2_csrc_shim", out_dir=None, force=False) -> str:
            "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
     cmd += ["-I" + p for p in cpp_extension.include_paths()] + ["-I" + sysconfig.get_paths()["include"], "-I" + cuda_inc,
                                                                 "-I" + os.path.join(ROOT, "include")]
-    cmd += [SRC, "-o", out, lib, "-L" + tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+    cmd += [SRC, "-o", out, lib, "-L" + tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-ldl",
             "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath," + tlib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

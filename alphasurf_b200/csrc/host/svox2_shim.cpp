@@ -7,6 +7,7 @@
 // ASURF_E_UNSUPPORTED).  It holds no arithmetic and no kernels: `g++` builds it (alphasurf_b200/build_shim.py), `nvcc` is not
 // involved.  alphasurf_b200/svox2_csrc.py is the same layer written with ctypes; the GPU parity suite currently runs through
 // that one, this file is the drop-in a maintainer installs as svox2/csrc*.so.
+// Every exported function runs inside an NVTX range named "svox2.csrc.<function>" (tracing).
 #include <torch/extension.h>
 
 #include <c10/cuda/CUDAGuard.h>
@@ -16,12 +17,31 @@
 #include <string>
 #include <tuple>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges show up in Nsight Systems / Compute timelines, cost nothing otherwise
+
 #include "asurf.h"
 
 namespace py = pybind11;
 using torch::Tensor;
 
 namespace {
+
+// NVTX range around an exported function: REG(fn) registers Traced<&fn>::call, which has fn's signature
+template <auto F>
+struct Traced;
+template <typename R, typename... A, R (*F)(A...)>
+struct Traced<F> {
+    static const char *name;
+    static R call(A... a) {
+        struct Range {
+            explicit Range(const char *n) { nvtxRangePushA(n); }
+            ~Range() { nvtxRangePop(); }
+        } range(name);
+        return F(std::forward<A>(a)...);
+    }
+};
+template <typename R, typename... A, R (*F)(A...)>
+const char *Traced<F>::name = "svox2.csrc";
 
 constexpr int BASIS_TYPE_SH = 1;            // include/data_spec.hpp:11-15
 constexpr int SURFACE_TYPE_NONE = 100;      // include/data_spec.hpp:17-23
@@ -853,7 +873,7 @@ py::object off_path(const std::string &name) {
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "alphasurf_b200: svox2.csrc-compatible module over libasurf.so (include/asurf.h)";
-#define REG(fn) m.def(#fn, &fn)
+#define REG(fn) (Traced<&fn>::name = "svox2.csrc." #fn, m.def(#fn, &Traced<&fn>::call))
     REG(sample_grid);
     REG(sample_grid_backward);
     REG(cubic_extract_iso_pts);

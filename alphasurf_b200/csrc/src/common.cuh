@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "asurf.h"
 
@@ -56,6 +57,17 @@ void misc_release();
 int work_cache_copy(uint64_t *out, int64_t words, cudaStream_t st);
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// The asurf_debug_set_* switches (algorithm variants the tests compare) are inert unless the process was started with
+// ASURF_DEBUG_HOOKS=1: a production process cannot be reconfigured through the ABI by accident.
+static inline bool debug_hooks_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ASURF_DEBUG_HOOKS");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 // ---- occupancy pyramid layout (accel.cu) -----------------------------------------------------------------
 // A "cell" (x,y,z) is the voxel spanned by vertices (x..x+1, y..y+1, z..z+1); it is ACTIVE iff its 8 corner

@@ -1369,7 +1369,7 @@ extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const
     return check_cuda(cudaGetLastError(), "alpha_surf_sparsify_grad_sparse launch");
 }
 
-extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { g_tile_path = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_normal_tile(int32_t enabled) { if (debug_hooks_enabled()) g_tile_path = enabled ? 1 : 0; }
 extern "C" int asurf_debug_last_verdict(int32_t *out4) {   // synchronises: {bad, lo, hi, tiles fetched} of the last list check
     ASURF_REQUIRE(out4 && g_ws_verdict.ptr, ASURF_E_INVALID, "debug_last_verdict: no list check has run");
     return check_cuda(cudaMemcpy(out4, g_ws_verdict.ptr, sizeof(TileVerdict), cudaMemcpyDeviceToHost), "debug_last_verdict");

@@ -2204,9 +2204,9 @@ extern "C" int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *r
     return debug_launch(grid, rays, opt, dbg, (cudaStream_t)stream);
 }
 
-extern "C" void asurf_debug_set_skip(int32_t enabled) { g_skip_enabled = enabled ? 1 : 0; }
-extern "C" void asurf_debug_set_wave(int32_t enabled) { g_wave_enabled = enabled ? 1 : 0; }
-extern "C" void asurf_debug_set_seg(int32_t enabled) { g_seg_enabled = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_skip(int32_t enabled) { if (debug_hooks_enabled()) g_skip_enabled = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_wave(int32_t enabled) { if (debug_hooks_enabled()) g_wave_enabled = enabled ? 1 : 0; }
+extern "C" void asurf_debug_set_seg(int32_t enabled) { if (debug_hooks_enabled()) g_seg_enabled = enabled ? 1 : 0; }
 extern "C" int asurf_debug_counters(uint64_t *out8) {   // synchronises: queue lengths of the last render call
     ASURF_REQUIRE(out8 && g_ws_ctr.ptr, ASURF_E_INVALID, "debug_counters: nothing to read");
     return check_cuda(cudaMemcpy(out8, g_ws_ctr.ptr, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost), "debug_counters");

@@ -143,33 +143,37 @@ class TrainStep:
         return cells[(n * rank) // world:(n * (rank + 1)) // world]
 
     def regularisers(self, rank=0, world=1, grad=None, mask=None):
-        """With world > 1 every rank takes 1/world of each cell list; the kernels normalise by the length of the list they
-        are given, so the scale is divided by world to keep the global normalisation, and GradExchange sums the shards
-        (dense all-reduce of the density / surface gradients, OR of the masks).  ``grad`` / ``mask``: accumulate into
-        these buffers instead of the step's own (the overlapped multi-GPU step keeps the regulariser gradients apart
-        until both exchanges are done)."""
+        """With world > 1 every rank takes 1/world of each cell list.  The kernels normalise by the length of the list they
+        are given (n_r on rank r), so the scale handed to them is lambda * n_r / n: every cell then weighs lambda / n, the
+        single-process normalisation, whether or not the list divides evenly.  GradExchange sums the shards (dense
+        all-reduce of the density / surface gradients, OR of the masks).  ``grad`` / ``mask``: accumulate into these
+        buffers instead of the step's own (the overlapped multi-GPU step keeps the regulariser gradients apart until both
+        exchanges are done)."""
         C, sg, hp = self.C, self.sg, self.hp
         g = self.grad if grad is None else grad
         mask_t = self.mask if mask is None else mask
-        hp = dict(hp)
-        sh_ = lambda cells: self._shard(cells, rank, world)
-        for k in ("lambda_tv_alpha", "lambda_tv_surface", "lambda_normal_loss"):
-            hp[k] = hp[k] / world       # the sparsity loss is NOT normalised by the list length (loss_kernel.cu:1555-1558)
+
+        def sh_(cells, lam):
+            """-> (this rank's share, its scale)"""
+            part = self._shard(cells, rank, world)
+            return part, (lam * part.shape[0] / cells.shape[0] if world > 1 else lam)
+
         if hp["lambda_tv_alpha"] > 0:      # inplace_tv_grad, opt.py:952-957
-            cells = sh_(self.rand_cells(hp["tv_sparsity"]))
-            C.tv_grad_sparse(sg.links, sg.density, cells, mask_t, 0, 1, hp["lambda_tv_alpha"], False, 2.0, False,
+            cells, lam = sh_(self.rand_cells(hp["tv_sparsity"]), hp["lambda_tv_alpha"])
+            C.tv_grad_sparse(sg.links, sg.density, cells, mask_t, 0, 1, lam, False, 2.0, False,
                              bool(self.opts["last_sample_opaque"]), -1.0, -1.0, g["density"])
         if hp["lambda_tv_surface"] > 0:    # inplace_tv_surface_grad, opt.py:959-968
-            cells = sh_(self.rand_cells_non_empty(hp["tv_surface_sparsity"]))
-            C.surf_tv_grad_sparse(sg.links, sg.surface, sg.density, cells, mask_t, 0, 1, hp["lambda_tv_surface"],
+            cells, lam = sh_(self.rand_cells_non_empty(hp["tv_surface_sparsity"]), hp["lambda_tv_surface"])
+            C.surf_tv_grad_sparse(sg.links, sg.surface, sg.density, cells, mask_t, 0, 1, lam,
                                   hp["surf_tv_ignore_edge"], hp["surf_tv_edge_value"], bool(self.opts["last_sample_opaque"]),
                                   -1.0, -1.0, hp["surf_tv_alpha_dependency"], g["surface"])
         if hp["lambda_normal_loss"] > 0:   # inplace_surface_normal_grad, opt.py:970-981
-            cells = sh_(self.rand_cells_non_empty(hp["norm_surface_sparsity"]))
-            C.surface_normal_grad_sparse(sg.links, sg.surface, cells, mask_t, 0.0, 0, 1, hp["lambda_normal_loss"], 0.0,
+            cells, lam = sh_(self.rand_cells_non_empty(hp["norm_surface_sparsity"]), hp["lambda_normal_loss"])
+            C.surface_normal_grad_sparse(sg.links, sg.surface, cells, mask_t, 0.0, 0, 1, lam, 0.0,
                                          -1.0, -1.0, hp["norm_con_check"], hp["norm_ignore_empty"], True, g["surface"])
         if hp["lambda_sparsify_alpha"] > 0 or hp["lambda_sparsify_surf"] > 0:   # opt.py:1046-1060
-            cells = sh_(self.rand_cells_non_empty(hp["alpha_surf_sparsify_sparsity"]))
+            # (the sparsity loss is NOT normalised by the list length, loss_kernel.cu:1555-1558: its scale stays)
+            cells = self._shard(self.rand_cells_non_empty(hp["alpha_surf_sparsify_sparsity"]), rank, world)
             C.alpha_surf_sparsify_grad_sparse(sg.links, sg.density, sg.surface, cells, mask_t, hp["lambda_sparsify_alpha"],
                                               hp["lambda_sparsify_surf"], hp["sparsify_surf_decrease"],
                                               hp["sparsify_surf_thresh"], hp["alpha_sparsify_bound"],

@@ -10,6 +10,13 @@
  *   links   int32 (X,Y,Z) contiguous, value = row in the data tensors or < 0 for an empty vertex
  *   density float32 (N,1);  surface float32 (N,1);  sh float32 (N,D) channel-major, D = 3*basis_dim
  * Gradients are ACCUMULATED (+=) into caller-owned buffers; mask bytes are set to 1 for touched rows.
+ *
+ * Threading / streams: like the reference extension (called from the Python main thread under the GIL, svox2.cpp), the
+ * library is NOT re-entrant: its device workspaces and caches (pre-march lists, wavefront records, work-pyramid cache, list
+ * verdicts) are per process.  Calls may be issued on any stream, but calls that share a workspace must be ordered with
+ * respect to each other: render calls (surf_trav / cuvol / msi) form one family, the regularisers another, the optimizer
+ * and exchange helpers use no workspace.  alphasurf_b200/dist.py relies on exactly this split (render lane and regulariser
+ * lane on two streams).
  */
 #ifndef ASURF_H
 #define ASURF_H
@@ -186,6 +193,8 @@ int asurf_debug_trace(const asurf_grid_t *grid, const asurf_rays_t *rays, const 
                       int32_t max_hits, int32_t *hit_count, int32_t *hit_cell, int32_t *hit_kind, float *hit_t,
                       void *stream);
 
+/* The asurf_debug_set_* switches below select algorithm variants that must give the same results (the tests compare them).
+ * They are INERT unless the process environment holds ASURF_DEBUG_HOOKS=1 when the library is first used. */
 /* test hook: switch the hierarchical empty-block skipping of the marchers off (0) / on (non-zero, default).  Results
  * must be bit-identical either way; tests/ use it as a full-size property check. */
 void asurf_debug_set_skip(int32_t enabled);

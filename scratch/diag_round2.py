@@ -1,5 +1,6 @@
 """scratch: (1) tile path on/off timings + verdict at 512^3; (2) where the C3 surface gradient differs from the reference."""
-import ctypes, sys, torch
+import ctypes, os, sys, torch
+os.environ.setdefault("ASURF_DEBUG_HOOKS", "1")
 sys.path.insert(0, ".")
 from alphasurf_b200 import svox2_csrc as ours, synth, step as S, capi
 from tests import helpers as H

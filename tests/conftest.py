@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("ASURF_DEBUG_HOOKS", "1")   # the tests compare algorithm variants through asurf_debug_set_*
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
