@@ -12,6 +12,8 @@ gradients (1.8 GB at 512^3 x 29 floats) are never sent: the masks are OR-ed firs
 rank the same list of touched rows, and only those rows travel -- packed into one (n_rows, 2 + D) bucket, summed with a
 single NCCL all-reduce over NVLink / NVSwitch, and scattered back.
 """
+import time
+
 import torch
 import torch.distributed as dist
 
@@ -35,6 +37,9 @@ class GradExchange:
         self.cap = None
         self._count_probe = None     # (pinned host count, event, capacity it was taken with)
         self._mask_bufs = {}
+        self._probe_bufs = None
+        self.host_ms = {}            # host time per section of step() (enqueue cost, no synchronisation), summed
+        self.host_steps = 0
         self.bitpack_masks = False
         self.render_first = True
         self.rank = dist.get_rank(group)
@@ -135,7 +140,7 @@ class GradExchange:
         if self._count_probe is not None:                 # the count of the PREVIOUS step: long since on the host
             host, ev, cap_used = self._count_probe
             ev.synchronize()
-            cnt = int(host.item())
+            cnt = int(host[0])
             if cnt > cap_used:
                 raise RuntimeError("GradExchange: %d touched rows exceeded the list capacity %d of the previous step; "
                                    "its gradient exchange was incomplete (use sync_free=False)" % (cnt, cap_used))
@@ -143,9 +148,12 @@ class GradExchange:
                 self.cap = min(int(mask.shape[0]), int(1.5 * cnt) + 1024)
         cap = self.cap
         rows = torch.nonzero_static(mask, size=cap, fill_value=-1).flatten()
-        host = torch.empty((), dtype=torch.int64).pin_memory()
-        host.copy_(mask.sum(), non_blocking=True)
-        ev = torch.cuda.Event()
+        if self._probe_bufs is None:      # two pinned words + two events, reused alternately (allocating pinned memory is slow)
+            self._probe_bufs = [(torch.zeros((1,), dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+            self._probe_i = 0
+        host, ev = self._probe_bufs[self._probe_i]
+        self._probe_i ^= 1
+        host.copy_(mask.sum().reshape(1), non_blocking=True)
         ev.record()
         self._count_probe = (host, ev, cap)
         return rows, cap
@@ -242,6 +250,12 @@ class GradExchange:
         ``events``: optional 4 CUDA events recorded at start / after render + begin / after the join / after the optimizer."""
         reg = self._lane_b(ts)
         cuda = self._side is not None
+        t_h = [time.perf_counter()]
+
+        def lap(name):
+            now = time.perf_counter()
+            self.host_ms[name] = self.host_ms.get(name, 0.0) + 1e3 * (now - t_h[0])
+            t_h[0] = now
         if events:
             events[0].record()
         import contextlib
@@ -274,14 +288,18 @@ class GradExchange:
         self.shard_regularisers = False           # begin / end: the sparse exchange of the render gradients alone
         try:
             ts.render(origins, dirs, rgb_gt, rgb_out)
+            lap("render")
             self.begin(ts)
+            lap("begin: mask OR, row list, pack, sparse all-reduce start")
             if events:
                 events[1].record()
             if self.render_first:
                 self.shard_regularisers = shard
                 side_lane()
                 self.shard_regularisers = False
+                lap("regulariser lane: kernels + mask OR + dense all-reduce")
             self.end(ts)
+            lap("end: wait + unpack")
         finally:
             self.shard_regularisers = shard
         if cuda:
@@ -289,10 +307,13 @@ class GradExchange:
         ts.grad["density"].add_(reg["grad"]["density"])
         ts.grad["surface"].add_(reg["grad"]["surface"])
         ts.mask.logical_or_(reg["mask"])
+        lap("join")
         if events:
             events[2].record()
         if not skip_optimizer:
             ts.optimizer()
+        lap("optimizer")
+        self.host_steps += 1
         if events:
             events[3].record()
 

@@ -39,11 +39,20 @@ def grid_to_cpp(C, sg):
     return g
 
 
+_RAY_MASKS = {}
+
+
 def rays_to_cpp(C, origins, dirs):
     r = C.RaysSpec()
     r.origins = origins
     r.dirs = dirs
-    r.masks = torch.ones((origins.shape[0],), dtype=torch.bool, device=origins.device)
+    key = (origins.shape[0], origins.device)
+    m = _RAY_MASKS.get(key)             # Rays.masks defaults to all-true (svox2.py:104-108); one tensor per batch size
+    if m is None:
+        if len(_RAY_MASKS) > 16:
+            _RAY_MASKS.clear()
+        m = _RAY_MASKS[key] = torch.ones((origins.shape[0],), dtype=torch.bool, device=origins.device)
+    r.masks = m
     return r
 
 

@@ -478,7 +478,9 @@ def run_ours(args, rank, world, local_rank):
 
     parity = breakdown = None
     if world > 1 and not args.no_extras:      # collective: every rank takes part, rank 0 reports
+        host_sections = {k: v / max(exchange.host_steps, 1) for k, v in exchange.host_ms.items()}
         breakdown = exchange.collective_breakdown(ts)
+        breakdown["host_enqueue_ms_by_section"] = host_sections
         parity = dist_parity(torch, dist, C, S, synth, sg, rank, world, Q, dev)
 
     if rank != 0:
