@@ -185,8 +185,10 @@ class GradExchange:
         out["mask_or_bytes_per_rank"] = (N + 31) // 32 * 4
         out["sparse_bucket_allreduce_ms"] = t(lambda: dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group))
         out["sparse_bucket_bytes"] = n * (2 + D) * 4
-        out["dense_regulariser_allreduce_ms"] = t(lambda: dist.all_reduce(dense, op=dist.ReduceOp.SUM, group=self.group))
-        out["dense_regulariser_bytes"] = 2 * N * 4
+        rep = hasattr(ts, "density_terms_replicable") and ts.density_terms_replicable()
+        dense_part = dense[1] if rep else dense
+        out["dense_regulariser_allreduce_ms"] = t(lambda: dist.all_reduce(dense_part, op=dist.ReduceOp.SUM, group=self.group))
+        out["dense_regulariser_bytes"] = dense_part.numel() * 4
         out["nonzero_static_ms"] = t(lambda: torch.nonzero_static(ts.mask, size=n, fill_value=-1))
         return out
 
@@ -274,9 +276,16 @@ class GradExchange:
                 reg["buf"].zero_()
                 reg["mask"].zero_()
                 if self.shard_regularisers:
-                    ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
+                    # the expensive terms (surface TV, normal loss: both write the SURFACE gradient) are sharded over the
+                    # ranks by cell; the cheap ones that write the density gradient run in full on every rank when that is
+                    # exact (TrainStep.density_terms_replicable), so that only the surface half of the buffer travels
+                    rep = hasattr(ts, "density_terms_replicable") and ts.density_terms_replicable()
+                    if rep:
+                        ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"], replicate_density_terms=True)
+                    else:
+                        ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
                     self.mask_or(reg["mask"], group=self._group_b)
-                    dist.all_reduce(reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
+                    dist.all_reduce(reg["buf"][1] if rep else reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
                 else:
                     ts.regularisers(grad=reg["grad"], mask=reg["mask"])     # every rank the whole lists: nothing to exchange
 

@@ -151,7 +151,14 @@ class TrainStep:
         n = cells.shape[0]
         return cells[(n * rank) // world:(n * (rank + 1)) // world]
 
-    def regularisers(self, rank=0, world=1, grad=None, mask=None):
+    def density_terms_replicable(self):
+        """True when the regularisers that write the density gradient (density TV over a 1 % window, opacity sparsity over a
+        10 % window: ~35 us together) can run in full on every rank of a multi-GPU step instead of being sharded -- the
+        density gradient of the regularisers then needs no exchange.  Not so when the sparsity term also pushes the
+        surface (lambda_sparsify_surf != 0): its surface part would be summed once per rank by the surface exchange."""
+        return self.hp["lambda_sparsify_surf"] == 0
+
+    def regularisers(self, rank=0, world=1, grad=None, mask=None, replicate_density_terms=False):
         """With world > 1 every rank takes 1/world of each cell list.  The kernels normalise by the length of the list they
         are given (n_r on rank r), so the scale handed to them is lambda * n_r / n: every cell then weighs lambda / n, the
         single-process normalisation, whether or not the list divides evenly.  GradExchange sums the shards (dense
@@ -162,13 +169,16 @@ class TrainStep:
         g = self.grad if grad is None else grad
         mask_t = self.mask if mask is None else mask
 
-        def sh_(cells, lam):
+        def sh_(cells, lam, replicate=False):
             """-> (this rank's share, its scale)"""
+            if replicate or world == 1:
+                return cells, lam
             part = self._shard(cells, rank, world)
-            return part, (lam * part.shape[0] / cells.shape[0] if world > 1 else lam)
+            return part, lam * part.shape[0] / cells.shape[0]
 
+        rep = bool(replicate_density_terms) and self.density_terms_replicable()
         if hp["lambda_tv_alpha"] > 0:      # inplace_tv_grad, opt.py:952-957
-            cells, lam = sh_(self.rand_cells(hp["tv_sparsity"]), hp["lambda_tv_alpha"])
+            cells, lam = sh_(self.rand_cells(hp["tv_sparsity"]), hp["lambda_tv_alpha"], rep)
             C.tv_grad_sparse(sg.links, sg.density, cells, mask_t, 0, 1, lam, False, 2.0, False,
                              bool(self.opts["last_sample_opaque"]), -1.0, -1.0, g["density"])
         if hp["lambda_tv_surface"] > 0:    # inplace_tv_surface_grad, opt.py:959-968
@@ -182,7 +192,9 @@ class TrainStep:
                                          -1.0, -1.0, hp["norm_con_check"], hp["norm_ignore_empty"], True, g["surface"])
         if hp["lambda_sparsify_alpha"] > 0 or hp["lambda_sparsify_surf"] > 0:   # opt.py:1046-1060
             # (the sparsity loss is NOT normalised by the list length, loss_kernel.cu:1555-1558: its scale stays)
-            cells = self._shard(self.rand_cells_non_empty(hp["alpha_surf_sparsify_sparsity"]), rank, world)
+            cells = self.rand_cells_non_empty(hp["alpha_surf_sparsify_sparsity"])
+            if not rep:
+                cells = self._shard(cells, rank, world)
             C.alpha_surf_sparsify_grad_sparse(sg.links, sg.density, sg.surface, cells, mask_t, hp["lambda_sparsify_alpha"],
                                               hp["lambda_sparsify_surf"], hp["sparsify_surf_decrease"],
                                               hp["sparsify_surf_thresh"], hp["alpha_sparsify_bound"],

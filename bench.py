@@ -420,6 +420,8 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()      # BEFORE the barrier: its start-up sleep must not delay rank 0 against the other ranks
     barrier()
     L.asurf_launch_count(ctypes.c_int32(1))
+    if exchange is not None:
+        exchange.host_ms, exchange.host_steps = {}, 0      # host-time sections of the timed steps only
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t_host0 = time.perf_counter()
@@ -427,6 +429,9 @@ def run_ours(args, rank, world, local_rank):
         device_step(*dev_batches[(args.warmup + i) % NB], record=True)
     ev1.record()
     host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps   # CPU time to ENQUEUE a step (no synchronisation inside)
+    host_sections = None
+    if exchange is not None:
+        host_sections = {k: v / max(exchange.host_steps, 1) for k, v in exchange.host_ms.items()}
     barrier()
     n_launch = int(L.asurf_launch_count(ctypes.c_int32(0)))
     clocks = sampler.stop() if rank == 0 else None
@@ -478,7 +483,6 @@ def run_ours(args, rank, world, local_rank):
 
     parity = breakdown = None
     if world > 1 and not args.no_extras:      # collective: every rank takes part, rank 0 reports
-        host_sections = {k: v / max(exchange.host_steps, 1) for k, v in exchange.host_ms.items()}
         breakdown = exchange.collective_breakdown(ts)
         breakdown["host_enqueue_ms_by_section"] = host_sections
         parity = dist_parity(torch, dist, C, S, synth, sg, rank, world, Q, dev)
@@ -519,8 +523,10 @@ def run_ours(args, rank, world, local_rank):
                 "api": "alphasurf_b200/csrc/svox2_csrc_shim*.so (compiled pybind11/torch module replacing svox2.csrc)"},
         "gpu_launches": n_launch,
         "host_enqueue_ms_per_step": host_enqueue_ms,
-        "host_enqueue_note": "CPU time the Python host needs to enqueue one step (rank 0); a value close to ms_per_step means the "
-                             "step is bound by the host's launch rate, not by the GPU",
+        "host_enqueue_note": "CPU time rank 0 spends issuing one step.  On one GPU nothing in the step waits for the device, so a "
+                             "value close to ms_per_step would mean a launch-bound step; the multi-GPU step waits once per step "
+                             "for the previous step's row count (GradExchange._touched_rows), so there the value tracks the "
+                             "device time by construction",
         "roofline": roof,
         "step_phases": phases,
         "step_phases_note": ("sequential: fused render | regularisers | optimizer" if world == 1 else
