@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ da
                                                            float *__restrict__ grad, const uint8_t *__restrict__ mask,
                                                            int64_t n_rows, int n_cols, float beta, float lr, float eps,
                                                            float minval, float lr_last) {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint8_t s_rows[256 / 32][128];
+    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool word_ok = ((uintptr_t)mask & 3u) == 0;
@@ -126,28 +127,36 @@ __global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ da
         }
         unsigned bits = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) |
                         ((w & 0xff000000u) ? 8u : 0u);
-        unsigned any = __ballot_sync(0xffffffffu, bits != 0u);
-        while (any) {
-            const int src = __ffs(any) - 1;
-            any &= any - 1;
-            unsigned b = __shfl_sync(0xffffffffu, bits, src);
-          while (b) {
-            const int r = src * 4 + __ffs(b) - 1;
-            b &= b - 1;
-            const int64_t off = (base + r) * n_cols;
-            for (int c = lane; c < n_cols; c += 32) {
-                const float l = (c == n_cols - 1) ? lr_last : lr;
-                if (RMS) {
-                    float x = data[off + c], q = rms[off + c], g = grad[off + c];
-                    rmsprop_once(x, q, g, beta, l, eps, minval);
-                    data[off + c] = x;
-                    rms[off + c] = q;
-                } else {
-                    data[off + c] = fmaf(-l, grad[off + c], data[off + c]);
-                }
-                grad[off + c] = 0.f;
+        if (!__ballot_sync(0xffffffffu, bits != 0u)) continue;
+        // the set rows of the round, compacted: the touched rows cluster (they follow the surface), so a round often holds
+        // dozens of them -- their (row, channel) elements are spread over the lanes instead of one row at a time
+        int incl = __popc(bits);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        const int n_set = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        {
+            int at = incl - __popc(bits);
+            for (unsigned b = bits; b; b &= b - 1) s_rows[warp_in_cta][at++] = (uint8_t)(lane * 4 + __ffs(b) - 1);
+        }
+        __syncwarp();
+        const int n_elem = n_set * n_cols;
+        for (int e = lane; e < n_elem; e += 32) {
+            const int k = e / n_cols, c = e - k * n_cols;
+            const int64_t off = (base + s_rows[warp_in_cta][k]) * n_cols + c;
+            const float l = (c == n_cols - 1) ? lr_last : lr;
+            if (RMS) {
+                float x = data[off], q = rms[off], g = grad[off];
+                rmsprop_once(x, q, g, beta, l, eps, minval);
+                data[off] = x;
+                rms[off] = q;
+            } else {
+                data[off] = fmaf(-l, grad[off], data[off]);
             }
-          }
+            grad[off] = 0.f;
         }
     }
 }
