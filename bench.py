@@ -581,8 +581,8 @@ def time_calls(torch, ts, kind, dev_batches, rgb_out, args):
             ("tv_grad_sparse(sigma, 1% window) + tv_grad_sparse(sh, 1% window)", lambda b: ts.regularisers()),
             ("rmsprop_step(sigma) + rmsprop_step(sh)", lambda b: ts.optimizer()),
         ]
-    n = 5
-    acc = [0.0] * len(calls)
+    n = 7
+    samples = [[] for _ in calls]
     for it in range(n + 1):
         b = dev_batches[it % len(dev_batches)]
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)]
@@ -593,8 +593,9 @@ def time_calls(torch, ts, kind, dev_batches, rgb_out, args):
         torch.cuda.synchronize()
         if it > 0:
             for k in range(len(calls)):
-                acc[k] += evs[k].elapsed_time(evs[k + 1]) / n
-    return [(name, ms) for (name, _), ms in zip(calls, acc)]
+                samples[k].append(evs[k].elapsed_time(evs[k + 1]))
+    # median over the repeats: an event interval also contains any wait of the GPU for the host between two calls
+    return [(name, sorted(s)[len(s) // 2], s) for (name, _), s in zip(calls, samples)]
 
 
 def annotate_calls(table, sg, Q, D, st, alg_fused, own_fused, traffic, peak):
@@ -602,10 +603,10 @@ def annotate_calls(table, sg, Q, D, st, alg_fused, own_fused, traffic, peak):
     (profiles/traffic.json), measured DRAM bytes -> both fractions of the HBM peak.  Sorted by time: dominant call first."""
     N = sg.capacity
     n_vert = sg.links.numel()
-    total = sum(ms for _, ms in table)
+    total = sum(t[1] for t in table)
     out = []
     touched = st["n_samples"] * 8          # upper bound of the rows the render touches
-    for name, ms in table:
+    for name, ms, raw in table:
         alg, key, note = None, None, None
         if name.startswith("volume_render"):
             alg, key = alg_fused, "fused"
@@ -624,6 +625,8 @@ def annotate_calls(table, sg, Q, D, st, alg_fused, own_fused, traffic, peak):
         elif name.startswith("rmsprop_step("):
             alg, key = N * (24 + 1), "rmsprop_col1"
         e = {"call": name, "ms": ms, "share": ms / total if total > 0 else None}
+        if max(raw) > 2.0 * max(min(raw), 1e-6):
+            e["ms_samples"] = [round(v, 4) for v in raw]     # an unsteady interval: shown in full
         if alg is not None and ms > 0:
             e["algorithmic_bytes"] = alg
             e["achieved_GBps"] = alg / (ms * 1e-3) / 1e9
