@@ -841,6 +841,20 @@ void surface_normal_grad_sparse(Tensor links, Tensor data, Tensor rand_cells, Te
              "surface_normal_grad_sparse");
 }
 
+// surf_sign_change_grad_sparse, loss_kernel.cu:1429-1466
+void surf_sign_change_grad_sparse(Tensor links, Tensor data, Tensor rand_cells, Tensor mask_out, int start_dim, int end_dim,
+                                  float scale, Tensor grad_data) {
+    check_loss_common(links, data, &grad_data);
+    check_cells(rand_cells);
+    const c10::cuda::CUDAGuard guard(data.device());
+    int32_t sz[3];
+    size3(links, sz);
+    check_rc(asurf_surf_sign_change_grad_sparse(links.data_ptr<int32_t>(), sz, data.data_ptr<float>(), (int32_t)data.size(1),
+                                                rand_cells.data_ptr<int32_t>(), rand_cells.size(0), mask_ptr(mask_out), start_dim,
+                                                end_dim, scale, grad_data.data_ptr<float>(), stream_of(data)),
+             "surf_sign_change_grad_sparse");
+}
+
 // msi_tv_grad_sparse, loss_kernel.cu:1624-1659
 void msi_tv_grad_sparse(Tensor links, Tensor msi, Tensor rand_cells, Tensor mask_out, float scale, float scale_last,
                         Tensor grad_msi) {
@@ -903,6 +917,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     REG(tv_grad_sparse);
     REG(surf_tv_grad_sparse);
     REG(msi_tv_grad_sparse);
+    REG(surf_sign_change_grad_sparse);
     REG(dilate);
     REG(accel_dist_prop);
     REG(grid_weight_render);
@@ -916,8 +931,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     for (const char *name : {"test_cubic_root_grad", "volume_render_surface", "volume_render_surface_backward",
                              "volume_render_surface_fused", "volume_render_nvol", "volume_render_nvol_backward",
                              "volume_render_nvol_fused", "volume_render_svox1", "volume_render_svox1_backward",
-                             "volume_render_svox1_fused", "surface_normal_grad", "surf_sign_change_grad_sparse",
-                             "lumisphere_tv_grad_sparse"})
+                             "volume_render_svox1_fused", "surface_normal_grad", "lumisphere_tv_grad_sparse"})
         m.attr(name) = off_path(name);
     m.def("set_loss_norm_rays", [](py::object n) { g_norm_rays = n.is_none() ? 0 : n.cast<int64_t>(); },
           "global ray count used to normalise the fused losses in a ray-sharded run (None: per call)");

@@ -265,6 +265,50 @@ tv_grad_sparse_runs_kernel(const int32_t *__restrict__ links, const float *__res
     }
 }
 
+// ---- surface sign-change penalty (surf_sign_change_grad_sparse_kernel, loss_kernel.cu:895-977) ----------------------------------
+// L = |s0 - s1| where a stored vertex and its +x / +y / +z neighbour have opposite signs: constant gradients sign(s) * axis
+// scale, averaged over the stored neighbours.  The reference's loop counter is uninitialised (`for (int i; i < 3; ++i)`,
+// :944, undefined behaviour); this is the documented intent, i from 0.
+__global__ void __launch_bounds__(LOSS_THREADS)
+sign_change_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols, const int32_t *__restrict__ cells,
+                   Dims d, int start_dim, int end_dim, float scale, int64_t Q, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    const int nch = end_dim - start_dim;
+    float sc[3];
+    ray_scale(d, sc);
+    const int64_t offx = (int64_t)d.sy * d.sz;
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int idx = (int)(tid % nch) + start_dim;
+        const int64_t xyz = __ldg(cells + tid / nch);
+        int x, y, z;
+        cell_xyz(xyz, d, x, y, z);
+        const int32_t *lp = links + xyz;
+        const int32_t l000 = __ldg(lp);
+        if (l000 < 0) continue;
+        const int32_t ln[3] = {(x + 1 < d.sx) ? __ldg(lp + offx) : -1, (y + 1 < d.sy) ? __ldg(lp + d.sz) : -1,
+                               (z + 1 < d.sz) ? __ldg(lp + 1) : -1};
+        const float v000 = __ldg(data + (int64_t)l000 * n_cols + idx);
+        float grad_0 = 0.f, gn[3] = {0.f, 0.f, 0.f}, valid = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (ln[i] < 0) continue;
+            valid += 1.f;
+            const float vi = __ldg(data + (int64_t)ln[i] * n_cols + idx);
+            if (v000 * vi < 0.f) {
+                grad_0 += ((v000 >= 0.f) ? 1.f : -1.f) * sc[i];
+                gn[i] += ((vi >= 0.f) ? 1.f : -1.f) * sc[i];
+            }
+        }
+        if (valid == 0.f) continue;
+        const float g0 = grad_0 / valid * scale;
+        if (g0 != 0.f) { atomicAdd(grad + (int64_t)l000 * n_cols + idx, g0); if (mask) mask[l000] = 1; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float gi = gn[i] / valid * scale;
+            if (ln[i] >= 0 && gi != 0.f) { atomicAdd(grad + (int64_t)ln[i] * n_cols + idx, gi); if (mask) mask[ln[i]] = 1; }
+        }
+    }
+}
+
 // ---- opacity / surface sparsity (alpha_surf_sparsify_grad_sparse_kernel) -------------------------------------------------
 __global__ void __launch_bounds__(LOSS_THREADS)
 sparsify_kernel(const int32_t *__restrict__ links, const float *__restrict__ alpha, int alpha_cols,
@@ -1349,6 +1393,25 @@ extern "C" int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t siz
             ignore_last_z, alpha_dependency, mask_out, grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_tv_grad_sparse launch");
+}
+
+extern "C" int asurf_surf_sign_change_grad_sparse(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
+                                                  const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out,
+                                                  int32_t start_dim, int32_t end_dim, float scale, float *grad_data,
+                                                  void *stream) {
+    int rc = check_common(links, size, data, grad_data, "surf_sign_change_grad_sparse");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID,
+                  "surf_sign_change_grad_sparse: bad channel range");
+    if (n_cells <= 0) return 0;
+    ASURF_REQUIRE(rand_cells, ASURF_E_INVALID, "surf_sign_change_grad_sparse: null cell list");
+    const int64_t Q = n_cells * (end_dim - start_dim);
+    Dims d = {size[0], size[1], size[2]};
+    sign_change_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(links, data, n_cols, rand_cells, d, start_dim,
+                                                                                end_dim, scale / (float)(int)n_cells, Q, mask_out,
+                                                                                grad_data);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "surf_sign_change_grad_sparse launch");
 }
 
 extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,

@@ -744,6 +744,17 @@ def surf_tv_grad_sparse(links, data, density_data, rand_cells, mask_out, start_d
             capi.ptr(accel_for(links)), capi.current_stream()), "surf_tv_grad_sparse")
 
 
+def surf_sign_change_grad_sparse(links, data, rand_cells, mask_out, start_dim, end_dim, scale, grad_data):
+    """constant-gradient penalty where a stored vertex and a +x / +y / +z neighbour differ in sign (loss_kernel.cu:895-977)"""
+    _check_loss_common(links, data, grad_data)
+    _check_cells(rand_cells)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_surf_sign_change_grad_sparse(
+            capi.ptr(links), capi.size3(links.shape), capi.ptr(data), C.c_int32(data.shape[1]), capi.ptr(rand_cells),
+            C.c_int64(rand_cells.shape[0]), _mask_ptr(mask_out), C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale),
+            capi.ptr(grad_data), capi.current_stream()), "surf_sign_change_grad_sparse")
+
+
 def alpha_surf_sparsify_grad_sparse(links, alpha_data, surf_data, rand_cells, mask_out, scale_alpha, scale_surf,
                                     surf_sparse_decrease, surf_sparse_thresh, alpha_bound, surf_bound, grad_alpha, grad_surf):
     _check_loss_common(links, alpha_data, grad_alpha)
@@ -863,8 +874,7 @@ def _not_on_hot_path(name):
     return fn
 
 
-for _name in ("surface_normal_grad",
-              "surf_sign_change_grad_sparse", "lumisphere_tv_grad_sparse",
+for _name in ("surface_normal_grad", "lumisphere_tv_grad_sparse",
               "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
               "volume_render_nvol", "volume_render_nvol_backward", "volume_render_nvol_fused", "volume_render_svox1",
               "volume_render_svox1_backward", "volume_render_svox1_fused", "test_cubic_root_grad"):

@@ -332,6 +332,11 @@ int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const
                               uint8_t *mask_out, int32_t start_dim, int32_t end_dim, float scale, int32_t ignore_edge,
                               float edge_value, int32_t ignore_last_z, int32_t alpha_dependency, float *grad_data,
                               const uint64_t *accel, void *stream);
+/* surf_sign_change_grad_sparse, :1429-1466 (kernel :895-977, with its loop counter started at 0: the reference leaves it
+ * uninitialised) */
+int asurf_surf_sign_change_grad_sparse(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
+                                       const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, int32_t start_dim,
+                                       int32_t end_dim, float scale, float *grad_data, void *stream);
 /* alpha_surf_sparsify_grad_sparse, :1512-1570 */
 int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,
                                           int32_t alpha_cols, const float *surf, int32_t surf_cols,

@@ -509,3 +509,10 @@ def msi_tv_grad_sparse(bg_links, msi, cells, mask, scale, scale_last, grad):
     lib().oracle_msi_tv_grad_sparse(_ptr(links), C.c_int(links.shape[0]), C.c_int(links.shape[1]), _ptr(data),
                                     C.c_int(data.shape[1]), C.c_int(data.shape[2]), _ptr(cells), C.c_int64(cells.shape[0]),
                                     _ptr(mask), C.c_float(scale), C.c_float(scale_last), _ptr(grad))
+
+
+def surf_sign_change_grad_sparse(links, data, cells, mask, start_dim, end_dim, scale, grad):
+    links, data, cells = _np(links, np.int32), _np(data, np.float32), _np(cells, np.int32)
+    lib().oracle_surf_sign_change_grad_sparse(_ptr(links), _sz(links), _ptr(data), C.c_int(data.shape[1]), _ptr(cells),
+                                              C.c_int64(cells.shape[0]), _ptr(mask), C.c_int(start_dim), C.c_int(end_dim),
+                                              C.c_float(scale), _ptr(grad))

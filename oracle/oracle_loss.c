@@ -241,3 +241,42 @@ void oracle_surface_normal_grad_sparse(const int32_t *links, const int32_t *size
             }
         }
 }
+
+/* surf_sign_change_grad_sparse_kernel :895-977 + host :1429-1466, with the loop counter started at 0 (the reference leaves it
+ * uninitialised: undefined behaviour) */
+void oracle_surf_sign_change_grad_sparse(const int32_t *links, const int32_t *size, const float *data, int n_cols,
+                                         const int32_t *cells, int64_t n_cells, uint8_t *mask, int start_dim, int end_dim,
+                                         float scale, float *grad) {
+    float sc[3];
+    ray_scale(size, sc);
+    scale = scale / (float)(int)n_cells;
+    for (int64_t c = 0; c < n_cells; ++c)
+        for (int idx = start_dim; idx < end_dim; ++idx) {
+            const int64_t xyz = cells[c];
+            const int z = (int)(xyz % size[2]);
+            const int64_t xy = xyz / size[2];
+            const int y = (int)(xy % size[1]), x = (int)(xy / size[1]);
+            const int32_t l000 = links[xyz];
+            if (l000 < 0) continue;
+            const int32_t ln[3] = {x + 1 < size[0] ? LNK(x + 1, y, z) : -1, y + 1 < size[1] ? LNK(x, y + 1, z) : -1,
+                                   z + 1 < size[2] ? LNK(x, y, z + 1) : -1};
+            const float v000 = data[(int64_t)l000 * n_cols + idx];
+            float g0 = 0.f, gn[3] = {0.f, 0.f, 0.f}, valid = 0.f;
+            for (int i = 0; i < 3; ++i) {
+                if (ln[i] < 0) continue;
+                valid += 1.f;
+                const float vi = data[(int64_t)ln[i] * n_cols + idx];
+                if (v000 * vi < 0.f) {
+                    g0 += ((v000 >= 0.f) ? 1.f : -1.f) * sc[i];
+                    gn[i] += ((vi >= 0.f) ? 1.f : -1.f) * sc[i];
+                }
+            }
+            if (valid == 0.f) continue;
+            const float a = g0 / valid * scale;
+            if (a != 0.f) { grad[(int64_t)l000 * n_cols + idx] += a; if (mask) mask[l000] = 1; }
+            for (int i = 0; i < 3; ++i) {
+                const float b = gn[i] / valid * scale;
+                if (ln[i] >= 0 && b != 0.f) { grad[(int64_t)ln[i] * n_cols + idx] += b; if (mask) mask[ln[i]] = 1; }
+            }
+        }
+}

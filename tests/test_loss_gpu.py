@@ -361,3 +361,21 @@ def test_lists_that_are_not_windows_fall_back_to_the_list_kernels():
         oracle.tv_grad_sparse(sg.links, sg.surface, sg.density, cells_c, m_o, 0, 1, 1e-3, True, -1.0, False, False, True, g_o)
         _close(grad, g_o, "surface TV, %s list" % name)
         assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o), name
+
+
+@pytest.mark.parametrize("contiguous", [True, False])
+def test_surf_sign_change_grad_sparse(contiguous):
+    """Against the oracle only: the reference kernel's loop counter is uninitialised (loss_kernel.cu:944, undefined
+    behaviour), both restatements implement the documented intent (SURVEY.md Appendix B #3)."""
+    from oracle import oracle
+    sg = _grid(32, variant="G*")
+    cells_c = _cells(sg, 0.6, 4, contiguous)
+    links, surf, cells = sg.links.cuda(), sg.surface.cuda(), cells_c.cuda()
+    grad = torch.zeros_like(surf)
+    mask = torch.zeros((sg.capacity,), dtype=torch.bool, device="cuda")
+    ours.surf_sign_change_grad_sparse(links, surf, cells, mask, 0, 1, 0.3, grad)
+    g_o = np.zeros(tuple(sg.surface.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.surf_sign_change_grad_sparse(sg.links, sg.surface, cells_c, m_o, 0, 1, 0.3, g_o)
+    _close(grad, g_o, "surf_sign_change_grad_sparse")
+    assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o) and 0 < m_o.sum() < sg.capacity
