@@ -89,7 +89,7 @@ EXPORTS = [
     "asurf_cuvol_forward", "asurf_cuvol_stats", "asurf_cuvol_image", "asurf_cuvol_scalar", "asurf_cuvol_backward", "asurf_cuvol_fused",
     "asurf_accel_dist_prop", "asurf_sample_grid", "asurf_sample_grid_backward", "asurf_cubic_extract_iso_pts", "asurf_dilate", "asurf_grid_weight_render", "asurf_sparse_grid_weight_render",
     "asurf_sparse_grid_mask_render", "asurf_sparse_grid_visibility_render_surf", "asurf_rmsprop_step", "asurf_sgd_step", "asurf_rows_pack", "asurf_rows_unpack_add", "asurf_mask_pack", "asurf_mask_unpack_or", "asurf_msi_forward", "asurf_msi_forward_image", "asurf_msi_backward", "asurf_msi_tv_grad_sparse", "asurf_debug_bg_state", "asurf_tv", "asurf_tv_grad", "asurf_tv_grad_sparse",
-    "asurf_surf_tv_grad_sparse", "asurf_surf_sign_change_grad_sparse", "asurf_alpha_surf_sparsify_grad_sparse", "asurf_surface_normal_grad_sparse", "asurf_profile_enable", "asurf_profile_read", "asurf_profile_read_stages", "asurf_launch_count", "asurf_release",
+    "asurf_surf_tv_grad_sparse", "asurf_surf_sign_change_grad_sparse", "asurf_surface_normal_grad", "asurf_lumisphere_tv_grad_sparse", "asurf_alpha_surf_sparsify_grad_sparse", "asurf_surface_normal_grad_sparse", "asurf_profile_enable", "asurf_profile_read", "asurf_profile_read_stages", "asurf_launch_count", "asurf_release",
 ]
 
 

@@ -855,6 +855,44 @@ void surf_sign_change_grad_sparse(Tensor links, Tensor data, Tensor rand_cells, 
              "surf_sign_change_grad_sparse");
 }
 
+// surface_normal_grad (dense), loss_kernel.cu:1289-1325 (the ndc coefficients are unused there too)
+void surface_normal_grad(Tensor links, Tensor data, float lv_set, int start_dim, int end_dim, float scale, float ndc_coeffx,
+                         float ndc_coeffy, Tensor grad_data) {
+    check_loss_common(links, data, &grad_data);
+    const c10::cuda::CUDAGuard guard(data.device());
+    int32_t sz[3];
+    size3(links, sz);
+    check_rc(asurf_surface_normal_grad(links.data_ptr<int32_t>(), sz, data.data_ptr<float>(), (int32_t)data.size(1), lv_set,
+                                       start_dim, end_dim, scale, grad_data.data_ptr<float>(), stream_of(data)),
+             "surface_normal_grad");
+}
+
+// lumisphere_tv_grad_sparse, loss_kernel.cu:1661-1697
+void lumisphere_tv_grad_sparse(SparseGridSpec &grid, Tensor rand_cells, Tensor basis_fn, Tensor basis_fn_u, float scale,
+                               float ndc_coeffx, float ndc_coeffy, float dir_factor, GridOutputGrads &grads) {
+    check_input(grid.sh_data, "grid.sh_data");
+    check_input(grid.links, "grid.links");
+    check_cells(rand_cells);
+    check_input(basis_fn, "basis_fn");
+    check_input(basis_fn_u, "basis_fn_u");
+    check_f32(basis_fn, "basis_fn");
+    check_f32(basis_fn_u, "basis_fn_u");
+    TORCH_CHECK(basis_fn.dim() == 1, "basis_fn must be 1-D");
+    TORCH_CHECK(grads.grad_sh_out.defined(), "grads.grad_sh_out is required");
+    check_input(grads.grad_sh_out, "grads.grad_sh_out");
+    TORCH_CHECK(basis_fn.numel() >= grid.basis_dim && basis_fn_u.numel() >= grid.basis_dim,
+                "basis_fn / basis_fn_u hold fewer than basis_dim values");
+    const c10::cuda::CUDAGuard guard(grid.sh_data.device());
+    int32_t sz[3];
+    size3(grid.links, sz);
+    check_rc(asurf_lumisphere_tv_grad_sparse(grid.links.data_ptr<int32_t>(), sz, grid.sh_data.data_ptr<float>(),
+                                             (int32_t)grid.sh_data.size(1), grid.basis_dim, rand_cells.data_ptr<int32_t>(),
+                                             rand_cells.size(0), basis_fn.data_ptr<float>(), basis_fn_u.data_ptr<float>(), scale,
+                                             dir_factor, grads.mask_out.defined() ? mask_ptr(grads.mask_out) : nullptr,
+                                             grads.grad_sh_out.data_ptr<float>(), stream_of(grid.sh_data)),
+             "lumisphere_tv_grad_sparse");
+}
+
 // msi_tv_grad_sparse, loss_kernel.cu:1624-1659
 void msi_tv_grad_sparse(Tensor links, Tensor msi, Tensor rand_cells, Tensor mask_out, float scale, float scale_last,
                         Tensor grad_msi) {
@@ -918,6 +956,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     REG(surf_tv_grad_sparse);
     REG(msi_tv_grad_sparse);
     REG(surf_sign_change_grad_sparse);
+    REG(surface_normal_grad);
+    REG(lumisphere_tv_grad_sparse);
     REG(dilate);
     REG(accel_dist_prop);
     REG(grid_weight_render);
@@ -931,7 +971,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     for (const char *name : {"test_cubic_root_grad", "volume_render_surface", "volume_render_surface_backward",
                              "volume_render_surface_fused", "volume_render_nvol", "volume_render_nvol_backward",
                              "volume_render_nvol_fused", "volume_render_svox1", "volume_render_svox1_backward",
-                             "volume_render_svox1_fused", "surface_normal_grad", "lumisphere_tv_grad_sparse"})
+                             "volume_render_svox1_fused"})
         m.attr(name) = off_path(name);
     m.def("set_loss_norm_rays", [](py::object n) { g_norm_rays = n.is_none() ? 0 : n.cast<int64_t>(); },
           "global ray count used to normalise the fused losses in a ray-sharded run (None: per call)");

@@ -387,6 +387,18 @@ __device__ __forceinline__ void scatter_normal_grad(const Cell8 &c, const float 
 #define CUB_(x) ((x) * (x) * (x))
 #define SQR_(x) ((x) * (x))
 
+// squared-difference form of the pair gradient: d|n0/N0 - n1/N1|^2 / d(n0), d(n1), in the reference's operation order
+// (render_util.cuh:2042-2080; the dense kernel repeats the expressions, loss_kernel.cu:343-380)
+__device__ __forceinline__ void pair_grad_l2(const float *n0, float N0, const float *n1, float N1, float *d0, float *d1) {
+    const float e0 = n0[0] / N0 - n1[0] / N1, e1 = n0[1] / N0 - n1[1] / N1, e2 = n0[2] / N0 - n1[2] / N1;
+    d0[0] = e0 * (-2.f * SQR_(n0[0]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e1 / CUB_(N0) + -2.f * n0[0] * n0[2] * e2 / CUB_(N0);
+    d0[1] = e1 * (-2.f * SQR_(n0[1]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e0 / CUB_(N0) + -2.f * n0[1] * n0[2] * e2 / CUB_(N0);
+    d0[2] = e2 * (-2.f * SQR_(n0[2]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[2] * e0 / CUB_(N0) + -2.f * n0[1] * n0[2] * e1 / CUB_(N0);
+    d1[0] = e0 * (2.f * SQR_(n1[0]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e1 / CUB_(N1) + 2.f * n1[0] * n1[2] * e2 / CUB_(N1);
+    d1[1] = e1 * (2.f * SQR_(n1[1]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e0 / CUB_(N1) + 2.f * n1[1] * n1[2] * e2 / CUB_(N1);
+    d1[2] = e2 * (2.f * SQR_(n1[2]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[2] * e0 / CUB_(N1) + 2.f * n1[1] * n1[2] * e1 / CUB_(N1);
+}
+
 __global__ void __launch_bounds__(LOSS_THREADS)
 surface_normal_kernel(const int32_t *__restrict__ links, const float *__restrict__ surf, const int32_t *__restrict__ cells,
                       Dims d, int n_rep, int64_t Q, float lv_set, float scale, int con_check, int ignore_empty, int use_l1,
@@ -441,18 +453,133 @@ surface_normal_kernel(const int32_t *__restrict__ links, const float *__restrict
                 d1[1] = s[0] * (n1[0] * n1[1] / CUB_(N1)) + s[1] * (SQR_(n1[1]) / CUB_(N1) - 1.f / N1) + s[2] * (n1[1] * n1[2] / CUB_(N1));
                 d1[2] = s[0] * (n1[0] * n1[2] / CUB_(N1)) + s[1] * (n1[1] * n1[2] / CUB_(N1)) + s[2] * (SQR_(n1[2]) / CUB_(N1) - 1.f / N1);
             } else {
-                const float e0 = n0[0] / N0 - n1[0] / N1, e1 = n0[1] / N0 - n1[1] / N1, e2 = n0[2] / N0 - n1[2] / N1;
-                d0[0] = e0 * (-2.f * SQR_(n0[0]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e1 / CUB_(N0) + -2.f * n0[0] * n0[2] * e2 / CUB_(N0);
-                d0[1] = e1 * (-2.f * SQR_(n0[1]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e0 / CUB_(N0) + -2.f * n0[1] * n0[2] * e2 / CUB_(N0);
-                d0[2] = e2 * (-2.f * SQR_(n0[2]) / CUB_(N0) + 2.f / N0) + -2.f * n0[0] * n0[2] * e0 / CUB_(N0) + -2.f * n0[1] * n0[2] * e1 / CUB_(N0);
-                d1[0] = e0 * (2.f * SQR_(n1[0]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e1 / CUB_(N1) + 2.f * n1[0] * n1[2] * e2 / CUB_(N1);
-                d1[1] = e1 * (2.f * SQR_(n1[1]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e0 / CUB_(N1) + 2.f * n1[1] * n1[2] * e2 / CUB_(N1);
-                d1[2] = e2 * (2.f * SQR_(n1[2]) / CUB_(N1) - 2.f / N1) + 2.f * n1[0] * n1[2] * e0 / CUB_(N1) + 2.f * n1[1] * n1[2] * e1 / CUB_(N1);
+                pair_grad_l2(n0, N0, n1, N1, d0, d1);
             }
             const float sc = scale * 1.f / norm_count;
             scatter_normal_grad(c0, d0, sc, mask, grad);
             scatter_normal_grad(cn[i], d1, sc, mask, grad);
         }
+    }
+}
+
+// ---- dense variant (surface_normal_grad_kernel, loss_kernel.cu:245-396): every cell of the (size - 1)^3 lattice, column idx of
+// a tensor with n_cols columns, the connectivity test always on, squared-difference form, no mask; a corner is skipped where
+// its UNSCALED weight is zero (_add_surface_grad :187-242).  Unreachable from the reference's Python (svox2.py:5725 raises
+// before the call), kept for the completeness of the module: one thread per (cell, column), no tiling. -------------------------
+__device__ __forceinline__ bool load_cell_col(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols, int idx,
+                                              const Dims &d, int x, int y, int z, Cell8 &c) {
+    if (!((x < d.sx - 1) && (y < d.sy - 1) && (z < d.sz - 1))) return false;
+    const int64_t offx = (int64_t)d.sy * d.sz;
+    const int32_t *lp = links + ((int64_t)x * offx + (int64_t)y * d.sz + z);
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        c.l[k] = __ldg(lp + (k >> 2) * offx + ((k >> 1) & 1) * d.sz + (k & 1));
+        ok &= (c.l[k] >= 0);
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c.s[k] = __ldg(data + (int64_t)c.l[k] * n_cols + idx);
+    return true;
+}
+__device__ __forceinline__ void scatter_normal_grad_col(const Cell8 &c, const float *g, float scale, int n_cols, int idx,
+                                                        float *__restrict__ grad) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float sx = (k & 4) ? 0.25f : -0.25f, sy = (k & 2) ? 0.25f : -0.25f, sz = (k & 1) ? 0.25f : -0.25f;
+        const float gk = sx * g[0] + sy * g[1] + sz * g[2];
+        if (gk != 0.f) atomicAdd(grad + (int64_t)c.l[k] * n_cols + idx, gk * scale);
+    }
+}
+__global__ void __launch_bounds__(LOSS_THREADS)
+surface_normal_dense_kernel(const int32_t *__restrict__ links, const float *__restrict__ data, int n_cols, Dims d, int start_dim,
+                            int n_rep, int64_t Q, float lv_set, float scale, float *__restrict__ grad) {
+    for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < Q; tid += (int64_t)gridDim.x * blockDim.x) {
+        const int idx = (int)(tid % n_rep) + start_dim;
+        const int64_t xyz = tid / n_rep;
+        const int z = (int)(xyz % (d.sz - 1));
+        const int64_t xy = xyz / (d.sz - 1);
+        const int y = (int)(xy % (d.sy - 1)), x = (int)(xy / (d.sy - 1));
+        Cell8 c0, cn[3];
+        if (!load_cell_col(links, data, n_cols, idx, d, x, y, z, c0)) continue;
+        float n0[3];
+        cell_normal(c0, n0);
+        bool use[3];
+        use[2] = load_cell_col(links, data, n_cols, idx, d, x, y, z + 1, cn[2]) && face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv_set);
+        use[1] = load_cell_col(links, data, n_cols, idx, d, x, y + 1, z, cn[1]) && face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv_set);
+        use[0] = load_cell_col(links, data, n_cols, idx, d, x + 1, y, z, cn[0]) && face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv_set);
+        const int norm_count = (int)use[0] + (int)use[1] + (int)use[2];
+        const float N0 = NORM3_(n0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (!use[i]) continue;
+            float n1[3], d0[3], d1[3];
+            cell_normal(cn[i], n1);
+            pair_grad_l2(n0, N0, n1, NORM3_(n1), d0, d1);
+            const float sc = scale * 1.f / norm_count;
+            scatter_normal_grad_col(c0, d0, sc, n_cols, idx, grad);
+            scatter_normal_grad_col(cn[i], d1, sc, n_cols, idx, grad);
+        }
+    }
+}
+
+// ---- lumisphere TV (lumisphere_tv_grad_sparse_kernel, loss_kernel.cu:1067-1177): total variation of the radiance seen from ONE
+// direction (basis values sv) plus its change towards a perturbed direction (su), per colour channel.  Warp per cell, lane per
+// SH coefficient as in the reference, because the per-channel sums must follow its HeadSegmentedSum order.  Cells are decoded
+// on the (size - 1) lattice; a cell is skipped only where its link is exactly 0 (:1110 -- a missing centre reads 0 and goes on).
+__global__ void __launch_bounds__(LOSS_THREADS)
+lumisphere_tv_kernel(const int32_t *__restrict__ links, const float *__restrict__ sh, int sh_dim, int basis_dim, Dims d,
+                     const int32_t *__restrict__ cells, int64_t n_cells, const float *__restrict__ sv_p, const float *__restrict__ su_p,
+                     float scale, float dir_factor, uint8_t *__restrict__ mask, float *__restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool live = lane < sh_dim;
+    const int pos = lane % basis_dim, grp_head = lane - pos;
+    const float sv = live ? __ldg(sv_p + pos) : 0.f, su = live ? __ldg(su_p + pos) : 0.f;
+    float sc[3];
+    ray_scale(d, sc);
+    const int64_t offx = (int64_t)d.sy * d.sz;
+    for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_cells; c += warps) {
+        const int xyz = __ldg(cells + c);
+        const int z = xyz % (d.sz - 1);
+        const int xy = xyz / (d.sz - 1);
+        const int y = xy % (d.sy - 1), x = xy / (d.sy - 1);
+        const int32_t *lp = links + ((int64_t)x * offx + (int64_t)y * d.sz + z);
+        const int32_t l0 = __ldg(lp);
+        if (l0 == 0) continue;
+        const int32_t l1 = __ldg(lp + 1), ly = __ldg(lp + d.sz), lx = __ldg(lp + offx);
+        float v000 = 0.f, v001 = 0.f, v010 = 0.f, v100 = 0.f;
+        if (live) {
+            v000 = l0 >= 0 ? __ldg(sh + (int64_t)l0 * sh_dim + lane) : 0.f;
+            v001 = l1 >= 0 ? __ldg(sh + (int64_t)l1 * sh_dim + lane) : v000;
+            v010 = ly >= 0 ? __ldg(sh + (int64_t)ly * sh_dim + lane) : v000;
+            v100 = lx >= 0 ? __ldg(sh + (int64_t)lx * sh_dim + lane) : v000;
+        }
+        float a0 = v000 * sv, a1 = v001 * sv, ay = v010 * sv, ax = v100 * sv, au = v000 * su;
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {   // HeadSegmentedSum order: shuffle-down tree clamped to the channel's segment
+            const float o0 = __shfl_down_sync(0xffffffffu, a0, off), o1 = __shfl_down_sync(0xffffffffu, a1, off),
+                        oy = __shfl_down_sync(0xffffffffu, ay, off), ox = __shfl_down_sync(0xffffffffu, ax, off),
+                        ou = __shfl_down_sync(0xffffffffu, au, off);
+            if (pos + off < basis_dim) { a0 += o0; a1 += o1; ay += oy; ax += ox; au += ou; }
+        }
+        float dx = (ax - a0) * sc[0], dy = (ay - a0) * sc[1], dz = (a1 - a0) * sc[2], du = (au - a0) * dir_factor;
+        dx = __shfl_sync(0xffffffffu, dx, grp_head & 31);
+        dy = __shfl_sync(0xffffffffu, dy, grp_head & 31);
+        dz = __shfl_sync(0xffffffffu, dz, grp_head & 31);
+        du = __shfl_sync(0xffffffffu, du, grp_head & 31);
+        if (!live) continue;
+        const float idelta = scale * rsqrtf(1e-9f + dx * dx + dy * dy + dz * dz + du * du);
+        dx *= sc[0]; dy *= sc[1]; dz *= sc[2]; du *= dir_factor;
+        const float sm = -dx * sv - dy * sv - dz * sv + du * (su - sv);
+        const float vals[4] = {sm, dz * sv, dy * sv, dx * sv};
+        const int32_t ls[4] = {l0, l1, ly, lx};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (ls[j] >= 0 && vals[j] != 0.f) {
+                atomicAdd(grad + (int64_t)ls[j] * sh_dim + lane, vals[j] * idelta);
+                if (mask) mask[ls[j]] = 1;
+            }
     }
 }
 
@@ -1412,6 +1539,43 @@ extern "C" int asurf_surf_sign_change_grad_sparse(const int32_t *links, const in
                                                                                 grad_data);
     note_launches(1);
     return check_cuda(cudaGetLastError(), "surf_sign_change_grad_sparse launch");
+}
+
+// surface_normal_grad (dense), loss_kernel.cu:1289-1325
+extern "C" int asurf_surface_normal_grad(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols, float lv_set,
+                                         int32_t start_dim, int32_t end_dim, float scale, float *grad_data, void *stream) {
+    int rc = check_common(links, size, data, grad_data, "surface_normal_grad");
+    if (rc) return rc;
+    ASURF_REQUIRE(end_dim > start_dim && start_dim >= 0 && end_dim <= n_cols, ASURF_E_INVALID, "surface_normal_grad: bad channel range");
+    const int64_t nl64 = (int64_t)(size[0] - 1) * (size[1] - 1) * (size[2] - 1);
+    ASURF_REQUIRE(nl64 < (int64_t)1 << 31, ASURF_E_INVALID, "surface_normal_grad: the reference counts cells in an int");
+    if (nl64 <= 0) return 0;
+    const int n_rep = end_dim - start_dim;
+    const int64_t Q = nl64 * n_rep;
+    Dims d = {size[0], size[1], size[2]};
+    surface_normal_dense_kernel<<<loss_grid(Q), LOSS_THREADS, 0, (cudaStream_t)stream>>>(links, data, n_cols, d, start_dim, n_rep, Q,
+                                                                                         lv_set, scale / (int)nl64, grad_data);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "surface_normal_grad launch");
+}
+
+// lumisphere_tv_grad_sparse, loss_kernel.cu:1661-1697
+extern "C" int asurf_lumisphere_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *sh_data, int32_t sh_data_dim,
+                                               int32_t basis_dim, const int32_t *rand_cells, int64_t n_cells, const float *basis_fn,
+                                               const float *basis_fn_u, float scale, float dir_factor, uint8_t *mask_out,
+                                               float *grad_sh, void *stream) {
+    int rc = check_common(links, size, sh_data, grad_sh, "lumisphere_tv_grad_sparse");
+    if (rc) return rc;
+    ASURF_REQUIRE(basis_dim >= 1 && basis_dim <= 16 && sh_data_dim >= basis_dim && sh_data_dim <= 32 && sh_data_dim % basis_dim == 0,
+                  ASURF_E_INVALID, "lumisphere_tv_grad_sparse: one warp lane per SH coefficient (sh_data_dim <= 32, basis_dim <= 16)");
+    if (n_cells <= 0) return 0;
+    ASURF_REQUIRE(rand_cells && basis_fn && basis_fn_u, ASURF_E_INVALID, "lumisphere_tv_grad_sparse: null cell list / basis values");
+    Dims d = {size[0], size[1], size[2]};
+    lumisphere_tv_kernel<<<loss_grid(n_cells * 32), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+        links, sh_data, sh_data_dim, basis_dim, d, rand_cells, n_cells, basis_fn, basis_fn_u, scale / (float)(int)n_cells, dir_factor,
+        mask_out, grad_sh);
+    note_launches(1);
+    return check_cuda(cudaGetLastError(), "lumisphere_tv_grad_sparse launch");
 }
 
 extern "C" int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,

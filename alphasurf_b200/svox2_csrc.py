@@ -755,6 +755,41 @@ def surf_sign_change_grad_sparse(links, data, rand_cells, mask_out, start_dim, e
             capi.ptr(grad_data), capi.current_stream()), "surf_sign_change_grad_sparse")
 
 
+def surface_normal_grad(links, data, lv_set, start_dim, end_dim, scale, ndc_coeffx, ndc_coeffy, grad_data):
+    """dense normal-consistency loss over the whole lattice (loss_kernel.cu:1289-1325; the ndc coefficients are unused there too)"""
+    _check_loss_common(links, data, grad_data)
+    with torch.cuda.device(data.device):
+        capi.check(capi.lib().asurf_surface_normal_grad(
+            capi.ptr(links), capi.size3(links.shape), capi.ptr(data), C.c_int32(data.shape[1]), C.c_float(lv_set),
+            C.c_int32(start_dim), C.c_int32(end_dim), C.c_float(scale), capi.ptr(grad_data), capi.current_stream()),
+            "surface_normal_grad")
+
+
+def lumisphere_tv_grad_sparse(grid, rand_cells, basis_fn, basis_fn_u, scale, ndc_coeffx, ndc_coeffy, dir_factor, grads):
+    """TV of the radiance seen from one direction (loss_kernel.cu:1661-1697); basis_fn must be 1-D (:1674), basis_fn_u is read
+    as its first basis_dim values like the reference kernel does (:1127)"""
+    _check_input(grid.sh_data, "grid.sh_data")
+    _check_input(grid.links, "grid.links")
+    _check_cells(rand_cells)
+    _check_input(basis_fn, "basis_fn")
+    _check_input(basis_fn_u, "basis_fn_u")
+    if basis_fn.dim() != 1:
+        raise RuntimeError("basis_fn must be 1-D (loss_kernel.cu:1674)")
+    if grads.grad_sh_out is None:
+        raise RuntimeError("grads.grad_sh_out is required")
+    _check_input(grads.grad_sh_out, "grads.grad_sh_out")
+    basis_dim = int(grid.basis_dim)
+    if basis_fn.numel() < basis_dim or basis_fn_u.numel() < basis_dim:
+        raise RuntimeError("basis_fn / basis_fn_u hold fewer than basis_dim values")
+    with torch.cuda.device(grid.sh_data.device):
+        capi.check(capi.lib().asurf_lumisphere_tv_grad_sparse(
+            capi.ptr(grid.links), capi.size3(grid.links.shape), capi.ptr(grid.sh_data), C.c_int32(grid.sh_data.shape[1]),
+            C.c_int32(basis_dim), capi.ptr(rand_cells), C.c_int64(rand_cells.shape[0]), capi.ptr(basis_fn.float()),
+            capi.ptr(basis_fn_u.float()), C.c_float(scale), C.c_float(dir_factor),
+            None if grads.mask_out is None else _mask_ptr(grads.mask_out),
+            capi.ptr(grads.grad_sh_out), capi.current_stream()), "lumisphere_tv_grad_sparse")
+
+
 def alpha_surf_sparsify_grad_sparse(links, alpha_data, surf_data, rand_cells, mask_out, scale_alpha, scale_surf,
                                     surf_sparse_decrease, surf_sparse_thresh, alpha_bound, surf_bound, grad_alpha, grad_surf):
     _check_loss_common(links, alpha_data, grad_alpha)
@@ -874,8 +909,7 @@ def _not_on_hot_path(name):
     return fn
 
 
-for _name in ("surface_normal_grad", "lumisphere_tv_grad_sparse",
-              "volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
+for _name in ("volume_render_surface", "volume_render_surface_backward", "volume_render_surface_fused",
               "volume_render_nvol", "volume_render_nvol_backward", "volume_render_nvol_fused", "volume_render_svox1",
               "volume_render_svox1_backward", "volume_render_svox1_fused", "test_cubic_root_grad"):
     if _name not in globals():

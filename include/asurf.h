@@ -337,6 +337,18 @@ int asurf_surf_tv_grad_sparse(const int32_t *links, const int32_t size[3], const
 int asurf_surf_sign_change_grad_sparse(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols,
                                        const int32_t *rand_cells, int64_t n_cells, uint8_t *mask_out, int32_t start_dim,
                                        int32_t end_dim, float scale, float *grad_data, void *stream);
+/* surface_normal_grad (dense), loss_kernel.cu:1289-1325 (kernel :245-396): the normal-consistency loss over EVERY cell of the
+ * (size - 1)^3 lattice on column(s) [start_dim, end_dim) of `data`, connectivity test always on, squared-difference form, no
+ * touched mask.  (Unreachable from the reference's Python -- svox2.py:5725 raises first -- present for module completeness.) */
+int asurf_surface_normal_grad(const int32_t *links, const int32_t size[3], const float *data, int32_t n_cols, float lv_set,
+                              int32_t start_dim, int32_t end_dim, float scale, float *grad_data, void *stream);
+/* lumisphere_tv_grad_sparse, :1661-1697 (kernel :1067-1177): TV of the radiance seen from one direction (basis values
+ * basis_fn[basis_dim]) plus its change towards a perturbed direction (basis_fn_u[basis_dim], weight dir_factor), per colour
+ * channel; cells are flat ids on the (size - 1) lattice.  One warp lane per SH coefficient: sh_data_dim <= 32. */
+int asurf_lumisphere_tv_grad_sparse(const int32_t *links, const int32_t size[3], const float *sh_data, int32_t sh_data_dim,
+                                    int32_t basis_dim, const int32_t *rand_cells, int64_t n_cells, const float *basis_fn,
+                                    const float *basis_fn_u, float scale, float dir_factor, uint8_t *mask_out, float *grad_sh,
+                                    void *stream);
 /* alpha_surf_sparsify_grad_sparse, :1512-1570 */
 int asurf_alpha_surf_sparsify_grad_sparse(const int32_t *links, const int32_t size[3], const float *alpha,
                                           int32_t alpha_cols, const float *surf, int32_t surf_cols,

@@ -516,3 +516,19 @@ def surf_sign_change_grad_sparse(links, data, cells, mask, start_dim, end_dim, s
     lib().oracle_surf_sign_change_grad_sparse(_ptr(links), _sz(links), _ptr(data), C.c_int(data.shape[1]), _ptr(cells),
                                               C.c_int64(cells.shape[0]), _ptr(mask), C.c_int(start_dim), C.c_int(end_dim),
                                               C.c_float(scale), _ptr(grad))
+
+
+def surface_normal_grad(links, data, lv_set, start_dim, end_dim, scale, grad):
+    """dense normal-consistency loss (loss_kernel.cu:245-396, :1289-1325); grad (N, n_cols) float32 numpy, accumulated"""
+    links, data = _np(links, np.int32), _np(data, np.float32)
+    lib().oracle_surface_normal_grad(_ptr(links), _sz(links), _ptr(data), C.c_int(data.shape[1]), C.c_float(lv_set),
+                                     C.c_int(start_dim), C.c_int(end_dim), C.c_float(scale), _ptr(grad))
+
+
+def lumisphere_tv_grad_sparse(links, sh, basis_dim, cells, basis_fn, basis_fn_u, scale, dir_factor, mask, grad):
+    """loss_kernel.cu:1067-1177, :1661-1697; grad (N, sh_dim) float32 numpy accumulated, mask uint8 (N,) or None"""
+    links, sh, cells = _np(links, np.int32), _np(sh, np.float32), _np(cells, np.int32)
+    sv, su = _np(basis_fn, np.float32), _np(basis_fn_u, np.float32)
+    lib().oracle_lumisphere_tv_grad_sparse(_ptr(links), _sz(links), _ptr(sh), C.c_int(sh.shape[1]), C.c_int(basis_dim), _ptr(cells),
+                                           C.c_int64(cells.shape[0]), _ptr(sv), _ptr(su), C.c_float(scale), C.c_float(dir_factor),
+                                           _ptr(mask), _ptr(grad))

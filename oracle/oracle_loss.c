@@ -181,6 +181,17 @@ static void scatter_normal(const Cell8 *c, const float *g, float scale, uint8_t 
 #define CUB(x) ((x) * (x) * (x))
 #define SQR(x) ((x) * (x))
 
+/* squared-difference form of the pair gradient (render_util.cuh:2042-2080; the same expressions in loss_kernel.cu:343-380) */
+static void pair_l2(const float *n0, float N0, const float *n1, float N1, float *d0, float *d1) {
+    const float e0 = n0[0] / N0 - n1[0] / N1, e1 = n0[1] / N0 - n1[1] / N1, e2 = n0[2] / N0 - n1[2] / N1;
+    d0[0] = e0 * (-2.f * SQR(n0[0]) / CUB(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e1 / CUB(N0) + -2.f * n0[0] * n0[2] * e2 / CUB(N0);
+    d0[1] = e1 * (-2.f * SQR(n0[1]) / CUB(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e0 / CUB(N0) + -2.f * n0[1] * n0[2] * e2 / CUB(N0);
+    d0[2] = e2 * (-2.f * SQR(n0[2]) / CUB(N0) + 2.f / N0) + -2.f * n0[0] * n0[2] * e0 / CUB(N0) + -2.f * n0[1] * n0[2] * e1 / CUB(N0);
+    d1[0] = e0 * (2.f * SQR(n1[0]) / CUB(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e1 / CUB(N1) + 2.f * n1[0] * n1[2] * e2 / CUB(N1);
+    d1[1] = e1 * (2.f * SQR(n1[1]) / CUB(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e0 / CUB(N1) + 2.f * n1[1] * n1[2] * e2 / CUB(N1);
+    d1[2] = e2 * (2.f * SQR(n1[2]) / CUB(N1) - 2.f / N1) + 2.f * n1[0] * n1[2] * e0 / CUB(N1) + 2.f * n1[1] * n1[2] * e1 / CUB(N1);
+}
+
 /* surface_normal_grad_sparse_kernel :397-441 + host :1572-1622 */
 void oracle_surface_normal_grad_sparse(const int32_t *links, const int32_t *size, const float *surf, const int32_t *cells,
                                        int64_t n_cells, uint8_t *mask, float lv, int start_dim, int end_dim, float scale,
@@ -227,13 +238,7 @@ void oracle_surface_normal_grad_sparse(const int32_t *links, const int32_t *size
                     d1[1] = s[0] * (n1[0] * n1[1] / CUB(N1)) + s[1] * (SQR(n1[1]) / CUB(N1) - 1.f / N1) + s[2] * (n1[1] * n1[2] / CUB(N1));
                     d1[2] = s[0] * (n1[0] * n1[2] / CUB(N1)) + s[1] * (n1[1] * n1[2] / CUB(N1)) + s[2] * (SQR(n1[2]) / CUB(N1) - 1.f / N1);
                 } else {
-                    const float e0 = n0[0] / N0 - n1[0] / N1, e1 = n0[1] / N0 - n1[1] / N1, e2 = n0[2] / N0 - n1[2] / N1;
-                    d0[0] = e0 * (-2.f * SQR(n0[0]) / CUB(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e1 / CUB(N0) + -2.f * n0[0] * n0[2] * e2 / CUB(N0);
-                    d0[1] = e1 * (-2.f * SQR(n0[1]) / CUB(N0) + 2.f / N0) + -2.f * n0[0] * n0[1] * e0 / CUB(N0) + -2.f * n0[1] * n0[2] * e2 / CUB(N0);
-                    d0[2] = e2 * (-2.f * SQR(n0[2]) / CUB(N0) + 2.f / N0) + -2.f * n0[0] * n0[2] * e0 / CUB(N0) + -2.f * n0[1] * n0[2] * e1 / CUB(N0);
-                    d1[0] = e0 * (2.f * SQR(n1[0]) / CUB(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e1 / CUB(N1) + 2.f * n1[0] * n1[2] * e2 / CUB(N1);
-                    d1[1] = e1 * (2.f * SQR(n1[1]) / CUB(N1) - 2.f / N1) + 2.f * n1[0] * n1[1] * e0 / CUB(N1) + 2.f * n1[1] * n1[2] * e2 / CUB(N1);
-                    d1[2] = e2 * (2.f * SQR(n1[2]) / CUB(N1) - 2.f / N1) + 2.f * n1[0] * n1[2] * e0 / CUB(N1) + 2.f * n1[1] * n1[2] * e1 / CUB(N1);
+                    pair_l2(n0, N0, n1, N1, d0, d1);
                 }
                 const float sc = scale * 1.f / norm_count;
                 scatter_normal(&c0, d0, sc, mask, grad);
@@ -279,4 +284,110 @@ void oracle_surf_sign_change_grad_sparse(const int32_t *links, const int32_t *si
                 if (ln[i] >= 0 && b != 0.f) { grad[(int64_t)ln[i] * n_cols + idx] += b; if (mask) mask[ln[i]] = 1; }
             }
         }
+}
+
+/* ---- dense surface_normal_grad, loss_kernel.cu:245-396 + host :1289-1325: every cell of the (size - 1)^3 lattice, column idx of
+ * a multi-column tensor, always the connectivity test, squared-difference form, no mask; the zero test is on the unscaled
+ * corner weight (_add_surface_grad :187-242) ---- */
+static int load_cell_col(const int32_t *links, const float *data, int n_cols, int idx, const int32_t *size, int x, int y, int z,
+                         Cell8 *c) {
+    if (!((x < size[0] - 1) && (y < size[1] - 1) && (z < size[2] - 1))) return 0;
+    for (int k = 0; k < 8; ++k) {
+        c->l[k] = LNK(x + (k >> 2), y + ((k >> 1) & 1), z + (k & 1));
+        if (c->l[k] < 0) return 0;
+    }
+    for (int k = 0; k < 8; ++k) c->s[k] = data[(int64_t)c->l[k] * n_cols + idx];
+    return 1;
+}
+static void scatter_normal_col(const Cell8 *c, const float *g, float scale, int n_cols, int idx, float *grad) {
+    for (int k = 0; k < 8; ++k) {
+        const float sx = (k & 4) ? 0.25f : -0.25f, sy = (k & 2) ? 0.25f : -0.25f, sz = (k & 1) ? 0.25f : -0.25f;
+        const float gk = sx * g[0] + sy * g[1] + sz * g[2];
+        if (gk != 0.f) ATOMIC_ADD(grad[(int64_t)c->l[k] * n_cols + idx], gk * scale);
+    }
+}
+void oracle_surface_normal_grad(const int32_t *links, const int32_t *size, const float *data, int n_cols, float lv, int start_dim,
+                                int end_dim, float scale, float *grad) {
+    const int nl = (size[0] - 1) * (size[1] - 1) * (size[2] - 1);
+    scale = scale / nl;
+#pragma omp parallel for schedule(static) if (nl > OMP_MIN_CELLS)
+    for (int64_t xyz = 0; xyz < nl; ++xyz)
+        for (int idx = start_dim; idx < end_dim; ++idx) {
+            const int z = (int)(xyz % (size[2] - 1));
+            const int64_t xy = xyz / (size[2] - 1);
+            const int y = (int)(xy % (size[1] - 1)), x = (int)(xy / (size[1] - 1));
+            Cell8 c0, cn[3];
+            if (!load_cell_col(links, data, n_cols, idx, size, x, y, z, &c0)) continue;
+            float n0[3];
+            cell_normal(&c0, n0);
+            int use[3];
+            use[2] = load_cell_col(links, data, n_cols, idx, size, x, y, z + 1, &cn[2]) && face_connected(c0.s[1], c0.s[3], c0.s[5], c0.s[7], lv);
+            use[1] = load_cell_col(links, data, n_cols, idx, size, x, y + 1, z, &cn[1]) && face_connected(c0.s[2], c0.s[3], c0.s[6], c0.s[7], lv);
+            use[0] = load_cell_col(links, data, n_cols, idx, size, x + 1, y, z, &cn[0]) && face_connected(c0.s[4], c0.s[5], c0.s[6], c0.s[7], lv);
+            const int norm_count = use[0] + use[1] + use[2];
+            const float N0 = NORM3(n0);
+            for (int a = 0; a < 3; ++a) {
+                if (!use[a]) continue;
+                float n1[3], d0[3], d1[3];
+                cell_normal(&cn[a], n1);
+                pair_l2(n0, N0, n1, NORM3(n1), d0, d1);
+                const float sc = scale * 1.f / norm_count;
+                scatter_normal_col(&c0, d0, sc, n_cols, idx, grad);
+                scatter_normal_col(&cn[a], d1, sc, n_cols, idx, grad);
+            }
+        }
+}
+
+/* ---- lumisphere_tv_grad_sparse, loss_kernel.cu:1067-1177 + host :1661-1697: TV of the radiance seen from ONE direction
+ * (basis values sv) plus the change towards a perturbed direction (basis values su), per colour channel; cells are decoded on
+ * the (size - 1) lattice; a cell is skipped only where its link is exactly 0 (:1110; a missing corner contributes v000 = 0) ---- */
+void oracle_lumisphere_tv_grad_sparse(const int32_t *links, const int32_t *size, const float *sh, int sh_dim, int basis_dim,
+                                      const int32_t *cells, int64_t n_cells, const float *sv, const float *su, float scale,
+                                      float dir_factor, uint8_t *mask, float *grad) {
+    float sc[3];
+    ray_scale(size, sc);
+    scale = scale / (float)(int)n_cells;
+    const int n_col = sh_dim / basis_dim;
+    for (int64_t c = 0; c < n_cells; ++c) {
+        const int xyz = cells[c];
+        const int z = xyz % (size[2] - 1);
+        const int xy = xyz / (size[2] - 1);
+        const int y = xy % (size[1] - 1), x = xy / (size[1] - 1);
+        const int32_t l0 = LNK(x, y, z);
+        if (l0 == 0) continue;
+        const int32_t ln[3] = {LNK(x + 1, y, z), LNK(x, y + 1, z), LNK(x, y, z + 1)};
+        for (int col = 0; col < n_col; ++col) {
+            /* per-channel sums in the warp's shuffle-down order clamped to the segment (HeadSegmentedSum) */
+            float a0[16], an[3][16], au[16];
+            for (int k = 0; k < basis_dim; ++k) {
+                const int idx = col * basis_dim + k;
+                const float v000 = l0 >= 0 ? sh[(int64_t)l0 * sh_dim + idx] : 0.f;
+                a0[k] = v000 * sv[k];
+                au[k] = v000 * su[k];
+                for (int i = 0; i < 3; ++i) an[i][k] = (ln[i] >= 0 ? sh[(int64_t)ln[i] * sh_dim + idx] : v000) * sv[k];
+            }
+            for (int off = 1; off < 16; off <<= 1)
+                for (int k = 0; k + off < basis_dim; ++k) {
+                    a0[k] += a0[k + off];
+                    au[k] += au[k + off];
+                    for (int i = 0; i < 3; ++i) an[i][k] += an[i][k + off];
+                }
+            float dx = (an[0][0] - a0[0]) * sc[0], dy = (an[1][0] - a0[0]) * sc[1], dz = (an[2][0] - a0[0]) * sc[2];
+            float du = (au[0] - a0[0]) * dir_factor;
+            const float idelta = scale * (1.f / sqrtf(1e-9f + dx * dx + dy * dy + dz * dz + du * du));
+            dx *= sc[0]; dy *= sc[1]; dz *= sc[2]; du *= dir_factor;
+            for (int k = 0; k < basis_dim; ++k) {
+                const int idx = col * basis_dim + k;
+                const float s = sv[k];
+                const float sm = -dx * s - dy * s - dz * s + du * (su[k] - s);
+                const float vals[4] = {sm, dx * s, dy * s, dz * s};
+                const int32_t ls[4] = {l0, ln[0], ln[1], ln[2]};
+                for (int j = 0; j < 4; ++j)
+                    if (ls[j] >= 0 && vals[j] != 0.f) {
+                        grad[(int64_t)ls[j] * sh_dim + idx] += vals[j] * idelta;
+                        if (mask) mask[ls[j]] = 1;
+                    }
+            }
+        }
+    }
 }

@@ -379,3 +379,59 @@ def test_surf_sign_change_grad_sparse(contiguous):
     oracle.surf_sign_change_grad_sparse(sg.links, sg.surface, cells_c, m_o, 0, 1, 0.3, g_o)
     _close(grad, g_o, "surf_sign_change_grad_sparse")
     assert np.array_equal(mask.cpu().numpy().astype(np.uint8), m_o) and 0 < m_o.sum() < sg.capacity
+
+
+@pytest.mark.parametrize("reso,cols,lv", [(24, (0, 1), 0.0), (20, (1, 3), 0.1)])
+def test_surface_normal_grad_dense(reso, cols, lv):
+    """dense variant over the whole lattice (loss_kernel.cu:1289-1325): vs the oracle and the reference kernel, on a
+    single-column tensor (the surface) and on two columns of a wider one"""
+    from oracle import oracle
+    ref = H.load_reference_cuda()
+    sg = _grid(reso, variant="G*")
+    data_c = sg.surface if cols == (0, 1) else (sg.sh[:, :4] * 0.5 + sg.surface).contiguous()
+    links, data = sg.links.cuda(), data_c.cuda()
+    grad = torch.zeros_like(data)
+    ours.surface_normal_grad(links, data, lv, cols[0], cols[1], 0.7, -1.0, -1.0, grad)
+    g_o = np.zeros(tuple(data_c.shape), np.float32)
+    oracle.surface_normal_grad(sg.links, data_c, lv, cols[0], cols[1], 0.7, g_o)
+    _close(grad, g_o, "surface_normal_grad vs oracle")
+    assert np.abs(g_o).max() > 0
+    g_r = torch.zeros_like(data)
+    ref.surface_normal_grad(links, data, lv, cols[0], cols[1], 0.7, -1.0, -1.0, g_r)
+    _close(grad, g_r.cpu().numpy(), "surface_normal_grad vs reference kernel")
+    untouched = [c for c in range(data.shape[1]) if not cols[0] <= c < cols[1]]
+    assert float(grad[:, untouched].abs().max()) == 0.0 if untouched else True
+
+
+@pytest.mark.parametrize("bd,dir_factor,with_mask", [(9, 1.0, True), (4, 0.0, True), (9, 0.5, False)])
+def test_lumisphere_tv_grad_sparse(bd, dir_factor, with_mask):
+    """loss_kernel.cu:1661-1697 through the GridSpec / GridOutputGrads objects, vs the oracle and the reference kernel.
+    Cell ids are decoded on the (size - 1) lattice (:1092-1096); row 0's cell is skipped (:1110)."""
+    from oracle import oracle
+    ref = H.load_reference_cuda()
+    reso = 24
+    sg = _grid(reso, bd=bd, variant="G*").to("cuda")
+    n_cells = (reso - 1) ** 3
+    cells = torch.randint(0, n_cells, (n_cells // 2,), generator=torch.Generator().manual_seed(6)).int().cuda()
+    g = torch.Generator().manual_seed(8)
+    sv, su = torch.randn(bd, generator=g).cuda(), torch.randn(bd, generator=g).cuda()
+    res = {}
+    for name, mod in (("ours", ours), ("ref", ref)):
+        grid = H.fill_grid_spec(mod, sg)
+        G = H.GradSet(sg, "cuda")
+        holder = mod.GridOutputGrads()
+        holder.grad_sh_out = G.sh
+        if with_mask:
+            holder.mask_out = G.mask
+        mod.lumisphere_tv_grad_sparse(grid, cells, sv, su, 0.4, -1.0, -1.0, dir_factor, holder)
+        torch.cuda.synchronize()
+        res[name] = G
+    g_o = np.zeros(tuple(sg.sh.shape), np.float32)
+    m_o = np.zeros((sg.capacity,), np.uint8)
+    oracle.lumisphere_tv_grad_sparse(sg.links, sg.sh, bd, cells, sv, su, 0.4, dir_factor, m_o if with_mask else None, g_o)
+    _close(res["ours"].sh, g_o, "lumisphere vs oracle")
+    _close(res["ours"].sh, res["ref"].sh.cpu().numpy(), "lumisphere vs reference kernel")
+    assert np.abs(g_o).max() > 0
+    if with_mask:
+        assert np.array_equal(res["ours"].mask.cpu().numpy().astype(np.uint8), m_o) and m_o.sum() > 0
+        assert torch.equal(res["ours"].mask, res["ref"].mask)

@@ -124,3 +124,81 @@ def test_accel_dist_prop_oracle_properties():
     o2 = oracle.accel_dist_prop(sg.links)
     assert np.array_equal(o2[sg.links.numpy() >= 0], sg.links.numpy()[sg.links.numpy() >= 0])
     assert o2[sg.links.numpy() < 0].max() == -1
+
+
+def test_dense_normal_loss_is_the_gradient_of_its_energy():
+    """oracle_surface_normal_grad (loss_kernel.cu:245-396) against autograd of the energy its expressions differentiate:
+    sum over cells and used +x/+y/+z pairs of |n0/|n0| - n1/|n1||^2 / norm_count, times scale / n_lattice_cells."""
+    R, lv = 20, 0.0
+    sg = synth.make_shell_grid(R, basis_dim=1, variant="G*")
+    links = sg.links.long()
+    s = sg.surface[:, 0].double().clone().requires_grad_(True)
+    ok8 = torch.ones((R - 1,) * 3, dtype=torch.bool)
+    corner = {}
+    for k in range(8):
+        dx, dy, dz = k >> 2, (k >> 1) & 1, k & 1
+        l = links[dx:R - 1 + dx, dy:R - 1 + dy, dz:R - 1 + dz]
+        ok8 &= l >= 0
+        corner[k] = s[l.clamp_min(0)]
+    c = corner
+    n = torch.stack([((c[4] + c[5] + c[6] + c[7]) - (c[0] + c[1] + c[2] + c[3])) / 4,
+                     ((c[2] + c[3] + c[6] + c[7]) - (c[0] + c[1] + c[4] + c[5])) / 4,
+                     ((c[1] + c[3] + c[5] + c[7]) - (c[0] + c[2] + c[4] + c[6])) / 4], -1)
+    nh = n / torch.sqrt(1e-9 + (n * n).sum(-1, keepdim=True))
+
+    def connected(vals):
+        v = torch.stack(vals, -1).detach()
+        return ~((v <= lv).all(-1) | (v >= lv).all(-1))
+    faces = [[c[4], c[5], c[6], c[7]], [c[2], c[3], c[6], c[7]], [c[1], c[3], c[5], c[7]]]
+    use, energy = [], []
+    for a in range(3):
+        sl_hi = [slice(None)] * 3
+        sl_lo = [slice(None)] * 3
+        sl_hi[a], sl_lo[a] = slice(1, None), slice(0, -1)
+        u = torch.zeros_like(ok8)
+        u[tuple(sl_lo)] = ok8[tuple(sl_lo)] & ok8[tuple(sl_hi)] & connected(faces[a])[tuple(sl_lo)]
+        e = torch.zeros(ok8.shape, dtype=torch.float64)
+        e[tuple(sl_lo)] = ((nh[tuple(sl_lo)] - nh[tuple(sl_hi)]) ** 2).sum(-1)
+        use.append(u)
+        energy.append(e)
+    cnt = (use[0].long() + use[1].long() + use[2].long()).clamp_min(1)
+    total = sum((energy[a] * use[a] / cnt).sum() for a in range(3)) * (0.7 / (R - 1) ** 3)
+    total.backward()
+    g = np.zeros(tuple(sg.surface.shape), np.float32)
+    oracle.surface_normal_grad(sg.links, sg.surface, lv, 0, 1, 0.7, g)
+    assert np.abs(g).max() > 0 and _rel(g[:, 0], s.grad.numpy()) < 2e-5
+
+
+def test_lumisphere_tv_is_the_gradient_of_its_energy():
+    """oracle_lumisphere_tv_grad_sparse (loss_kernel.cu:1067-1177) against autograd of
+    scale / n * sum_cells sum_colour sqrt(1e-9 + dx^2 + dy^2 + dz^2 + du^2) over a list of DISTINCT cells."""
+    R, bd = 20, 4
+    sg = synth.make_shell_grid(R, basis_dim=bd, variant="G*")
+    links = sg.links.long()
+    g = torch.Generator().manual_seed(2)
+    sv, su = torch.randn(bd, generator=g), torch.randn(bd, generator=g)
+    n_lat = (R - 1) ** 3
+    cells = torch.randperm(n_lat, generator=g)[: n_lat // 2].int()
+    z, xy = cells.long() % (R - 1), cells.long() // (R - 1)
+    y, x = xy % (R - 1), xy // (R - 1)
+    sh = sg.sh.double().clone().requires_grad_(True)
+    l0 = links[x, y, z]
+    keep = l0 != 0
+    v000 = torch.where((l0 >= 0)[:, None], sh[l0.clamp_min(0)], torch.zeros((), dtype=torch.float64))
+
+    def nb(l):
+        return torch.where((l >= 0)[:, None], sh[l.clamp_min(0)], v000)
+    proj = lambda v, b: (v.view(-1, 3, bd) * b.double()).sum(-1)
+    a0 = proj(v000, sv)
+    sc = [R / 256.0] * 3
+    dx = (proj(nb(links[x + 1, y, z]), sv) - a0) * sc[0]
+    dy = (proj(nb(links[x, y + 1, z]), sv) - a0) * sc[1]
+    dz = (proj(nb(links[x, y, z + 1]), sv) - a0) * sc[2]
+    du = (proj(v000, su) - a0) * 0.8
+    e = torch.sqrt(1e-9 + dx * dx + dy * dy + dz * dz + du * du)
+    (e[keep].sum() * (0.4 / cells.shape[0])).backward()
+    got = np.zeros(tuple(sg.sh.shape), np.float32)
+    mask = np.zeros((sg.capacity,), np.uint8)
+    oracle.lumisphere_tv_grad_sparse(sg.links, sg.sh, bd, cells, sv, su, 0.4, 0.8, mask, got)
+    assert np.abs(got).max() > 0 and _rel(got, sh.grad.numpy()) < 2e-5
+    assert mask.sum() > 0 and not mask[np.abs(got).max(1) == 0].all()

@@ -217,8 +217,8 @@ def test_wavefront_path_equals_persistent_path(name, reso, bd, Q, variant, optfn
         assert torch.equal(ga.mask, gb.mask) and int(ga.mask.sum()) > 0
         for k in ("sh", "density", "surface"):
             assert H.rel_err(getattr(ga, k), getattr(gb, k)) < 2e-5, k
-        if ga.std is not None:
-            assert H.rel_err(ga.std, gb.std) < 2e-5 or float(gb.std.abs().max()) == 0.0
+        if ga.std is not None:      # ONE scalar summed by atomics over every sample of the batch: order noise of that sum
+            assert H.rel_err(ga.std, gb.std) < 1e-4 or float(gb.std.abs().max()) == 0.0
 
 
 SEG_CASES = [("G-512", 512, "G", 65536, synth.alphasurf_render_options), ("G-200", 200, "G", 16384, synth.parity_render_options),
