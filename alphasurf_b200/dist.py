@@ -12,6 +12,7 @@ gradients (1.8 GB at 512^3 x 29 floats) are never sent: the masks are OR-ed firs
 rank the same list of touched rows, and only those rows travel -- packed into one (n_rows, 2 + D) bucket, summed with a
 single NCCL all-reduce over NVLink / NVSwitch, and scattered back.
 """
+import os
 import time
 
 import torch
@@ -41,7 +42,10 @@ class GradExchange:
         self.host_ms = {}            # host time per section of step() (enqueue cost, no synchronisation), summed
         self.host_steps = 0
         self.bitpack_masks = False
-        self.render_first = True
+        # order of the two lanes of step(): "render_first" / "regs_first" -- both lanes start together in that enqueue order
+        # (their kernels share the SMs); "regs_kernels_first" -- the regulariser kernels run first and alone, the render starts
+        # when they are done and overlaps their collectives.  Measured at 2 GPUs (C3 step): 1.717 / 1.699 / 1.789 ms.
+        self.lane_order = os.environ.get("ASURF_LANE_ORDER", "render_first")
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.shard_regularisers = shard_regularisers   # end() also sums the cell-sharded regulariser gradients
@@ -284,15 +288,22 @@ class GradExchange:
                         ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"], replicate_density_terms=True)
                     else:
                         ts.regularisers(self.rank, self.world, grad=reg["grad"], mask=reg["mask"])
+                    if cuda:
+                        ev_kernels.record()       # the regulariser kernels are done: what follows on this lane is communication
                     self.mask_or(reg["mask"], group=self._group_b)
                     dist.all_reduce(reg["buf"][1] if rep else reg["buf"], op=dist.ReduceOp.SUM, group=self._group_b)
                 else:
                     ts.regularisers(grad=reg["grad"], mask=reg["mask"])     # every rank the whole lists: nothing to exchange
 
-        # Enqueue order: the render lane first (it then has the GPU to itself, as on one GPU, and its exchange -- mostly waiting
-        # for the wire -- overlaps the regulariser kernels), or the regulariser lane first.  Same order on every rank either way.
-        if not self.render_first:
+        # Enqueue order (self.lane_order), the same on every rank.  Both lanes are compute-bound in their kernels and wire-bound in
+        # their collectives, and concurrent kernels only share the SMs; what can be hidden is communication under computation.
+        render_first = self.lane_order == "render_first"
+        ev_kernels = torch.cuda.Event() if cuda else None
+        if not render_first:
             side_lane()
+            if cuda and self.lane_order == "regs_kernels_first" and self.shard_regularisers:
+                torch.cuda.current_stream().wait_event(ev_kernels)
+            lap("regulariser lane: kernels + mask OR + dense all-reduce")
         shard = self.shard_regularisers
         self.shard_regularisers = False           # begin / end: the sparse exchange of the render gradients alone
         try:
@@ -302,7 +313,7 @@ class GradExchange:
             lap("begin: mask OR, row list, pack, sparse all-reduce start")
             if events:
                 events[1].record()
-            if self.render_first:
+            if render_first:
                 self.shard_regularisers = shard
                 side_lane()
                 self.shard_regularisers = False
