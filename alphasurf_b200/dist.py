@@ -42,6 +42,11 @@ class GradExchange:
         self.host_ms = {}            # host time per section of step() (enqueue cost, no synchronisation), summed
         self.host_steps = 0
         self.bitpack_masks = False
+        # step() with ONE gradient and ONE mask all-reduce (_step_merged).  Measured (C3 step): 1.780 ms against 1.718 ms for
+        # the two lanes at 2 GPUs, 1.991 against 2.002 ms at 8 GPUs -- no gain, so it is off unless asked for.
+        self.merged_exchange = os.environ.get("ASURF_MERGED_EXCHANGE", "0") != "0"
+        self._merged = None
+        self._masks2 = None
         # order of the two lanes of step(): "render_first" / "regs_first" -- both lanes start together in that enqueue order
         # (their kernels share the SMs); "regs_kernels_first" -- the regulariser kernels run first and alone, the render starts
         # when they are done and overlaps their collectives.  Measured at 2 GPUs (C3 step): 1.717 / 1.699 / 1.789 ms.
@@ -115,19 +120,7 @@ class GradExchange:
             return n
         D = g["sh"].shape[1]
         buf = self._bucket(n, 2 + D, g["sh"])
-        if buf.is_cuda:    # one kernel: rows -> bucket, rows cleared (asurf_rows_pack)
-            from . import capi
-            import ctypes as C
-            capi.check(capi.lib().asurf_rows_pack(capi.ptr(rows), C.c_int64(n), capi.ptr(g["density"]), capi.ptr(g["surface"]),
-                                                  capi.ptr(g["sh"]), C.c_int32(D), capi.ptr(buf), C.c_int32(1),
-                                                  capi.current_stream(buf.device)), "rows_pack")
-        else:              # host tensors (gloo tests of the protocol)
-            buf[:, 0] = g["density"].view(-1)[rows]
-            buf[:, 1] = g["surface"].view(-1)[rows]
-            buf[:, 2:] = g["sh"][rows]
-            g["density"].view(-1).index_fill_(0, rows, 0.0)
-            g["surface"].view(-1).index_fill_(0, rows, 0.0)
-            g["sh"].index_fill_(0, rows, 0.0)
+        self._pack(g, rows, n, buf)
         work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._pending = (work, rows, buf)
         return n
@@ -213,6 +206,28 @@ class GradExchange:
         work, rows, buf = self._pending
         self._pending = None
         work.wait()
+        self._unpack(g, rows, buf)
+
+    @staticmethod
+    def _pack(g, rows, n, buf):
+        """touched rows of the three gradients -> bucket (n, 2 + D), rows cleared; negative (padding) rows give zero rows"""
+        D = g["sh"].shape[1]
+        if buf.is_cuda:    # one kernel (asurf_rows_pack)
+            from . import capi
+            import ctypes as C
+            capi.check(capi.lib().asurf_rows_pack(capi.ptr(rows), C.c_int64(n), capi.ptr(g["density"]), capi.ptr(g["surface"]),
+                                                  capi.ptr(g["sh"]), C.c_int32(D), capi.ptr(buf), C.c_int32(1),
+                                                  capi.current_stream(buf.device)), "rows_pack")
+        else:              # host tensors (gloo tests of the protocol)
+            buf[:, 0] = g["density"].view(-1)[rows]
+            buf[:, 1] = g["surface"].view(-1)[rows]
+            buf[:, 2:] = g["sh"][rows]
+            g["density"].view(-1).index_fill_(0, rows, 0.0)
+            g["surface"].view(-1).index_fill_(0, rows, 0.0)
+            g["sh"].index_fill_(0, rows, 0.0)
+
+    @staticmethod
+    def _unpack(g, rows, buf):
         if buf.is_cuda:
             from . import capi
             import ctypes as C
@@ -254,6 +269,9 @@ class GradExchange:
         bytes) proceeds on a second communicator WHILE the main stream renders, ORs the touched masks and exchanges the
         touched rows (begin / end above with shard_regularisers off).  Both lanes join before the optimizer.
         ``events``: optional 4 CUDA events recorded at start / after render + begin / after the join / after the optimizer."""
+        if (self.merged_exchange and self.shard_regularisers and self.world > 1 and hasattr(ts, "density_terms_replicable")
+                and ts.density_terms_replicable()):
+            return self._step_merged(ts, origins, dirs, rgb_gt, rgb_out, events, skip_optimizer)
         reg = self._lane_b(ts)
         cuda = self._side is not None
         t_h = [time.perf_counter()]
@@ -327,6 +345,85 @@ class GradExchange:
         ts.grad["density"].add_(reg["grad"]["density"])
         ts.grad["surface"].add_(reg["grad"]["surface"])
         ts.mask.logical_or_(reg["mask"])
+        lap("join")
+        if events:
+            events[2].record()
+        if not skip_optimizer:
+            ts.optimizer()
+        lap("optimizer")
+        self.host_steps += 1
+        if events:
+            events[3].record()
+
+    def _step_merged(self, ts, origins, dirs, rgb_gt, rgb_out, events=None, skip_optimizer=False):
+        """The iteration with ONE gradient all-reduce and ONE mask all-reduce (optional: self.merged_exchange).  At 8 GPUs the
+        four collectives of step() (two mask ORs, the sparse bucket, the dense regulariser gradient) add up to the time the
+        step spends outside its kernels, so this variant sends them as two: the cell-sharded surface regularisers still run on
+        the side stream beside the render, but write their gradient into the HEAD of the exchange buffer, the touched rows of
+        the render gradients are packed behind it, and the whole buffer travels once; the render mask and the regulariser
+        mask travel as one 2N-byte MAX all-reduce.  (The density regularisers run in full on every rank:
+        TrainStep.density_terms_replicable.)  Same results as step(); not faster on NVSwitch (see merged_exchange above)."""
+        reg = self._lane_b(ts)
+        cuda = self._side is not None
+        g = ts.grad
+        N, D = ts.mask.shape[0], g["sh"].shape[1]
+        dev, dt = g["sh"].device, g["sh"].dtype
+        max_rows = int(self.dense_threshold * N) + 1          # beyond this the exchange is dense anyway
+        if self._merged is None:
+            self._merged = torch.zeros((N + max_rows * (2 + D),), dtype=dt, device=dev)
+            self._masks2 = torch.zeros((2 * N,), dtype=torch.bool, device=dev)
+        head = self._merged[:N].view(N, 1)                    # surface gradient of this rank's regulariser shard
+        mask_reg = self._masks2[N:]
+        t_h = [time.perf_counter()]
+
+        def lap(name):
+            now = time.perf_counter()
+            self.host_ms[name] = self.host_ms.get(name, 0.0) + 1e3 * (now - t_h[0])
+            t_h[0] = now
+        if events:
+            events[0].record()
+        import contextlib
+        ev_start = ev_side = None
+        if cuda:
+            ev_start = torch.cuda.Event()
+            ev_start.record()                     # the previous optimizer step has updated the parameters
+            self._side.wait_event(ev_start)
+        with (torch.cuda.stream(self._side) if cuda else contextlib.nullcontext()):
+            head.zero_()
+            reg["grad"]["density"].zero_()
+            mask_reg.zero_()
+            ts.regularisers(self.rank, self.world, grad={"density": reg["grad"]["density"], "surface": head}, mask=mask_reg,
+                            replicate_density_terms=True)
+            if cuda:
+                ev_side = torch.cuda.Event()
+                ev_side.record()
+        lap("regulariser lane: kernels")
+        ts.render(origins, dirs, rgb_gt, rgb_out)
+        lap("render")
+        if cuda:
+            torch.cuda.current_stream().wait_event(ev_side)
+        self._masks2[:N].copy_(ts.mask)
+        dist.all_reduce(self._masks2.view(torch.uint8), op=dist.ReduceOp.MAX, group=self.group)
+        ts.mask_sh.copy_(self._masks2[:N])
+        rows, n = self._touched_rows(self._masks2[:N])        # identical on every rank
+        self.last_rows = n
+        if n > max_rows:                                      # dense fallback: the three gradients whole, the head alone
+            for k in ("density", "surface", "sh"):
+                dist.all_reduce(g[k], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self._merged[:N], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            bucket = self._merged[N:N + n * (2 + D)].view(n, 2 + D)
+            if n:
+                self._pack(g, rows, n, bucket)
+            dist.all_reduce(self._merged[:N + n * (2 + D)], op=dist.ReduceOp.SUM, group=self.group)
+            if n:
+                self._unpack(g, rows, bucket)
+        lap("exchange: masks, row list, pack, all-reduce, unpack")
+        if events:
+            events[1].record()
+        g["density"].add_(reg["grad"]["density"])
+        g["surface"].add_(head)
+        torch.logical_or(self._masks2[:N], mask_reg, out=ts.mask)
         lap("join")
         if events:
             events[2].record()

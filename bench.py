@@ -530,9 +530,11 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roof,
         "step_phases": phases,
         "step_phases_note": ("sequential: fused render | regularisers | optimizer" if world == 1 else
-                             "two lanes (dist.GradExchange.step): render_ms = render + mask OR + row pack on the main stream while the "
-                             "cell-sharded regularisers and their dense all-reduce run on a side stream; regularisers_ms = sparse row "
-                             "all-reduce wait + join of the lanes; optimizer_ms = RMSprop steps"),
+                             "two lanes (dist.GradExchange.step): render_ms = render + mask OR + row pack + sparse row all-reduce + "
+                             "unpack on the main stream while the cell-sharded surface regularisers and their dense all-reduce run "
+                             "on a side stream; regularisers_ms = wait for that lane + join; optimizer_ms = RMSprop steps "
+                             "(ASURF_MERGED_EXCHANGE=1: one gradient and one mask all-reduce instead, then render_ms holds the whole "
+                             "exchange)"),
         "render_only_rays_per_s": Q * world / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
     }
     if parity is not None:

@@ -5,6 +5,7 @@ import os
 import socket
 import types
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -203,6 +204,65 @@ def test_overlapped_step_world2():
     ret = mgr.dict()
     port = _free_port()
     procs = [mp.get_context("spawn").Process(target=_worker_step, args=(r, world, port, 3000, 12, 0.03, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+class _FakeStepRep(_FakeStep):
+    """density regularisers replicated (the same full gradient on every rank), surface regularisers sharded: the shape of
+    TrainStep that takes GradExchange's merged exchange (one gradient all-reduce, one mask all-reduce)"""
+
+    def density_terms_replicable(self):
+        return True
+
+    @staticmethod
+    def dens_full(N):
+        return torch.randn((N, 1), generator=torch.Generator().manual_seed(77))
+
+    def regularisers(self, rank, world, grad=None, mask=None, replicate_density_terms=False):
+        assert replicate_density_terms
+        _, ds, m = self.reg_part(rank, world, self.N)
+        grad["density"] += self.dens_full(self.N)
+        grad["surface"] += ds
+        mask |= m
+
+
+def _worker_step_merged(rank, world, port, N, D, frac, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ts = _FakeStepRep(rank, N, D, frac)
+        ex = adist.GradExchange()
+        ex.merged_exchange = True
+        ok = True
+        for _ in range(2):
+            ex.step(ts, None, None, None, None)
+            grads, mask, mask_sh = ts.seen
+            states = [_local_state(r, N, D, frac) for r in range(world)]
+            regs = [_FakeStep.reg_part(r, world, N) for r in range(world)]
+            ok = ok and ex._merged is not None                      # the merged path ran
+            ok = ok and torch.equal(mask, torch.ones((N,), dtype=torch.bool))
+            ok = ok and torch.equal(mask_sh, torch.stack([s.mask for s in states]).any(0))
+            ok = ok and torch.allclose(grads["density"], sum(s.grad["density"] for s in states) + _FakeStepRep.dens_full(N), atol=1e-6)
+            ok = ok and torch.allclose(grads["surface"], sum(s.grad["surface"] for s in states) + sum(x[1] for x in regs), atol=1e-6)
+            ok = ok and torch.allclose(grads["sh"], sum(s.grad["sh"] for s in states), atol=1e-6)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("frac", [0.03, 0.6])     # sparse bucket behind the regulariser head / dense fallback
+def test_merged_exchange_step_world2(frac):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [mp.get_context("spawn").Process(target=_worker_step_merged, args=(r, world, port, 3000, 12, frac, ret)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
