@@ -490,7 +490,8 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    traffic = load_traffic(args.workload)
+    # the ncu captures are of the workload's own size: another grid size / ray count has no measured traffic
+    traffic = load_traffic(args.workload) if (Q == w["rays"] and args.reso == w["reso"]) else {}
     alg = fwd_bytes + bwd_bytes
     achieved = alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     tr_fused = traffic.get("fused")
