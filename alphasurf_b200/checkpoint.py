@@ -23,8 +23,8 @@ import torch
 from .synth import SynthGrid
 
 BASIS_TYPE_SH = 1            # data_spec.hpp: BASIS_TYPE_SH (svox2/defs.py)
-SURFACE_TYPE_NONE = 100      # svox2/defs.py
-SURFACE_TYPE_SDF = 0
+SURFACE_TYPE_NONE = 100      # svox2/defs.py:7-9
+SURFACE_TYPE_SDF = 102
 
 
 @dataclass

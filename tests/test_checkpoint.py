@@ -72,6 +72,7 @@ def test_against_the_reference_reader_and_writer(tmp_path):
     assert torch.equal(ref.links, g.links) and torch.equal(ref.density_data.data, g.density)
     assert torch.equal(ref.surface_data.data, g.surface) and torch.equal(ref.sh_data.data, g.sh.half().float())
     assert torch.equal(ref.level_set_data, g.level_set) and ref.step_id == 7
+    assert ref.surface_type == svox2.defs.SURFACE_TYPE_SDF == ckpt.SURFACE_TYPE_SDF and ckpt.BASIS_TYPE_SH == svox2.defs.BASIS_TYPE_SH
     assert torch.allclose(ref._offset, 0.5 * (1 - ck.center / ck.radius)) and torch.allclose(ref._scaling, 0.5 / ck.radius)
     # and we open the reference's
     q = str(tmp_path / "ref.npz")
