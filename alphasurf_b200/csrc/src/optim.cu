@@ -143,20 +143,38 @@ __global__ void __launch_bounds__(256) masked_rows_kernel(float *__restrict__ da
             for (unsigned b = bits; b; b &= b - 1) s_rows[warp_in_cta][at++] = (uint8_t)(lane * 4 + __ffs(b) - 1);
         }
         __syncwarp();
+        // four elements per lane and pass: the touched rows cluster, so a few warps hold most of the work, and one dependent
+        // load -> update -> store round trip per 32 elements made them the whole kernel
         const int n_elem = n_set * n_cols;
-        for (int e = lane; e < n_elem; e += 32) {
-            const int k = e / n_cols, c = e - k * n_cols;
-            const int64_t off = (base + s_rows[warp_in_cta][k]) * n_cols + c;
-            const float l = (c == n_cols - 1) ? lr_last : lr;
-            if (RMS) {
-                float x = data[off], q = rms[off], g = grad[off];
-                rmsprop_once(x, q, g, beta, l, eps, minval);
-                data[off] = x;
-                rms[off] = q;
-            } else {
-                data[off] = fmaf(-l, grad[off], data[off]);
+        constexpr int U = 4;
+        for (int e0 = lane; e0 < n_elem; e0 += 32 * U) {
+            int64_t off[U];
+            float x[U], q[U], g[U], l[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + 32 * u;
+                off[u] = -1;
+                if (e < n_elem) {
+                    const int k = e / n_cols, c = e - k * n_cols;
+                    off[u] = (base + s_rows[warp_in_cta][k]) * n_cols + c;
+                    l[u] = (c == n_cols - 1) ? lr_last : lr;
+                    x[u] = data[off[u]];
+                    g[u] = grad[off[u]];
+                    if (RMS) q[u] = rms[off[u]];
+                }
             }
-            grad[off] = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (off[u] < 0) continue;
+                if (RMS) {
+                    rmsprop_once(x[u], q[u], g[u], beta, l[u], eps, minval);
+                    data[off[u]] = x[u];
+                    rms[off[u]] = q[u];
+                } else {
+                    data[off[u]] = fmaf(-l[u], g[u], x[u]);
+                }
+                grad[off[u]] = 0.f;
+            }
         }
     }
 }
