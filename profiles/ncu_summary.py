@@ -10,7 +10,13 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio','smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio','smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio','smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
-        'sm__inst_executed_pipe_fp64.sum','sm__cycles_elapsed.max']
+        'sm__inst_executed_pipe_fp64.sum','sm__cycles_elapsed.max',
+        # L2 / atomic (red) traffic: sectors of red.global.add reaching L2, their L2 lookup hits / misses, L2 throughput
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sectors_srcunit_tex_op_red.sum',
+        'lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed', 'lts__t_sectors_srcunit_tex_op_red.sum.per_second',
+        'lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum', 'lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum',
+        'l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum', 'l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum',
+        'lts__t_sector_op_read_hit_rate.pct', 'lts__t_sector_op_write_hit_rate.pct']
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
