@@ -4,6 +4,10 @@ import sys, json, torch
 sys.path.insert(0, '.')
 from alphasurf_b200 import svox2_csrc as ours, synth
 from tests import helpers as H
+if "--shim" in sys.argv:          # the compiled svox2.csrc module instead of the ctypes layer (lower per-call host cost)
+    sys.argv.remove("--shim")
+    from alphasurf_b200 import build_shim
+    ours = build_shim.load()
 ref = H.load_reference_cuda()
 opts = synth.alphasurf_render_options()
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 640
