@@ -202,3 +202,43 @@ def test_lumisphere_tv_is_the_gradient_of_its_energy():
     oracle.lumisphere_tv_grad_sparse(sg.links, sg.sh, bd, cells, sv, su, 0.4, 0.8, mask, got)
     assert np.abs(got).max() > 0 and _rel(got, sh.grad.numpy()) < 2e-5
     assert mask.sum() > 0 and not mask[np.abs(got).max(1) == 0].all()
+
+
+def test_msi_tv_matches_autograd_of_its_surrogate():
+    """oracle_msi_tv_grad_sparse (loss_kernel.cu:979-1064).  The kernel's update is idelta * axis_scale * d_axis per
+    neighbour (the axis scale is applied AFTER the norm), i.e. the gradient of the surrogate
+    sum_cells idelta.detach() * sum_axis axis_scale * d_axis.detach() * d_axis -- which autograd differentiates here through an
+    independent gather (wrap-around in both texel axes, missing texels read 0, the layer past the last one reads v00, or 0 for
+    sigma).  Distinct cells, so that every (texel, layer) is updated by a deterministic set of cells."""
+    R, L = 10, 6
+    g = torch.Generator().manual_seed(3)
+    keep = torch.rand((2 * R, R), generator=g) > 0.2
+    links = torch.full((2 * R, R), -1, dtype=torch.int32)
+    links[keep] = torch.arange(int(keep.sum()), dtype=torch.int32)
+    data = torch.randn((int(keep.sum()), L, 4), generator=g)
+    n_cells = links.numel() * L
+    cells = torch.randperm(n_cells, generator=g)[: n_cells // 2].int()
+    scale, scale_last = 0.7, 0.3
+    msi = data.double().clone().requires_grad_(True)
+    z = cells.long() % L
+    t = cells.long() // L
+    y, x = t % R, t // R
+    nx, ny = (x + 1) % (2 * R), (y + 1) % R
+    l00, l01, l10 = links[x, y].long(), links[x, ny].long(), links[nx, y].long()
+
+    def at(l, zz):
+        return torch.where((l >= 0)[:, None], msi[l.clamp_min(0), zz], torch.zeros((), dtype=torch.float64))
+    v00, v01, v10 = at(l00, z), at(l01, z), at(l10, z)
+    has_next = (l00 >= 0) & (z + 1 < L)
+    last = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64)
+    v_nx = torch.where(has_next[:, None], msi[l00.clamp_min(0), (z + 1).clamp_max(L - 1)], v00 * (1.0 - last))
+    dx, dy, dz = v10 - v00, v01 - v00, v_nx - v00
+    sc = torch.tensor([scale, scale, scale, scale_last], dtype=torch.float64) / (n_cells // 2)
+    idelta = (sc * torch.rsqrt(1e-9 + dx * dx + dy * dy + dz * dz)).detach()
+    ax = (2 * R / 256.0, R / 256.0, L / 256.0)
+    (idelta * (ax[0] * dx.detach() * dx + ax[1] * dy.detach() * dy + ax[2] * dz.detach() * dz)).sum().backward()
+    got = np.zeros(tuple(data.shape), np.float32)
+    mask = np.zeros(tuple(data.shape[:2]), np.uint8)
+    oracle.msi_tv_grad_sparse(links, data, cells, mask, scale, scale_last, got)
+    assert np.abs(got).max() > 0 and _rel(got, msi.grad.numpy()) < 2e-5
+    assert mask.sum() > 0 and (np.abs(got).max(-1)[mask == 0] == 0).all()
