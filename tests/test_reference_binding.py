@@ -25,8 +25,10 @@ def ref_svox2(request):
     else:
         from alphasurf_b200 import build_shim
         ours = build_shim.load()          # csrc/host/svox2_shim.cpp: pybind11 + torch C++ over the same C ABI
-    saved = {k: sys.modules.get(k) for k in ("mcubes", "svox2", "svox2.csrc", "svox2.svox2", "svox2.utils", "svox2.defs",
-                                             "svox2.version")}
+    names = ("mcubes", "svox2", "svox2.csrc", "svox2.svox2", "svox2.utils", "svox2.defs", "svox2.version")
+    saved = {k: sys.modules.get(k) for k in names}
+    for k in names[1:]:          # a copy imported earlier in the session (e.g. without an extension, by the L0 harness) must
+        sys.modules.pop(k, None)  # not be reused: svox2/utils.py looks for svox2.csrc once, at import
     sys.modules.setdefault("mcubes", types.ModuleType("mcubes"))     # module-level import of an absent package (svox2.py:16)
     sys.modules["svox2.csrc"] = ours                                 # what INTEGRATION.md's svox2/csrc.py amounts to
     sys.path.insert(0, REF)
