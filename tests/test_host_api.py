@@ -77,3 +77,28 @@ def test_accel_cache_is_keyed_by_tensor_identity(monkeypatch):
     assert alias.data_ptr() == storage.data_ptr() and alias._version == storage._version
     C.accel_for(alias)
     assert len(builds) == 3                                        # not trusted: rebuilt
+
+
+def test_round_two_entries_check_their_inputs_like_the_reference():
+    """surface_normal_grad (loss_kernel.cu:1297-1306), lumisphere_tv_grad_sparse (:1671-1676), msi_tv_grad_sparse,
+    surf_sign_change_grad_sparse: CHECK_INPUT -> RuntimeError on CPU tensors; basis_fn must be 1-D; positional arity of
+    svox2.cpp:117-135."""
+    sg = synth.make_shell_grid(8, basis_dim=4)
+    assert len(inspect.signature(C.surface_normal_grad).parameters) == 9
+    assert len(inspect.signature(C.lumisphere_tv_grad_sparse).parameters) == 9
+    assert len(inspect.signature(C.msi_tv_grad_sparse).parameters) == 7
+    assert len(inspect.signature(C.surf_sign_change_grad_sparse).parameters) == 8
+    with pytest.raises(RuntimeError):
+        C.surface_normal_grad(sg.links, sg.surface, 0.0, 0, 1, 1.0, -1.0, -1.0, torch.zeros_like(sg.surface))
+    cells = torch.zeros((4,), dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        C.surf_sign_change_grad_sparse(sg.links, sg.surface, cells, torch.zeros((0,), dtype=torch.bool), 0, 1, 1.0,
+                                       torch.zeros_like(sg.surface))
+    grid = H.fill_grid_spec(C, sg)
+    holder = C.GridOutputGrads()
+    holder.grad_sh_out = torch.zeros_like(sg.sh)
+    with pytest.raises(RuntimeError):
+        C.lumisphere_tv_grad_sparse(grid, cells, torch.zeros(4), torch.zeros(4), 1.0, -1.0, -1.0, 1.0, holder)
+    for name in ("volume_render_surface_fused", "volume_render_nvol", "volume_render_svox1", "test_cubic_root_grad"):
+        with pytest.raises(NotImplementedError):            # the out-of-scope backends exist and refuse, never fall back
+            getattr(C, name)()
